@@ -1,0 +1,118 @@
+/*
+ * rt_b200.h — C-ABI of the B200 (sm_100a) ray-tracing hot path (librt_b200.so).
+ *
+ * Every entry point replaces one Metal interface the reference's host code drives; the reference-side call it
+ * stands in for is cited per function. Plain pointers and sizes only. All functions return 0 on success and a
+ * non-zero code on failure (the reference traps or silently skips instead — SURVEY.md §5); rt_last_error()
+ * returns the message for the calling thread. Nothing here falls back to the CPU: without a CUDA device
+ * rt_create fails.
+ *
+ * Memory model: the host owns every buffer. "dev" pointers are CUDA device pointers from any
+ * allocator (rt_malloc, cudaMalloc, a torch tensor's data_ptr). Work is enqueued on the context's stream in
+ * call order, so skin -> refit -> TLAS update -> trace need no explicit barriers (the reference's missing
+ * skinning->refit barrier, Renderer.swift:1312-1317, cannot occur).
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include "rt_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rt_context rt_context;
+
+/* ---- context / stream (Renderer.init: device, MTL4CommandQueue; Renderer.swift:228-262) ----------------- */
+int rt_create(int device, rt_context **out);
+int rt_destroy(rt_context *ctx);
+const char *rt_last_error(void);
+/* Use an external CUDA stream (cudaStream_t as void*), e.g. torch's current stream; NULL = the context's own. */
+int rt_set_stream(rt_context *ctx, void *cudaStream);
+/* commitAndWait (Utilities.swift:122-128,240-246) */
+int rt_sync(rt_context *ctx);
+/* CUDA-event timer on the context's stream: begin/end bracket enqueued work; end synchronises. */
+int rt_timer_begin(rt_context *ctx);
+int rt_timer_end(rt_context *ctx, float *milliseconds);
+
+/* ---- buffers (device.makeBuffer / contents().copyMemory; Renderer.swift:342-420) ------------------------- */
+int rt_malloc(rt_context *ctx, size_t bytes, void **dev);
+int rt_free(rt_context *ctx, void *dev);
+int rt_malloc_host(rt_context *ctx, size_t bytes, void **pinnedHost); /* pinned staging memory */
+int rt_free_host(rt_context *ctx, void *pinnedHost);
+int rt_upload(rt_context *ctx, void *dstDev, const void *srcHost, size_t bytes);   /* stream-ordered */
+int rt_download(rt_context *ctx, void *dstHost, const void *srcDev, size_t bytes); /* stream-ordered + sync */
+int rt_copy(rt_context *ctx, void *dstDev, const void *srcDev, size_t bytes);      /* blit, Renderer.swift:1290-1303 */
+int rt_memset(rt_context *ctx, void *dstDev, int value, size_t bytes);
+
+/* ---- acceleration structures ------------------------------------------------------------------------------
+ * rt_blas_build: MTLAccelerationStructure build (+ compaction) of one primitive AS with one triangle geometry
+ * per submesh (Utilities.swift:100-290, Renderer.swift:509-529, Mesh.swift:84-101). geoms is a HOST array whose
+ * vertex/index pointers are DEVICE pointers. flags: RT_AS_FLAG_COMPACT | RT_AS_FLAG_REFITTABLE. The returned id
+ * is what instance descriptors carry in accelerationStructureID.
+ * rt_blas_refit: refit of a skinned mesh's BLAS in place (Renderer.swift:1084-1202): same topology, boxes and
+ * triangle records recomputed from the current vertex buffer contents.
+ * rt_tlas_build / rt_tlas_update: instance AS over `count` 72-byte descriptors in DEVICE memory
+ * (Renderer.swift:547-606, 937-973); update = rebuild from the descriptors' current contents. */
+int rt_blas_build(rt_context *ctx, const rt_triangle_geometry *geoms, uint32_t geometryCount, uint32_t flags,
+                  uint64_t *outId);
+int rt_blas_refit(rt_context *ctx, uint64_t id, const rt_triangle_geometry *geoms, uint32_t geometryCount);
+int rt_blas_destroy(rt_context *ctx, uint64_t id);
+int rt_tlas_build(rt_context *ctx, const rt_instance_descriptor *descriptorsDev, uint32_t count, uint64_t *outId);
+int rt_tlas_update(rt_context *ctx, uint64_t id, const rt_instance_descriptor *descriptorsDev, uint32_t count);
+int rt_tlas_destroy(rt_context *ctx, uint64_t id);
+
+typedef struct rt_as_info {
+  uint32_t primitiveCount; /* triangles (BLAS) or instances (TLAS) */
+  uint32_t wideNodeCount;  /* 80-byte 8-wide nodes */
+  uint32_t levelCount;
+  uint32_t _pad;
+  uint64_t bytes;          /* resident device bytes */
+  float boundsMin[3], boundsMax[3];
+  float sahCost;           /* surface-area-heuristic cost of the wide tree (node + leaf terms) */
+  float _pad2;
+} rt_as_info;
+int rt_as_get_info(rt_context *ctx, uint64_t id, rt_as_info *out);
+
+/* ---- kernels ------------------------------------------------------------------------------------------------
+ * rt_skin: skinningKernel dispatch (Skinning.metal:7-49; SkinningPass.swift:160-211). buffers[] is the argument
+ * table indexed by BufferIndex: 10 rest positions, 11 rest normals, 12 joint indices (ushort4), 13 joint weights
+ * (float4), 14 joint matrices (float4x4 column-major), 15 skinned positions (out), 16 skinned normals (out); all
+ * device pointers. Index 0 (vertexCount in the reference) is passed by value. */
+int rt_skin(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], uint32_t vertexCount);
+
+/* Optional extras of rt_trace that have no counterpart in the reference's binding table. Zero-initialise. */
+typedef struct rt_trace_options {
+  int32_t tileModulo;    /* multi-GPU ownership: this call renders 16x16 tiles with tile % tileModulo == */
+  int32_t tileRemainder; /*   tileRemainder (0/1 and 0 = every tile) */
+  uint32_t *primaryIdsDev;   /* probe: 4 x u32 per pixel (instance, geometry, primitive, t bits) of sample 0's
+                                first intersect call; 0xFFFFFFFF x4 on a miss. NULL = off */
+  uint64_t *rayCountersDev;  /* probe: 3 x u64 {closest-hit rays, any-hit rays, closest hits}, accumulated */
+  void *const *peerAccumulation; /* multi-GPU: tileModulo device pointers to every rank's destination
+                                    accumulation image (same format/size); owned tiles are also stored there
+                                    through NVLink peer mappings. NULL = local only */
+} rt_trace_options;
+
+/* rt_trace: raytracingKernel dispatch (Raytracing.metal:220-831; binding block Renderer.swift:1453-1490).
+ * buffers[]: 0 Uniforms (HOST pointer; copied into the launch like a `constant` argument), 5 Resource rows (dev),
+ * 6 lights (dev), 8 TLAS id from rt_tlas_build (cast to pointer), 9 instance descriptors (dev), 17 previous
+ * instance descriptors (dev). textures[]: the nine images of TextureIndex (device memory): 2 random (read),
+ * 0 history (read), 1 destination (write), 3 depth, 4 motion (read-write), 5..8 G-buffer.
+ * Function constants: 0 resourcesStride (accepted, unused — as in the reference), 1 maxSubmeshes. */
+int rt_trace(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], const rt_image textures[RT_TEXTURE_COUNT],
+             int resourcesStride, int maxSubmeshes, const rt_trace_options *options);
+
+/* Upload an RGBA8 texture and return the device address of its rt_texture2d record (a Resource texture slot). */
+int rt_texture_create(rt_context *ctx, const uint8_t *rgba8Host, int width, int height, int srgb,
+                      const rt_texture2d **outRecordDev);
+int rt_texture_destroy(rt_context *ctx, const rt_texture2d *recordDev);
+
+/* Number of kernels this library has launched on the context since creation (bench.py's gpu_launches). */
+uint64_t rt_launch_count(rt_context *ctx);
+/* Select the trace kernel layout: 0 = megakernel (default), 1 = wavefront. */
+int rt_set_trace_mode(rt_context *ctx, int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */

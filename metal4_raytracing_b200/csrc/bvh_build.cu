@@ -1,0 +1,939 @@
+// bvh_build.cu — GPU acceleration-structure builder for sm_100a.
+//
+// Replaces MTLAccelerationStructure build / compact / refit, which the reference drives from
+// MetalRaytracing/Utilities.swift:100-290 and MetalRaytracing/Renderer.swift:464-606,1084-1202 and whose
+// implementation is a closed Apple driver. Pipeline (all on the device, one stream):
+//   primitive boxes -> 63-bit Morton keys -> radix sort (CUB) -> LBVH hierarchy (Karras 2012) -> bottom-up
+//   boxes + subtree sizes -> level-synchronous collapse into 80-byte 8-wide quantised nodes (common.cuh)
+//   -> triangle / instance leaf records.
+// A refit keeps the wide topology and recomputes triangle records, exact node boxes and quantised child boxes
+// level by level from the leaves up; the BVH2 scratch is not needed for it.
+// Compiled with -fmad=false: the instance-matrix inverse must round exactly like the host double arithmetic the
+// oracle uses (DESIGN.md "numeric contract").
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace rtb {
+
+namespace {
+
+constexpr uint32_t kLeafBit = 0x80000000u;
+constexpr int kMaxLeafPrims = 3;
+
+struct GeomEntry {
+  const uint8_t *vertices;
+  const uint8_t *indices;
+  uint32_t vertexStride;
+  uint32_t indexStride;
+  uint32_t firstTriangle; // prefix offset into the BLAS-wide triangle numbering
+  uint32_t triangleCount;
+};
+
+// ---- ordered-uint encoding so float min/max can use integer atomics --------------------------------------
+__device__ __forceinline__ uint32_t orderedFromFloat(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float floatFromOrdered(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+struct BoundsAtomics {
+  uint32_t lo[3], hi[3];
+};
+
+__global__ void k_init_bounds(BoundsAtomics *b) {
+  if (threadIdx.x == 0) {
+    for (int a = 0; a < 3; ++a) {
+      b->lo[a] = 0xFFFFFFFFu;
+      b->hi[a] = 0u;
+    }
+  }
+}
+
+__device__ __forceinline__ void reduceBounds(BoundsAtomics *b, float3 lo, float3 hi, bool valid) {
+  // warp reduce, then one atomic per warp
+  const unsigned full = 0xFFFFFFFFu;
+  if (!valid) {
+    lo = make_float3(FLT_MAX, FLT_MAX, FLT_MAX);
+    hi = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo.x = fminf(lo.x, __shfl_xor_sync(full, lo.x, o));
+    lo.y = fminf(lo.y, __shfl_xor_sync(full, lo.y, o));
+    lo.z = fminf(lo.z, __shfl_xor_sync(full, lo.z, o));
+    hi.x = fmaxf(hi.x, __shfl_xor_sync(full, hi.x, o));
+    hi.y = fmaxf(hi.y, __shfl_xor_sync(full, hi.y, o));
+    hi.z = fmaxf(hi.z, __shfl_xor_sync(full, hi.z, o));
+  }
+  if ((threadIdx.x & 31) == 0 && lo.x <= hi.x) {
+    atomicMin(&b->lo[0], orderedFromFloat(lo.x));
+    atomicMin(&b->lo[1], orderedFromFloat(lo.y));
+    atomicMin(&b->lo[2], orderedFromFloat(lo.z));
+    atomicMax(&b->hi[0], orderedFromFloat(hi.x));
+    atomicMax(&b->hi[1], orderedFromFloat(hi.y));
+    atomicMax(&b->hi[2], orderedFromFloat(hi.z));
+  }
+}
+
+__device__ __forceinline__ void loadTriangle(const GeomEntry *geoms, uint32_t geomCount, uint32_t tri, float3 &a,
+                                             float3 &b, float3 &c, uint32_t &geom, uint32_t &prim) {
+  uint32_t g = 0;
+  while (g + 1 < geomCount && tri >= geoms[g + 1].firstTriangle) ++g;
+  const GeomEntry ge = geoms[g];
+  uint32_t p = tri - ge.firstTriangle;
+  uint32_t i0, i1, i2;
+  if (ge.indexStride == 2) {
+    const uint16_t *ix = reinterpret_cast<const uint16_t *>(ge.indices);
+    i0 = ix[3 * p], i1 = ix[3 * p + 1], i2 = ix[3 * p + 2];
+  } else {
+    const uint32_t *ix = reinterpret_cast<const uint32_t *>(ge.indices);
+    i0 = ix[3 * p], i1 = ix[3 * p + 1], i2 = ix[3 * p + 2];
+  }
+  const float *pa = reinterpret_cast<const float *>(ge.vertices + size_t(i0) * ge.vertexStride);
+  const float *pb = reinterpret_cast<const float *>(ge.vertices + size_t(i1) * ge.vertexStride);
+  const float *pc = reinterpret_cast<const float *>(ge.vertices + size_t(i2) * ge.vertexStride);
+  a = make_float3(pa[0], pa[1], pa[2]);
+  b = make_float3(pb[0], pb[1], pb[2]);
+  c = make_float3(pc[0], pc[1], pc[2]);
+  geom = g;
+  prim = p;
+}
+
+// One thread per triangle: box + centroid bounds.
+__global__ void k_triangle_bounds(const GeomEntry *geoms, uint32_t geomCount, uint32_t n, float4 *primLo,
+                                  float4 *primHi, BoundsAtomics *bounds) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = i < n;
+  float3 lo = make_float3(0, 0, 0), hi = lo;
+  if (valid) {
+    float3 a, b, c;
+    uint32_t g, p;
+    loadTriangle(geoms, geomCount, i, a, b, c, g, p);
+    lo = make_float3(fminf(fminf(a.x, b.x), c.x), fminf(fminf(a.y, b.y), c.y), fminf(fminf(a.z, b.z), c.z));
+    hi = make_float3(fmaxf(fmaxf(a.x, b.x), c.x), fmaxf(fmaxf(a.y, b.y), c.y), fmaxf(fmaxf(a.z, b.z), c.z));
+    primLo[i] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+    primHi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+  }
+  reduceBounds(bounds, lo, hi, valid);
+}
+
+// One thread per instance: world box of the BLAS bounds, world->object matrix (double cofactor inverse, the
+// exact op order of oracle/oracle_bvh.cpp invertAffine4x3), traversal record.
+__global__ void k_instance_bounds(const rt_instance_descriptor *desc, uint32_t n, InstanceRecord *records,
+                                  float4 *primLo, float4 *primHi, BoundsAtomics *bounds) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = i < n;
+  float3 lo = make_float3(0, 0, 0), hi = lo;
+  if (valid) {
+    const rt_instance_descriptor d = desc[i];
+    const BlasHeader *blas = reinterpret_cast<const BlasHeader *>(static_cast<uintptr_t>(d.accelerationStructureID));
+    const float(*m)[3] = d.transformationMatrix;
+    double a00 = m[0][0], a10 = m[0][1], a20 = m[0][2];
+    double a01 = m[1][0], a11 = m[1][1], a21 = m[1][2];
+    double a02 = m[2][0], a12 = m[2][1], a22 = m[2][2];
+    double t0 = m[3][0], t1 = m[3][1], t2 = m[3][2];
+    double c00 = a11 * a22 - a12 * a21;
+    double c01 = a12 * a20 - a10 * a22;
+    double c02 = a10 * a21 - a11 * a20;
+    double det = (a00 * c00 + a01 * c01) + a02 * c02;
+    double id = 1.0 / det;
+    double i00 = c00 * id, i01 = (a02 * a21 - a01 * a22) * id, i02 = (a01 * a12 - a02 * a11) * id;
+    double i10 = c01 * id, i11 = (a00 * a22 - a02 * a20) * id, i12 = (a02 * a10 - a00 * a12) * id;
+    double i20 = c02 * id, i21 = (a01 * a20 - a00 * a21) * id, i22 = (a00 * a11 - a01 * a10) * id;
+    double it0 = -((i00 * t0 + i01 * t1) + i02 * t2);
+    double it1 = -((i10 * t0 + i11 * t1) + i12 * t2);
+    double it2 = -((i20 * t0 + i21 * t1) + i22 * t2);
+    InstanceRecord r;
+    r.row0 = make_float4(float(i00), float(i01), float(i02), float(it0));
+    r.row1 = make_float4(float(i10), float(i11), float(i12), float(it1));
+    r.row2 = make_float4(float(i20), float(i21), float(i22), float(it2));
+    bool empty = blas == nullptr || blas->triCount == 0;
+    r.nodes = empty ? nullptr : blas->nodes;
+    r.tris = empty ? nullptr : blas->tris;
+    records[i] = r;
+    if (!empty) {
+      lo = make_float3(FLT_MAX, FLT_MAX, FLT_MAX);
+      hi = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+      for (int corner = 0; corner < 8; ++corner) {
+        float px = (corner & 1) ? blas->boundsHi[0] : blas->boundsLo[0];
+        float py = (corner & 2) ? blas->boundsHi[1] : blas->boundsLo[1];
+        float pz = (corner & 4) ? blas->boundsHi[2] : blas->boundsLo[2];
+        float wx = ((m[0][0] * px + m[1][0] * py) + m[2][0] * pz) + m[3][0];
+        float wy = ((m[0][1] * px + m[1][1] * py) + m[2][1] * pz) + m[3][1];
+        float wz = ((m[0][2] * px + m[1][2] * py) + m[2][2] * pz) + m[3][2];
+        lo = make_float3(fminf(lo.x, wx), fminf(lo.y, wy), fminf(lo.z, wz));
+        hi = make_float3(fmaxf(hi.x, wx), fmaxf(hi.y, wy), fmaxf(hi.z, wz));
+      }
+      // pad for the world->object->world round trip (same rule as the oracle's TLAS)
+      float px = 1.0e-5f * fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), 1.0e-3f);
+      float py = 1.0e-5f * fmaxf(fmaxf(fabsf(lo.y), fabsf(hi.y)), 1.0e-3f);
+      float pz = 1.0e-5f * fmaxf(fmaxf(fabsf(lo.z), fabsf(hi.z)), 1.0e-3f);
+      lo = make_float3(lo.x - px, lo.y - py, lo.z - pz);
+      hi = make_float3(hi.x + px, hi.y + py, hi.z + pz);
+    } else {
+      valid = false; // keeps the global bounds clean; the box below is a point at the origin of the instance
+      lo = hi = make_float3(float(t0), float(t1), float(t2));
+    }
+    primLo[i] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+    primHi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+  }
+  reduceBounds(bounds, lo, hi, valid);
+}
+
+__device__ __forceinline__ uint64_t expandBits21(uint32_t v) {
+  uint64_t x = v & 0x1FFFFFu;
+  x = (x | x << 32) & 0x1F00000000FFFFull;
+  x = (x | x << 16) & 0x1F0000FF0000FFull;
+  x = (x | x << 8) & 0x100F00F00F00F00Full;
+  x = (x | x << 4) & 0x10C30C30C30C30C3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+
+__global__ void k_morton(const float4 *primLo, const float4 *primHi, uint32_t n, const BoundsAtomics *bounds,
+                         uint64_t *keys, uint32_t *vals) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float lo[3], ext[3];
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = floatFromOrdered(bounds->lo[a]);
+    float h = floatFromOrdered(bounds->hi[a]);
+    ext[a] = h > lo[a] ? h - lo[a] : 1.0f;
+  }
+  float4 l = primLo[i], h = primHi[i];
+  float c[3] = {0.5f * (l.x + h.x), 0.5f * (l.y + h.y), 0.5f * (l.z + h.z)};
+  uint32_t q[3];
+  for (int a = 0; a < 3; ++a) {
+    float f = (c[a] - lo[a]) / ext[a];
+    f = fminf(fmaxf(f, 0.0f), 1.0f);
+    q[a] = min(uint32_t(f * 2097152.0f), 2097151u);
+  }
+  keys[i] = (expandBits21(q[0]) << 2) | (expandBits21(q[1]) << 1) | expandBits21(q[2]);
+  vals[i] = i;
+}
+
+// ---- LBVH hierarchy (Karras 2012) ---------------------------------------------------------------------------
+__device__ __forceinline__ int deltaKey(const uint64_t *keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  uint64_t a = keys[i], b = keys[j];
+  if (a == b) return 64 + __clz(uint32_t(i) ^ uint32_t(j));
+  return __clzll(static_cast<long long>(a ^ b));
+}
+
+struct Bvh2 {
+  uint32_t n;
+  uint32_t *left, *right; // [n-1]
+  uint32_t *parent;       // [2n-1]: internal i -> i, leaf j -> (n-1) + j
+  float4 *lo, *hi;        // [n-1]
+  uint32_t *count;        // [n-1]
+  uint32_t *flag;         // [n-1]
+};
+
+__global__ void k_karras(const uint64_t *keys, Bvh2 t) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int n = int(t.n);
+  if (i >= n - 1) return;
+  int d = (deltaKey(keys, n, i, i + 1) - deltaKey(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = deltaKey(keys, n, i, i - d);
+  int lmax = 2;
+  while (deltaKey(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+  int l = 0;
+  for (int s = lmax >> 1; s >= 1; s >>= 1)
+    if (deltaKey(keys, n, i, i + (l + s) * d) > dmin) l += s;
+  int j = i + l * d;
+  int dnode = deltaKey(keys, n, i, j);
+  int s = 0, step = l;
+  do {
+    step = (step + 1) >> 1;
+    if (deltaKey(keys, n, i, i + (s + step) * d) > dnode) s += step;
+  } while (step > 1);
+  int gamma = i + s * d + min(d, 0);
+  uint32_t L = (min(i, j) == gamma) ? (uint32_t(gamma) | kLeafBit) : uint32_t(gamma);
+  uint32_t R = (max(i, j) == gamma + 1) ? (uint32_t(gamma + 1) | kLeafBit) : uint32_t(gamma + 1);
+  t.left[i] = L;
+  t.right[i] = R;
+  t.parent[(L & kLeafBit) ? (n - 1) + int(L & ~kLeafBit) : int(L)] = uint32_t(i);
+  t.parent[(R & kLeafBit) ? (n - 1) + int(R & ~kLeafBit) : int(R)] = uint32_t(i);
+  if (i == 0) t.parent[0] = 0xFFFFFFFFu;
+  t.flag[i] = 0;
+}
+
+// One thread per leaf walks up; the second visitor of a node merges its children.
+__global__ void k_bvh2_bounds(const float4 *primLo, const float4 *primHi, const uint32_t *sorted, Bvh2 t) {
+  uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (leaf >= t.n || t.n < 2) return;
+  uint32_t node = t.parent[(t.n - 1) + leaf];
+  while (node != 0xFFFFFFFFu) {
+    if (atomicAdd(&t.flag[node], 1u) == 0u) return; // first visitor leaves
+    __threadfence();
+    uint32_t L = t.left[node], R = t.right[node];
+    float4 llo, lhi, rlo, rhi;
+    uint32_t lc, rc;
+    if (L & kLeafBit) {
+      uint32_t p = sorted[L & ~kLeafBit];
+      llo = primLo[p], lhi = primHi[p], lc = 1;
+    } else {
+      llo = t.lo[L], lhi = t.hi[L], lc = t.count[L];
+    }
+    if (R & kLeafBit) {
+      uint32_t p = sorted[R & ~kLeafBit];
+      rlo = primLo[p], rhi = primHi[p], rc = 1;
+    } else {
+      rlo = t.lo[R], rhi = t.hi[R], rc = t.count[R];
+    }
+    t.lo[node] = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.0f);
+    t.hi[node] = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.0f);
+    t.count[node] = lc + rc;
+    __threadfence();
+    node = t.parent[node];
+  }
+}
+
+// ---- quantisation of one wide node ---------------------------------------------------------------------------
+struct ChildBox {
+  float lo[3], hi[3];
+};
+
+// Chooses origin/exponents for `box` and quantises the child boxes conservatively (checked in double, where
+// origin + q * 2^e is exact). Writes w0 (keeping imask), w2..w4.
+__device__ void quantiseNode(WideNode &node, const float lo[3], const float hi[3], const ChildBox child[8],
+                             const uint8_t present[8], uint8_t imask) {
+  uint32_t ebyte[3];
+  float scale[3];
+  for (int a = 0; a < 3; ++a) {
+    float ext = hi[a] - lo[a];
+    int e;
+    if (!(ext > 0.0f)) {
+      e = -126;
+    } else {
+      // smallest e with ext / 2^e <= 255
+      float m = frexpf(ext / 255.0f, &e); // ext/255 = m * 2^e, m in [0.5, 1)
+      if (m == 0.5f) e -= 1;
+      e = max(e, -126);
+      while (double(ext) / ldexp(1.0, e) > 255.0) ++e;
+    }
+    e = min(e, 127);
+    ebyte[a] = uint32_t(e + 127);
+    scale[a] = __uint_as_float(ebyte[a] << 23);
+  }
+  uint32_t q[6][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}}; // [lo xyz, hi xyz][word]
+  for (int s = 0; s < 8; ++s) {
+    if (!present[s]) continue;
+    for (int a = 0; a < 3; ++a) {
+      double sc = double(scale[a]), org = double(lo[a]);
+      int ql = int(floor((double(child[s].lo[a]) - org) / sc));
+      int qh = int(ceil((double(child[s].hi[a]) - org) / sc));
+      ql = max(0, min(255, ql));
+      qh = max(0, min(255, qh));
+      while (ql > 0 && org + double(ql) * sc > double(child[s].lo[a])) --ql;
+      while (qh < 255 && org + double(qh) * sc < double(child[s].hi[a])) ++qh;
+      if (qh < ql) qh = ql;
+      q[a][s >> 2] |= uint32_t(ql) << (8 * (s & 3));
+      q[3 + a][s >> 2] |= uint32_t(qh) << (8 * (s & 3));
+    }
+  }
+  node.w[0] = make_uint4(__float_as_uint(lo[0]), __float_as_uint(lo[1]), __float_as_uint(lo[2]),
+                         ebyte[0] | (ebyte[1] << 8) | (ebyte[2] << 16) | (uint32_t(imask) << 24));
+  node.w[2] = make_uint4(q[0][0], q[0][1], q[1][0], q[1][1]);
+  node.w[3] = make_uint4(q[2][0], q[2][1], q[3][0], q[3][1]);
+  node.w[4] = make_uint4(q[4][0], q[4][1], q[5][0], q[5][1]);
+}
+
+__device__ __forceinline__ float halfArea(const float lo[3], const float hi[3]) {
+  float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+  return dx * dy + dy * dz + dz * dx;
+}
+
+struct CollapseCounters {
+  uint32_t nodeCount; // next free wide-node index
+  uint32_t primCount; // next free leaf-primitive slot
+};
+
+// One thread per wide node of the current level. queueIn[i] = BVH2 reference of wide node levelStart + i.
+__global__ void k_collapse_level(Bvh2 t, const float4 *primLo, const float4 *primHi, const uint32_t *sorted,
+                                 const uint32_t *queueIn, uint32_t *queueOut, uint32_t levelStart,
+                                 uint32_t levelCount, uint32_t nextLevelStart, CollapseCounters *counters,
+                                 WideNode *nodes, float4 *nodeBox, uint32_t *leafPrim) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= levelCount) return;
+  const uint32_t self = queueIn[i];
+  auto boxOf = [&](uint32_t ref, float lo[3], float hi[3]) {
+    float4 l, h;
+    if (ref & kLeafBit) {
+      uint32_t p = sorted[ref & ~kLeafBit];
+      l = primLo[p], h = primHi[p];
+    } else {
+      l = t.lo[ref], h = t.hi[ref];
+    }
+    lo[0] = l.x, lo[1] = l.y, lo[2] = l.z, hi[0] = h.x, hi[1] = h.y, hi[2] = h.z;
+  };
+  auto countOf = [&](uint32_t ref) { return (ref & kLeafBit) ? 1u : t.count[ref]; };
+
+  uint32_t list[8];
+  float area[8];
+  int n = 0;
+  if (self & kLeafBit) {
+    list[n++] = self;
+  } else {
+    list[n++] = t.left[self];
+    list[n++] = t.right[self];
+  }
+  for (int k = 0; k < n; ++k) {
+    float lo[3], hi[3];
+    boxOf(list[k], lo, hi);
+    area[k] = halfArea(lo, hi);
+  }
+  // open the largest multi-primitive entry until eight children exist
+  while (n < 8) {
+    int best = -1;
+    float bestArea = -1.0f;
+    for (int k = 0; k < n; ++k)
+      if (!(list[k] & kLeafBit) && area[k] > bestArea) {
+        bestArea = area[k];
+        best = k;
+      }
+    if (best < 0) break;
+    uint32_t ref = list[best];
+    uint32_t L = t.left[ref], R = t.right[ref];
+    float lo[3], hi[3];
+    list[best] = L;
+    boxOf(L, lo, hi);
+    area[best] = halfArea(lo, hi);
+    list[n] = R;
+    boxOf(R, lo, hi);
+    area[n] = halfArea(lo, hi);
+    ++n;
+  }
+  // node box = union of children (exact floats)
+  float nlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, nhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  ChildBox cb[8];
+  for (int k = 0; k < n; ++k) {
+    boxOf(list[k], cb[k].lo, cb[k].hi);
+    for (int a = 0; a < 3; ++a) {
+      nlo[a] = fminf(nlo[a], cb[k].lo[a]);
+      nhi[a] = fmaxf(nhi[a], cb[k].hi[a]);
+    }
+  }
+  // slot assignment: child k goes to the free slot whose octant diagonal best matches its offset from the centre
+  float centre[3] = {0.5f * (nlo[0] + nhi[0]), 0.5f * (nlo[1] + nhi[1]), 0.5f * (nlo[2] + nhi[2])};
+  int slotOf[8];
+  bool childDone[8] = {false, false, false, false, false, false, false, false};
+  bool slotUsed[8] = {false, false, false, false, false, false, false, false};
+  for (int round = 0; round < n; ++round) {
+    float bestScore = -FLT_MAX;
+    int bk = 0, bs = 0;
+    for (int k = 0; k < n; ++k) {
+      if (childDone[k]) continue;
+      float dx = 0.5f * (cb[k].lo[0] + cb[k].hi[0]) - centre[0];
+      float dy = 0.5f * (cb[k].lo[1] + cb[k].hi[1]) - centre[1];
+      float dz = 0.5f * (cb[k].lo[2] + cb[k].hi[2]) - centre[2];
+      for (int s = 0; s < 8; ++s) {
+        if (slotUsed[s]) continue;
+        float score = ((s & 1) ? dx : -dx) + ((s & 2) ? dy : -dy) + ((s & 4) ? dz : -dz);
+        if (score > bestScore) {
+          bestScore = score;
+          bk = k;
+          bs = s;
+        }
+      }
+    }
+    childDone[bk] = true;
+    slotUsed[bs] = true;
+    slotOf[bk] = bs;
+  }
+  // classify + allocate
+  uint32_t refAt[8];
+  uint8_t present[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  ChildBox slotBox[8];
+  for (int k = 0; k < n; ++k) {
+    refAt[slotOf[k]] = list[k];
+    present[slotOf[k]] = 1;
+    slotBox[slotOf[k]] = cb[k];
+  }
+  uint32_t internalCount = 0, primTotal = 0;
+  uint8_t imask = 0;
+  for (int s = 0; s < 8; ++s) {
+    if (!present[s]) continue;
+    uint32_t c = countOf(refAt[s]);
+    if (c > kMaxLeafPrims) {
+      imask |= uint8_t(1u << s);
+      ++internalCount;
+    } else {
+      primTotal += c;
+    }
+  }
+  uint32_t childBase = internalCount ? atomicAdd(&counters->nodeCount, internalCount) : 0u;
+  uint32_t primBase = primTotal ? atomicAdd(&counters->primCount, primTotal) : 0u;
+  uint32_t meta[2] = {0, 0};
+  uint32_t nextChild = childBase, primOffset = 0;
+  for (int s = 0; s < 8; ++s) {
+    if (!present[s]) continue;
+    uint32_t ref = refAt[s];
+    uint32_t m;
+    if (imask & (1u << s)) {
+      m = 0x20u | (24u + uint32_t(s));
+      queueOut[nextChild - nextLevelStart] = ref;
+      ++nextChild;
+    } else {
+      uint32_t c = countOf(ref);
+      m = (c == 1 ? 0x20u : c == 2 ? 0x60u : 0xE0u) | primOffset;
+      // gather the (<= 3) primitives of this subtree
+      uint32_t stack[4];
+      int sp = 0;
+      stack[sp++] = ref;
+      while (sp) {
+        uint32_t r = stack[--sp];
+        if (r & kLeafBit) {
+          leafPrim[primBase + primOffset] = sorted[r & ~kLeafBit];
+          ++primOffset;
+        } else {
+          stack[sp++] = t.right[r];
+          stack[sp++] = t.left[r];
+        }
+      }
+    }
+    meta[s >> 2] |= m << (8 * (s & 3));
+  }
+  WideNode node;
+  quantiseNode(node, nlo, nhi, slotBox, present, imask);
+  node.w[1] = make_uint4(childBase, primBase, meta[0], meta[1]);
+  uint32_t idx = levelStart + i;
+  nodes[idx] = node;
+  nodeBox[2 * idx] = make_float4(nlo[0], nlo[1], nlo[2], 0.0f);
+  nodeBox[2 * idx + 1] = make_float4(nhi[0], nhi[1], nhi[2], 0.0f);
+}
+
+// BLAS leaves: write 48-byte triangle records in leaf order + remember where each came from (for refits).
+__global__ void k_emit_triangles(const GeomEntry *geoms, uint32_t geomCount, const uint32_t *leafPrim, uint32_t n,
+                                 TriRecord *tris, uint2 *triSource) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float3 a, b, c;
+  uint32_t g, p;
+  loadTriangle(geoms, geomCount, leafPrim[i], a, b, c, g, p);
+  TriRecord r;
+  r.v0 = make_float4(a.x, a.y, a.z, __uint_as_float(p));
+  r.v1 = make_float4(b.x, b.y, b.z, __uint_as_float(g));
+  r.v2 = make_float4(c.x, c.y, c.z, 0.0f);
+  tris[i] = r;
+  triSource[i] = make_uint2(g, p);
+}
+
+// Refit step 1: re-read the vertices of every triangle slot.
+__global__ void k_refresh_triangles(const GeomEntry *geoms, uint32_t n, const uint2 *triSource, TriRecord *tris) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint2 src = triSource[i];
+  const GeomEntry ge = geoms[src.x];
+  uint32_t i0, i1, i2;
+  if (ge.indexStride == 2) {
+    const uint16_t *ix = reinterpret_cast<const uint16_t *>(ge.indices);
+    i0 = ix[3 * src.y], i1 = ix[3 * src.y + 1], i2 = ix[3 * src.y + 2];
+  } else {
+    const uint32_t *ix = reinterpret_cast<const uint32_t *>(ge.indices);
+    i0 = ix[3 * src.y], i1 = ix[3 * src.y + 1], i2 = ix[3 * src.y + 2];
+  }
+  const float *pa = reinterpret_cast<const float *>(ge.vertices + size_t(i0) * ge.vertexStride);
+  const float *pb = reinterpret_cast<const float *>(ge.vertices + size_t(i1) * ge.vertexStride);
+  const float *pc = reinterpret_cast<const float *>(ge.vertices + size_t(i2) * ge.vertexStride);
+  TriRecord r;
+  r.v0 = make_float4(pa[0], pa[1], pa[2], __uint_as_float(src.y));
+  r.v1 = make_float4(pb[0], pb[1], pb[2], __uint_as_float(src.x));
+  r.v2 = make_float4(pc[0], pc[1], pc[2], 0.0f);
+  tris[i] = r;
+}
+
+// Refit step 2, one level at a time from the deepest: recompute child boxes (triangles or already-refitted child
+// nodes), the exact node box and the quantised boxes. Topology words (w1, imask) are untouched.
+__global__ void k_refit_level(WideNode *nodes, float4 *nodeBox, const TriRecord *tris, uint32_t levelStart,
+                              uint32_t levelCount) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= levelCount) return;
+  uint32_t idx = levelStart + i;
+  WideNode node = nodes[idx];
+  uint8_t imask = uint8_t(node.w[0].w >> 24);
+  uint32_t childBase = node.w[1].x, primBase = node.w[1].y;
+  ChildBox cb[8];
+  uint8_t present[8];
+  float nlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, nhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  uint32_t rank = 0;
+  for (int s = 0; s < 8; ++s) {
+    uint32_t m = ((s < 4 ? node.w[1].z : node.w[1].w) >> (8 * (s & 3))) & 0xFFu;
+    present[s] = m != 0;
+    if (!m) continue;
+    if (imask & (1u << s)) {
+      uint32_t c = childBase + rank++;
+      float4 l = nodeBox[2 * c], h = nodeBox[2 * c + 1];
+      cb[s].lo[0] = l.x, cb[s].lo[1] = l.y, cb[s].lo[2] = l.z;
+      cb[s].hi[0] = h.x, cb[s].hi[1] = h.y, cb[s].hi[2] = h.z;
+    } else {
+      uint32_t cnt = (m >> 5) == 1 ? 1 : ((m >> 5) == 3 ? 2 : 3);
+      uint32_t first = primBase + (m & 31u);
+      for (int a = 0; a < 3; ++a) cb[s].lo[a] = FLT_MAX, cb[s].hi[a] = -FLT_MAX;
+      for (uint32_t k = 0; k < cnt; ++k) {
+        TriRecord tr = tris[first + k];
+        float v[3][3] = {{tr.v0.x, tr.v0.y, tr.v0.z}, {tr.v1.x, tr.v1.y, tr.v1.z}, {tr.v2.x, tr.v2.y, tr.v2.z}};
+        for (int q = 0; q < 3; ++q)
+          for (int a = 0; a < 3; ++a) {
+            cb[s].lo[a] = fminf(cb[s].lo[a], v[q][a]);
+            cb[s].hi[a] = fmaxf(cb[s].hi[a], v[q][a]);
+          }
+      }
+    }
+    for (int a = 0; a < 3; ++a) {
+      nlo[a] = fminf(nlo[a], cb[s].lo[a]);
+      nhi[a] = fmaxf(nhi[a], cb[s].hi[a]);
+    }
+  }
+  quantiseNode(node, nlo, nhi, cb, present, imask);
+  nodes[idx] = node;
+  nodeBox[2 * idx] = make_float4(nlo[0], nlo[1], nlo[2], 0.0f);
+  nodeBox[2 * idx + 1] = make_float4(nhi[0], nhi[1], nhi[2], 0.0f);
+}
+
+__global__ void k_write_blas_header(BlasHeader *h, const WideNode *nodes, const TriRecord *tris,
+                                    const float4 *nodeBox, uint32_t triCount, uint32_t nodeCount) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  h->nodes = nodes;
+  h->tris = tris;
+  h->triCount = triCount;
+  h->nodeCount = nodeCount;
+  float4 lo = nodeBox[0], hi = nodeBox[1];
+  h->boundsLo[0] = lo.x, h->boundsLo[1] = lo.y, h->boundsLo[2] = lo.z;
+  h->boundsHi[0] = hi.x, h->boundsHi[1] = hi.y, h->boundsHi[2] = hi.z;
+}
+
+__global__ void k_write_tlas_header(TlasHeader *h, const WideNode *nodes, const InstanceRecord *instances,
+                                    const uint32_t *leafInstance, uint32_t instanceCount, uint32_t nodeCount) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  h->nodes = nodes;
+  h->instances = instances;
+  h->leafInstance = leafInstance;
+  h->instanceCount = instanceCount;
+  h->nodeCount = nodeCount;
+}
+
+struct Bump {
+  uint8_t *base;
+  size_t offset = 0, capacity;
+  template <typename T>
+  T *take(size_t count) {
+    offset = (offset + 255) & ~size_t(255);
+    T *p = reinterpret_cast<T *>(base + offset);
+    offset += count * sizeof(T);
+    return p;
+  }
+};
+
+size_t scratchNeed(uint32_t n, size_t cubBytes) {
+  size_t per = 16 + 16 + 8 + 8 + 4 + 4 + (4 + 4 + 8 + 16 + 16 + 4 + 4) + 4 + 4 + 4;
+  return size_t(n) * per + cubBytes + 64 * 1024;
+}
+
+inline uint32_t gridFor(uint32_t n, uint32_t block) { return (n + block - 1) / block; }
+
+} // namespace
+
+// Builds the wide tree over `n` primitives whose boxes are already in primLo/primHi (scratch). Fills as->nodes,
+// as->nodeBox, as->levelStart, as->nodeCount and leafPrim (device array of n primitive ids in leaf order).
+static int buildWideTree(rt_context *ctx, AccelObject *as, uint32_t n, const float4 *primLo, const float4 *primHi,
+                         BoundsAtomics *bounds, Bump &bump, uint32_t *leafPrim) {
+  cudaStream_t st = ctx->stream;
+  const uint32_t B = 256;
+  uint64_t *keysA = bump.take<uint64_t>(n), *keysB = bump.take<uint64_t>(n);
+  uint32_t *valsA = bump.take<uint32_t>(n), *valsB = bump.take<uint32_t>(n);
+  k_morton<<<gridFor(n, B), B, 0, st>>>(primLo, primHi, n, bounds, keysA, valsA);
+  ++ctx->launches;
+  size_t cubBytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cubBytes, keysA, keysB, valsA, valsB, int(n), 0, 63, st);
+  void *cubTemp = bump.take<uint8_t>(cubBytes);
+  RT_CUDA(cub::DeviceRadixSort::SortPairs(cubTemp, cubBytes, keysA, keysB, valsA, valsB, int(n), 0, 63, st));
+  ctx->launches += 4; // CUB's histogram + onesweep passes (library kernels)
+  const uint64_t *keys = keysB;
+  const uint32_t *sorted = valsB;
+
+  Bvh2 t{};
+  t.n = n;
+  uint32_t ni = n > 1 ? n - 1 : 1;
+  t.left = bump.take<uint32_t>(ni);
+  t.right = bump.take<uint32_t>(ni);
+  t.parent = bump.take<uint32_t>(size_t(2) * n);
+  t.lo = bump.take<float4>(ni);
+  t.hi = bump.take<float4>(ni);
+  t.count = bump.take<uint32_t>(ni);
+  t.flag = bump.take<uint32_t>(ni);
+  if (n > 1) {
+    k_karras<<<gridFor(n - 1, B), B, 0, st>>>(keys, t);
+    k_bvh2_bounds<<<gridFor(n, B), B, 0, st>>>(primLo, primHi, sorted, t);
+    ctx->launches += 2;
+  }
+  uint32_t *queueA = bump.take<uint32_t>(n), *queueB = bump.take<uint32_t>(n);
+  CollapseCounters *counters = bump.take<CollapseCounters>(1);
+  RT_CHECK(bump.offset <= bump.capacity, "internal: build scratch overflow");
+
+  CollapseCounters init{1u, 0u};
+  RT_CUDA(cudaMemcpyAsync(counters, &init, sizeof init, cudaMemcpyHostToDevice, st));
+  uint32_t rootRef = n > 1 ? 0u : kLeafBit;
+  RT_CUDA(cudaMemcpyAsync(queueA, &rootRef, 4, cudaMemcpyHostToDevice, st));
+  as->levelStart.clear();
+  uint32_t levelStart = 0, levelCount = 1;
+  uint32_t *qin = queueA, *qout = queueB;
+  while (levelCount) {
+    as->levelStart.push_back(levelStart);
+    uint32_t nextStart = levelStart + levelCount;
+    RT_CHECK(nextStart <= as->nodeCapacity, "internal: wide node capacity exceeded");
+    k_collapse_level<<<gridFor(levelCount, 128), 128, 0, st>>>(t, primLo, primHi, sorted, qin, qout, levelStart,
+                                                                levelCount, nextStart, counters, as->nodes,
+                                                                as->nodeBox, leafPrim);
+    ++ctx->launches;
+    CollapseCounters now;
+    RT_CUDA(cudaMemcpyAsync(&now, counters, sizeof now, cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaStreamSynchronize(st));
+    levelStart = nextStart;
+    levelCount = now.nodeCount - nextStart;
+    std::swap(qin, qout);
+  }
+  as->levelStart.push_back(levelStart);
+  as->nodeCount = levelStart;
+  return 0;
+}
+
+static int uploadGeomTable(rt_context *ctx, AccelObject *as, const rt_triangle_geometry *geoms, uint32_t n,
+                           uint32_t *totalOut) {
+  std::vector<GeomEntry> table(n);
+  uint32_t total = 0;
+  for (uint32_t g = 0; g < n; ++g) {
+    RT_CHECK(geoms[g].indexStride == 2 || geoms[g].indexStride == 4, "rt_blas: indexStride must be 2 or 4");
+    RT_CHECK(geoms[g].vertexStride >= 12 && geoms[g].vertexStride % 4 == 0, "rt_blas: vertexStride must be >= 12 and a multiple of 4");
+    RT_CHECK(geoms[g].triangleCount == 0 || (geoms[g].vertexBuffer && geoms[g].indexBuffer), "rt_blas: null geometry buffer");
+    table[g] = {static_cast<const uint8_t *>(geoms[g].vertexBuffer), static_cast<const uint8_t *>(geoms[g].indexBuffer),
+                geoms[g].vertexStride, geoms[g].indexStride, total, geoms[g].triangleCount};
+    total += geoms[g].triangleCount;
+  }
+  if (!as->geomTableDev || as->geomCount != n) {
+    if (as->geomTableDev) cudaFree(as->geomTableDev);
+    RT_CUDA(cudaMalloc(&as->geomTableDev, std::max<size_t>(1, n) * sizeof(GeomEntry)));
+    as->geomCount = n;
+  }
+  if (n) RT_CUDA(cudaMemcpyAsync(as->geomTableDev, table.data(), n * sizeof(GeomEntry), cudaMemcpyHostToDevice, ctx->stream));
+  RT_CUDA(cudaStreamSynchronize(ctx->stream)); // `table` is a stack-lifetime staging buffer
+  *totalOut = total;
+  return 0;
+}
+
+static int shrinkNodes(rt_context *ctx, AccelObject *as) {
+  if (as->nodeCount == as->nodeCapacity) return 0;
+  uint32_t cap = std::max(1u, as->nodeCount);
+  WideNode *nodes = nullptr;
+  float4 *boxes = nullptr;
+  RT_CUDA(cudaMalloc(&nodes, size_t(cap) * sizeof(WideNode)));
+  RT_CUDA(cudaMalloc(&boxes, size_t(cap) * 2 * sizeof(float4)));
+  RT_CUDA(cudaMemcpyAsync(nodes, as->nodes, size_t(cap) * sizeof(WideNode), cudaMemcpyDeviceToDevice, ctx->stream));
+  RT_CUDA(cudaMemcpyAsync(boxes, as->nodeBox, size_t(cap) * 2 * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(as->nodes);
+  cudaFree(as->nodeBox);
+  as->nodes = nodes;
+  as->nodeBox = boxes;
+  as->nodeCapacity = cap;
+  return 0;
+}
+
+static int finishInfo(rt_context *ctx, AccelObject *as) {
+  // bounds + SAH cost from the exact node boxes (host side; build-time only)
+  std::vector<float4> boxes(size_t(as->nodeCount) * 2);
+  std::vector<WideNode> nodes(as->nodeCount);
+  if (as->nodeCount) {
+    RT_CUDA(cudaMemcpyAsync(boxes.data(), as->nodeBox, boxes.size() * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(cudaMemcpyAsync(nodes.data(), as->nodes, nodes.size() * sizeof(WideNode), cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  auto area = [&](uint32_t i) {
+    float dx = boxes[2 * i + 1].x - boxes[2 * i].x, dy = boxes[2 * i + 1].y - boxes[2 * i].y,
+          dz = boxes[2 * i + 1].z - boxes[2 * i].z;
+    return std::max(0.0f, dx * dy + dy * dz + dz * dx);
+  };
+  double cost = 0.0;
+  if (as->nodeCount) {
+    as->bounds = {{boxes[0].x, boxes[0].y, boxes[0].z}, {boxes[1].x, boxes[1].y, boxes[1].z}};
+    double rootArea = std::max(1e-30f, area(0));
+    for (uint32_t i = 0; i < as->nodeCount; ++i) {
+      int prims = 0;
+      for (int s = 0; s < 8; ++s) {
+        uint32_t m = ((s < 4 ? nodes[i].w[1].z : nodes[i].w[1].w) >> (8 * (s & 3))) & 0xFFu;
+        bool internal = (nodes[i].w[0].w >> 24) & (1u << s);
+        if (m && !internal) prims += (m >> 5) == 1 ? 1 : ((m >> 5) == 3 ? 2 : 3);
+      }
+      cost += double(area(i)) / rootArea * (1.0 + 0.3 * prims); // node visit = 1, triangle test = 0.3
+    }
+  }
+  as->sahCost = float(cost);
+  return 0;
+}
+
+int buildBlas(rt_context *ctx, const rt_triangle_geometry *geoms, uint32_t geomCount, uint32_t flags,
+              AccelObject **out) {
+  AccelObject *as = new AccelObject();
+  as->isTlas = false;
+  as->flags = flags;
+  uint32_t n = 0;
+  int rc = uploadGeomTable(ctx, as, geoms, geomCount, &n);
+  if (rc) {
+    destroyAccel(as);
+    return rc;
+  }
+  cudaStream_t st = ctx->stream;
+  as->primCount = as->primCapacity = n;
+  auto fail = [&](int code) {
+    destroyAccel(as);
+    return code;
+  };
+#define RT_TRYF(expr)             \
+  do {                            \
+    int _r = (expr);              \
+    if (_r != 0) return fail(_r); \
+  } while (0)
+#define RT_CUDAF(expr)                                                                               \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      setError(std::string(#expr) + " failed: " + cudaGetErrorString(_e));                           \
+      return fail(1);                                                                                \
+    }                                                                                                \
+  } while (0)
+  RT_CUDAF(cudaMalloc(&as->headerDev, sizeof(BlasHeader)));
+  RT_CUDAF(cudaMemsetAsync(as->headerDev, 0, sizeof(BlasHeader), st));
+  if (n == 0) { // empty mesh: header with triCount 0, instances of it are skipped
+    *out = as;
+    as->bytes = sizeof(BlasHeader);
+    return 0;
+  }
+  as->nodeCapacity = n;
+  RT_CUDAF(cudaMalloc(&as->nodes, size_t(as->nodeCapacity) * sizeof(WideNode)));
+  RT_CUDAF(cudaMalloc(&as->nodeBox, size_t(as->nodeCapacity) * 2 * sizeof(float4)));
+  RT_CUDAF(cudaMalloc(&as->tris, size_t(n) * sizeof(TriRecord)));
+  RT_CUDAF(cudaMalloc(&as->triSource, size_t(n) * sizeof(uint2)));
+  size_t cubBytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cubBytes, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr,
+                                  (uint32_t *)nullptr, int(n), 0, 63, st);
+  RT_TRYF(ensureScratch(ctx, scratchNeed(n, cubBytes)));
+  Bump bump{static_cast<uint8_t *>(ctx->scratch), 0, ctx->scratchBytes};
+  float4 *primLo = bump.take<float4>(n), *primHi = bump.take<float4>(n);
+  BoundsAtomics *bounds = bump.take<BoundsAtomics>(1);
+  uint32_t *leafPrim = bump.take<uint32_t>(n);
+  const GeomEntry *table = static_cast<const GeomEntry *>(as->geomTableDev);
+  k_init_bounds<<<1, 32, 0, st>>>(bounds);
+  k_triangle_bounds<<<gridFor(n, 256), 256, 0, st>>>(table, geomCount, n, primLo, primHi, bounds);
+  ctx->launches += 2;
+  RT_TRYF(buildWideTree(ctx, as, n, primLo, primHi, bounds, bump, leafPrim));
+  k_emit_triangles<<<gridFor(n, 256), 256, 0, st>>>(table, geomCount, leafPrim, n, as->tris, as->triSource);
+  ++ctx->launches;
+  RT_CUDAF(cudaStreamSynchronize(st));
+  RT_TRYF(shrinkNodes(ctx, as));
+  k_write_blas_header<<<1, 32, 0, st>>>(static_cast<BlasHeader *>(as->headerDev), as->nodes, as->tris, as->nodeBox, n,
+                                        as->nodeCount);
+  ++ctx->launches;
+  RT_CUDAF(cudaGetLastError());
+  RT_TRYF(finishInfo(ctx, as));
+  if (!(flags & RT_AS_FLAG_REFITTABLE)) { // compaction: drop what only a refit needs
+    cudaFree(as->triSource);
+    as->triSource = nullptr;
+  }
+  as->bytes = sizeof(BlasHeader) + size_t(as->nodeCapacity) * (sizeof(WideNode) + 2 * sizeof(float4)) +
+              size_t(n) * sizeof(TriRecord) + (as->triSource ? size_t(n) * sizeof(uint2) : 0);
+  *out = as;
+  return 0;
+#undef RT_TRYF
+#undef RT_CUDAF
+}
+
+int refitBlas(rt_context *ctx, AccelObject *as, const rt_triangle_geometry *geoms, uint32_t geomCount) {
+  RT_CHECK(!as->isTlas, "rt_blas_refit: id is a TLAS");
+  RT_CHECK(as->flags & RT_AS_FLAG_REFITTABLE, "rt_blas_refit: BLAS was not built with RT_AS_FLAG_REFITTABLE");
+  RT_CHECK(geomCount == as->geomCount, "rt_blas_refit: geometry count differs from the build");
+  uint32_t n = 0;
+  RT_TRY(uploadGeomTable(ctx, as, geoms, geomCount, &n));
+  RT_CHECK(n == as->primCount, "rt_blas_refit: triangle count differs from the build");
+  if (n == 0) return 0;
+  cudaStream_t st = ctx->stream;
+  k_refresh_triangles<<<gridFor(n, 256), 256, 0, st>>>(static_cast<const GeomEntry *>(as->geomTableDev), n,
+                                                        as->triSource, as->tris);
+  ++ctx->launches;
+  for (int level = int(as->levelStart.size()) - 2; level >= 0; --level) {
+    uint32_t start = as->levelStart[level], count = as->levelStart[level + 1] - start;
+    if (!count) continue;
+    k_refit_level<<<gridFor(count, 128), 128, 0, st>>>(as->nodes, as->nodeBox, as->tris, start, count);
+    ++ctx->launches;
+  }
+  k_write_blas_header<<<1, 32, 0, st>>>(static_cast<BlasHeader *>(as->headerDev), as->nodes, as->tris, as->nodeBox, n,
+                                        as->nodeCount);
+  ++ctx->launches;
+  RT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int buildTlas(rt_context *ctx, AccelObject *as, const rt_instance_descriptor *descDev, uint32_t count) {
+  cudaStream_t st = ctx->stream;
+  as->isTlas = true;
+  if (!as->headerDev) RT_CUDA(cudaMalloc(&as->headerDev, sizeof(TlasHeader)));
+  if (count > as->primCapacity) {
+    if (as->instances) cudaFree(as->instances);
+    if (as->leafPrim) cudaFree(as->leafPrim);
+    if (as->nodes) cudaFree(as->nodes);
+    if (as->nodeBox) cudaFree(as->nodeBox);
+    as->instances = nullptr, as->leafPrim = nullptr, as->nodes = nullptr, as->nodeBox = nullptr;
+    RT_CUDA(cudaMalloc(&as->instances, size_t(count) * sizeof(InstanceRecord)));
+    RT_CUDA(cudaMalloc(&as->leafPrim, size_t(count) * sizeof(uint32_t)));
+    RT_CUDA(cudaMalloc(&as->nodes, size_t(count) * sizeof(WideNode)));
+    RT_CUDA(cudaMalloc(&as->nodeBox, size_t(count) * 2 * sizeof(float4)));
+    as->primCapacity = count;
+    as->nodeCapacity = count;
+  }
+  as->primCount = count;
+  if (count == 0) {
+    as->nodeCount = 0;
+    k_write_tlas_header<<<1, 32, 0, st>>>(static_cast<TlasHeader *>(as->headerDev), nullptr, nullptr, nullptr, 0, 0);
+    ++ctx->launches;
+    return 0;
+  }
+  RT_CHECK(descDev != nullptr, "rt_tlas: null descriptor buffer");
+  size_t cubBytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cubBytes, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr,
+                                  (uint32_t *)nullptr, int(count), 0, 63, st);
+  RT_TRY(ensureScratch(ctx, scratchNeed(count, cubBytes)));
+  Bump bump{static_cast<uint8_t *>(ctx->scratch), 0, ctx->scratchBytes};
+  float4 *primLo = bump.take<float4>(count), *primHi = bump.take<float4>(count);
+  BoundsAtomics *bounds = bump.take<BoundsAtomics>(1);
+  k_init_bounds<<<1, 32, 0, st>>>(bounds);
+  k_instance_bounds<<<gridFor(count, 128), 128, 0, st>>>(descDev, count, as->instances, primLo, primHi, bounds);
+  ctx->launches += 2;
+  RT_TRY(buildWideTree(ctx, as, count, primLo, primHi, bounds, bump, as->leafPrim));
+  k_write_tlas_header<<<1, 32, 0, st>>>(static_cast<TlasHeader *>(as->headerDev), as->nodes, as->instances,
+                                        as->leafPrim, count, as->nodeCount);
+  ++ctx->launches;
+  RT_CUDA(cudaGetLastError());
+  as->bytes = sizeof(TlasHeader) + size_t(as->primCapacity) * (sizeof(InstanceRecord) + 4 + sizeof(WideNode) + 32);
+  return 0;
+}
+
+void destroyAccel(AccelObject *as) {
+  if (!as) return;
+  cudaFree(as->headerDev);
+  cudaFree(as->nodes);
+  cudaFree(as->nodeBox);
+  cudaFree(as->tris);
+  cudaFree(as->instances);
+  cudaFree(as->leafPrim);
+  cudaFree(as->triSource);
+  cudaFree(as->geomTableDev);
+  delete as;
+}
+
+} // namespace rtb

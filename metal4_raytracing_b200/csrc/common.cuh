@@ -1,0 +1,146 @@
+// common.cuh — shared declarations of the sm_100a library: context, error plumbing, acceleration-structure
+// records. Device layouts are sized for 128-bit loads (LDG.128): an 8-wide node is 5 x 16 B, a triangle 3 x 16 B,
+// an instance record 4 x 16 B.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+
+namespace rtb {
+
+void setError(const std::string &msg);
+#define RT_CUDA(expr)                                                                                         \
+  do {                                                                                                         \
+    cudaError_t _e = (expr);                                                                                   \
+    if (_e != cudaSuccess) {                                                                                   \
+      rtb::setError(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" +        \
+                    std::to_string(__LINE__) + ")");                                                           \
+      return 1;                                                                                                \
+    }                                                                                                          \
+  } while (0)
+#define RT_CHECK(cond, msg)          \
+  do {                               \
+    if (!(cond)) {                   \
+      rtb::setError(msg);            \
+      return 2;                      \
+    }                                \
+  } while (0)
+#define RT_TRY(expr)       \
+  do {                     \
+    int _r = (expr);       \
+    if (_r != 0) return _r; \
+  } while (0)
+
+// ---- 8-wide quantised node, 80 bytes (after Ylitie, Karras, Laine 2017 "compressed wide BVH") ---------------
+//  w0: origin.x, origin.y, origin.z (float bits), {ex, ey, ez, imask} bytes
+//  w1: childBase, primBase, meta[0..3], meta[4..7]
+//  w2: qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7]
+//  w3: qlo_z[0..3], qlo_z[4..7], qhi_x[0..3], qhi_x[4..7]
+//  w4: qhi_y[0..3], qhi_y[4..7], qhi_z[0..3], qhi_z[4..7]
+// child box = origin + q * 2^(e-127) per axis. meta[s]: 0 = empty slot; internal child = 0b001'11sss
+// (low five bits 24 + slot); leaf child = unary primitive count in bits 5..7 (1 -> 001, 2 -> 011, 3 -> 111) and the
+// primitive's offset from primBase (0..23) in the low five bits.
+struct alignas(16) WideNode {
+  uint4 w[5];
+};
+static_assert(sizeof(WideNode) == 80, "wide node is 80 bytes");
+
+// Triangle record, 48 bytes: raw vertices (the watertight test needs them untransformed) + ids in the w lanes.
+struct alignas(16) TriRecord {
+  float4 v0; // w = primitive index within its geometry (bits)
+  float4 v1; // w = geometry index (bits)
+  float4 v2; // w = unused
+};
+static_assert(sizeof(TriRecord) == 48, "triangle record is 48 bytes");
+
+// Device-resident header of a BLAS; its address is the accelerationStructureID the host writes into descriptors.
+struct BlasHeader {
+  const WideNode *nodes;
+  const TriRecord *tris;
+  float boundsLo[3];
+  uint32_t triCount;
+  float boundsHi[3];
+  uint32_t nodeCount;
+};
+
+// Per-instance traversal record, 64 bytes: world->object 3x4 (rows), then the BLAS arrays.
+struct alignas(16) InstanceRecord {
+  float4 row0, row1, row2; // object = row_r . (world, 1)
+  const WideNode *nodes;
+  const TriRecord *tris;
+};
+static_assert(sizeof(InstanceRecord) == 64, "instance record is 64 bytes");
+
+struct TlasHeader {
+  const WideNode *nodes;
+  const InstanceRecord *instances; // indexed by instance id (descriptor order)
+  const uint32_t *leafInstance;    // leaf slot (primBase + offset) -> instance id
+  uint32_t instanceCount;
+  uint32_t nodeCount;
+};
+
+struct Aabb {
+  float lo[3], hi[3];
+};
+
+// Host-side bookkeeping of one acceleration structure (BLAS or TLAS).
+struct AccelObject {
+  bool isTlas = false;
+  uint32_t flags = 0;
+  uint32_t primCount = 0;      // triangles or instances
+  uint32_t primCapacity = 0;
+  uint32_t nodeCount = 0;
+  uint32_t nodeCapacity = 0;
+  std::vector<uint32_t> levelStart; // wide-node index where each BFS level starts (+ end sentinel)
+  void *headerDev = nullptr;   // BlasHeader / TlasHeader
+  WideNode *nodes = nullptr;
+  float4 *nodeBox = nullptr;   // exact float box of each wide node: 2 x float4 per node
+  TriRecord *tris = nullptr;   // BLAS
+  InstanceRecord *instances = nullptr; // TLAS (in descriptor order)
+  uint32_t *leafPrim = nullptr; // TLAS: leaf slot -> instance index (the node's primBase + offset indexes this)
+  uint2 *triSource = nullptr;   // BLAS: per triangle slot (geometry, primitive) — refit source mapping
+  // geometry table for refit: device copy of per-geometry (vertex ptr, stride, index ptr, index stride)
+  void *geomTableDev = nullptr;
+  uint32_t geomCount = 0;
+  uint64_t bytes = 0;
+  float sahCost = 0.0f;
+  Aabb bounds{};
+};
+
+} // namespace rtb
+
+struct rt_context {
+  int device = 0;
+  cudaStream_t ownStream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t evBegin = nullptr, evEnd = nullptr;
+  uint64_t launches = 0;
+  int traceMode = 0;
+  std::unordered_map<uint64_t, rtb::AccelObject *> accels;
+  // reusable build scratch
+  void *scratch = nullptr;
+  size_t scratchBytes = 0;
+  float *srgbLutDev = nullptr;
+  int smCount = 148;
+  // wavefront state (trace_wavefront.cu)
+  void *wfState = nullptr;
+  size_t wfBytes = 0;
+};
+
+namespace rtb {
+int ensureScratch(rt_context *ctx, size_t bytes);
+int buildBlas(rt_context *ctx, const rt_triangle_geometry *geoms, uint32_t n, uint32_t flags, AccelObject **out);
+int refitBlas(rt_context *ctx, AccelObject *as, const rt_triangle_geometry *geoms, uint32_t n);
+int buildTlas(rt_context *ctx, AccelObject *as, const rt_instance_descriptor *descDev, uint32_t count);
+void destroyAccel(AccelObject *as);
+int launchSkin(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], uint32_t vertexCount);
+int launchTrace(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], const rt_image textures[RT_TEXTURE_COUNT],
+                int maxSubmeshes, const rt_trace_options *opt);
+} // namespace rtb

@@ -1,0 +1,331 @@
+// rt_api.cu — extern "C" entry points of librt_b200.so (include/rt_b200.h).
+// Thin: argument validation, handle bookkeeping, stream plumbing. No CPU fallback anywhere: every compute entry
+// point enqueues CUDA kernels or fails with an error code.
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace rtb {
+
+static thread_local std::string g_lastError;
+void setError(const std::string &msg) { g_lastError = msg; }
+
+int ensureScratch(rt_context *ctx, size_t bytes) {
+  if (bytes <= ctx->scratchBytes) return 0;
+  RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  ctx->scratch = nullptr;
+  ctx->scratchBytes = 0;
+  size_t want = bytes + bytes / 4;
+  RT_CUDA(cudaMalloc(&ctx->scratch, want));
+  ctx->scratchBytes = want;
+  return 0;
+}
+
+} // namespace rtb
+
+using namespace rtb;
+
+#define RT_CTX(ctx)                             \
+  do {                                          \
+    if (!(ctx)) {                               \
+      rtb::setError("null rt_context");         \
+      return 3;                                 \
+    }                                           \
+    cudaError_t _e = cudaSetDevice((ctx)->device); \
+    if (_e != cudaSuccess) {                    \
+      rtb::setError(std::string("cudaSetDevice failed: ") + cudaGetErrorString(_e)); \
+      return 1;                                 \
+    }                                           \
+  } while (0)
+
+extern "C" {
+
+const char *rt_last_error(void) { return g_lastError.c_str(); }
+
+int rt_create(int device, rt_context **out) {
+  RT_CHECK(out != nullptr, "rt_create: null out pointer");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    setError(std::string("rt_create: no CUDA device available (") + cudaGetErrorString(e) +
+             "); this library has no CPU path");
+    return 1;
+  }
+  RT_CHECK(device >= 0 && device < count, "rt_create: device index out of range");
+  RT_CUDA(cudaSetDevice(device));
+  rt_context *ctx = new rt_context();
+  ctx->device = device;
+  cudaDeviceProp prop{};
+  RT_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->smCount = prop.multiProcessorCount;
+  RT_CUDA(cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking));
+  ctx->stream = ctx->ownStream;
+  RT_CUDA(cudaEventCreate(&ctx->evBegin));
+  RT_CUDA(cudaEventCreate(&ctx->evEnd));
+  // sRGB decode table, evaluated in double and rounded once (same table as the oracle's)
+  float lut[256];
+  for (int i = 0; i < 256; ++i) {
+    double c = double(i) / 255.0;
+    lut[i] = float(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
+  }
+  RT_CUDA(cudaMalloc(&ctx->srgbLutDev, sizeof lut));
+  RT_CUDA(cudaMemcpy(ctx->srgbLutDev, lut, sizeof lut, cudaMemcpyHostToDevice));
+  *out = ctx;
+  return 0;
+}
+
+int rt_destroy(rt_context *ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &kv : ctx->accels) destroyAccel(kv.second);
+  ctx->accels.clear();
+  cudaFree(ctx->scratch);
+  cudaFree(ctx->srgbLutDev);
+  cudaFree(ctx->wfState);
+  cudaEventDestroy(ctx->evBegin);
+  cudaEventDestroy(ctx->evEnd);
+  cudaStreamDestroy(ctx->ownStream);
+  delete ctx;
+  return 0;
+}
+
+int rt_set_stream(rt_context *ctx, void *cudaStream) {
+  RT_CTX(ctx);
+  RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cudaStream ? static_cast<cudaStream_t>(cudaStream) : ctx->ownStream;
+  return 0;
+}
+
+int rt_sync(rt_context *ctx) {
+  RT_CTX(ctx);
+  RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int rt_timer_begin(rt_context *ctx) {
+  RT_CTX(ctx);
+  RT_CUDA(cudaEventRecord(ctx->evBegin, ctx->stream));
+  return 0;
+}
+
+int rt_timer_end(rt_context *ctx, float *milliseconds) {
+  RT_CTX(ctx);
+  RT_CUDA(cudaEventRecord(ctx->evEnd, ctx->stream));
+  RT_CUDA(cudaEventSynchronize(ctx->evEnd));
+  float ms = 0.0f;
+  RT_CUDA(cudaEventElapsedTime(&ms, ctx->evBegin, ctx->evEnd));
+  if (milliseconds) *milliseconds = ms;
+  return 0;
+}
+
+int rt_malloc(rt_context *ctx, size_t bytes, void **dev) {
+  RT_CTX(ctx);
+  RT_CHECK(dev != nullptr, "rt_malloc: null out pointer");
+  RT_CUDA(cudaMalloc(dev, bytes ? bytes : 16));
+  return 0;
+}
+
+int rt_free(rt_context *ctx, void *dev) {
+  RT_CTX(ctx);
+  if (dev) {
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    RT_CUDA(cudaFree(dev));
+  }
+  return 0;
+}
+
+int rt_malloc_host(rt_context *ctx, size_t bytes, void **pinnedHost) {
+  RT_CTX(ctx);
+  RT_CHECK(pinnedHost != nullptr, "rt_malloc_host: null out pointer");
+  RT_CUDA(cudaMallocHost(pinnedHost, bytes ? bytes : 16));
+  return 0;
+}
+
+int rt_free_host(rt_context *ctx, void *pinnedHost) {
+  RT_CTX(ctx);
+  if (pinnedHost) RT_CUDA(cudaFreeHost(pinnedHost));
+  return 0;
+}
+
+int rt_upload(rt_context *ctx, void *dstDev, const void *srcHost, size_t bytes) {
+  RT_CTX(ctx);
+  if (!bytes) return 0;
+  RT_CHECK(dstDev && srcHost, "rt_upload: null pointer");
+  RT_CUDA(cudaMemcpyAsync(dstDev, srcHost, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  cudaPointerAttributes attr{};
+  bool pinned = cudaPointerGetAttributes(&attr, srcHost) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (!pinned) RT_CUDA(cudaStreamSynchronize(ctx->stream)); // pageable source: caller may reuse it right away
+  return 0;
+}
+
+int rt_download(rt_context *ctx, void *dstHost, const void *srcDev, size_t bytes) {
+  RT_CTX(ctx);
+  if (!bytes) return 0;
+  RT_CHECK(dstHost && srcDev, "rt_download: null pointer");
+  RT_CUDA(cudaMemcpyAsync(dstHost, srcDev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int rt_copy(rt_context *ctx, void *dstDev, const void *srcDev, size_t bytes) {
+  RT_CTX(ctx);
+  if (!bytes) return 0;
+  RT_CHECK(dstDev && srcDev, "rt_copy: null pointer");
+  RT_CUDA(cudaMemcpyAsync(dstDev, srcDev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
+int rt_memset(rt_context *ctx, void *dstDev, int value, size_t bytes) {
+  RT_CTX(ctx);
+  if (!bytes) return 0;
+  RT_CHECK(dstDev != nullptr, "rt_memset: null pointer");
+  RT_CUDA(cudaMemsetAsync(dstDev, value, bytes, ctx->stream));
+  return 0;
+}
+
+int rt_blas_build(rt_context *ctx, const rt_triangle_geometry *geoms, uint32_t geometryCount, uint32_t flags,
+                  uint64_t *outId) {
+  RT_CTX(ctx);
+  RT_CHECK(outId != nullptr, "rt_blas_build: null out pointer");
+  RT_CHECK(geometryCount == 0 || geoms != nullptr, "rt_blas_build: null geometry array");
+  AccelObject *as = nullptr;
+  RT_TRY(buildBlas(ctx, geoms, geometryCount, flags, &as));
+  uint64_t id = uint64_t(reinterpret_cast<uintptr_t>(as->headerDev));
+  ctx->accels[id] = as;
+  *outId = id;
+  return 0;
+}
+
+static int findAccel(rt_context *ctx, uint64_t id, bool tlas, AccelObject **out) {
+  auto it = ctx->accels.find(id);
+  RT_CHECK(it != ctx->accels.end(), "unknown acceleration structure id");
+  RT_CHECK(it->second->isTlas == tlas, tlas ? "id is not a TLAS" : "id is not a BLAS");
+  *out = it->second;
+  return 0;
+}
+
+int rt_blas_refit(rt_context *ctx, uint64_t id, const rt_triangle_geometry *geoms, uint32_t geometryCount) {
+  RT_CTX(ctx);
+  AccelObject *as = nullptr;
+  RT_TRY(findAccel(ctx, id, false, &as));
+  return refitBlas(ctx, as, geoms, geometryCount);
+}
+
+int rt_blas_destroy(rt_context *ctx, uint64_t id) {
+  RT_CTX(ctx);
+  AccelObject *as = nullptr;
+  RT_TRY(findAccel(ctx, id, false, &as));
+  RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->accels.erase(id);
+  destroyAccel(as);
+  return 0;
+}
+
+int rt_tlas_build(rt_context *ctx, const rt_instance_descriptor *descriptorsDev, uint32_t count, uint64_t *outId) {
+  RT_CTX(ctx);
+  RT_CHECK(outId != nullptr, "rt_tlas_build: null out pointer");
+  AccelObject *as = new AccelObject();
+  as->isTlas = true;
+  int rc = buildTlas(ctx, as, descriptorsDev, count);
+  if (rc) {
+    destroyAccel(as);
+    return rc;
+  }
+  uint64_t id = uint64_t(reinterpret_cast<uintptr_t>(as->headerDev));
+  ctx->accels[id] = as;
+  *outId = id;
+  return 0;
+}
+
+int rt_tlas_update(rt_context *ctx, uint64_t id, const rt_instance_descriptor *descriptorsDev, uint32_t count) {
+  RT_CTX(ctx);
+  AccelObject *as = nullptr;
+  RT_TRY(findAccel(ctx, id, true, &as));
+  return buildTlas(ctx, as, descriptorsDev, count);
+}
+
+int rt_tlas_destroy(rt_context *ctx, uint64_t id) {
+  RT_CTX(ctx);
+  AccelObject *as = nullptr;
+  RT_TRY(findAccel(ctx, id, true, &as));
+  RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->accels.erase(id);
+  destroyAccel(as);
+  return 0;
+}
+
+int rt_as_get_info(rt_context *ctx, uint64_t id, rt_as_info *out) {
+  RT_CTX(ctx);
+  RT_CHECK(out != nullptr, "rt_as_get_info: null out pointer");
+  auto it = ctx->accels.find(id);
+  RT_CHECK(it != ctx->accels.end(), "unknown acceleration structure id");
+  const AccelObject *as = it->second;
+  std::memset(out, 0, sizeof *out);
+  out->primitiveCount = as->primCount;
+  out->wideNodeCount = as->nodeCount;
+  out->levelCount = as->levelStart.empty() ? 0 : uint32_t(as->levelStart.size() - 1);
+  out->bytes = as->bytes;
+  for (int a = 0; a < 3; ++a) {
+    out->boundsMin[a] = as->bounds.lo[a];
+    out->boundsMax[a] = as->bounds.hi[a];
+  }
+  out->sahCost = as->sahCost;
+  return 0;
+}
+
+int rt_skin(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], uint32_t vertexCount) {
+  RT_CTX(ctx);
+  return launchSkin(ctx, buffers, vertexCount);
+}
+
+int rt_trace(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], const rt_image textures[RT_TEXTURE_COUNT],
+             int resourcesStride, int maxSubmeshes, const rt_trace_options *options) {
+  RT_CTX(ctx);
+  (void)resourcesStride; // function constant 0 is declared but unused by the reference kernel as well
+  return launchTrace(ctx, buffers, textures, maxSubmeshes, options);
+}
+
+int rt_texture_create(rt_context *ctx, const uint8_t *rgba8Host, int width, int height, int srgb,
+                      const rt_texture2d **outRecordDev) {
+  RT_CTX(ctx);
+  RT_CHECK(rgba8Host && outRecordDev && width > 0 && height > 0, "rt_texture_create: bad arguments");
+  size_t bytes = size_t(width) * size_t(height) * 4;
+  // one allocation: [record (32 B, padded)] [texels]
+  uint8_t *block = nullptr;
+  RT_CUDA(cudaMalloc(&block, 32 + bytes));
+  rt_texture2d rec{};
+  rec.texels = block + 32;
+  rec.width = width;
+  rec.height = height;
+  rec.srgb = srgb ? 1 : 0;
+  RT_CUDA(cudaMemcpyAsync(block, &rec, sizeof rec, cudaMemcpyHostToDevice, ctx->stream));
+  RT_CUDA(cudaMemcpyAsync(block + 32, rgba8Host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  *outRecordDev = reinterpret_cast<const rt_texture2d *>(block);
+  return 0;
+}
+
+int rt_texture_destroy(rt_context *ctx, const rt_texture2d *recordDev) {
+  RT_CTX(ctx);
+  if (recordDev) {
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    RT_CUDA(cudaFree(const_cast<rt_texture2d *>(recordDev)));
+  }
+  return 0;
+}
+
+uint64_t rt_launch_count(rt_context *ctx) { return ctx ? ctx->launches : 0; }
+
+int rt_set_trace_mode(rt_context *ctx, int mode) {
+  RT_CTX(ctx);
+  RT_CHECK(mode == 0, "rt_set_trace_mode: only the megakernel layout (0) is built");
+  ctx->traceMode = mode;
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,280 @@
+// traverse.cuh — software ray traversal for sm_100a (B200 has no RT cores).
+//
+// Stands in for Metal's intersector<triangle_data, instancing>::intersect as the reference calls it
+// (MetalRaytracing/Raytracing.metal:301-318 closest hit, :664-665 and :730-737 any hit): two-level traversal of
+// the 8-wide quantised BVH built by bvh_build.cu, closest hit with the deterministic tie rule, or any hit.
+//
+// Contract shared with the CPU oracle (oracle/oracle_bvh.cpp) so primary-hit ids agree bit for bit:
+//   * the ray enters an instance through the float world->object matrix, direction not renormalised;
+//   * ray/triangle = watertight test of Woop, Benthin, Wald 2013, same operation order, every float op rounded
+//     on its own (this file must be compiled with -fmad=false; FMAs appear only where written as fmaf, i.e. in
+//     the box tests, which only have to be conservative);
+//   * hit iff tmin < t < tmax; closest = smallest t, ties -> smallest (instance, geometry, primitive).
+// Traversal order follows Ylitie et al. 2017: children sit in slots matched to octants, a node's hit mask is
+// permuted by the ray octant so the highest set bit is the nearest child, and triangle hits of one node form a
+// 24-bit mask over a contiguous primitive range.
+#pragma once
+#include "common.cuh"
+
+namespace rtb {
+
+struct RayHit {
+  float t, u, v;
+  uint32_t instance, geometry, primitive;
+};
+
+constexpr int kStackSize = 48;
+
+__device__ __forceinline__ float pick3(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
+
+struct TriSetup { // Woop et al. per-ray constants in the current space
+  int kx, ky, kz;
+  float Sx, Sy, Sz;
+  float ox, oy, oz; // origin permuted to (kx, ky, kz)
+};
+
+__device__ __forceinline__ TriSetup makeTriSetup(float ox, float oy, float oz, float dx, float dy, float dz) {
+  TriSetup s;
+  float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+  s.kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
+  s.kx = s.kz + 1 == 3 ? 0 : s.kz + 1;
+  s.ky = s.kx + 1 == 3 ? 0 : s.kx + 1;
+  float dkz = pick3(dx, dy, dz, s.kz);
+  if (dkz < 0.0f) {
+    int tmp = s.kx;
+    s.kx = s.ky;
+    s.ky = tmp;
+  }
+  s.Sx = pick3(dx, dy, dz, s.kx) / dkz;
+  s.Sy = pick3(dx, dy, dz, s.ky) / dkz;
+  s.Sz = 1.0f / dkz;
+  s.ox = pick3(ox, oy, oz, s.kx);
+  s.oy = pick3(ox, oy, oz, s.ky);
+  s.oz = pick3(ox, oy, oz, s.kz);
+  return s;
+}
+
+// Returns true when tmin < t < tmax; same arithmetic as oracle intersectTriangle().
+__device__ __forceinline__ bool intersectTriangle(const TriSetup &s, const float4 &v0, const float4 &v1,
+                                                  const float4 &v2, float tmin, float tmax, float &tOut, float &uOut,
+                                                  float &vOut) {
+  const float Akx = pick3(v0.x, v0.y, v0.z, s.kx) - s.ox, Aky = pick3(v0.x, v0.y, v0.z, s.ky) - s.oy,
+              Akz = pick3(v0.x, v0.y, v0.z, s.kz) - s.oz;
+  const float Bkx = pick3(v1.x, v1.y, v1.z, s.kx) - s.ox, Bky = pick3(v1.x, v1.y, v1.z, s.ky) - s.oy,
+              Bkz = pick3(v1.x, v1.y, v1.z, s.kz) - s.oz;
+  const float Ckx = pick3(v2.x, v2.y, v2.z, s.kx) - s.ox, Cky = pick3(v2.x, v2.y, v2.z, s.ky) - s.oy,
+              Ckz = pick3(v2.x, v2.y, v2.z, s.kz) - s.oz;
+  const float Ax = Akx - s.Sx * Akz, Ay = Aky - s.Sy * Akz;
+  const float Bx = Bkx - s.Sx * Bkz, By = Bky - s.Sy * Bkz;
+  const float Cx = Ckx - s.Sx * Ckz, Cy = Cky - s.Sy * Ckz;
+  float U = Cx * By - Cy * Bx;
+  float V = Ax * Cy - Ay * Cx;
+  float W = Bx * Ay - By * Ax;
+  if (U == 0.0f || V == 0.0f || W == 0.0f) {
+    double CxBy = double(Cx) * double(By), CyBx = double(Cy) * double(Bx);
+    U = float(CxBy - CyBx);
+    double AxCy = double(Ax) * double(Cy), AyCx = double(Ay) * double(Cx);
+    V = float(AxCy - AyCx);
+    double BxAy = double(Bx) * double(Ay), ByAx = double(By) * double(Ax);
+    W = float(BxAy - ByAx);
+  }
+  if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+  const float det = (U + V) + W;
+  if (det == 0.0f) return false;
+  const float Az = s.Sz * Akz, Bz = s.Sz * Bkz, Cz = s.Sz * Ckz;
+  const float T = (U * Az + V * Bz) + W * Cz;
+  const float invDet = 1.0f / det;
+  const float t = T * invDet;
+  if (!(t > tmin && t < tmax)) return false;
+  tOut = t;
+  uOut = V * invDet;
+  vOut = W * invDet;
+  return true;
+}
+
+struct BoxSetup { // per-ray constants for the quantised child-box tests in the current space
+  float idx, idy, idz; // 1 / direction (zero components replaced by a tiny value of the same sign)
+  float ox, oy, oz;
+  uint32_t octinv;     // 7 ^ (sign bits of the direction): permutes slots into front-to-back priority
+};
+
+__device__ __forceinline__ float safeInverse(float d) {
+  const float tiny = 1.0e-20f;
+  float a = fabsf(d) < tiny ? copysignf(tiny, d) : d;
+  return 1.0f / a;
+}
+
+__device__ __forceinline__ BoxSetup makeBoxSetup(float ox, float oy, float oz, float dx, float dy, float dz) {
+  BoxSetup b;
+  b.idx = safeInverse(dx);
+  b.idy = safeInverse(dy);
+  b.idz = safeInverse(dz);
+  b.ox = ox, b.oy = oy, b.oz = oz;
+  uint32_t neg = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
+  b.octinv = 7u ^ neg;
+  return b;
+}
+
+__device__ __forceinline__ float byteToFloat(uint32_t word, int byteIndex) {
+  return float((word >> (8 * byteIndex)) & 0xFFu);
+}
+
+// Tests the eight children of one node; returns the hit mask: bits 24..31 internal children in traversal
+// priority, bits 0..23 leaf primitives relative to primBase.
+__device__ __forceinline__ uint32_t intersectChildren(const uint4 &n0, const uint4 &n1, const uint4 &n2,
+                                                      const uint4 &n3, const uint4 &n4, const BoxSetup &b, float tmin,
+                                                      float tmax) {
+  const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23),
+              sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23);
+  const float aix = sx * b.idx, aiy = sy * b.idy, aiz = sz * b.idz;
+  const float aox = (__uint_as_float(n0.x) - b.ox) * b.idx, aoy = (__uint_as_float(n0.y) - b.oy) * b.idy,
+              aoz = (__uint_as_float(n0.z) - b.oz) * b.idz;
+  // conservative widening: |t| <= |ao| + 255 |ai| along each axis; a few ulp of that covers the rounding of the
+  // two products and the fma below, so a box is never missed because of float error
+  const float eps = 4.8e-7f;
+  const float wx = eps * (fabsf(aox) + 255.0f * fabsf(aix)), wy = eps * (fabsf(aoy) + 255.0f * fabsf(aiy)),
+              wz = eps * (fabsf(aoz) + 255.0f * fabsf(aiz));
+  const float nox = aox - wx, noy = aoy - wy, noz = aoz - wz; // near-plane offsets
+  const float fox = aox + wx, foy = aoy + wy, foz = aoz + wz; // far-plane offsets
+  const bool negx = b.idx < 0.0f, negy = b.idy < 0.0f, negz = b.idz < 0.0f;
+  // word pairs: lo_x = n2.xy, lo_y = n2.zw, lo_z = n3.xy, hi_x = n3.zw, hi_y = n4.xy, hi_z = n4.zw
+  uint32_t hitmask = 0;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
+    const uint32_t hix = half ? n3.w : n3.z, hiy = half ? n4.y : n4.x, hiz = half ? n4.w : n4.z;
+    const uint32_t nearx = negx ? hix : lox, farx = negx ? lox : hix;
+    const uint32_t neary = negy ? hiy : loy, fary = negy ? loy : hiy;
+    const uint32_t nearz = negz ? hiz : loz, farz = negz ? loz : hiz;
+    const uint32_t meta4 = half ? n1.w : n1.z;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t m = (meta4 >> (8 * k)) & 0xFFu;
+      const float tnx = fmaf(byteToFloat(nearx, k), aix, nox), tfx = fmaf(byteToFloat(farx, k), aix, fox);
+      const float tny = fmaf(byteToFloat(neary, k), aiy, noy), tfy = fmaf(byteToFloat(fary, k), aiy, foy);
+      const float tnz = fmaf(byteToFloat(nearz, k), aiz, noz), tfz = fmaf(byteToFloat(farz, k), aiz, foz);
+      const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+      const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+      if (m != 0u && tn <= tf) {
+        const bool inner = (m & 0x18u) == 0x18u;
+        const uint32_t bitIndex = (m & 31u) ^ (inner ? b.octinv : 0u);
+        hitmask |= (m >> 5) << bitIndex;
+      }
+    }
+  }
+  return hitmask;
+}
+
+// Two-level traversal. kAny: return true at the first accepted triangle. Otherwise `hit` holds the closest hit
+// (hit.t == tmax and return false when nothing was hit).
+template <bool kAny>
+__device__ __forceinline__ bool traverseScene(const TlasHeader *__restrict__ tlas, float ox, float oy, float oz,
+                                              float dx, float dy, float dz, float tmin, float tmax, RayHit &hit) {
+  hit.t = tmax;
+  hit.u = hit.v = 0.0f;
+  hit.instance = hit.geometry = hit.primitive = 0u;
+  bool found = false;
+  if (tlas->nodeCount == 0) return false;
+
+  uint2 stack[kStackSize];
+  int sp = 0;
+  int instanceSp = -1; // stack depth at which the current instance was entered; -1 = world space
+  uint32_t instance = 0;
+
+  const uint4 *nodes = reinterpret_cast<const uint4 *>(tlas->nodes);
+  const float4 *tris = nullptr;
+  BoxSetup box = makeBoxSetup(ox, oy, oz, dx, dy, dz);
+  TriSetup tri{};
+
+  uint2 ngroup = make_uint2(0u, 0x80000000u);
+  uint2 tgroup = make_uint2(0u, 0u);
+
+  while (true) {
+    if (ngroup.y > 0x00FFFFFFu) {
+      const uint32_t hits = ngroup.y;
+      const uint32_t bit = 31u - uint32_t(__clz(int(hits)));
+      ngroup.y &= ~(1u << bit);
+      if (ngroup.y > 0x00FFFFFFu) {
+        if (sp < kStackSize) stack[sp++] = ngroup;
+      }
+      const uint32_t slot = (bit - 24u) ^ (box.octinv & 7u);
+      const uint32_t rel = __popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
+      const uint4 *np = nodes + size_t(ngroup.x + rel) * 5;
+      const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+      const uint32_t hitmask = intersectChildren(n0, n1, n2, n3, n4, box, tmin, hit.t);
+      ngroup = make_uint2(n1.x, (hitmask & 0xFF000000u) | (n0.w >> 24));
+      tgroup = make_uint2(n1.y, hitmask & 0x00FFFFFFu);
+    } else {
+      tgroup = ngroup;
+      ngroup = make_uint2(0u, 0u);
+    }
+
+    while (tgroup.y != 0u) {
+      const uint32_t bit = uint32_t(__ffs(int(tgroup.y))) - 1u;
+      tgroup.y &= ~(1u << bit);
+      if (instanceSp < 0) {
+        // TLAS leaf: enter the instance. Pending world-space work goes to the stack first.
+        if (tgroup.y != 0u && sp < kStackSize) stack[sp++] = tgroup;
+        if (ngroup.y > 0x00FFFFFFu && sp < kStackSize) stack[sp++] = ngroup;
+        instance = __ldg(tlas->leafInstance + tgroup.x + bit);
+        const InstanceRecord *rec = tlas->instances + instance;
+        const float4 r0 = __ldg(&rec->row0), r1 = __ldg(&rec->row1), r2 = __ldg(&rec->row2);
+        const WideNode *bn = rec->nodes;
+        tgroup.y = 0u;
+        ngroup = make_uint2(0u, 0u);
+        if (bn != nullptr) {
+          const float lox = ((r0.x * ox + r0.y * oy) + r0.z * oz) + r0.w;
+          const float loy = ((r1.x * ox + r1.y * oy) + r1.z * oz) + r1.w;
+          const float loz = ((r2.x * ox + r2.y * oy) + r2.z * oz) + r2.w;
+          const float ldx = (r0.x * dx + r0.y * dy) + r0.z * dz;
+          const float ldy = (r1.x * dx + r1.y * dy) + r1.z * dz;
+          const float ldz = (r2.x * dx + r2.y * dy) + r2.z * dz;
+          box = makeBoxSetup(lox, loy, loz, ldx, ldy, ldz);
+          tri = makeTriSetup(lox, loy, loz, ldx, ldy, ldz);
+          nodes = reinterpret_cast<const uint4 *>(bn);
+          tris = reinterpret_cast<const float4 *>(rec->tris);
+          instanceSp = sp;
+          ngroup = make_uint2(0u, 0x80000000u);
+        }
+        break;
+      } else {
+        const float4 *tp = tris + size_t(tgroup.x + bit) * 3;
+        const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+        float t, u, v;
+        // accept bound: strictly inside (tmin, tmax) for the first hit, <= current best for tie handling
+        if (intersectTriangle(tri, v0, v1, v2, tmin, tmax, t, u, v)) {
+          if (kAny) return true;
+          const uint32_t prim = __float_as_uint(v0.w), geom = __float_as_uint(v1.w);
+          bool better = t < hit.t;
+          if (!better && found && t == hit.t) {
+            better = instance < hit.instance ||
+                     (instance == hit.instance &&
+                      (geom < hit.geometry || (geom == hit.geometry && prim < hit.primitive)));
+          }
+          if (better) {
+            found = true;
+            hit.t = t;
+            hit.u = u;
+            hit.v = v;
+            hit.instance = instance;
+            hit.geometry = geom;
+            hit.primitive = prim;
+          }
+        }
+      }
+    }
+
+    if (ngroup.y <= 0x00FFFFFFu) {
+      if (sp == instanceSp) { // the instance's subtree is exhausted: back to world space
+        instanceSp = -1;
+        box = makeBoxSetup(ox, oy, oz, dx, dy, dz);
+        nodes = reinterpret_cast<const uint4 *>(tlas->nodes);
+      }
+      if (sp == 0) break;
+      ngroup = stack[--sp];
+    }
+  }
+  return found;
+}
+
+} // namespace rtb

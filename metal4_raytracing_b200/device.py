@@ -1,0 +1,337 @@
+"""ctypes bridge to librt_b200.so — the sm_100a ray-tracing hot path (include/rt_b200.h, include/rt_renderer.h).
+
+`Context` wraps rt_create and the kernel-level entry points (the argument-table API that replaces the reference's
+Metal bindings, MetalRaytracing/Renderer.swift:1453-1490 and SkinningPass.swift:160-211); `Renderer` wraps the host
+orchestrator that mirrors Renderer.swift's createBuffers / updateSkinningAndBLAS / draw. There is no CPU fallback:
+a missing library or a missing GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi as A
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librt_b200.so")
+_lib = None
+
+RTR_FLAG_FP32_IMAGES = 1
+RTR_FLAG_REBUILD_SKINNED = 2
+
+
+class TraceOptions(C.Structure):
+    _fields_ = [("tileModulo", C.c_int32), ("tileRemainder", C.c_int32), ("primaryIdsDev", C.c_void_p),
+                ("rayCountersDev", C.c_void_p), ("peerAccumulation", C.POINTER(C.c_void_p))]
+
+
+class AsInfo(C.Structure):
+    _fields_ = [("primitiveCount", C.c_uint32), ("wideNodeCount", C.c_uint32), ("levelCount", C.c_uint32),
+                ("_pad", C.c_uint32), ("bytes", C.c_uint64), ("boundsMin", C.c_float * 3),
+                ("boundsMax", C.c_float * 3), ("sahCost", C.c_float), ("_pad2", C.c_float)]
+
+
+# every symbol include/rt_b200.h and include/rt_renderer.h declare (tests/test_abi.py checks the library exports them)
+EXPORTS = [
+    "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_sync", "rt_timer_begin", "rt_timer_end",
+    "rt_malloc", "rt_free", "rt_malloc_host", "rt_free_host", "rt_upload", "rt_download", "rt_copy", "rt_memset",
+    "rt_blas_build", "rt_blas_refit", "rt_blas_destroy", "rt_tlas_build", "rt_tlas_update", "rt_tlas_destroy",
+    "rt_as_get_info", "rt_skin", "rt_trace", "rt_texture_create", "rt_texture_destroy", "rt_launch_count",
+    "rt_set_trace_mode",
+    "rtr_last_error", "rtr_create", "rtr_destroy", "rtr_set_seeds", "rtr_update", "rtr_draw", "rtr_read_image",
+    "rtr_image_info", "rtr_reset_accumulation", "rtr_read_mesh_streams", "rtr_get_blas_id", "rtr_get_tlas_id",
+    "rtr_mesh_count",
+]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+                           "this package has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32, sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_size_t
+    L.rt_last_error.restype = C.c_char_p
+    L.rtr_last_error.restype = C.c_char_p
+    L.rt_create.argtypes = [i32, C.POINTER(vp)]
+    L.rt_destroy.argtypes = [vp]
+    L.rt_set_stream.argtypes = [vp, vp]
+    L.rt_sync.argtypes = [vp]
+    L.rt_timer_begin.argtypes = [vp]
+    L.rt_timer_end.argtypes = [vp, C.POINTER(C.c_float)]
+    L.rt_malloc.argtypes = [vp, sz, C.POINTER(vp)]
+    L.rt_free.argtypes = [vp, vp]
+    L.rt_malloc_host.argtypes = [vp, sz, C.POINTER(vp)]
+    L.rt_free_host.argtypes = [vp, vp]
+    L.rt_upload.argtypes = [vp, vp, vp, sz]
+    L.rt_download.argtypes = [vp, vp, vp, sz]
+    L.rt_copy.argtypes = [vp, vp, vp, sz]
+    L.rt_memset.argtypes = [vp, vp, i32, sz]
+    L.rt_blas_build.argtypes = [vp, C.POINTER(A.TriangleGeometry), u32, u32, C.POINTER(u64)]
+    L.rt_blas_refit.argtypes = [vp, u64, C.POINTER(A.TriangleGeometry), u32]
+    L.rt_blas_destroy.argtypes = [vp, u64]
+    L.rt_tlas_build.argtypes = [vp, vp, u32, C.POINTER(u64)]
+    L.rt_tlas_update.argtypes = [vp, u64, vp, u32]
+    L.rt_tlas_destroy.argtypes = [vp, u64]
+    L.rt_as_get_info.argtypes = [vp, u64, C.POINTER(AsInfo)]
+    L.rt_skin.argtypes = [vp, C.POINTER(vp), u32]
+    L.rt_trace.argtypes = [vp, C.POINTER(vp), C.POINTER(A.Image), i32, i32, C.POINTER(TraceOptions)]
+    L.rt_texture_create.argtypes = [vp, vp, i32, i32, i32, C.POINTER(vp)]
+    L.rt_texture_destroy.argtypes = [vp, vp]
+    L.rt_launch_count.restype = u64
+    L.rt_launch_count.argtypes = [vp]
+    L.rt_set_trace_mode.argtypes = [vp, i32]
+    L.rtr_create.argtypes = [vp, C.POINTER(A.SceneDesc), i32, i32, u32, C.POINTER(vp)]
+    L.rtr_destroy.argtypes = [vp]
+    L.rtr_set_seeds.argtypes = [vp, vp]
+    L.rtr_update.argtypes = [vp, C.POINTER(A.SceneDesc)]
+    L.rtr_draw.argtypes = [vp, C.POINTER(A.Uniforms), C.POINTER(TraceOptions)]
+    L.rtr_read_image.argtypes = [vp, i32, vp, sz]
+    L.rtr_image_info.argtypes = [vp, i32, C.POINTER(A.Image)]
+    L.rtr_reset_accumulation.argtypes = [vp]
+    L.rtr_read_mesh_streams.argtypes = [vp, i32, vp, vp, vp]
+    L.rtr_get_blas_id.argtypes = [vp, i32, C.POINTER(u64)]
+    L.rtr_get_tlas_id.argtypes = [vp, C.POINTER(u64)]
+    L.rtr_mesh_count.argtypes = [vp]
+    _lib = L
+    return L
+
+
+class RtError(RuntimeError):
+    pass
+
+
+def _check(rc, renderer=False):
+    if rc != 0:
+        L = lib()
+        msg = (L.rtr_last_error() if renderer else L.rt_last_error()).decode() or L.rt_last_error().decode()
+        raise RtError(f"rc={rc}: {msg}")
+
+
+_FORMAT_DTYPE = {
+    A.FORMAT_R32_UINT: (np.uint32, 1), A.FORMAT_R32_FLOAT: (np.float32, 1), A.FORMAT_RG16_FLOAT: (np.float16, 2),
+    A.FORMAT_RGBA16_FLOAT: (np.float16, 4), A.FORMAT_R16_FLOAT: (np.float16, 1),
+    A.FORMAT_RG32_FLOAT: (np.float32, 2), A.FORMAT_RGBA32_FLOAT: (np.float32, 4),
+}
+
+
+class Context:
+    """rt_context: one CUDA device + stream. Raises RtError when no GPU is present."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        _check(lib().rt_create(device, C.byref(h)))
+        self._h = h
+        self.device = device
+        self._owned = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- memory -------------------------------------------------------------------------------------------
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        _check(lib().rt_malloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def free(self, ptr):
+        _check(lib().rt_free(self._h, ptr))
+
+    def upload(self, array, ptr=None):
+        a = np.ascontiguousarray(array)
+        if ptr is None:
+            ptr = self.malloc(a.nbytes)
+        _check(lib().rt_upload(self._h, ptr, a.ctypes.data, a.nbytes))
+        return ptr
+
+    def download(self, ptr, shape, dtype):
+        out = np.empty(shape, dtype)
+        _check(lib().rt_download(self._h, out.ctypes.data, ptr, out.nbytes))
+        return out
+
+    def memset(self, ptr, value, nbytes):
+        _check(lib().rt_memset(self._h, ptr, value, nbytes))
+
+    def copy(self, dst, src, nbytes):
+        _check(lib().rt_copy(self._h, dst, src, nbytes))
+
+    def sync(self):
+        _check(lib().rt_sync(self._h))
+
+    def set_stream(self, cuda_stream):
+        _check(lib().rt_set_stream(self._h, cuda_stream))
+
+    def timer_begin(self):
+        _check(lib().rt_timer_begin(self._h))
+
+    def timer_end(self):
+        ms = C.c_float()
+        _check(lib().rt_timer_end(self._h, C.byref(ms)))
+        return ms.value
+
+    @property
+    def launches(self):
+        return lib().rt_launch_count(self._h)
+
+    # -- acceleration structures -----------------------------------------------------------------------------
+    def blas_build(self, geoms, flags=A.AS_FLAG_COMPACT):
+        arr = (A.TriangleGeometry * max(1, len(geoms)))(*geoms)
+        out = C.c_uint64()
+        _check(lib().rt_blas_build(self._h, arr, len(geoms), flags, C.byref(out)))
+        return out.value
+
+    def blas_refit(self, blas, geoms):
+        arr = (A.TriangleGeometry * max(1, len(geoms)))(*geoms)
+        _check(lib().rt_blas_refit(self._h, blas, arr, len(geoms)))
+
+    def blas_destroy(self, blas):
+        _check(lib().rt_blas_destroy(self._h, blas))
+
+    def tlas_build(self, descriptors_dev, count):
+        out = C.c_uint64()
+        _check(lib().rt_tlas_build(self._h, descriptors_dev, count, C.byref(out)))
+        return out.value
+
+    def tlas_update(self, tlas, descriptors_dev, count):
+        _check(lib().rt_tlas_update(self._h, tlas, descriptors_dev, count))
+
+    def tlas_destroy(self, tlas):
+        _check(lib().rt_tlas_destroy(self._h, tlas))
+
+    def as_info(self, as_id):
+        info = AsInfo()
+        _check(lib().rt_as_get_info(self._h, as_id, C.byref(info)))
+        return info
+
+    # -- kernels -----------------------------------------------------------------------------------------------
+    def skin(self, table, vertex_count):
+        """table: dict BufferIndex -> device pointer (Skinning.metal:7-15 bindings)."""
+        bufs = (C.c_void_p * A.BUFFER_COUNT)()
+        for k, v in table.items():
+            bufs[k] = v
+        _check(lib().rt_skin(self._h, bufs, vertex_count))
+
+    def trace(self, table, images, uniforms, max_submeshes, options=None):
+        """table: dict BufferIndex -> device pointer / TLAS id; images: (A.Image * 9)."""
+        bufs = (C.c_void_p * A.BUFFER_COUNT)()
+        for k, v in table.items():
+            bufs[k] = v
+        bufs[A.BUFFER_UNIFORMS] = C.addressof(uniforms)
+        _check(lib().rt_trace(self._h, bufs, images, C.sizeof(A.Resource), max_submeshes,
+                              C.byref(options) if options is not None else None))
+
+    def texture_create(self, rgba8, srgb=False):
+        t = np.ascontiguousarray(rgba8, np.uint8)
+        out = C.c_void_p()
+        _check(lib().rt_texture_create(self._h, t.ctypes.data, t.shape[1], t.shape[0], int(srgb), C.byref(out)))
+        return out.value
+
+
+class Renderer:
+    """rtr_renderer: scene resident in HBM + per-frame update/draw (Renderer.swift's hot-path half)."""
+
+    def __init__(self, ctx, scene, width, height, seeds=None, fp32=False, rebuild_skinned=False):
+        self.ctx = ctx
+        self.scene = scene
+        self.width, self.height = width, height
+        flags = (RTR_FLAG_FP32_IMAGES if fp32 else 0) | (RTR_FLAG_REBUILD_SKINNED if rebuild_skinned else 0)
+        desc = scene.desc()
+        h = C.c_void_p()
+        _check(lib().rtr_create(ctx._h, C.byref(desc), width, height, flags, C.byref(h)), True)
+        self._h = h
+        self._ids_dev = None
+        self._counters_dev = None
+        if seeds is not None:
+            self.set_seeds(seeds)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            if self._ids_dev:
+                self.ctx.free(self._ids_dev)
+            if self._counters_dev:
+                self.ctx.free(self._counters_dev)
+            lib().rtr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_seeds(self, seeds):
+        s = np.ascontiguousarray(seeds, np.uint32)
+        assert s.shape == (self.height, self.width)
+        _check(lib().rtr_set_seeds(self._h, s.ctypes.data), True)
+
+    def update(self):
+        desc = self.scene.desc()
+        _check(lib().rtr_update(self._h, C.byref(desc)), True)
+
+    def draw(self, uniforms, want_ids=False, count_rays=False, tile_modulo=1, tile_remainder=0, peers=None):
+        opt = TraceOptions()
+        opt.tileModulo, opt.tileRemainder = tile_modulo, tile_remainder
+        if want_ids:
+            if self._ids_dev is None:
+                self._ids_dev = self.ctx.malloc(self.width * self.height * 16)
+            self.ctx.memset(self._ids_dev, 0xFF, self.width * self.height * 16)
+            opt.primaryIdsDev = self._ids_dev
+        if count_rays:
+            if self._counters_dev is None:
+                self._counters_dev = self.ctx.malloc(24)
+            self.ctx.memset(self._counters_dev, 0, 24)
+            opt.rayCountersDev = self._counters_dev
+        if peers is not None:
+            arr = (C.c_void_p * len(peers))(*peers)
+            opt.peerAccumulation = arr
+        _check(lib().rtr_draw(self._h, C.byref(uniforms), C.byref(opt)), True)
+
+    def read_ids(self):
+        return self.ctx.download(self._ids_dev, (self.height, self.width, 4), np.uint32)
+
+    def read_ray_counters(self):
+        c = self.ctx.download(self._counters_dev, (3,), np.uint64)
+        return {"closest": int(c[0]), "any": int(c[1]), "hits": int(c[2]), "rays": int(c[0] + c[1])}
+
+    def image_info(self, index):
+        img = A.Image()
+        _check(lib().rtr_image_info(self._h, index, C.byref(img)), True)
+        return img
+
+    def read_image(self, index=A.TEXTURE_ACCUMULATION):
+        """Host copy of the image bound at `index`; after draw(), index 0 is the frame just rendered."""
+        info = self.image_info(index)
+        dt, ch = _FORMAT_DTYPE[info.format]
+        out = np.empty((self.height, self.width, ch), dt)
+        _check(lib().rtr_read_image(self._h, index, out.ctypes.data, out.nbytes), True)
+        return out
+
+    def reset_accumulation(self):
+        _check(lib().rtr_reset_accumulation(self._h), True)
+
+    def mesh_streams(self, mesh, vertex_count):
+        p = np.zeros((vertex_count, 4), np.float32)
+        n = np.zeros((vertex_count, 4), np.float32)
+        q = np.zeros((vertex_count, 4), np.float32)
+        _check(lib().rtr_read_mesh_streams(self._h, mesh, p.ctypes.data, n.ctypes.data, q.ctypes.data), True)
+        return p, n, q
+
+    def blas_id(self, mesh):
+        out = C.c_uint64()
+        _check(lib().rtr_get_blas_id(self._h, mesh, C.byref(out)), True)
+        return out.value
+
+    def tlas_id(self):
+        out = C.c_uint64()
+        _check(lib().rtr_get_tlas_id(self._h, C.byref(out)), True)
+        return out.value
