@@ -107,6 +107,18 @@ int rt_texture_create(rt_context *ctx, const uint8_t *rgba8Host, int width, int 
                       const rt_texture2d **outRecordDev);
 int rt_texture_destroy(rt_context *ctx, const rt_texture2d *recordDev);
 
+/* ---- multi-GPU frame exchange (no counterpart in the single-device reference) ---------------
+ * Rank g of N owns 16x16 tiles with tile % N == g. Two ways to assemble the frame:
+ *  (a) rt_trace with options->peerAccumulation: the kernel stores owned pixels straight into every rank's frame
+ *      through NVLink peer mappings obtained with rt_ipc_export / rt_ipc_import (one kernel = compute + exchange);
+ *  (b) rt_pack_tiles -> NCCL all-gather of the slabs (done by the caller) -> rt_unpack_tiles.
+ * Slab layout: [ceil(tileCount / N) tiles][256 pixels][bytes per pixel]; rank-major after the gather. */
+int rt_pack_tiles(rt_context *ctx, const rt_image *imageDev, void *slabDev, int tileModulo, int tileRemainder);
+int rt_unpack_tiles(rt_context *ctx, const void *slabsDev, const rt_image *imageDev, int tileModulo);
+int rt_ipc_export(rt_context *ctx, void *dev, unsigned char handle[64]);
+int rt_ipc_import(rt_context *ctx, const unsigned char handle[64], void **outDev);
+int rt_ipc_close(rt_context *ctx, void *importedDev);
+
 /* Number of kernels this library has launched on the context since creation (bench.py's gpu_launches). */
 uint64_t rt_launch_count(rt_context *ctx);
 /* Select the trace kernel layout: 0 = megakernel (default), 1 = wavefront. */

@@ -141,6 +141,8 @@ int refitBlas(rt_context *ctx, AccelObject *as, const rt_triangle_geometry *geom
 int buildTlas(rt_context *ctx, AccelObject *as, const rt_instance_descriptor *descDev, uint32_t count);
 void destroyAccel(AccelObject *as);
 int launchSkin(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], uint32_t vertexCount);
+int packTiles(rt_context *ctx, const rt_image *image, void *slab, int modulo, int remainder);
+int unpackTiles(rt_context *ctx, const void *slabs, const rt_image *image, int modulo);
 int launchTrace(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], const rt_image textures[RT_TEXTURE_COUNT],
                 int maxSubmeshes, const rt_trace_options *opt);
 } // namespace rtb

@@ -319,6 +319,41 @@ int rt_texture_destroy(rt_context *ctx, const rt_texture2d *recordDev) {
   return 0;
 }
 
+int rt_pack_tiles(rt_context *ctx, const rt_image *imageDev, void *slabDev, int tileModulo, int tileRemainder) {
+  RT_CTX(ctx);
+  return packTiles(ctx, imageDev, slabDev, tileModulo, tileRemainder);
+}
+
+int rt_unpack_tiles(rt_context *ctx, const void *slabsDev, const rt_image *imageDev, int tileModulo) {
+  RT_CTX(ctx);
+  return unpackTiles(ctx, slabsDev, imageDev, tileModulo);
+}
+
+int rt_ipc_export(rt_context *ctx, void *dev, unsigned char handle[64]) {
+  RT_CTX(ctx);
+  RT_CHECK(dev && handle, "rt_ipc_export: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+  cudaIpcMemHandle_t h;
+  RT_CUDA(cudaIpcGetMemHandle(&h, dev));
+  std::memcpy(handle, &h, 64);
+  return 0;
+}
+
+int rt_ipc_import(rt_context *ctx, const unsigned char handle[64], void **outDev) {
+  RT_CTX(ctx);
+  RT_CHECK(handle && outDev, "rt_ipc_import: null pointer");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  RT_CUDA(cudaIpcOpenMemHandle(outDev, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int rt_ipc_close(rt_context *ctx, void *importedDev) {
+  RT_CTX(ctx);
+  if (importedDev) RT_CUDA(cudaIpcCloseMemHandle(importedDev));
+  return 0;
+}
+
 uint64_t rt_launch_count(rt_context *ctx) { return ctx ? ctx->launches : 0; }
 
 int rt_set_trace_mode(rt_context *ctx, int mode) {

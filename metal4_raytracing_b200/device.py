@@ -286,10 +286,12 @@ class Renderer:
                 self._ids_dev = self.ctx.malloc(self.width * self.height * 16)
             self.ctx.memset(self._ids_dev, 0xFF, self.width * self.height * 16)
             opt.primaryIdsDev = self._ids_dev
-        if count_rays:
+        if count_rays:  # True: reset then count this frame; "accumulate": keep adding to the counters
             if self._counters_dev is None:
                 self._counters_dev = self.ctx.malloc(24)
-            self.ctx.memset(self._counters_dev, 0, 24)
+                self.ctx.memset(self._counters_dev, 0, 24)
+            if count_rays is True:
+                self.ctx.memset(self._counters_dev, 0, 24)
             opt.rayCountersDev = self._counters_dev
         if peers is not None:
             arr = (C.c_void_p * len(peers))(*peers)
@@ -298,6 +300,11 @@ class Renderer:
 
     def read_ids(self):
         return self.ctx.download(self._ids_dev, (self.height, self.width, 4), np.uint32)
+
+    def reset_ray_counters(self):
+        if self._counters_dev is None:
+            self._counters_dev = self.ctx.malloc(24)
+        self.ctx.memset(self._counters_dev, 0, 24)
 
     def read_ray_counters(self):
         c = self.ctx.download(self._counters_dev, (3,), np.uint64)

@@ -1,0 +1,154 @@
+"""Multi-GPU frame sharding: one process per GPU, scene + BVH replicated, interleaved 16x16 screen tiles.
+
+The reference is single-device (MetalRaytracing/Renderer.swift:229); the unit of ownership here is its 16x16
+threadgroup tile (Renderer.swift:1445-1451): rank g of N renders tiles with tile % N == g. The EMA history of a
+pixel lives on the rank that owns it (Raytracing.metal:796-819 only ever reads the same pixel), so the only exchange
+is the assembly of the displayed frame:
+
+  * "peer"   — rt_trace stores owned pixels straight into every rank's frame over NVLink peer mappings (CUDA IPC),
+               compute and exchange in one kernel; ranks then meet at a stream-ordered NCCL barrier;
+  * "gather" — rt_pack_tiles -> torch.distributed all_gather_into_tensor (NCCL) -> rt_unpack_tiles.
+
+The tile arithmetic and the slab layout are plain host logic and are shared with the CPU (gloo) tests.
+"""
+import ctypes as C
+
+import numpy as np
+
+TILE = 16
+
+
+def tile_grid(width, height):
+    return (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
+
+
+def owned_tiles(width, height, world_size, rank):
+    tx, ty = tile_grid(width, height)
+    return list(range(rank, tx * ty, world_size))
+
+
+def slab_tiles(width, height, world_size):
+    tx, ty = tile_grid(width, height)
+    return (tx * ty + world_size - 1) // world_size
+
+
+def owner_mask(width, height, world_size, rank):
+    """Boolean (height, width) mask of the pixels rank `rank` owns."""
+    tx, _ = tile_grid(width, height)
+    ys, xs = np.mgrid[0:height, 0:width]
+    tile = (ys // TILE) * tx + (xs // TILE)
+    return (tile % world_size) == rank
+
+
+def pack_tiles_host(image, world_size, rank):
+    """numpy restatement of rt_pack_tiles: (H, W, C) -> (slab_tiles, 256, C), missing pixels zero."""
+    h, w = image.shape[:2]
+    tx, _ = tile_grid(w, h)
+    n = slab_tiles(w, h, world_size)
+    slab = np.zeros((n, TILE * TILE) + image.shape[2:], image.dtype)
+    for k, t in enumerate(owned_tiles(w, h, world_size, rank)):
+        x0, y0 = (t % tx) * TILE, (t // tx) * TILE
+        block = image[y0:y0 + TILE, x0:x0 + TILE]
+        full = np.zeros((TILE, TILE) + image.shape[2:], image.dtype)
+        full[:block.shape[0], :block.shape[1]] = block
+        slab[k] = full.reshape((TILE * TILE,) + image.shape[2:])
+    return slab
+
+
+def unpack_tiles_host(slabs, width, height, world_size):
+    """numpy restatement of rt_unpack_tiles: (world, slab_tiles, 256, C) -> (H, W, C)."""
+    tx, ty = tile_grid(width, height)
+    out = np.zeros((height, width) + slabs.shape[3:], slabs.dtype)
+    for t in range(tx * ty):
+        r, k = t % world_size, t // world_size
+        x0, y0 = (t % tx) * TILE, (t // tx) * TILE
+        block = slabs[r, k].reshape((TILE, TILE) + slabs.shape[3:])
+        hh, ww = min(TILE, height - y0), min(TILE, width - x0)
+        out[y0:y0 + hh, x0:x0 + ww] = block[:hh, :ww]
+    return out
+
+
+def gather_frame_host(local_image, world_size, rank, dist):
+    """Frame assembly with torch.distributed on host tensors (gloo): the N>1 host logic under test on CPU."""
+    import torch
+    h, w = local_image.shape[:2]
+    slab = pack_tiles_host(local_image, world_size, rank)
+    raw = np.ascontiguousarray(slab).view(np.uint8).reshape(-1)
+    mine = torch.from_numpy(raw.copy())
+    parts = [torch.empty_like(mine) for _ in range(world_size)]
+    dist.all_gather(parts, mine)
+    allslabs = np.stack([p.numpy().view(local_image.dtype).reshape(slab.shape) for p in parts])
+    return unpack_tiles_host(allslabs, w, h, world_size)
+
+
+class FrameExchange:
+    """Device-side frame assembly for a `device.Renderer` under torch.distributed (NCCL)."""
+
+    def __init__(self, renderer, world_size, rank, mode="peer"):
+        import torch
+        import torch.distributed as dist
+        from . import _abi as A
+        from . import device as D
+        self.r, self.world, self.rank, self.mode = renderer, world_size, rank, mode
+        self.dist, self.torch, self.A, self.D = dist, torch, A, D
+        self.ctx = renderer.ctx
+        self._flag = torch.zeros(1, device=f"cuda:{self.ctx.device}")
+        self._peers = None  # [image slot][rank] -> device pointer
+        L = D.lib()
+        L.rt_pack_tiles.argtypes = [C.c_void_p, C.POINTER(A.Image), C.c_void_p, C.c_int, C.c_int]
+        L.rt_unpack_tiles.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(A.Image), C.c_int]
+        L.rt_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
+        L.rt_ipc_import.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        if world_size > 1 and mode == "peer":
+            self._open_peers()
+        if world_size > 1 and mode == "gather":
+            info = renderer.image_info(A.TEXTURE_ACCUMULATION)
+            bpp = {A.FORMAT_RGBA16_FLOAT: 8, A.FORMAT_RGBA32_FLOAT: 16}[info.format]
+            n = slab_tiles(renderer.width, renderer.height, world_size) * 256 * bpp
+            self._slab = torch.empty(n, dtype=torch.uint8, device=f"cuda:{self.ctx.device}")
+            self._all = torch.empty(n * world_size, dtype=torch.uint8, device=f"cuda:{self.ctx.device}")
+
+    def _open_peers(self):
+        """Exchange CUDA IPC handles of both accumulation images; keyed by local device pointer."""
+        A, D, L = self.A, self.D, self.D.lib()
+        mine = {}
+        for slot in (A.TEXTURE_ACCUMULATION, A.TEXTURE_PREVIOUS_ACCUMULATION):
+            ptr = self.r.image_info(slot).data
+            buf = C.create_string_buffer(64)
+            D._check(L.rt_ipc_export(self.ctx._h, ptr, buf))
+            mine[slot] = (ptr, buf.raw)
+        everyone = [None] * self.world
+        self.dist.all_gather_object(everyone, mine)
+        # local pointer of slot s on this rank -> list of every rank's pointer for the same slot
+        self._peers = {}
+        for slot, (ptr, _) in mine.items():
+            ptrs = []
+            for rk in range(self.world):
+                if rk == self.rank:
+                    ptrs.append(ptr)
+                else:
+                    out = C.c_void_p()
+                    D._check(L.rt_ipc_import(self.ctx._h, everyone[rk][slot][1], C.byref(out)))
+                    ptrs.append(out.value)
+            self._peers[ptr] = ptrs
+
+    def peers_for_next_draw(self):
+        """Peer pointers matching the image the next draw writes (TextureIndexPreviousAccumulation)."""
+        if self.world == 1 or self.mode != "peer":
+            return None
+        dst = self.r.image_info(self.A.TEXTURE_PREVIOUS_ACCUMULATION).data
+        return self._peers[dst]
+
+    def finish_frame(self):
+        """After draw(): make the full frame visible at TextureIndexAccumulation on every rank."""
+        if self.world == 1:
+            return
+        A, L = self.A, self.D.lib()
+        if self.mode == "gather":
+            img = self.r.image_info(A.TEXTURE_ACCUMULATION)
+            self.D._check(L.rt_pack_tiles(self.ctx._h, C.byref(img), self._slab.data_ptr(), self.world, self.rank))
+            self.dist.all_gather_into_tensor(self._all, self._slab)
+            self.D._check(L.rt_unpack_tiles(self.ctx._h, self._all.data_ptr(), C.byref(img), self.world))
+        else:
+            # peer stores are complete when every rank's kernel has finished: stream-ordered barrier
+            self.dist.all_reduce(self._flag)
