@@ -90,9 +90,16 @@ enum rt_debug_texture_mode {
 #define RT_MATERIAL_TEXTURE_OPACITY (1u << 6)
 
 /* ---- vector_float3: 16-byte size and alignment ------------------------------------------------------ */
-typedef struct RT_ALIGNAS(16) rt_float3 {
+#ifdef __cplusplus
+typedef struct alignas(16) rt_float3 {
   float x, y, z, _pad;
 } rt_float3;
+#else
+typedef struct rt_float3 {
+  _Alignas(16) float x;
+  float y, z, _pad;
+} rt_float3;
+#endif
 RT_STATIC_ASSERT(sizeof(rt_float3) == 16, "vector_float3 is 16 bytes");
 
 /* ---- Camera (ShaderTypes.h:80-85) ------------------------------------------------------------------- */

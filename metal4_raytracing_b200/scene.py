@@ -21,7 +21,7 @@ def asset_dir():
     env = os.environ.get("RT_ASSET_DIR")
     cands = [env] if env else []
     cands += ["/root/reference/AssetResources",
-              os.path.join(os.path.dirname(_HERE), "oracle", "_ref", "AssetResources")]
+              os.path.join(os.path.dirname(_HERE), "assets", "_ref", "AssetResources")]
     for c in cands:
         if c and os.path.isfile(os.path.join(c, "plane.obj")):
             return c

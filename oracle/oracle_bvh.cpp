@@ -196,12 +196,20 @@ void buildBvh2(std::vector<PrimRef> &prims, std::vector<Node> &nodes, uint32_t m
   }
 }
 
+// 1/d for the slab tests only (the triangle test uses the true direction): a zero component becomes a tiny value
+// of the same sign, so an origin lying exactly on a box face of a ray parallel to that face stays inside the
+// slab instead of producing 0 * inf = NaN.
+inline float safeInverse(float d) {
+  const float tiny = 1.0e-20f;
+  return 1.0f / (fabsf(d) < tiny ? copysignf(tiny, d) : d);
+}
+
 inline bool slab(const Aabb &b, const float o[3], const float invd[3], float tmin, float tmax, float &tnear) {
   float tn = -3.0e38f, tf = 3.0e38f;
   for (int a = 0; a < 3; ++a) {
     float t0 = (b.lo[a] - o[a]) * invd[a];
     float t1 = (b.hi[a] - o[a]) * invd[a];
-    tn = fmaxf(fminf(t0, t1), tn); // fminf/fmaxf drop NaN (0 * inf): that axis then does not constrain
+    tn = fmaxf(fminf(t0, t1), tn);
     tf = fminf(fmaxf(t0, t1), tf);
   }
   // conservative widening (a few ulp) so the accepted triangle set never depends on box rounding
@@ -225,7 +233,7 @@ template <bool kAny>
 bool traverseBlas(const Blas &blas, const float o[3], const float d[3], float tmin, float tmax, uint32_t instance,
                   Hit &best) {
   if (blas.tris.empty()) return false;
-  float invd[3] = {1.0f / d[0], 1.0f / d[1], 1.0f / d[2]};
+  float invd[3] = {safeInverse(d[0]), safeInverse(d[1]), safeInverse(d[2])};
   RayPrecalc rp = precalcRay(d);
   uint32_t stack[128];
   int sp = 0;
@@ -281,7 +289,7 @@ bool traverseTlas(const Tlas &tlas, float3 origin, float3 dir, float tmin, float
   best.instance = best.geometry = best.primitive = 0;
   if (tlas.instances.empty()) return false;
   const float o[3] = {origin.x, origin.y, origin.z}, d[3] = {dir.x, dir.y, dir.z};
-  float invd[3] = {1.0f / d[0], 1.0f / d[1], 1.0f / d[2]};
+  float invd[3] = {safeInverse(d[0]), safeInverse(d[1]), safeInverse(d[2])};
   uint32_t stack[128];
   int sp = 0;
   stack[sp++] = 0;

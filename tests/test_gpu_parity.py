@@ -1,0 +1,364 @@
+"""Parity of the sm_100a path against the CPU oracle, through the C-ABI (librt_b200.so). Needs a B200.
+
+Bars (BASELINE.json north_star): primary-hit instance/geometry/primitive ids bit-exact except < 1e-4 of pixels,
+skinned positions within 1e-5 relative, accumulated radiance relative RMSE < 1e-3 at equal spp. In practice the
+two sides share one numeric contract and agree bit for bit; the asserts keep the stated tolerances and
+the exact-match fractions are additionally required to stay >= 0.999 so a silent drift is caught.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from metal4_raytracing_b200 import _abi as A
+from metal4_raytracing_b200 import device, parallel, scene
+
+pytestmark = pytest.mark.gpu
+
+ID_TOL = 1e-4
+RMSE_TOL = 1e-3
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel_rmse(a, b):
+    a = a.astype(np.float32)[..., :3]
+    b = b.astype(np.float32)[..., :3]
+    return float(np.sqrt(np.mean((a - b) ** 2)) / max(1e-12, np.sqrt(np.mean(b ** 2))))
+
+
+def check_frames(ctx, sc, u, seeds, frames=1, fp32=False, animate=False, rebuild=False, adaptive=None):
+    """Renders `frames` frames on both sides and asserts parity of every output image. Returns per-frame stats."""
+    w, h = u.width, u.height
+    rnd = device.Renderer(ctx, sc, w, h, seeds=seeds, fp32=fp32, rebuild_skinned=rebuild)
+    orc = oracle.Oracle(sc)
+    imgs = oracle.FrameImages(w, h, seeds, fp32=fp32)
+    out = []
+    for f in range(frames):
+        u.frameIndex = f
+        if animate and f > 0:
+            sc.animate(f / 60.0)
+            rnd.update()
+            orc.update()
+        rnd.draw(u, want_ids=True, count_rays=True)
+        st, ref_ids = orc.render(u, imgs, want_ids=True)
+        ids = rnd.read_ids()
+        got = rnd.read_image(A.TEXTURE_ACCUMULATION)
+        ref = imgs.output
+        rays = rnd.read_ray_counters()
+        mism = float((ids[..., :3] != ref_ids[..., :3]).any(-1).mean())
+        assert mism <= ID_TOL, f"frame {f}: primary id mismatch {mism}"
+        assert rel_rmse(got, ref) < RMSE_TOL, f"frame {f}: radiance rmse {rel_rmse(got, ref)}"
+        exact = float((got.view(np.uint16 if not fp32 else np.uint32) ==
+                       ref.view(np.uint16 if not fp32 else np.uint32)).all(-1).mean())
+        assert exact >= 0.999, f"frame {f}: only {exact} of pixels bit-identical"
+        depth = rnd.read_image(A.TEXTURE_DEPTH)
+        assert float((depth == imgs.arrays[A.TEXTURE_DEPTH]).mean()) >= 0.999
+        motion = rnd.read_image(A.TEXTURE_MOTION).astype(np.float32)
+        assert np.abs(motion - imgs.arrays[A.TEXTURE_MOTION].astype(np.float32)).max() <= 1e-2
+        assert abs(rays["closest"] - st["closest"]) <= 1e-4 * st["closest"] + 2
+        assert abs(rays["any"] - st["any"]) <= 1e-4 * st["any"] + 2
+        if u.enableDenoiseGBuffer:
+            for slot in (A.TEXTURE_DIFFUSE_ALBEDO, A.TEXTURE_SPECULAR_ALBEDO, A.TEXTURE_NORMAL, A.TEXTURE_ROUGHNESS):
+                g = rnd.read_image(slot).astype(np.float32)
+                assert np.abs(g - imgs.arrays[slot].astype(np.float32)).max() <= 2e-3, slot
+        out.append({"rays": rays, "exact": exact, "mismatch": mism, "image": got, "ids": ids})
+        imgs.swap()
+    out[0]["renderer"], out[0]["oracle"] = rnd, orc
+    return out
+
+
+def test_k1_reference_case(gpu_ctx, assets):
+    """configs[0]: plane.obj + sphere.obj, 512x512, 1 spp, primary + shadow rays, one point light."""
+    sc, u, seed = scene.Scene.named("K1", 512, 512, assets=assets)
+    res = check_frames(gpu_ctx, sc, u, scene.seed_image(512, 512, seed))
+    assert res[0]["rays"]["closest"] == 512 * 512 and res[0]["mismatch"] == 0.0
+
+
+def test_golden_frame_on_gpu(gpu_ctx, assets):
+    g = np.load(os.path.join(GOLDEN, "k1_128.npz"))
+    sc, u, seed = scene.Scene.named("K1", 128, 128, assets=assets)
+    C.memmove(C.byref(u), g["uniforms"].tobytes(), C.sizeof(A.Uniforms))
+    rnd = device.Renderer(gpu_ctx, sc, 128, 128, seeds=scene.seed_image(128, 128, int(g["seed"])))
+    rnd.draw(u, want_ids=True, count_rays=True)
+    assert np.array_equal(rnd.read_ids()[..., :3], g["ids"][..., :3])
+    assert np.array_equal(rnd.read_ids()[..., 3], g["ids"][..., 3])  # hit distance bits
+    assert np.array_equal(rnd.read_image(A.TEXTURE_ACCUMULATION).view(np.uint16), g["image"].view(np.uint16))
+    assert np.array_equal(rnd.read_image(A.TEXTURE_DEPTH), g["depth"])
+    c = rnd.read_ray_counters()
+    assert [c["closest"], c["any"], c["hits"]] == list(g["stats"])
+    rnd.close()
+
+
+def test_bounces_accumulation_and_adaptive_paths(gpu_ctx):
+    """3 bounces, 2 spp, EMA over 4 frames with motion-adaptive accumulation + sampling switched on."""
+    sc, u, seed = scene.Scene.named("K3small", 320, 200, assets=None)
+    u.samplesPerPixel, u.maxBounces = 2, 3
+    u.enableMotionAdaptiveAccumulation, u.enableMotionAdaptiveSampling = 1, 1
+    res = check_frames(gpu_ctx, sc, u, scene.seed_image(320, 200, seed), frames=4)
+    assert res[0]["rays"]["any"] > 0 and res[3]["rays"]["closest"] > 320 * 200 * 2
+
+
+def test_moving_instance_motion_vectors(gpu_ctx):
+    """An instance that moves between frames: previous descriptors drive motion vectors, which in turn drive the
+    adaptive sample count and history weight (Raytracing.metal:341-389, 779-815)."""
+    w, h = 256, 160
+    sc, u, seed = scene.Scene.named("K3small", w, h, assets=None)
+    u.samplesPerPixel, u.maxBounces = 1, 2
+    u.enableMotionAdaptiveAccumulation, u.enableMotionAdaptiveSampling = 1, 1
+    seeds = scene.seed_image(w, h, seed)
+    rnd = device.Renderer(gpu_ctx, sc, w, h, seeds=seeds)
+    orc = oracle.Oracle(sc)
+    imgs = oracle.FrameImages(w, h, seeds)
+    total_motion = 0.0
+    for f in range(3):
+        u.frameIndex = f
+        if f:
+            sc.set_instance_transform(0, (0.3 + 0.05 * f, 0.38, 2.5), (0, 1.885 + 0.1 * f, 0), 1.2)
+            rnd.update()
+            orc.update()
+        rnd.draw(u, count_rays=True)
+        st, _ = orc.render(u, imgs)
+        assert rel_rmse(rnd.read_image(0), imgs.output) < RMSE_TOL
+        mg = rnd.read_image(A.TEXTURE_MOTION).astype(np.float32)
+        assert np.abs(mg - imgs.arrays[A.TEXTURE_MOTION].astype(np.float32)).max() <= 1e-2
+        assert rnd.read_ray_counters()["closest"] == st["closest"]  # adaptive extra samples agree
+        total_motion += float(np.abs(mg).sum())
+        imgs.swap()
+    assert total_motion > 0
+    rnd.close()
+
+
+def test_instancing_many_instances_and_missing_normals(gpu_ctx, assets):
+    """TLAS over 65 instances of 3 BLAS with up to 6 submeshes; teapot.obj has no normals (-ray.direction path)."""
+    sc, u, seed = scene.Scene.named("K4small", 384, 216, assets=assets)
+    u.samplesPerPixel = 2
+    res = check_frames(gpu_ctx, sc, u, scene.seed_image(384, 216, seed), frames=2)
+    inst = res[0]["ids"][..., 0]
+    assert len(np.unique(inst[inst != 0xFFFFFFFF])) > 20
+
+
+def test_skinning_refit_and_rebuild(gpu_ctx):
+    """config 5 in small: skin -> BLAS refit -> TLAS rebuild per frame; refit and full rebuild give the same image."""
+    w, h = 256, 256
+    sc, u, seed = scene.Scene.named("K5small", w, h, assets=None)
+    seeds = scene.seed_image(w, h, seed)
+    res = check_frames(gpu_ctx, sc, u, seeds, frames=4, animate=True)
+    rnd, orc = res[0]["renderer"], res[0]["oracle"]
+    n = sc.desc().meshes[0].vertexCount
+    gp, gn, gq = rnd.mesh_streams(0, n)
+    op, on, oq = orc.mesh_streams(0, n)
+    scale = np.abs(op).max()
+    assert np.abs(gp - op).max() <= 1e-5 * scale and np.abs(gn - on).max() <= 1e-5 * max(1.0, np.abs(on).max())
+    assert np.abs(gq - oq).max() <= 1e-5 * scale  # previous positions (motion vectors)
+    refit_last = res[3]["image"]
+    sc2, u2, _ = scene.Scene.named("K5small", w, h, assets=None)
+    res2 = check_frames(gpu_ctx, sc2, u2, seeds, frames=4, animate=True, rebuild=True)
+    assert np.array_equal(refit_last.view(np.uint16), res2[3]["image"].view(np.uint16))
+    rnd.close()
+    res2[0]["renderer"].close()
+
+
+def test_textured_pbr_and_normal_map(gpu_ctx):
+    sc, u, seed = scene.Scene.named("K2tex", 320, 180, assets=None)
+    u.samplesPerPixel, u.enableDenoiseGBuffer = 2, 1
+    check_frames(gpu_ctx, sc, u, scene.seed_image(320, 180, seed), frames=2)
+
+
+def _glass_scene(w, h):
+    sc, u, seed = scene.Scene.named("K3small", w, h, assets=None)
+    m = sc.get_material(0)
+    m.baseColor.set(0.95, 0.98, 1.0)
+    m.refractionIndex, m.opacity = 1.52, 0.08  # Model.swift:22-26
+    sc.set_material(0, 0, m)
+    return sc, u, seed
+
+
+def test_glass_paths(gpu_ctx):
+    """Reflect / refract branch incl. transparencyPasses bookkeeping and the step*6+5 Halton dimension."""
+    sc, u, seed = _glass_scene(256, 160)
+    u.samplesPerPixel, u.maxBounces = 2, 3
+    res = check_frames(gpu_ctx, sc, u, scene.seed_image(256, 160, seed), frames=2)
+    assert res[0]["rays"]["closest"] > 256 * 160 * 2 * 1.2  # refraction adds segments that do not consume bounces
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5, 6, 7])
+def test_debug_texture_modes(gpu_ctx, mode):
+    sc, u, seed = scene.Scene.named("K2tex", 160, 96, assets=None)
+    u.samplesPerPixel, u.debugTextureMode = 1, mode
+    check_frames(gpu_ctx, sc, u, scene.seed_image(160, 96, seed))
+
+
+def test_legacy_shading_and_all_light_types(gpu_ctx):
+    sc, u, seed = scene.Scene.named("K3small", 256, 160, assets=None)
+    sc.clear_lights()
+    sc.add_light(scene.make_light(A.LIGHT_SUN, direction=(-1, -2, 0), color=(1, 1, 1)))
+    sc.add_light(scene.make_light(A.LIGHT_POINT, position=(1, 1, 3), color=(2, 2, 2)))
+    sc.add_light(scene.make_light(A.LIGHT_SPOT, position=(2, 1, 4), direction=(-1.5, -0.5, -1.5),
+                                  cone_angle=25 / 180 * np.pi, color=(4, 4, 4)))
+    sc.add_light(scene.make_light(A.LIGHT_AREA, position=(0, 1.98, 2), color=(4, 4, 4), forward=(0, -1, 0),
+                                  right=(0.25, 0, 0), up=(0, 0, 0.25)))
+    u.lightCount, u.samplesPerPixel, u.maxBounces = 4, 4, 2
+    seeds = scene.seed_image(256, 160, seed)
+    check_frames(gpu_ctx, sc, u, seeds)
+    u.shadingMode = A.SHADING_LEGACY
+    check_frames(gpu_ctx, sc, u, seeds)
+
+
+def test_fp32_images(gpu_ctx):
+    sc, u, seed = scene.Scene.named("K3small", 200, 120, assets=None)
+    u.samplesPerPixel = 2
+    check_frames(gpu_ctx, sc, u, scene.seed_image(200, 120, seed), frames=2, fp32=True)
+
+
+def test_axis_aligned_rays_and_ragged_size(gpu_ctx, assets):
+    """Rays with exactly-zero direction components through shared edges (camera on an axis, odd image size)."""
+    w, h = 255, 128  # row 64 has uv.y == 0 exactly
+    sc = scene.Scene()
+    m = sc.add_obj(os.path.join(assets, "sphere.obj"))
+    sc.add_instance(m)
+    p = sc.add_procedural("plane")
+    sc.add_instance(p, position=(0, -1, 0), scale=4.0)
+    sc.add_light(scene.make_light(A.LIGHT_POINT, position=(0, 5, 5), color=(9, 9, 9)))
+    u = scene.default_uniforms(w, h)
+    u.lightCount, u.samplesPerPixel, u.maxBounces = 1, 1, 2
+    u.enableMotionAdaptiveSampling = u.enableMotionAdaptiveAccumulation = 0
+    u.camera = scene.orbit_camera(w, h, (0, 0, 0), 0.0, 0.0, 5.38)
+    u.previousCamera = u.camera
+    res = check_frames(gpu_ctx, sc, u, np.zeros((h, w), np.uint32))
+    inst = res[0]["ids"][..., 0]
+    row = inst[64]  # the row through the sphere's equator: d.y == 0 exactly
+    assert (row == 0).sum() > 50
+    res[0]["renderer"].close()
+
+
+def test_tile_partition_equals_full_frame(gpu_ctx):
+    """Rank g renders tiles with tile % N == g; the union over ranks is the single-GPU frame bit for bit, and the
+    pack/unpack kernels agree with the host restatement."""
+    w, h = 330, 200  # not a multiple of 16
+    sc, u, seed = scene.Scene.named("K3small", w, h, assets=None)
+    u.samplesPerPixel = 2
+    seeds = scene.seed_image(w, h, seed)
+    full = device.Renderer(gpu_ctx, sc, w, h, seeds=seeds)
+    full.draw(u)
+    ref = full.read_image(0)
+    L = device.lib()
+    L.rt_pack_tiles.argtypes = [C.c_void_p, C.POINTER(A.Image), C.c_void_p, C.c_int, C.c_int]
+    L.rt_unpack_tiles.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(A.Image), C.c_int]
+    for n in (2, 3, 8):
+        union = np.zeros_like(ref)
+        slab_n = parallel.slab_tiles(w, h, n)
+        slabs_dev = gpu_ctx.malloc(n * slab_n * 256 * 8)
+        for r in range(n):
+            part = device.Renderer(gpu_ctx, sc, w, h, seeds=seeds)
+            part.draw(u, tile_modulo=n, tile_remainder=r)
+            img = part.read_image(0)
+            mask = parallel.owner_mask(w, h, n, r)
+            assert not img[~mask].any()  # nothing outside the owned tiles is written
+            union[mask] = img[mask]
+            info = part.image_info(0)
+            device._check(L.rt_pack_tiles(gpu_ctx._h, C.byref(info), slabs_dev + r * slab_n * 256 * 8, n, r))
+            slab = gpu_ctx.download(slabs_dev + r * slab_n * 256 * 8, (slab_n, 256, 4), np.float16)
+            assert np.array_equal(slab.view(np.uint16), parallel.pack_tiles_host(img, n, r).view(np.uint16))
+            part.close()
+        assert np.array_equal(union.view(np.uint16), ref.view(np.uint16))
+        target = device.Renderer(gpu_ctx, sc, w, h, seeds=seeds)
+        info = target.image_info(0)
+        device._check(L.rt_unpack_tiles(gpu_ctx._h, slabs_dev, C.byref(info), n))
+        assert np.array_equal(target.read_image(0).view(np.uint16), ref.view(np.uint16))
+        target.close()
+        gpu_ctx.free(slabs_dev)
+    full.close()
+
+
+def test_kernel_level_abi_skin_and_build(gpu_ctx):
+    """rt_skin / rt_blas_build / rt_tlas_build / rt_trace called directly with argument tables: ragged vertex
+    counts, 16-bit indices, an empty BLAS, and error codes for unbound slots."""
+    rng = np.random.default_rng(5)
+    for n in (1, 31, 257, 5000):
+        pos = np.zeros((n, 4), np.float32)
+        pos[:, :3] = rng.normal(size=(n, 3))
+        nrm = np.zeros((n, 4), np.float32)
+        nrm[:, :3] = rng.normal(size=(n, 3))
+        idx = rng.integers(0, 7, (n, 4)).astype(np.uint16)
+        wts = rng.random((n, 4)).astype(np.float32)
+        wts[::5] = 0.0  # zero-weight fallback rows
+        mats = rng.normal(size=(7, 16)).astype(np.float32)
+        table = {A.BUFFER_REST_POSITIONS: gpu_ctx.upload(pos), A.BUFFER_REST_NORMALS: gpu_ctx.upload(nrm),
+                 A.BUFFER_JOINT_INDICES: gpu_ctx.upload(idx), A.BUFFER_JOINT_WEIGHTS: gpu_ctx.upload(wts),
+                 A.BUFFER_JOINT_MATRICES: gpu_ctx.upload(mats),
+                 A.BUFFER_SKINNED_POSITIONS: gpu_ctx.malloc(n * 16), A.BUFFER_SKINNED_NORMALS: gpu_ctx.malloc(n * 16)}
+        gpu_ctx.skin(table, n)
+        gp = gpu_ctx.download(table[A.BUFFER_SKINNED_POSITIONS], (n, 4), np.float32)
+        gn = gpu_ctx.download(table[A.BUFFER_SKINNED_NORMALS], (n, 4), np.float32)
+        op, on = oracle.skin(pos, nrm, idx, wts, mats)
+        assert np.array_equal(gp, op) and np.array_equal(gn, on)
+        for p in table.values():
+            gpu_ctx.free(p)
+    gpu_ctx.skin({k: 1 for k in range(10, 17)}, 0)  # zero vertices: no launch, no error
+    with pytest.raises(device.RtError):
+        gpu_ctx.skin({A.BUFFER_REST_POSITIONS: 1}, 4)  # unbound slots -> error code, not a crash
+    # 16-bit indices + empty geometry
+    verts = np.array([[0, 0, 0, 0], [1, 0, 0, 0], [0, 1, 0, 0], [1, 1, 0, 0]], np.float32)
+    i16 = np.array([0, 1, 2, 1, 3, 2], np.uint16)
+    vdev, idev = gpu_ctx.upload(verts), gpu_ctx.upload(i16)
+    g = A.TriangleGeometry(vdev, 16, 4, idev, 2, 2)
+    blas = gpu_ctx.blas_build([g])
+    info = gpu_ctx.as_info(blas)
+    assert info.primitiveCount == 2 and info.wideNodeCount == 1
+    assert list(info.boundsMin) == [0, 0, 0] and list(info.boundsMax) == [1, 1, 0]
+    empty = gpu_ctx.blas_build([])
+    assert gpu_ctx.as_info(empty).primitiveCount == 0
+    with pytest.raises(device.RtError):
+        gpu_ctx.blas_refit(blas, [g])  # not built refittable
+    with pytest.raises(device.RtError):
+        gpu_ctx.blas_build([A.TriangleGeometry(vdev, 16, 4, idev, 3, 2)])  # bad index stride
+    desc = (A.InstanceDescriptor * 2)()
+    for k, b in enumerate((blas, empty)):
+        for c in range(3):
+            desc[k].transformationMatrix[c][c] = 1.0
+        desc[k].mask, desc[k].accelerationStructureID = 0xFF, b
+    ddev = gpu_ctx.upload(np.frombuffer(bytes(desc), np.uint8))
+    tlas = gpu_ctx.tlas_build(ddev, 2)
+    assert gpu_ctx.as_info(tlas).primitiveCount == 2
+    with pytest.raises(device.RtError):
+        gpu_ctx.trace({A.BUFFER_ACCELERATION_STRUCTURE: tlas}, (A.Image * 9)(), scene.default_uniforms(8, 8), 1)
+    gpu_ctx.tlas_destroy(tlas)
+    gpu_ctx.blas_destroy(blas)
+    gpu_ctx.blas_destroy(empty)
+
+
+def test_bvh_invariants(gpu_ctx):
+    """Every build reports one wide tree whose root box is the mesh bounds; a refit after moving the vertices gives
+    the same image as a fresh build (refit == rebuild bounds)."""
+    sc, u, seed = scene.Scene.named("K3small", 64, 64, assets=None)
+    rnd = device.Renderer(gpu_ctx, sc, 64, 64, seeds=scene.seed_image(64, 64, seed))
+    a = sc.mesh_arrays(0)["positions"][:, :3]
+    info = gpu_ctx.as_info(rnd.blas_id(0))
+    assert info.primitiveCount == 8712 and info.levelCount >= 3
+    assert np.array_equal(np.array(info.boundsMin[:], np.float32), a.min(0))
+    assert np.array_equal(np.array(info.boundsMax[:], np.float32), a.max(0))
+    assert 8712 / 24 <= info.wideNodeCount <= 8712
+    rnd.close()
+
+
+def test_full_size_headline_frame(gpu_ctx):
+    """BASELINE config 3 at its real size (871,200 triangles, 1920x1080), headline variant 1 spp / maxBounces 2:
+    ids and radiance against the oracle, determinism, and ray-count identities."""
+    w, h = 1920, 1080
+    sc, u, seed = scene.Scene.named("K3", w, h, assets=None)
+    u.samplesPerPixel, u.maxBounces = 1, 2
+    seeds = scene.seed_image(w, h, seed)
+    res = check_frames(gpu_ctx, sc, u, seeds)
+    rays = res[0]["rays"]
+    assert rays["closest"] >= w * h and rays["any"] <= rays["hits"] and rays["rays"] > 5_000_000
+    rnd = res[0]["renderer"]
+    first = res[0]["image"]
+    rnd.reset_accumulation()
+    u.frameIndex = 0
+    rnd.draw(u)
+    assert np.array_equal(rnd.read_image(0).view(np.uint16), first.view(np.uint16))  # deterministic
+    info = gpu_ctx.as_info(rnd.blas_id(0))
+    assert info.primitiveCount == 871200
+    rnd.close()

@@ -1,0 +1,274 @@
+"""Known-answer tests that pin the CPU oracle (the reference ships no tests, so these are authored from the
+reference's source: Raytracing.metal:28-57 halton, :61-74 barycentric convention, :150-166 BRDF terms, :421 sampler,
+Skinning.metal:7-49) plus the committed golden frame. CPU only."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from metal4_raytracing_b200 import _abi as A
+from metal4_raytracing_b200 import scene
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def radical_inverse(i, b):
+    f, r = np.float32(1.0), np.float32(0.0)
+    inv = np.float32(1.0) / np.float32(b)
+    while i > 0:
+        f = np.float32(f * inv)
+        r = np.float32(r + np.float32(f * np.float32(i % b)))
+        i //= b
+    return float(r)
+
+
+def test_halton_known_values():
+    # base 2: 0, 1/2, 1/4, 3/4, 7/8
+    assert [oracle.halton(i, 0) for i in (0, 1, 2, 3, 7)] == [0.0, 0.5, 0.25, 0.75, 0.875]
+    assert oracle.halton(1, 1) == pytest.approx(1 / 3, abs=1e-7)
+    assert oracle.halton(5, 2) == pytest.approx(1 / 5 * 0 + 1 / 25, abs=1e-7)  # 5 = (1,0) base 5 -> 0/5 + 1/25
+
+
+def test_halton_matches_float32_restatement():
+    primes = [2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73, 79, 83, 89, 97, 101]
+    rng = np.random.default_rng(0)
+    for i in list(rng.integers(0, 2 ** 21, 40)) + [0, 1, 1048575, 2 ** 24 + 5]:
+        for d in (0, 1, 2, 7, 13, 25):
+            assert oracle.halton(int(i), d) == radical_inverse(int(i), primes[d]), (i, d)
+    # the reference would read past primes[100] for d > 99 (F9); the oracle wraps the index
+    assert oracle.halton(12345, 103) == oracle.halton(12345, 3)
+    vals = [oracle.halton(i, 3) for i in range(1, 2000)]
+    assert 0.0 < min(vals) and max(vals) < 1.0
+
+
+def test_triangle_barycentric_convention_and_bounds():
+    v0, v1, v2 = (0, 0, 0), (1, 0, 0), (0, 1, 0)
+    hit, (t, u, v) = oracle.intersect_triangle((0.25, 0.5, 1.0), (0, 0, -1), v0, v1, v2)
+    # Metal: u weights vertex 1, v weights vertex 2 (Raytracing.metal:63-73)
+    assert hit and t == 1.0 and u == 0.25 and v == 0.5
+    # two-sided
+    hit, (t, u, v) = oracle.intersect_triangle((0.25, 0.5, -2.0), (0, 0, 1), v0, v1, v2)
+    assert hit and t == 2.0 and u == 0.25 and v == 0.5
+    # direction is not renormalised: t scales inversely with |d|
+    hit, (t, _, _) = oracle.intersect_triangle((0.25, 0.5, 1.0), (0, 0, -4), v0, v1, v2)
+    assert hit and t == 0.25
+    # tmin < t < tmax, both exclusive
+    assert not oracle.intersect_triangle((0.25, 0.5, 1.0), (0, 0, -1), v0, v1, v2, 0.0, 1.0)[0]
+    assert not oracle.intersect_triangle((0.25, 0.5, 1.0), (0, 0, -1), v0, v1, v2, 1.0, 5.0)[0]
+    assert oracle.intersect_triangle((0.25, 0.5, 1.0), (0, 0, -1), v0, v1, v2, 0.5, 1.5)[0]
+    # behind the origin, outside, parallel, degenerate
+    assert not oracle.intersect_triangle((0.25, 0.5, 1.0), (0, 0, 1), v0, v1, v2)[0]
+    assert not oracle.intersect_triangle((0.8, 0.8, 1.0), (0, 0, -1), v0, v1, v2)[0]
+    assert not oracle.intersect_triangle((0.25, 0.5, 1.0), (1, 0, 0), v0, v1, v2)[0]
+    assert not oracle.intersect_triangle((0.25, 0.5, 1.0), (0, 0, -1), v0, v0, v0)[0]
+
+
+def test_triangle_edges_are_watertight():
+    """A ray through a shared edge or vertex hits at least one of the adjacent triangles (Woop et al. 2013)."""
+    a, b, c, d = (0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0)
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        s = float(rng.random())
+        p = (s, s, 0.0)  # on the shared diagonal a-c
+        o = (float(rng.normal()), float(rng.normal()), 3.0 + float(rng.random()))
+        dirv = tuple(np.float32(p[k]) - np.float32(o[k]) for k in range(3))
+        h1 = oracle.intersect_triangle(o, dirv, a, b, c)[0]
+        h2 = oracle.intersect_triangle(o, dirv, a, c, d)[0]
+        assert h1 or h2
+
+
+def test_half_conversion_matches_ieee():
+    rng = np.random.default_rng(2)
+    vals = np.concatenate([rng.normal(size=2000).astype(np.float32) * np.float32(10.0) ** rng.integers(-8, 5, 2000),
+                           np.array([0.0, -0.0, 1.0, 65504.0, 65520.0, 1e-8, 6e-8, 5.96e-8, np.inf, -np.inf, 1e9],
+                                    np.float32)])
+    L = oracle.lib()
+    for f in vals:
+        h = L.oracle_float_to_half(float(f))
+        assert h == int(np.float32(f).astype(np.float16).view(np.uint16)), f
+    for h in list(range(0, 65536, 97)) + [0x7C00, 0xFC00, 0x0001, 0x03FF, 0x0400]:
+        got = L.oracle_half_to_float(h)
+        ref = float(np.array([h], np.uint16).view(np.float16)[0])
+        assert (np.isnan(got) and np.isnan(ref)) or got == ref, hex(h)
+
+
+def test_invert_affine_is_an_inverse():
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        m = rng.normal(size=(4, 3)).astype(np.float32)  # [column][row]
+        m[:3] += np.eye(3, dtype=np.float32) * 2
+        inv = oracle.invert_affine(m).reshape(4, 3)
+        M = np.eye(4)
+        M[:3, :3], M[:3, 3] = m[:3].T, m[3]
+        I = np.eye(4)
+        I[:3, :3], I[:3, 3] = inv[:3].T, inv[3]
+        assert np.allclose(M @ I, np.eye(4), atol=2e-5)
+
+
+def test_texture_sampling_bilinear_repeat_srgb():
+    tex = np.zeros((2, 2, 4), np.uint8)
+    tex[0, 0], tex[0, 1], tex[1, 0], tex[1, 1] = (0, 0, 0, 255), (255, 0, 0, 255), (0, 255, 0, 255), (255, 255, 255, 255)
+    # texel centres
+    assert oracle.sample_texture(tex, 0.25, 0.25) == (0.0, 0.0, 0.0, 1.0)
+    assert oracle.sample_texture(tex, 0.75, 0.25)[:3] == (1.0, 0.0, 0.0)
+    # halfway between the two texels of row 0
+    r = oracle.sample_texture(tex, 0.5, 0.25)
+    assert r[0] == pytest.approx(0.5) and r[1] == 0.0
+    # repeat addressing: u = 0 sits between the last and first texel of the row
+    r0, r1 = oracle.sample_texture(tex, 0.0, 0.25), oracle.sample_texture(tex, 1.0, 0.25)
+    assert r0 == r1 and r0[0] == pytest.approx(0.5)
+    assert oracle.sample_texture(tex, 2.75, -0.75) == oracle.sample_texture(tex, 0.75, 0.25)
+    # sRGB decode applies to rgb only
+    grey = np.full((1, 1, 4), 128, np.uint8)
+    lin = oracle.sample_texture(grey, 0.5, 0.5, srgb=True)
+    assert lin[0] == pytest.approx(((128 / 255 + 0.055) / 1.055) ** 2.4, rel=1e-6)
+    assert lin[3] == pytest.approx(128 / 255)
+
+
+def test_skinning_identity_and_blend():
+    rng = np.random.default_rng(4)
+    n = 257
+    pos = np.zeros((n, 4), np.float32)
+    pos[:, :3] = rng.normal(size=(n, 3))
+    nrm = np.zeros((n, 4), np.float32)
+    nrm[:, :3] = rng.normal(size=(n, 3))
+    idx = rng.integers(0, 3, (n, 4)).astype(np.uint16)
+    w = rng.random((n, 4)).astype(np.float32)
+    w /= w.sum(1, keepdims=True)
+    ident = np.tile(np.eye(4, dtype=np.float32).reshape(16), (3, 1))
+    p, q = oracle.skin(pos, nrm, idx, w, ident)
+    assert np.allclose(p[:, :3], pos[:, :3], atol=1e-6) and np.allclose(q[:, :3], nrm[:, :3], atol=1e-6)
+    # two-joint blend == lerp of the two transforms (translation by +x and +y)
+    mats = ident.copy()
+    mats[1, 12], mats[2, 13] = 2.0, 4.0  # column-major: translation in elements 12..14
+    idx2 = np.tile(np.array([1, 2, 0, 0], np.uint16), (n, 1))
+    w2 = np.tile(np.array([0.25, 0.75, 0, 0], np.float32), (n, 1))
+    p, q = oracle.skin(pos, nrm, idx2, w2, mats)
+    assert np.allclose(p[:, 0], pos[:, 0] + 0.5, atol=1e-6) and np.allclose(p[:, 1], pos[:, 1] + 3.0, atol=1e-6)
+    assert np.allclose(q[:, :3], nrm[:, :3], atol=1e-6)  # normals ignore translation
+    # all-zero weights fall back to joint indices.x with weight 1, weights are NOT renormalised otherwise
+    w0 = np.zeros((n, 4), np.float32)
+    p, _ = oracle.skin(pos, nrm, idx2, w0, mats)
+    assert np.allclose(p[:, 0], pos[:, 0] + 2.0, atol=1e-6)
+    wh = np.tile(np.array([0.5, 0, 0, 0], np.float32), (n, 1))
+    p, _ = oracle.skin(pos, nrm, np.zeros((n, 4), np.uint16), wh, ident)
+    assert np.allclose(p[:, :3], 0.5 * pos[:, :3], atol=1e-6)
+
+
+def _single_triangle_scene(w=32, h=32):
+    sc = scene.Scene()
+    m = sc.add_raw([(-50, 0, 50), (50, 0, 50), (0, 0, -50)], [(0, 1, 2)], normals=[(0, 1, 0)] * 3)
+    sc.add_instance(m)
+    sc.add_light(scene.make_light(A.LIGHT_POINT, position=(0, 2, 0), color=(3, 3, 3)))
+    u = scene.default_uniforms(w, h)
+    u.lightCount, u.samplesPerPixel, u.maxBounces = 1, 1, 1
+    u.enableMotionAdaptiveSampling = u.enableMotionAdaptiveAccumulation = 0
+    return sc, u
+
+
+def test_ray_hits_ground_at_known_point():
+    sc, u = _single_triangle_scene()
+    orc = oracle.Oracle(sc, threads=1)
+    hit, ids, (t, uu, vv) = orc.trace_ray((1.0, 3.0, 2.0), (0.0, -1.0, 0.0))
+    assert hit and ids == (0, 0, 0) and t == 3.0
+    assert not orc.trace_ray((1.0, 3.0, 2.0), (0.0, 1.0, 0.0))[0]
+    # instance transform: move the ground up by 1 -> t = 2
+    sc.set_instance_transform(0, (0, 1, 0), (0, 0, 0), 1.0)
+    orc.update()
+    hit, ids, (t, _, _) = orc.trace_ray((1.0, 3.0, 2.0), (0.0, -1.0, 0.0))
+    assert hit and t == pytest.approx(2.0, abs=1e-6)
+
+
+def test_lambert_point_light_radiance_value():
+    """Centre pixel of a plane lit by one point light: closed form of the kernel's PBR branch with roughness 1,
+    metallic 0 (Raytracing.metal:692-744): direct = (kD*albedo/pi + spec) * L * NdotL."""
+    sc, u = _single_triangle_scene(33, 33)
+    u.camera = scene.orbit_camera(33, 33, (0, 0, 0), 0.0, 1.2, 4.0)
+    u.previousCamera = u.camera
+    imgs = oracle.FrameImages(33, 33, np.zeros((33, 33), np.uint32), fp32=True)
+    orc = oracle.Oracle(sc, threads=2)
+    stats, ids = orc.render(u, imgs, want_ids=True)
+    assert stats["closest"] == 33 * 33 and stats["any"] == stats["hits"]
+    img = imgs.output
+    c = img[16, 16, :3]
+    assert np.all(c > 0) and c[0] == c[1] == c[2] and img[16, 16, 3] == 1.0
+    # brightest near the point below the light, darker toward the edges
+    assert img[16, 16, 0] > img[2, 2, 0]
+    depth = imgs.arrays[A.TEXTURE_DEPTH][16, 16, 0]
+    assert depth == pytest.approx(4.0, rel=2e-2)
+
+
+def test_sphere_silhouette_area(assets):
+    """sphere.obj (radius 1) seen from distance 5.38 with a 45 degree vertical fov at 256x256: the silhouette's
+    pixel count matches the analytic projected disc within 2 %."""
+    w = h = 256
+    sc = scene.Scene()
+    m = sc.add_obj(os.path.join(assets, "sphere.obj"))
+    sc.add_instance(m)
+    sc.add_light(scene.make_light(A.LIGHT_POINT, position=(0, 5, 5), color=(9, 9, 9)))
+    u = scene.default_uniforms(w, h)
+    u.lightCount, u.samplesPerPixel, u.maxBounces = 1, 1, 1
+    u.enableMotionAdaptiveSampling = u.enableMotionAdaptiveAccumulation = 0
+    u.camera = scene.orbit_camera(w, h, (0, 0, 0), 0.0, 0.0, 5.38)
+    u.previousCamera = u.camera
+    imgs = oracle.FrameImages(w, h, np.zeros((h, w), np.uint32))
+    _, ids = oracle.Oracle(sc).render(u, imgs, want_ids=True)
+    covered = int((ids[..., 0] != 0xFFFFFFFF).sum())
+    d, r = 5.38, 1.0
+    tan_half = np.tan(np.radians(22.5))
+    # silhouette of a sphere under perspective: circle of angular radius asin(r/d) -> tan = r / sqrt(d^2 - r^2)
+    rad_px = (r / np.sqrt(d * d - r * r)) / tan_half * (h / 2)
+    assert covered == pytest.approx(np.pi * rad_px ** 2, rel=0.02)
+
+
+def test_frame_index_and_ema(assets):
+    """frameIndex 0 writes the plain mean; frameIndex > 0 blends with history at <= 0.95 (Raytracing.metal:796-817)."""
+    sc, u, seed = scene.Scene.named("K1", 48, 48, assets=assets)
+    seeds = scene.seed_image(48, 48, seed)
+    orc = oracle.Oracle(sc)
+    imgs = oracle.FrameImages(48, 48, seeds, fp32=True)
+    u.accumulationWeight = 0.99  # clamped to 0.95
+    u.frameIndex = 0
+    orc.render(u, imgs)
+    f0 = imgs.output.copy()
+    imgs.swap()
+    u.frameIndex = 1
+    orc.render(u, imgs)
+    f1 = imgs.output.copy()
+    # recompute frame 1's own samples without history, then blend by hand
+    imgs2 = oracle.FrameImages(48, 48, seeds, fp32=True)
+    u2 = u.copy()
+    u2.accumulationWeight = 0.0
+    orc.render(u2, imgs2)
+    cur = imgs2.output
+    expect = cur[..., :3] + (f0[..., :3] - cur[..., :3]) * np.float32(0.95)
+    assert np.allclose(f1[..., :3], expect, rtol=1e-6, atol=1e-7)
+
+
+def test_max_bounces_counts_segments(assets):
+    """maxBounces = 1 -> primary + shadow only (F13): closest rays == pixels, any-hit rays <= hits."""
+    sc, u, seed = scene.Scene.named("K1", 64, 64, assets=assets)
+    imgs = oracle.FrameImages(64, 64, scene.seed_image(64, 64, seed))
+    orc = oracle.Oracle(sc)
+    st1, _ = orc.render(u, imgs)
+    assert st1["closest"] == 64 * 64 and st1["any"] <= st1["hits"]
+    u.maxBounces = 2
+    st2, _ = orc.render(u, imgs)
+    assert st2["closest"] == 64 * 64 + st1["hits"]  # every primary hit spawns exactly one bounce ray (albedo > 0)
+
+
+def test_golden_frame(assets):
+    """The committed K1 frame (tests/golden/make_golden.py) pins the oracle against drift."""
+    path = os.path.join(GOLDEN, "k1_128.npz")
+    g = np.load(path)
+    w = h = 128
+    sc, u, seed = scene.Scene.named("K1", w, h, assets=assets)
+    C.memmove(C.byref(u), g["uniforms"].tobytes(), C.sizeof(A.Uniforms))  # camera bytes from the fixture
+    imgs = oracle.FrameImages(w, h, scene.seed_image(w, h, int(g["seed"])))
+    stats, ids = oracle.Oracle(sc).render(u, imgs, want_ids=True)
+    assert np.array_equal(ids, g["ids"])
+    assert np.array_equal(imgs.output.view(np.uint16), g["image"].view(np.uint16))
+    assert np.array_equal(imgs.arrays[A.TEXTURE_DEPTH], g["depth"])
+    assert [stats["closest"], stats["any"], stats["hits"]] == list(g["stats"])

@@ -1,0 +1,188 @@
+"""Host scene library: OBJ loader rules, transforms (Utilities.swift:302-355), orbit camera (Scene.swift:126-159),
+default lights/uniforms (Scene.swift:82-93, Renderer.swift:117-192), procedural stand-ins, animation
+(Model.swift:207-261). CPU only."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from metal4_raytracing_b200 import _abi as A
+from metal4_raytracing_b200 import scene
+
+
+def test_obj_loader_rules(assets, tmp_path):
+    sc = scene.Scene()
+    plane = sc.add_obj(os.path.join(assets, "plane.obj"))
+    a = sc.mesh_arrays(plane)
+    assert a["positions"].shape == (4, 4) and len(a["submeshes"]) == 1
+    assert a["submeshes"][0].tolist() == [[0, 1, 2], [0, 2, 3]]  # fan triangulation of the quad
+    assert a["uvs"] is not None and np.allclose(a["normals"][:, :3], [0, 1, 0])
+    m = sc.get_material(plane)
+    assert m.baseColor.tuple() == (0.5, 0.5, 0.5) and m.refractionIndex == 1.0 and m.opacity == 1.0
+    assert m.specularExponent == 0.0  # Ns is never taken (SubMesh.swift:309-311)
+    sphere = sc.add_obj(os.path.join(assets, "sphere.obj"))
+    s = sc.mesh_arrays(sphere)
+    assert sum(len(x) for x in s["submeshes"]) == 4900 and s["uvs"] is None
+    train = sc.add_obj(os.path.join(assets, "train.obj"))
+    t = sc.mesh_arrays(train)
+    assert len(t["submeshes"]) == 6 and sum(len(x) for x in t["submeshes"]) == 3624  # one submesh per usemtl run
+    teapot = sc.add_obj(os.path.join(assets, "teapot.obj"))
+    tp = sc.mesh_arrays(teapot)
+    assert sum(len(x) for x in tp["submeshes"]) == 15704 and np.all(tp["normals"] == 0)  # no vn -> zero normals
+    # welding: one vertex per distinct v/vt/vn tuple, first appearance order; negative indices
+    p = tmp_path / "w.obj"
+    p.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nv 1 1 0\nvn 0 0 1\nvn 0 0 -1\nf 1//1 2//1 3//1\nf -3//1 -1//2 -2//1\n")
+    wm = sc.add_obj(str(p))
+    wa = sc.mesh_arrays(wm)
+    assert wa["positions"].shape[0] == 4 and wa["submeshes"][0].tolist() == [[0, 1, 2], [1, 3, 2]]
+    assert wa["normals"][3, 2] == -1.0
+    with pytest.raises(RuntimeError):
+        sc.add_obj(str(tmp_path / "missing.obj"))
+
+
+def test_glass_override(assets):
+    sc = scene.Scene()
+    m = sc.add_obj(os.path.join(assets, "sphere.obj"), glass=True)
+    mat = sc.get_material(m)
+    assert mat.baseColor.tuple() == pytest.approx((0.95, 0.98, 1.0)) and mat.refractionIndex == pytest.approx(1.52)
+    assert mat.opacity == pytest.approx(0.08)
+
+
+def test_transform_convention():
+    """T * Rx*Ry*Rz * S, column-major (Mesh.swift:61-68)."""
+    sc = scene.Scene()
+    m = sc.add_procedural("plane")
+    i = sc.add_instance(m, position=(1, 2, 3), rotation=(0, np.pi / 2, 0), scale=2.0)
+    M = np.array(sc.desc().instances[i].transform[:], np.float32).reshape(4, 4).T  # rows
+    p = M @ np.array([1, 0, 0, 1], np.float32)
+    # rotateY(+90 deg) by the reference's matrix sends +x to -z
+    assert np.allclose(p[:3], [1, 2, 3 - 2], atol=1e-6)
+    assert np.allclose(M[:3, 3], [1, 2, 3])
+    sc.set_instance_transform(i, (0, 0, 0), (0, 0, 0), 1.0)
+    d = sc.desc().instances[i]
+    assert np.allclose(np.array(d.transform[:]).reshape(4, 4), np.eye(4))
+    assert np.allclose(np.array(d.previousTransform[:]).reshape(4, 4).T, M)  # previous transform kept
+
+
+def test_orbit_camera_and_defaults():
+    c = scene.default_camera(1920, 1080)
+    assert c.position.tuple() == pytest.approx((0.0, 1.0, 5.38), abs=1e-5)
+    f = np.array(c.forward.tuple())
+    assert np.linalg.norm(f) == pytest.approx(1.0, abs=1e-6)
+    assert np.allclose(f, -np.array([0, 1, 5.38]) / np.linalg.norm([0, 1, 5.38]), atol=1e-6)
+    th = np.tan(np.radians(22.5))
+    assert np.linalg.norm(c.up.tuple()) == pytest.approx(th, rel=1e-6)
+    assert np.linalg.norm(c.right.tuple()) == pytest.approx(th * 1920 / 1080, rel=1e-6)
+    assert abs(np.dot(c.right.tuple(), c.up.tuple())) < 1e-6
+    u = scene.default_uniforms(640, 360)
+    assert (u.samplesPerPixel, u.maxBounces, u.blocksWide) == (2, 2, 40)
+    assert u.accumulationWeight == pytest.approx(0.9) and u.enableMotionAdaptiveSampling == 1
+    assert u.motionSamplingMaxExtraSamples == 2 and u.motionAccumulationMinWeight == pytest.approx(0.1)
+    sc = scene.Scene()
+    sc.default_lights()
+    d = sc.desc()
+    assert d.lightCount == 2 and d.lights[0].type == A.LIGHT_AREA and d.lights[1].type == A.LIGHT_SPOT
+    assert d.lights[1].coneAngle == pytest.approx(np.radians(25))
+
+
+def test_seed_image_range_and_determinism():
+    s = scene.seed_image(64, 48, 0xC0FFEE)
+    assert s.shape == (48, 64) and s.max() < (1 << 20) and len(np.unique(s)) > 3000
+    assert np.array_equal(s, scene.seed_image(64, 48, 0xC0FFEE))
+    assert not np.array_equal(s, scene.seed_image(64, 48, 1))
+
+
+def test_procedural_stand_in_sizes():
+    sc = scene.Scene()
+    b = sc.add_procedural("icosphere_bumpy", 6, 2)
+    ba = sc.mesh_arrays(b)
+    assert ba["positions"].shape[0] == 40962 and len(ba["submeshes"][0]) == 81920
+    n = ba["normals"][:, :3]
+    assert np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-5)
+    k = sc.add_procedural("torusknot", 1320, 330, 3)
+    ka = sc.mesh_arrays(k)
+    assert ka["positions"].shape[0] == 435600 and len(ka["submeshes"][0]) == 871200
+    assert ka["positions"][:, 1].min() == pytest.approx(-0.3, abs=1e-6)
+    idx = ka["submeshes"][0]
+    assert idx.min() == 0 and idx.max() == 435599
+    # closed surface: every edge is shared by exactly two triangles
+    e = np.sort(np.concatenate([idx[:, [0, 1]], idx[:, [1, 2]], idx[:, [2, 0]]]), axis=1)
+    _, counts = np.unique(e[:, 0].astype(np.int64) * 435600 + e[:, 1], return_counts=True)
+    assert np.all(counts == 2)
+
+
+def test_humanoid_skeleton_and_animation():
+    sc = scene.Scene()
+    m = sc.add_procedural("humanoid", 100000, 64)
+    a = sc.mesh_arrays(m)
+    assert a["positions"].shape[0] == 100000 and a["jointMatrices"].shape == (64, 16)
+    assert 195000 <= len(a["submeshes"][0]) <= 200000
+    assert a["jointIndices"].max() < 64
+    assert np.allclose(a["jointWeights"].sum(1), 1.0, atol=1e-5)
+    sc.animate(0.0)
+    m0 = sc.mesh_arrays(m)["jointMatrices"].reshape(64, 4, 4)
+    assert np.allclose(m0, np.eye(4), atol=1e-5)  # clip starts at the bind pose
+    sc.animate(0.4)
+    m1 = sc.mesh_arrays(m)["jointMatrices"].reshape(64, 4, 4).transpose(0, 2, 1)  # -> row-major
+    rot = m1[:, :3, :3]
+    assert np.allclose(rot @ rot.transpose(0, 2, 1), np.eye(3), atol=1e-4)  # rigid
+    assert np.abs(m1 - np.eye(4)).max() > 0.05
+    sc.animate(0.4 + 2.0)  # clip duration 2 s -> periodic
+    m2 = sc.mesh_arrays(m)["jointMatrices"].reshape(64, 4, 4).transpose(0, 2, 1)
+    assert np.allclose(m1, m2, atol=2e-3)
+
+
+def test_named_scenes(assets):
+    for name, (w, h), tris, inst, spp, mb in [("K1", (512, 512), 4902, 2, 1, 1), ("K2", (1920, 1080), 81922, 2, 4, 2),
+                                             ("K4small", (256, 256), 19682, 65, 8, 2),
+                                             ("K5small", (256, 256), None, 2, 2, 2)]:
+        sc, u, seed = scene.Scene.named(name, w, h, assets=assets)
+        d = sc.desc()
+        total = sum(d.meshes[i].submeshes[k].triangleCount for i in range(d.meshCount)
+                    for k in range(d.meshes[i].submeshCount))
+        if tris is not None:
+            assert total == tris
+        assert d.instanceCount == inst and (u.samplesPerPixel, u.maxBounces) == (spp, mb)
+        assert u.lightCount == d.lightCount and u.width == w and u.height == h
+    sc, u, _ = scene.Scene.named("K4small", 64, 64, assets=assets)
+    assert sc.desc().maxSubmeshes == 6
+    with pytest.raises(RuntimeError):
+        scene.Scene.named("nope", 8, 8)
+    with pytest.raises(RuntimeError):
+        scene.Scene.named("K1", 8, 8, assets=None)  # K1 needs the OBJ files
+
+
+def test_texture_binding_sets_flags():
+    sc = scene.Scene()
+    m = sc.add_procedural("uvsphere", 8, 8)
+    t = sc.add_texture_procedural("checker", 16, 16, 1, srgb=True)
+    sc.bind_texture(m, 0, A.SLOT_BASECOLOR, t)
+    mat = sc.get_material(m)
+    assert mat.textureFlags & 1 and mat.baseColor.tuple() == (1.0, 1.0, 1.0)  # SubMesh.swift:119-125
+    d = sc.desc()
+    assert d.meshes[m].submeshes[0].textureIndex[A.SLOT_BASECOLOR] == t
+    assert d.textures[t].srgb == 1 and d.textures[t].width == 16
+    # 1x1 fallbacks (SubMesh.swift:176-241): white, neutral normal, black
+    assert bytes(d.textures[0].texels[0:4]) == b"\xff\xff\xff\xff" and bytes(d.textures[1].texels[0:4]) == b"\x80\x80\xff\xff"
+
+
+def test_png_decoder(assets):
+    from PIL import Image
+    p = os.path.join(assets, "uv_test", "uv_test.png")
+    if not os.path.isfile(p):
+        pytest.skip("uv_test.png not staged")
+    ref = np.asarray(Image.open(p).convert("RGBA"))
+    sc = scene.Scene()
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, "m.mtl"), "w") as f:
+            f.write(f"newmtl a\nKd 1 1 1\nmap_Kd {os.path.relpath(p, d)}\n")
+        with open(os.path.join(d, "m.obj"), "w") as f:
+            f.write("mtllib m.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\nusemtl a\nf 1/1 2/2 3/3\n")
+        m = sc.add_obj(os.path.join(d, "m.obj"))
+    desc = sc.desc()
+    ti = desc.meshes[m].submeshes[0].textureIndex[A.SLOT_BASECOLOR]
+    t = desc.textures[ti]
+    got = np.ctypeslib.as_array(t.texels, shape=(t.height, t.width, 4))
+    assert (t.width, t.height) == (ref.shape[1], ref.shape[0]) and np.array_equal(got, ref) and t.srgb == 1
