@@ -196,17 +196,18 @@ void buildBvh2(std::vector<PrimRef> &prims, std::vector<Node> &nodes, uint32_t m
   }
 }
 
-// 1/d for the slab tests only (the triangle test uses the true direction): a zero component becomes a tiny value
-// of the same sign, so an origin lying exactly on a box face of a ray parallel to that face stays inside the
-// slab instead of producing 0 * inf = NaN.
-inline float safeInverse(float d) {
-  const float tiny = 1.0e-20f;
-  return 1.0f / (fabsf(d) < tiny ? copysignf(tiny, d) : d);
-}
+// 1/d for the slab tests only (the triangle test uses the true direction). A (near-)zero component returns 0 as
+// a marker: the ray is parallel to that slab, which then constrains nothing when the origin lies inside it
+// (faces included, so a ray running exactly in a box face still enters the box) and rejects the box otherwise.
+inline float safeInverse(float d) { return fabsf(d) < 1.0e-20f ? 0.0f : 1.0f / d; }
 
 inline bool slab(const Aabb &b, const float o[3], const float invd[3], float tmin, float tmax, float &tnear) {
   float tn = -3.0e38f, tf = 3.0e38f;
   for (int a = 0; a < 3; ++a) {
+    if (invd[a] == 0.0f) {
+      if (o[a] < b.lo[a] || o[a] > b.hi[a]) return false;
+      continue;
+    }
     float t0 = (b.lo[a] - o[a]) * invd[a];
     float t1 = (b.hi[a] - o[a]) * invd[a];
     tn = fmaxf(fminf(t0, t1), tn);
