@@ -121,8 +121,15 @@ int rt_ipc_close(rt_context *ctx, void *importedDev);
 
 /* Number of kernels this library has launched on the context since creation (bench.py's gpu_launches). */
 uint64_t rt_launch_count(rt_context *ctx);
-/* Select the trace kernel layout: 0 = megakernel (default), 1 = wavefront. */
+/* Select the trace kernel layout: 0 = megakernel, 1 = wavefront (default). */
 int rt_set_trace_mode(rt_context *ctx, int mode);
+/* Tuning knobs that never change results: "trace_mode" (0/1), "traversal_variant" (0..2, traverse.cuh),
+ * "blocks_per_sm" (persistent grid size of the wavefront kernels). */
+int rt_set_option(rt_context *ctx, const char *key, int value);
+/* Device self-test: for raysPerNode pseudo-random rays per wide node of an acceleration structure, the fast child-box
+ * test must report every child the plain-conversion form reports. out[0] = missed children (must be 0), out[1] = extra
+ * (allowed: the fast form is slightly more conservative), out[2] = tests run, out[3..10] = first failure details. */
+int rt_selftest_child_boxes(rt_context *ctx, uint64_t id, uint32_t raysPerNode, uint32_t seed, uint64_t out[11]);
 
 #ifdef __cplusplus
 }

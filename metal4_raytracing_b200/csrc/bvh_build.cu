@@ -319,7 +319,7 @@ __device__ void quantiseNode(WideNode &node, const float lo[3], const float hi[3
       e = max(e, -126);
       while (double(ext) / ldexp(1.0, e) > 255.0) ++e;
     }
-    e = min(e, 127);
+    e = min(e, 100); // traversal adds 15 to the exponent byte (traverse.cuh); extents beyond 2^108 are not scenes
     ebyte[a] = uint32_t(e + 127);
     scale[a] = __uint_as_float(ebyte[a] << 23);
   }

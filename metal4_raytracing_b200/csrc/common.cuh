@@ -122,7 +122,9 @@ struct rt_context {
   cudaStream_t stream = nullptr;
   cudaEvent_t evBegin = nullptr, evEnd = nullptr;
   uint64_t launches = 0;
-  int traceMode = 0;
+  int traceMode = 1;        // 0 megakernel, 1 wavefront
+  int traversalVariant = 0; // traverse.cuh loop variant used by the wavefront kernels
+  int blocksPerSm = 8;      // persistent grid size of the wavefront kernels = smCount * blocksPerSm
   std::unordered_map<uint64_t, rtb::AccelObject *> accels;
   // reusable build scratch
   void *scratch = nullptr;
@@ -143,6 +145,7 @@ void destroyAccel(AccelObject *as);
 int launchSkin(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], uint32_t vertexCount);
 int packTiles(rt_context *ctx, const rt_image *image, void *slab, int modulo, int remainder);
 int unpackTiles(rt_context *ctx, const void *slabs, const rt_image *image, int modulo);
+int selftestChildBoxes(rt_context *ctx, AccelObject *as, uint32_t raysPerNode, uint32_t seed, unsigned long long outHost[11]);
 int launchTrace(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], const rt_image textures[RT_TEXTURE_COUNT],
                 int maxSubmeshes, const rt_trace_options *opt);
 } // namespace rtb

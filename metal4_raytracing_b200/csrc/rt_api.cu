@@ -358,9 +358,37 @@ uint64_t rt_launch_count(rt_context *ctx) { return ctx ? ctx->launches : 0; }
 
 int rt_set_trace_mode(rt_context *ctx, int mode) {
   RT_CTX(ctx);
-  RT_CHECK(mode == 0, "rt_set_trace_mode: only the megakernel layout (0) is built");
+  RT_CHECK(mode == 0 || mode == 1, "rt_set_trace_mode: 0 = megakernel, 1 = wavefront");
   ctx->traceMode = mode;
   return 0;
+}
+
+int rt_selftest_child_boxes(rt_context *ctx, uint64_t id, uint32_t raysPerNode, uint32_t seed, uint64_t out[11]) {
+  RT_CTX(ctx);
+  RT_CHECK(out != nullptr && raysPerNode > 0, "rt_selftest_child_boxes: bad arguments");
+  auto it = ctx->accels.find(id);
+  RT_CHECK(it != ctx->accels.end(), "unknown acceleration structure id");
+  static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "u64");
+  return selftestChildBoxes(ctx, it->second, raysPerNode, seed, reinterpret_cast<unsigned long long *>(out));
+}
+
+int rt_set_option(rt_context *ctx, const char *key, int value) {
+  RT_CTX(ctx);
+  RT_CHECK(key != nullptr, "rt_set_option: null key");
+  const std::string k(key);
+  if (k == "trace_mode") return rt_set_trace_mode(ctx, value);
+  if (k == "traversal_variant") {
+    RT_CHECK(value >= 0 && value <= 2, "rt_set_option: traversal_variant is 0, 1 or 2");
+    ctx->traversalVariant = value;
+    return 0;
+  }
+  if (k == "blocks_per_sm") {
+    RT_CHECK(value >= 1 && value <= 32, "rt_set_option: blocks_per_sm is 1..32");
+    ctx->blocksPerSm = value;
+    return 0;
+  }
+  setError("rt_set_option: unknown key " + k);
+  return 2;
 }
 
 } // extern "C"

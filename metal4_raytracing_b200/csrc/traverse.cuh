@@ -115,13 +115,15 @@ __device__ __forceinline__ BoxSetup makeBoxSetup(float ox, float oy, float oz, f
   return b;
 }
 
+// Plain-conversion form of the child test: the specification the fast PRMT form below is checked against
+// (rt_selftest_child_boxes) and a drop-in fallback when RT_LEGACY_CHILD_TEST is defined.
 __device__ __forceinline__ float byteToFloat(uint32_t word, int byteIndex) {
   return float((word >> (8 * byteIndex)) & 0xFFu);
 }
 
 // Tests the eight children of one node; returns the hit mask: bits 24..31 internal children in traversal
 // priority, bits 0..23 leaf primitives relative to primBase.
-__device__ __forceinline__ uint32_t intersectChildren(const uint4 &n0, const uint4 &n1, const uint4 &n2,
+__device__ __forceinline__ uint32_t intersectChildrenLegacy(const uint4 &n0, const uint4 &n1, const uint4 &n2,
                                                       const uint4 &n3, const uint4 &n4, const BoxSetup &b, float tmin,
                                                       float tmax) {
   const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23),
@@ -165,9 +167,84 @@ __device__ __forceinline__ uint32_t intersectChildren(const uint4 &n0, const uin
   return hitmask;
 }
 
+
+// Quantised byte -> float without an integer conversion: PRMT drops the byte into mantissa bits 8..15 of 1.0f,
+// giving 1 + q * 2^-15 exactly; the 2^15 is folded into the per-axis scale and the 1 into the offset.
+template <int k>
+__device__ __forceinline__ float byteAsUnitFloat(uint32_t word) {
+  return __uint_as_float(__byte_perm(word, 0x3F800000u, 0x7604u | (uint32_t(k) << 4)));
+}
+
+// Tests the eight children of one node; returns the hit mask: bits 24..31 internal children in traversal
+// priority, bits 0..23 leaf primitives relative to primBase.
+__device__ __forceinline__ uint32_t intersectChildren(const uint4 &n0, const uint4 &n1, const uint4 &n2,
+                                                      const uint4 &n3, const uint4 &n4, const BoxSetup &b, float tmin,
+                                                      float tmax) {
+  // per-axis scale 2^(e-127) times 2^15 (the builder keeps e small enough for the sum not to overflow)
+  const float sx = __uint_as_float(((n0.w & 0xFFu) + 15u) << 23), sy = __uint_as_float((((n0.w >> 8) & 0xFFu) + 15u) << 23),
+              sz = __uint_as_float((((n0.w >> 16) & 0xFFu) + 15u) << 23);
+  const float aix = sx * b.idx, aiy = sy * b.idy, aiz = sz * b.idz;
+  const float aox = (__uint_as_float(n0.x) - b.ox) * b.idx, aoy = (__uint_as_float(n0.y) - b.oy) * b.idy,
+              aoz = (__uint_as_float(n0.z) - b.oz) * b.idz;
+  // plane distance t = (1 + q 2^-15) * ai + (ao - ai). Conservative widening: a few ulp of |ao| + |ai| covers
+  // the rounding of both products, the difference and the fma, so no box is missed because of float error
+  // (in units of one quantisation step this is < 0.02, far below the outward rounding of the boxes themselves).
+  const float eps = 4.8e-7f;
+  const float wx = eps * (fabsf(aox) + fabsf(aix)), wy = eps * (fabsf(aoy) + fabsf(aiy)), wz = eps * (fabsf(aoz) + fabsf(aiz));
+  const float cx = aox - aix, cy = aoy - aiy, cz = aoz - aiz;
+  const float nox = cx - wx, noy = cy - wy, noz = cz - wz; // near-plane offsets
+  const float fox = cx + wx, foy = cy + wy, foz = cz + wz; // far-plane offsets
+  const bool negx = b.idx < 0.0f, negy = b.idy < 0.0f, negz = b.idz < 0.0f;
+  const uint32_t octinv4 = b.octinv * 0x01010101u;
+  // word pairs: lo_x = n2.xy, lo_y = n2.zw, lo_z = n3.xy, hi_x = n3.zw, hi_y = n4.xy, hi_z = n4.zw
+  uint32_t hitmask = 0;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
+    const uint32_t hix = half ? n3.w : n3.z, hiy = half ? n4.y : n4.x, hiz = half ? n4.w : n4.z;
+    const uint32_t nearx = negx ? hix : lox, farx = negx ? lox : hix;
+    const uint32_t neary = negy ? hiy : loy, fary = negy ? loy : hiy;
+    const uint32_t nearz = negz ? hiz : loz, farz = negz ? loz : hiz;
+    const uint32_t meta4 = half ? n1.w : n1.z;
+    // four children at once: internal children have both of bits 3,4 set in their low five bits (24..31)
+    const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    // 0xFF in every internal child's byte: PTX prmt replicates a byte's sign bit when the selector nibble's msb is
+    // set (the __byte_perm intrinsic only honours three selector bits, so this one is spelled in PTX)
+    uint32_t innerMask4;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(innerMask4) : "r"(isInner4 << 3), "r"(0u), "r"(0xBA98u));
+    const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1F1F1F1Fu;
+    const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u; // empty slots contribute no bits
+#define RT_CHILD(k)                                                                                                  \
+  {                                                                                                                  \
+    const float tnx = fmaf(byteAsUnitFloat<k>(nearx), aix, nox), tfx = fmaf(byteAsUnitFloat<k>(farx), aix, fox);     \
+    const float tny = fmaf(byteAsUnitFloat<k>(neary), aiy, noy), tfy = fmaf(byteAsUnitFloat<k>(fary), aiy, foy);     \
+    const float tnz = fmaf(byteAsUnitFloat<k>(nearz), aiz, noz), tfz = fmaf(byteAsUnitFloat<k>(farz), aiz, foz);     \
+    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                                       \
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                                       \
+    if (tn <= tf) {                                                                                                  \
+      const uint32_t bits = __byte_perm(childBits4, 0u, 0x4440u | uint32_t(k));                                      \
+      const uint32_t index = __byte_perm(bitIndex4, 0u, 0x4440u | uint32_t(k));                                      \
+      hitmask |= bits << index;                                                                                      \
+    }                                                                                                                \
+  }
+    RT_CHILD(0) RT_CHILD(1) RT_CHILD(2) RT_CHILD(3)
+#undef RT_CHILD
+  }
+  return hitmask;
+}
+
+// Traversal loop variants (same results, different warp behaviour; chosen from ncu measurements, profiles/):
+//   0  per iteration: one node step, then ALL pending primitives of that node, then pop
+//   1  per iteration: exactly one of {one primitive, one node step, pop}
+//   2  as 0, but a lane postpones its primitives (pushes them) while fewer than kPostponeLanes lanes have any
+#ifndef RT_TRAVERSAL_VARIANT
+#define RT_TRAVERSAL_VARIANT 0
+#endif
+constexpr int kPostponeLanes = 8;
+
 // Two-level traversal. kAny: return true at the first accepted triangle. Otherwise `hit` holds the closest hit
 // (hit.t == tmax and return false when nothing was hit).
-template <bool kAny>
+template <bool kAny, int kVariant = RT_TRAVERSAL_VARIANT>
 __device__ __forceinline__ bool traverseScene(const TlasHeader *__restrict__ tlas, float ox, float oy, float oz,
                                               float dx, float dy, float dz, float tmin, float tmax, RayHit &hit) {
   hit.t = tmax;
@@ -181,7 +258,10 @@ __device__ __forceinline__ bool traverseScene(const TlasHeader *__restrict__ tla
   int instanceSp = -1; // stack depth at which the current instance was entered; -1 = world space
   uint32_t instance = 0;
 
-  const uint4 *nodes = reinterpret_cast<const uint4 *>(tlas->nodes);
+  const uint4 *const tlasNodes = reinterpret_cast<const uint4 *>(tlas->nodes);
+  const InstanceRecord *const instanceRecords = tlas->instances;
+  const uint32_t *const leafInstance = tlas->leafInstance;
+  const uint4 *nodes = tlasNodes;
   const float4 *tris = nullptr;
   BoxSetup box = makeBoxSetup(ox, oy, oz, dx, dy, dz);
   TriSetup tri{};
@@ -189,89 +269,127 @@ __device__ __forceinline__ bool traverseScene(const TlasHeader *__restrict__ tla
   uint2 ngroup = make_uint2(0u, 0x80000000u);
   uint2 tgroup = make_uint2(0u, 0u);
 
-  while (true) {
-    if (ngroup.y > 0x00FFFFFFu) {
-      const uint32_t hits = ngroup.y;
-      const uint32_t bit = 31u - uint32_t(__clz(int(hits)));
-      ngroup.y &= ~(1u << bit);
-      if (ngroup.y > 0x00FFFFFFu) {
-        if (sp < kStackSize) stack[sp++] = ngroup;
+  // one node step: take the nearest pending child of ngroup, test its eight children
+  auto nodeStep = [&]() {
+    const uint32_t hits = ngroup.y;
+    const uint32_t bit = 31u - uint32_t(__clz(int(hits)));
+    ngroup.y &= ~(1u << bit);
+    if (ngroup.y > 0x00FFFFFFu && sp < kStackSize) stack[sp++] = ngroup;
+    const uint32_t slot = (bit - 24u) ^ (box.octinv & 7u);
+    const uint32_t rel = __popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
+    const uint4 *np = nodes + size_t(ngroup.x + rel) * 5;
+    const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+#ifdef RT_LEGACY_CHILD_TEST
+    const uint32_t hitmask = intersectChildrenLegacy(n0, n1, n2, n3, n4, box, tmin, hit.t);
+#else
+    const uint32_t hitmask = intersectChildren(n0, n1, n2, n3, n4, box, tmin, hit.t);
+#endif
+    ngroup = make_uint2(n1.x, (hitmask & 0xFF000000u) | (n0.w >> 24));
+    tgroup = make_uint2(n1.y, hitmask & 0x00FFFFFFu);
+  };
+  // one primitive of tgroup: a triangle (inside an instance) or an instance to enter (in the TLAS).
+  // Returns true when an any-hit query is satisfied.
+  auto primitiveStep = [&]() -> bool {
+    const uint32_t bit = uint32_t(__ffs(int(tgroup.y))) - 1u;
+    tgroup.y &= ~(1u << bit);
+    if (instanceSp < 0) {
+      // TLAS leaf: enter the instance. Pending world-space work goes to the stack first.
+      if (tgroup.y != 0u && sp < kStackSize) stack[sp++] = tgroup;
+      if (ngroup.y > 0x00FFFFFFu && sp < kStackSize) stack[sp++] = ngroup;
+      instance = __ldg(leafInstance + tgroup.x + bit);
+      const InstanceRecord *rec = instanceRecords + instance;
+      const float4 r0 = __ldg(&rec->row0), r1 = __ldg(&rec->row1), r2 = __ldg(&rec->row2);
+      const WideNode *bn = rec->nodes;
+      tgroup.y = 0u;
+      ngroup = make_uint2(0u, 0u);
+      if (bn != nullptr) {
+        const float lox = ((r0.x * ox + r0.y * oy) + r0.z * oz) + r0.w;
+        const float loy = ((r1.x * ox + r1.y * oy) + r1.z * oz) + r1.w;
+        const float loz = ((r2.x * ox + r2.y * oy) + r2.z * oz) + r2.w;
+        const float ldx = (r0.x * dx + r0.y * dy) + r0.z * dz;
+        const float ldy = (r1.x * dx + r1.y * dy) + r1.z * dz;
+        const float ldz = (r2.x * dx + r2.y * dy) + r2.z * dz;
+        box = makeBoxSetup(lox, loy, loz, ldx, ldy, ldz);
+        tri = makeTriSetup(lox, loy, loz, ldx, ldy, ldz);
+        nodes = reinterpret_cast<const uint4 *>(bn);
+        tris = reinterpret_cast<const float4 *>(rec->tris);
+        instanceSp = sp;
+        ngroup = make_uint2(0u, 0x80000000u);
       }
-      const uint32_t slot = (bit - 24u) ^ (box.octinv & 7u);
-      const uint32_t rel = __popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
-      const uint4 *np = nodes + size_t(ngroup.x + rel) * 5;
-      const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-      const uint32_t hitmask = intersectChildren(n0, n1, n2, n3, n4, box, tmin, hit.t);
-      ngroup = make_uint2(n1.x, (hitmask & 0xFF000000u) | (n0.w >> 24));
-      tgroup = make_uint2(n1.y, hitmask & 0x00FFFFFFu);
+      return false;
+    }
+    const float4 *tp = tris + size_t(tgroup.x + bit) * 3;
+    const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+    float t, u, v;
+    if (intersectTriangle(tri, v0, v1, v2, tmin, tmax, t, u, v)) {
+      if (kAny) return true;
+      const uint32_t prim = __float_as_uint(v0.w), geom = __float_as_uint(v1.w);
+      bool better = t < hit.t;
+      if (!better && found && t == hit.t) {
+        better = instance < hit.instance ||
+                 (instance == hit.instance && (geom < hit.geometry || (geom == hit.geometry && prim < hit.primitive)));
+      }
+      if (better) {
+        found = true;
+        hit.t = t;
+        hit.u = u;
+        hit.v = v;
+        hit.instance = instance;
+        hit.geometry = geom;
+        hit.primitive = prim;
+      }
+    }
+    return false;
+  };
+  // no node work left in the registers: leave the instance if its subtree is exhausted, then pop.
+  // Returns false when the traversal is complete.
+  auto popStep = [&]() -> bool {
+    if (sp == instanceSp) {
+      instanceSp = -1;
+      box = makeBoxSetup(ox, oy, oz, dx, dy, dz);
+      nodes = tlasNodes;
+    }
+    if (sp == 0) return false;
+    const uint2 e = stack[--sp];
+    if (e.y > 0x00FFFFFFu) {
+      ngroup = e;
     } else {
-      tgroup = ngroup;
+      tgroup = e;
       ngroup = make_uint2(0u, 0u);
     }
+    return true;
+  };
 
-    while (tgroup.y != 0u) {
-      const uint32_t bit = uint32_t(__ffs(int(tgroup.y))) - 1u;
-      tgroup.y &= ~(1u << bit);
-      if (instanceSp < 0) {
-        // TLAS leaf: enter the instance. Pending world-space work goes to the stack first.
-        if (tgroup.y != 0u && sp < kStackSize) stack[sp++] = tgroup;
-        if (ngroup.y > 0x00FFFFFFu && sp < kStackSize) stack[sp++] = ngroup;
-        instance = __ldg(tlas->leafInstance + tgroup.x + bit);
-        const InstanceRecord *rec = tlas->instances + instance;
-        const float4 r0 = __ldg(&rec->row0), r1 = __ldg(&rec->row1), r2 = __ldg(&rec->row2);
-        const WideNode *bn = rec->nodes;
-        tgroup.y = 0u;
-        ngroup = make_uint2(0u, 0u);
-        if (bn != nullptr) {
-          const float lox = ((r0.x * ox + r0.y * oy) + r0.z * oz) + r0.w;
-          const float loy = ((r1.x * ox + r1.y * oy) + r1.z * oz) + r1.w;
-          const float loz = ((r2.x * ox + r2.y * oy) + r2.z * oz) + r2.w;
-          const float ldx = (r0.x * dx + r0.y * dy) + r0.z * dz;
-          const float ldy = (r1.x * dx + r1.y * dy) + r1.z * dz;
-          const float ldz = (r2.x * dx + r2.y * dy) + r2.z * dz;
-          box = makeBoxSetup(lox, loy, loz, ldx, ldy, ldz);
-          tri = makeTriSetup(lox, loy, loz, ldx, ldy, ldz);
-          nodes = reinterpret_cast<const uint4 *>(bn);
-          tris = reinterpret_cast<const float4 *>(rec->tris);
-          instanceSp = sp;
-          ngroup = make_uint2(0u, 0x80000000u);
-        }
+  if (kVariant == 1) {
+    while (true) {
+      if (tgroup.y != 0u) {
+        if (primitiveStep()) return true;
+      } else if (ngroup.y > 0x00FFFFFFu) {
+        nodeStep();
+      } else if (!popStep()) {
         break;
-      } else {
-        const float4 *tp = tris + size_t(tgroup.x + bit) * 3;
-        const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
-        float t, u, v;
-        // accept bound: strictly inside (tmin, tmax) for the first hit, <= current best for tie handling
-        if (intersectTriangle(tri, v0, v1, v2, tmin, tmax, t, u, v)) {
-          if (kAny) return true;
-          const uint32_t prim = __float_as_uint(v0.w), geom = __float_as_uint(v1.w);
-          bool better = t < hit.t;
-          if (!better && found && t == hit.t) {
-            better = instance < hit.instance ||
-                     (instance == hit.instance &&
-                      (geom < hit.geometry || (geom == hit.geometry && prim < hit.primitive)));
-          }
-          if (better) {
-            found = true;
-            hit.t = t;
-            hit.u = u;
-            hit.v = v;
-            hit.instance = instance;
-            hit.geometry = geom;
-            hit.primitive = prim;
-          }
-        }
       }
     }
-
-    if (ngroup.y <= 0x00FFFFFFu) {
-      if (sp == instanceSp) { // the instance's subtree is exhausted: back to world space
-        instanceSp = -1;
-        box = makeBoxSetup(ox, oy, oz, dx, dy, dz);
-        nodes = reinterpret_cast<const uint4 *>(tlas->nodes);
+  } else {
+    while (true) {
+      if (ngroup.y > 0x00FFFFFFu) {
+        nodeStep();
       }
-      if (sp == 0) break;
-      ngroup = stack[--sp];
+      while (tgroup.y != 0u) {
+        if (kVariant == 2 && instanceSp >= 0) {
+          if (__popc(__activemask()) < kPostponeLanes && ngroup.y > 0x00FFFFFFu) { // too few lanes: do it later
+            if (sp < kStackSize) stack[sp++] = tgroup;
+            tgroup.y = 0u;
+            break;
+          }
+        }
+        const bool inWorld = instanceSp < 0;
+        if (primitiveStep()) return true;
+        if (inWorld) break; // entered an instance: go traverse it
+      }
+      if (ngroup.y <= 0x00FFFFFFu && tgroup.y == 0u) {
+        if (!popStep()) break;
+      }
     }
   }
   return found;

@@ -13,7 +13,7 @@ import numpy as np
 from . import _abi as A
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librt_b200.so")
+LIB_PATH = os.path.join(_HERE, "lib", os.environ.get("RT_B200_LIBNAME", "librt_b200.so"))
 _lib = None
 
 RTR_FLAG_FP32_IMAGES = 1
@@ -37,7 +37,7 @@ EXPORTS = [
     "rt_malloc", "rt_free", "rt_malloc_host", "rt_free_host", "rt_upload", "rt_download", "rt_copy", "rt_memset",
     "rt_blas_build", "rt_blas_refit", "rt_blas_destroy", "rt_tlas_build", "rt_tlas_update", "rt_tlas_destroy",
     "rt_as_get_info", "rt_skin", "rt_trace", "rt_texture_create", "rt_texture_destroy", "rt_launch_count",
-    "rt_set_trace_mode",
+    "rt_set_trace_mode", "rt_set_option",
     "rtr_last_error", "rtr_create", "rtr_destroy", "rtr_set_seeds", "rtr_update", "rtr_draw", "rtr_read_image",
     "rtr_image_info", "rtr_reset_accumulation", "rtr_read_mesh_streams", "rtr_get_blas_id", "rtr_get_tlas_id",
     "rtr_mesh_count",
@@ -83,6 +83,7 @@ def lib():
     L.rt_launch_count.restype = u64
     L.rt_launch_count.argtypes = [vp]
     L.rt_set_trace_mode.argtypes = [vp, i32]
+    L.rt_set_option.argtypes = [vp, C.c_char_p, i32]
     L.rtr_create.argtypes = [vp, C.POINTER(A.SceneDesc), i32, i32, u32, C.POINTER(vp)]
     L.rtr_destroy.argtypes = [vp]
     L.rtr_set_seeds.argtypes = [vp, vp]
@@ -170,6 +171,13 @@ class Context:
 
     def set_stream(self, cuda_stream):
         _check(lib().rt_set_stream(self._h, cuda_stream))
+
+    def set_trace_mode(self, mode):
+        """0 = megakernel, 1 = wavefront (default). Both produce identical images."""
+        _check(lib().rt_set_trace_mode(self._h, int(mode)))
+
+    def set_option(self, key, value):
+        _check(lib().rt_set_option(self._h, key.encode(), int(value)))
 
     def timer_begin(self):
         _check(lib().rt_timer_begin(self._h))
