@@ -123,8 +123,8 @@ struct rt_context {
   cudaEvent_t evBegin = nullptr, evEnd = nullptr;
   uint64_t launches = 0;
   int traceMode = 1;        // 0 megakernel, 1 wavefront
-  int traversalVariant = 0; // traverse.cuh loop variant used by the wavefront kernels
-  int blocksPerSm = 8;      // persistent grid size of the wavefront kernels = smCount * blocksPerSm
+  int traversalVariant = 1; // lane refill threshold of the traversal kernels: 0 none, 1 = 8, 2 = 16, 3 = 24 idle lanes
+  int blocksPerSm = 6;      // persistent grid of the traversal kernels = smCount * blocksPerSm (resident CTAs at 80 regs)
   std::unordered_map<uint64_t, rtb::AccelObject *> accels;
   // reusable build scratch
   void *scratch = nullptr;

@@ -15,10 +15,9 @@ __global__ void k_pack_tiles(const Pixel *__restrict__ image, Pixel *__restrict_
                              int tilesX, int tileCount, int modulo, int remainder) {
   const int owned = blockIdx.x;
   const int tile = owned * modulo + remainder;
-  if (tile >= tileCount) return;
   const int x = (tile % tilesX) * 16 + (threadIdx.x & 15), y = (tile / tilesX) * 16 + (threadIdx.x >> 4);
-  Pixel v{};
-  if (x < width && y < height) v = image[size_t(y) * width + x];
+  Pixel v{}; // slab padding (a rank with one tile fewer, pixels beyond a ragged edge) is zero
+  if (tile < tileCount && x < width && y < height) v = image[size_t(y) * width + x];
   slab[size_t(owned) * 256 + threadIdx.x] = v;
 }
 

@@ -26,6 +26,22 @@ namespace rtb {
 namespace {
 
 constexpr int kBlock = 256;
+// traversal kernels: small CTAs free their registers as soon as their rays finish; min-blocks caps registers
+#ifndef RT_TRACE_BLOCK
+#define RT_TRACE_BLOCK 128
+#endif
+#ifndef RT_TRACE_MINBLOCKS
+#define RT_TRACE_MINBLOCKS 6
+#endif
+constexpr int kTraceBlock = RT_TRACE_BLOCK;
+// streaming (evict-first) access for the per-path state so it does not push the BVH out of L2
+#ifdef RT_NO_STREAMING_HINTS
+#define RT_LDS(ptr) (*(ptr))
+#define RT_STS(ptr, v) (*(ptr) = (v))
+#else
+#define RT_LDS(ptr) __ldcs(ptr)
+#define RT_STS(ptr, v) __stcs(ptr, v)
+#endif
 
 struct WfState {
   uint32_t capacity; // slots = owned tiles * 256
@@ -79,8 +95,8 @@ __global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ 
         const f4 pm = readImage(P.images[RT_TEXTURE_MOTION], px, py);
         total = mk3(0.0f);
         totalSamples = baseSamples;
-        W.mot[slot] = make_float4(0.0f, 0.0f, pm.x, pm.y);
-        W.misc[slot] = make_float4(1.0e8f, __uint_as_float(0u), __uint_as_float(offset), 0.0f);
+        RT_STS(W.mot + slot, make_float4(0.0f, 0.0f, pm.x, pm.y));
+        RT_STS(W.misc + slot, make_float4(1.0e8f, __uint_as_float(0u), __uint_as_float(offset), 0.0f));
         if (U.enableDenoiseGBuffer != 0) { // a pixel whose first segment misses keeps zeros (Raytracing.metal:257-260)
           const f4 z = {0.0f, 0.0f, 0.0f, 0.0f};
           writeImage(P.images[RT_TEXTURE_DIFFUSE_ALBEDO], px, py, z);
@@ -89,29 +105,29 @@ __global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ 
           writeImage(P.images[RT_TEXTURE_ROUGHNESS], px, py, z);
         }
       } else {
-        const float4 t4 = W.tot[slot];
+        const float4 t4 = RT_LDS(W.tot + slot);
         total = mk3(t4.x, t4.y, t4.z);
         totalSamples = int(__float_as_uint(t4.w));
-        offset = __float_as_uint(W.misc[slot].z);
+        offset = __float_as_uint(RT_LDS(W.misc + slot).z);
         if (sampleIndex - 1 < totalSamples) { // finish the previous sample in sample order
-          const float4 r4 = W.rad[slot];
+          const float4 r4 = RT_LDS(W.rad + slot);
           total += mk3(r4.x, r4.y, r4.z);
         }
         if (sampleIndex == 1 && maxExtraSamples > 0) {
-          const float4 m4 = W.mot[slot];
+          const float4 m4 = RT_LDS(W.mot + slot);
           totalSamples = adaptiveSampleCount(U, baseSamples, maxExtraSamples, mk2(m4.x, m4.y), mk2(m4.z, m4.w));
         }
       }
-      W.tot[slot] = make_float4(total.x, total.y, total.z, __uint_as_float(uint32_t(totalSamples)));
+      RT_STS(W.tot + slot, make_float4(total.x, total.y, total.z, __uint_as_float(uint32_t(totalSamples))));
       if (sampleIndex < totalSamples) {
         const int hIndex = haltonIndex(U, offset, sampleStride, sampleIndex);
         PathState s;
         startPath(U, px, py, hIndex, s);
-        W.rayO[slot] = make_float4(s.origin.x, s.origin.y, s.origin.z, 0.0f);
-        W.rayD[slot] = make_float4(s.dir.x, s.dir.y, s.dir.z, 0.0f);
-        W.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(hIndex));
-        W.rad[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        W.ctr[slot] = make_int4(0, 0, 0, 0);
+        RT_STS(W.rayO + slot, make_float4(s.origin.x, s.origin.y, s.origin.z, 0.0f));
+        RT_STS(W.rayD + slot, make_float4(s.dir.x, s.dir.y, s.dir.z, 0.0f));
+        RT_STS(W.thr + slot, make_float4(1.0f, 1.0f, 1.0f, __int_as_float(hIndex)));
+        RT_STS(W.rad + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+        RT_STS(W.ctr + slot, make_int4(0, 0, 0, 0));
         push = U.maxBounces > 0;
       }
     }
@@ -119,36 +135,81 @@ __global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ 
   }
 }
 
-template <int kVariant>
-__global__ void __launch_bounds__(kBlock) k_wf_trace(const __grid_constant__ TraceParams P, const WfState W, int qin,
-                                                     int firstSegment) {
+// The two traversal kernels are persistent: a fixed grid of resident CTAs pulls rays from a device-side cursor.
+// A warp claims rays for its idle lanes whenever at least kRefill of them are idle (or all are), so lanes whose
+// rays ended early are refilled instead of idling until the warp's longest ray finishes; ballot + popc give each
+// idle lane its rank in the claimed range (warp-level ray compaction). kRefill == 0 claims 32 rays at a time only
+// when the whole warp is idle.
+constexpr int kStepsPerCheck = 4;
+
+template <bool kAny, int kRefill, typename Finish>
+__device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t *__restrict__ queue, uint32_t count,
+                                           uint32_t *cursor, const float4 *__restrict__ rayO,
+                                           const float4 *__restrict__ rayD, Finish finish) {
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  LaneTraversal<kAny> t;
+  uint2 stack[kStackSize];
+  bool active = false, exhausted = false;
+  uint32_t slot = 0;
+  while (true) {
+    const unsigned idle = __ballot_sync(full, !active);
+    if (idle == full && exhausted) break;
+    if (!exhausted && (idle == full || (kRefill > 0 && __popc(idle) >= kRefill))) {
+      const uint32_t want = uint32_t(__popc(idle));
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(cursor, want);
+      base = __shfl_sync(full, base, 0);
+      if (base + want >= count) exhausted = true;
+      if (!active) {
+        const uint32_t j = base + uint32_t(__popc(idle & ((1u << lane) - 1u)));
+        if (j < count) {
+          slot = queue[j];
+          const float4 o = RT_LDS(rayO + slot), d = RT_LDS(rayD + slot);
+          t.begin(P.tlas, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, kAny ? o.w : INFINITY);
+          active = true;
+        }
+      }
+      if (base >= count && idle == full) break;
+    }
+#pragma unroll 1
+    for (int k = 0; k < kStepsPerCheck; ++k) {
+      if (active && !t.step(stack)) {
+        finish(slot, t);
+        active = false;
+      }
+    }
+  }
+}
+
+template <int kRefill>
+__global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_trace(const __grid_constant__ TraceParams P, const WfState W,
+                                                                              int qin, int firstSegment) {
   if (blockIdx.x == 0 && threadIdx.x == 0) { // the queues the next two phases append to start empty
     W.counts[qin ^ 1] = 0u;
     W.counts[2] = 0u;
+    W.counts[4] = 0u; // cursor of the shadow kernel
   }
   const uint32_t count = W.counts[qin];
-  const uint32_t *queue = W.queue[qin];
-  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
-    const uint32_t slot = queue[j];
-    const float4 o = W.rayO[slot], d = W.rayD[slot];
-    RayHit hit;
-    const bool found = traverseScene<false, kVariant>(P.tlas, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, INFINITY, hit);
-    W.hitA[slot] = make_float4(hit.t, hit.u, hit.v, found ? 1.0f : 0.0f);
-    W.hitB[slot] = make_uint4(hit.instance, hit.geometry, hit.primitive, 0u);
-    if (firstSegment && P.primaryIds != nullptr) {
-      int px, py;
-      bool valid;
-      slotPixel(P, slot, px, py, valid);
-      const uint4 id = found ? make_uint4(hit.instance, hit.geometry, hit.primitive, __float_as_uint(hit.t))
-                             : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-      reinterpret_cast<uint4 *>(P.primaryIds)[size_t(py) * size_t(P.uniforms.width) + size_t(px)] = id;
-    }
-  }
+  traceQueue<false, kRefill>(P, W.queue[qin], count, W.counts + 3, W.rayO, W.rayD,
+                             [&](uint32_t slot, const LaneTraversal<false> &t) {
+                               RT_STS(W.hitA + slot, make_float4(t.hit.t, t.hit.u, t.hit.v, t.found ? 1.0f : 0.0f));
+                               RT_STS(W.hitB + slot, make_uint4(t.hit.instance, t.hit.geometry, t.hit.primitive, 0u));
+                               if (firstSegment && P.primaryIds != nullptr) {
+                                 int px, py;
+                                 bool valid;
+                                 slotPixel(P, slot, px, py, valid);
+                                 const uint4 id = t.found ? make_uint4(t.hit.instance, t.hit.geometry, t.hit.primitive, __float_as_uint(t.hit.t))
+                                                          : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                                 reinterpret_cast<uint4 *>(P.primaryIds)[size_t(py) * size_t(P.uniforms.width) + size_t(px)] = id;
+                               }
+                             });
   if (P.rayCounters != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.rayCounters + 0, (unsigned long long)count);
 }
 
 __global__ void __launch_bounds__(kBlock) k_wf_shade(const __grid_constant__ TraceParams P, const WfState W, int qin,
                                                      int sampleIndex) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) W.counts[3] = 0u; // cursor of the next trace kernel
   const uint32_t count = W.counts[qin];
   const uint32_t *queue = W.queue[qin];
   const uint32_t rounds = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
@@ -158,17 +219,17 @@ __global__ void __launch_bounds__(kBlock) k_wf_shade(const __grid_constant__ Tra
     uint32_t slot = 0;
     if (j < count) {
       slot = queue[j];
-      const float4 ha = W.hitA[slot];
+      const float4 ha = RT_LDS(W.hitA + slot);
       if (ha.w != 0.0f) {
         isHit = true;
-        const uint4 hb = W.hitB[slot];
+        const uint4 hb = RT_LDS(W.hitB + slot);
         RayHit hit;
         hit.t = ha.x, hit.u = ha.y, hit.v = ha.z;
         hit.instance = hb.x, hit.geometry = hb.y, hit.primitive = hb.z;
-        const float4 o = W.rayO[slot], d = W.rayD[slot], th = W.thr[slot], ra = W.rad[slot];
-        const int4 c = W.ctr[slot];
-        const float4 m4 = W.mot[slot];
-        const float4 mi = W.misc[slot];
+        const float4 o = RT_LDS(W.rayO + slot), d = RT_LDS(W.rayD + slot), th = RT_LDS(W.thr + slot), ra = RT_LDS(W.rad + slot);
+        const int4 c = RT_LDS(W.ctr + slot);
+        const float4 m4 = RT_LDS(W.mot + slot);
+        const float4 mi = RT_LDS(W.misc + slot);
         PathState s;
         s.origin = mk3(o.x, o.y, o.z);
         s.dir = mk3(d.x, d.y, d.z);
@@ -186,15 +247,15 @@ __global__ void __launch_bounds__(kBlock) k_wf_shade(const __grid_constant__ Tra
         const bool hadGBuffer = prim.wroteGBuffer;
         ShadowRequest shadow;
         pushPath = shadeSegment(P, s, hit, hIndex, sampleIndex, mk2(m4.z, m4.w), prim, shadow);
-        W.rayO[slot] = make_float4(s.origin.x, s.origin.y, s.origin.z, 0.0f);
-        W.rayD[slot] = make_float4(s.dir.x, s.dir.y, s.dir.z, 0.0f);
-        W.thr[slot] = make_float4(s.throughput.x, s.throughput.y, s.throughput.z, th.w);
-        W.rad[slot] = make_float4(s.radiance.x, s.radiance.y, s.radiance.z, 0.0f);
-        W.ctr[slot] = make_int4(s.bounce, s.step, s.transparencyPasses, 0);
+        RT_STS(W.rayO + slot, make_float4(s.origin.x, s.origin.y, s.origin.z, 0.0f));
+        RT_STS(W.rayD + slot, make_float4(s.dir.x, s.dir.y, s.dir.z, 0.0f));
+        RT_STS(W.thr + slot, make_float4(s.throughput.x, s.throughput.y, s.throughput.z, th.w));
+        RT_STS(W.rad + slot, make_float4(s.radiance.x, s.radiance.y, s.radiance.z, 0.0f));
+        RT_STS(W.ctr + slot, make_int4(s.bounce, s.step, s.transparencyPasses, 0));
         if (primarySegment || (prim.wroteGBuffer && !hadGBuffer)) {
           const uint32_t nf = (prim.hadPrimaryHit ? 1u : 0u) | (prim.wroteGBuffer ? 2u : 0u);
-          W.mot[slot] = make_float4(prim.motion.x, prim.motion.y, m4.z, m4.w);
-          W.misc[slot] = make_float4(prim.depth, __uint_as_float(nf), mi.z, 0.0f);
+          RT_STS(W.mot + slot, make_float4(prim.motion.x, prim.motion.y, m4.z, m4.w));
+          RT_STS(W.misc + slot, make_float4(prim.depth, __uint_as_float(nf), mi.z, 0.0f));
         }
         if (prim.wroteGBuffer && !hadGBuffer) {
           int px, py;
@@ -207,9 +268,9 @@ __global__ void __launch_bounds__(kBlock) k_wf_shade(const __grid_constant__ Tra
         }
         if (shadow.valid) {
           pushShadow = true;
-          W.shO[slot] = make_float4(shadow.origin.x, shadow.origin.y, shadow.origin.z, shadow.tmax);
-          W.shD[slot] = make_float4(shadow.dir.x, shadow.dir.y, shadow.dir.z, 0.0f);
-          W.shC[slot] = make_float4(shadow.contribution.x, shadow.contribution.y, shadow.contribution.z, 0.0f);
+          RT_STS(W.shO + slot, make_float4(shadow.origin.x, shadow.origin.y, shadow.origin.z, shadow.tmax));
+          RT_STS(W.shD + slot, make_float4(shadow.dir.x, shadow.dir.y, shadow.dir.z, 0.0f));
+          RT_STS(W.shC + slot, make_float4(shadow.contribution.x, shadow.contribution.y, shadow.contribution.z, 0.0f));
         }
       }
     }
@@ -223,20 +284,18 @@ __global__ void __launch_bounds__(kBlock) k_wf_shade(const __grid_constant__ Tra
   }
 }
 
-template <int kVariant>
-__global__ void __launch_bounds__(kBlock) k_wf_shadow(const __grid_constant__ TraceParams P, const WfState W) {
+template <int kRefill>
+__global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_shadow(const __grid_constant__ TraceParams P, const WfState W) {
   const uint32_t count = W.counts[2];
-  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
-    const uint32_t slot = W.shadowQueue[j];
-    const float4 o = W.shO[slot], d = W.shD[slot];
-    RayHit hit;
-    if (!traverseScene<true, kVariant>(P.tlas, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, o.w, hit)) {
-      const float4 c = W.shC[slot];
-      float4 r = W.rad[slot];
-      r.x = r.x + c.x, r.y = r.y + c.y, r.z = r.z + c.z;
-      W.rad[slot] = r;
-    }
-  }
+  traceQueue<true, kRefill>(P, W.shadowQueue, count, W.counts + 4, W.shO, W.shD,
+                            [&](uint32_t slot, const LaneTraversal<true> &t) {
+                              if (!t.found) { // unoccluded: the light sample contributes
+                                const float4 c = RT_LDS(W.shC + slot);
+                                float4 r = RT_LDS(W.rad + slot);
+                                r.x = r.x + c.x, r.y = r.y + c.y, r.z = r.z + c.z;
+                                RT_STS(W.rad + slot, r);
+                              }
+                            });
   if (P.rayCounters != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.rayCounters + 1, (unsigned long long)count);
 }
 
@@ -247,15 +306,15 @@ __global__ void __launch_bounds__(kBlock) k_wf_resolve(const __grid_constant__ T
     bool valid;
     slotPixel(P, slot, px, py, valid);
     if (!valid) continue;
-    const float4 t4 = W.tot[slot];
+    const float4 t4 = RT_LDS(W.tot + slot);
     f3 total = mk3(t4.x, t4.y, t4.z);
     const int totalSamples = int(__float_as_uint(t4.w));
     if (sampleLoopBound - 1 < totalSamples) {
-      const float4 r4 = W.rad[slot];
+      const float4 r4 = RT_LDS(W.rad + slot);
       total += mk3(r4.x, r4.y, r4.z);
     }
-    const float4 m4 = W.mot[slot];
-    const float4 mi = W.misc[slot];
+    const float4 m4 = RT_LDS(W.mot + slot);
+    const float4 mi = RT_LDS(W.misc + slot);
     PrimaryOutputs prim = emptyPrimaryOutputs();
     prim.depth = mi.x;
     prim.motion = mk2(m4.x, m4.y);
@@ -320,9 +379,11 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
   // a refraction does not consume a bounce until transparencyPasses > maxBounces (Raytracing.metal:563-575)
   const int maxSegments = maxBounces * (maxBounces + 1);
   const int slotBlocks = (int(W.capacity) + kBlock - 1) / kBlock;
-  const int persistent = std::min(slotBlocks, ctx->smCount * std::max(1, ctx->blocksPerSm));
+  const int persistent = std::min(slotBlocks, ctx->smCount * 8);
+  // traversal kernels: exactly the resident CTA count (they pull work from a cursor), blocks_per_sm overrides
+  const int traceGrid = ctx->smCount * std::max(1, ctx->blocksPerSm);
   for (int s = 0; s < sampleLoopBound; ++s) {
-    RT_CUDA(cudaMemsetAsync(W.counts, 0, 16, st));
+    RT_CUDA(cudaMemsetAsync(W.counts, 0, 32, st));
     k_wf_generate<<<persistent, kBlock, 0, st>>>(P, W, s, baseSamples, maxExtraSamples);
     ++ctx->launches;
     int qin = 0;
@@ -335,15 +396,17 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
       }
       const int first = (s == 0 && segment == 0) ? 1 : 0;
       switch (ctx->traversalVariant) {
-        case 1: k_wf_trace<1><<<persistent, kBlock, 0, st>>>(P, W, qin, first); break;
-        case 2: k_wf_trace<2><<<persistent, kBlock, 0, st>>>(P, W, qin, first); break;
-        default: k_wf_trace<0><<<persistent, kBlock, 0, st>>>(P, W, qin, first); break;
+        case 1: k_wf_trace<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
+        case 2: k_wf_trace<16><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
+        case 3: k_wf_trace<24><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
+        default: k_wf_trace<0><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
       }
       k_wf_shade<<<persistent, kBlock, 0, st>>>(P, W, qin, s);
       switch (ctx->traversalVariant) {
-        case 1: k_wf_shadow<1><<<persistent, kBlock, 0, st>>>(P, W); break;
-        case 2: k_wf_shadow<2><<<persistent, kBlock, 0, st>>>(P, W); break;
-        default: k_wf_shadow<0><<<persistent, kBlock, 0, st>>>(P, W); break;
+        case 1: k_wf_shadow<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
+        case 2: k_wf_shadow<16><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
+        case 3: k_wf_shadow<24><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
+        default: k_wf_shadow<0><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
       }
       ctx->launches += 3;
       qin ^= 1;

@@ -233,44 +233,54 @@ __device__ __forceinline__ uint32_t intersectChildren(const uint4 &n0, const uin
   return hitmask;
 }
 
-// Traversal loop variants (same results, different warp behaviour; chosen from ncu measurements, profiles/):
-//   0  per iteration: one node step, then ALL pending primitives of that node, then pop
-//   1  per iteration: exactly one of {one primitive, one node step, pop}
-//   2  as 0, but a lane postpones its primitives (pushes them) while fewer than kPostponeLanes lanes have any
-#ifndef RT_TRAVERSAL_VARIANT
-#define RT_TRAVERSAL_VARIANT 0
-#endif
-constexpr int kPostponeLanes = 8;
+// Two-level traversal of one ray as an explicit state machine, so a kernel can either run it to completion
+// (traverseScene) or interleave it with fetching new rays into idle lanes (trace_wavefront.cu).
+// Each step() does exactly one of: one primitive (a triangle test, or entering an instance from a TLAS leaf), one
+// node step (take the nearest pending child, test its eight children), or a pop. ncu showed this "one unit of
+// work per iteration" shape keeps more lanes of a warp busy than draining all of a node's triangles in place.
+// kAny: the traversal ends at the first accepted triangle (found == occluded).
+template <bool kAny>
+struct LaneTraversal {
+  float ox, oy, oz, dx, dy, dz, tmin, tmax; // world-space ray
+  const uint4 *tlasNodes;
+  const InstanceRecord *instanceRecords;
+  const uint32_t *leafInstance;
+  const uint4 *nodes;
+  const float4 *tris;
+  BoxSetup box;
+  TriSetup tri;
+  uint2 ngroup, tgroup;
+  int sp, instanceSp; // instanceSp: stack depth at which the current instance was entered; -1 = world space
+  uint32_t instance;
+  RayHit hit;
+  bool found;
+  // the traversal stack lives outside (a plain local array passed to every step) so that the compiler keeps the
+  // scalar members above in registers instead of placing the whole object in local memory
 
-// Two-level traversal. kAny: return true at the first accepted triangle. Otherwise `hit` holds the closest hit
-// (hit.t == tmax and return false when nothing was hit).
-template <bool kAny, int kVariant = RT_TRAVERSAL_VARIANT>
-__device__ __forceinline__ bool traverseScene(const TlasHeader *__restrict__ tlas, float ox, float oy, float oz,
-                                              float dx, float dy, float dz, float tmin, float tmax, RayHit &hit) {
-  hit.t = tmax;
-  hit.u = hit.v = 0.0f;
-  hit.instance = hit.geometry = hit.primitive = 0u;
-  bool found = false;
-  if (tlas->nodeCount == 0) return false;
+  __device__ __forceinline__ void begin(const TlasHeader *__restrict__ tlas, float ox_, float oy_, float oz_, float dx_,
+                                        float dy_, float dz_, float tmin_, float tmax_) {
+    ox = ox_, oy = oy_, oz = oz_, dx = dx_, dy = dy_, dz = dz_, tmin = tmin_, tmax = tmax_;
+    hit.t = tmax_;
+    hit.u = hit.v = 0.0f;
+    hit.instance = hit.geometry = hit.primitive = 0u;
+    found = false;
+    sp = 0;
+    instanceSp = -1;
+    instance = 0;
+    tlasNodes = reinterpret_cast<const uint4 *>(tlas->nodes);
+    instanceRecords = tlas->instances;
+    leafInstance = tlas->leafInstance;
+    nodes = tlasNodes;
+    tris = nullptr;
+    box = makeBoxSetup(ox, oy, oz, dx, dy, dz);
+    tri = TriSetup{};
+    // an empty TLAS has nothing pending: the first step() pops an empty stack and finishes
+    ngroup = make_uint2(0u, tlas->nodeCount != 0 ? 0x80000000u : 0u);
+    tgroup = make_uint2(0u, 0u);
+  }
 
-  uint2 stack[kStackSize];
-  int sp = 0;
-  int instanceSp = -1; // stack depth at which the current instance was entered; -1 = world space
-  uint32_t instance = 0;
-
-  const uint4 *const tlasNodes = reinterpret_cast<const uint4 *>(tlas->nodes);
-  const InstanceRecord *const instanceRecords = tlas->instances;
-  const uint32_t *const leafInstance = tlas->leafInstance;
-  const uint4 *nodes = tlasNodes;
-  const float4 *tris = nullptr;
-  BoxSetup box = makeBoxSetup(ox, oy, oz, dx, dy, dz);
-  TriSetup tri{};
-
-  uint2 ngroup = make_uint2(0u, 0x80000000u);
-  uint2 tgroup = make_uint2(0u, 0u);
-
-  // one node step: take the nearest pending child of ngroup, test its eight children
-  auto nodeStep = [&]() {
+  // take the nearest pending child of ngroup, test its eight children
+  __device__ __forceinline__ void nodeStep(uint2 *stack) {
     const uint32_t hits = ngroup.y;
     const uint32_t bit = 31u - uint32_t(__clz(int(hits)));
     ngroup.y &= ~(1u << bit);
@@ -286,10 +296,10 @@ __device__ __forceinline__ bool traverseScene(const TlasHeader *__restrict__ tla
 #endif
     ngroup = make_uint2(n1.x, (hitmask & 0xFF000000u) | (n0.w >> 24));
     tgroup = make_uint2(n1.y, hitmask & 0x00FFFFFFu);
-  };
-  // one primitive of tgroup: a triangle (inside an instance) or an instance to enter (in the TLAS).
-  // Returns true when an any-hit query is satisfied.
-  auto primitiveStep = [&]() -> bool {
+  }
+
+  // one primitive of tgroup. Returns true when an any-hit query is satisfied.
+  __device__ __forceinline__ bool primitiveStep(uint2 *stack) {
     const uint32_t bit = uint32_t(__ffs(int(tgroup.y))) - 1u;
     tgroup.y &= ~(1u << bit);
     if (instanceSp < 0) {
@@ -340,10 +350,11 @@ __device__ __forceinline__ bool traverseScene(const TlasHeader *__restrict__ tla
       }
     }
     return false;
-  };
-  // no node work left in the registers: leave the instance if its subtree is exhausted, then pop.
+  }
+
+  // nothing pending in registers: leave the instance if its subtree is exhausted, then pop.
   // Returns false when the traversal is complete.
-  auto popStep = [&]() -> bool {
+  __device__ __forceinline__ bool popStep(uint2 *stack) {
     if (sp == instanceSp) {
       instanceSp = -1;
       box = makeBoxSetup(ox, oy, oz, dx, dy, dz);
@@ -358,41 +369,37 @@ __device__ __forceinline__ bool traverseScene(const TlasHeader *__restrict__ tla
       ngroup = make_uint2(0u, 0u);
     }
     return true;
-  };
-
-  if (kVariant == 1) {
-    while (true) {
-      if (tgroup.y != 0u) {
-        if (primitiveStep()) return true;
-      } else if (ngroup.y > 0x00FFFFFFu) {
-        nodeStep();
-      } else if (!popStep()) {
-        break;
-      }
-    }
-  } else {
-    while (true) {
-      if (ngroup.y > 0x00FFFFFFu) {
-        nodeStep();
-      }
-      while (tgroup.y != 0u) {
-        if (kVariant == 2 && instanceSp >= 0) {
-          if (__popc(__activemask()) < kPostponeLanes && ngroup.y > 0x00FFFFFFu) { // too few lanes: do it later
-            if (sp < kStackSize) stack[sp++] = tgroup;
-            tgroup.y = 0u;
-            break;
-          }
-        }
-        const bool inWorld = instanceSp < 0;
-        if (primitiveStep()) return true;
-        if (inWorld) break; // entered an instance: go traverse it
-      }
-      if (ngroup.y <= 0x00FFFFFFu && tgroup.y == 0u) {
-        if (!popStep()) break;
-      }
-    }
   }
-  return found;
+
+  // One unit of work. Returns false when the traversal has finished (result in `hit` / `found`).
+  __device__ __forceinline__ bool step(uint2 *stack) {
+    if (tgroup.y != 0u) {
+      if (primitiveStep(stack)) {
+        found = true;
+        return false;
+      }
+      return true;
+    }
+    if (ngroup.y > 0x00FFFFFFu) {
+      nodeStep(stack);
+      return true;
+    }
+    return popStep(stack);
+  }
+};
+
+// Runs one ray to completion. Closest hit: `hit` holds the result (hit.t == tmax and false when nothing was
+// hit). kAny: true at the first accepted triangle.
+template <bool kAny>
+__device__ __forceinline__ bool traverseScene(const TlasHeader *__restrict__ tlas, float ox, float oy, float oz,
+                                              float dx, float dy, float dz, float tmin, float tmax, RayHit &hit) {
+  LaneTraversal<kAny> t;
+  uint2 stack[kStackSize];
+  t.begin(tlas, ox, oy, oz, dx, dy, dz, tmin, tmax);
+  while (t.step(stack)) {
+  }
+  hit = t.hit;
+  return t.found;
 }
 
 } // namespace rtb

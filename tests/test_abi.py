@@ -150,7 +150,7 @@ def test_python_export_list_is_complete():
     from metal4_raytracing_b200 import device
     declared = set(_declared("rt_b200.h", "rt") + _declared("rt_renderer.h", "rtr"))
     assert declared - set(device.EXPORTS) <= {"rt_pack_tiles", "rt_unpack_tiles", "rt_ipc_export", "rt_ipc_import",
-                                               "rt_ipc_close"}
+                                               "rt_ipc_close", "rt_selftest_child_boxes"}
     assert set(device.EXPORTS) <= declared
 
 

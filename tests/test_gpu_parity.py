@@ -352,7 +352,7 @@ def test_full_size_headline_frame(gpu_ctx):
     seeds = scene.seed_image(w, h, seed)
     res = check_frames(gpu_ctx, sc, u, seeds)
     rays = res[0]["rays"]
-    assert rays["closest"] >= w * h and rays["any"] <= rays["hits"] and rays["rays"] > 5_000_000
+    assert rays["closest"] >= w * h and rays["any"] <= rays["hits"] and rays["rays"] > 4_000_000
     rnd = res[0]["renderer"]
     first = res[0]["image"]
     rnd.reset_accumulation()
