@@ -11,7 +11,9 @@ new Halton index, so timed frames are not repeats of cached work; an L2 flush be
   value     whole-job Mrays/s, device-timed, inputs resident in HBM (max over ranks for N > 1)
   e2e       the same metric through the public host API with HOST inputs: per frame rtr_update (pinned H2D of
             instance descriptors + lights, TLAS rebuild) + draw + D2H of the finished frame, wall clock
-  roofline  dominant kernel (k_trace_megakernel) vs the measured HBM peak, algorithmic bytes per SURVEY.md §8(d)
+  roofline  dominant kernel (k_wf_trace, the closest-hit traversal) vs the measured HBM peak: algorithmic bytes per
+            SURVEY.md §8(d) (closest-hit rays of the timed frames x bytes/ray) over that kernel's own launch time,
+            measured live with CUDA events the library records around each of its launches during the timed region
   cpu_baseline  the CPU oracle (oracle/, a port of the reference kernels) on a bounded tile sample of the same frame
 
 `--impl reference` times the oracle alone (the reference itself is Swift/Metal and cannot run on Linux).
@@ -40,6 +42,15 @@ WORKLOADS = {
 }
 B_RAY = {"K3": 672.0, "K3headline": 672.0, "K2": 592.0, "K4": 904.0, "K5": 592.0, "K3small": 512.0}
 B_HIT, B_PIXEL, B_VERTEX = 300.0, 32.0, 120.0
+
+
+def load_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return json.load(f).get(workload)
+    return None
 
 
 def load_peaks():
@@ -222,6 +233,7 @@ def main():
     launches0 = ctx.launches
     rnd.reset_ray_counters()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ctx.kernel_timing(True)  # one event after each library launch, on the launching stream, inside the timed region
     barrier()
     total_ms = 0.0
     for k, i in enumerate(range(warmup, warmup + steps)):
@@ -231,8 +243,11 @@ def main():
         ev[k][1].record()
     barrier()
     frame_ms = [a.elapsed_time(b) for a, b in ev]
+    ktimes = ctx.kernel_times()
+    ctx.kernel_timing(False)
     counters = rnd.read_ray_counters()
     rays, hits = counters["rays"], counters["hits"]
+    closest_rays, shadow_rays = counters["closest"], counters["any"]
     total_ms = float(sum(frame_ms))
     launches = ctx.launches - launches0
     sampler.stop()
@@ -250,15 +265,34 @@ def main():
     mrays = rays_all / (total_ms_max * 1e-3) / 1e6
 
     # ---- roofline of the dominant kernel on this rank -----------------------------------------------------------
+    # algorithmic bytes per SURVEY.md §8(d): B_RAY per ray (root-to-leaf node path + 4 leaf triangles); the closest-
+    # hit traversal kernel processed `closest_rays` rays in `trace_launches` launches taking `trace_ms` in total
     peak, peak_src = load_peaks()
     verts = 100000 if animated else 0
-    alg_bytes = rays * B_RAY[args.workload] + hits * B_HIT + pixels_owned * B_PIXEL * steps + verts * B_VERTEX * steps
-    achieved = alg_bytes / (total_ms * 1e-3) / 1e9
+    b_ray = B_RAY[args.workload]
+    trace_ms, trace_launches = ktimes.get("trace", ktimes.get("megakernel", (total_ms, steps)))
+    dominant = "k_wf_trace" if "trace" in ktimes else "k_trace_megakernel"
+    dom_rays = closest_rays if "trace" in ktimes else rays
+    achieved = dom_rays * b_ray / (trace_ms * 1e-3) / 1e9
+    frame_bytes = rays * b_ray + hits * B_HIT + pixels_owned * B_PIXEL * steps + verts * B_VERTEX * steps
+    kernels = {k: {"ms_per_step": round(v[0] / steps, 3), "launches_per_step": round(v[1] / steps, 1),
+                   "share": round(v[0] / max(1e-9, total_ms), 4)} for k, v in ktimes.items()}
+    if "shadow" in ktimes:
+        kernels["shadow"]["achieved_gbs"] = round(shadow_rays * b_ray / (ktimes["shadow"][0] * 1e-3) / 1e9, 1)
+    if "shade" in ktimes:
+        kernels["shade"]["achieved_gbs"] = round(hits * B_HIT / (ktimes["shade"][0] * 1e-3) / 1e9, 1)
     roofline = {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
-                "kernel": "k_trace_megakernel",
-                "note": "algorithmic bytes = rays x %.0f + closest hits x 300 + pixels x 32 per frame; the scene fits "
-                        "L2, so the kernel is latency/issue bound, not DRAM bound (see profiles/)" % B_RAY[args.workload]}
+                "frac": round(achieved / peak, 4), "traffic": load_traffic(args.workload), "peak_source": peak_src,
+                "kernel": dominant, "launches": int(trace_launches),
+                "avg_launch_ms": round(trace_ms / max(1, trace_launches), 4),
+                "bytes_per_launch": round(dom_rays * b_ray / max(1, trace_launches)),
+                "whole_frame": {"achieved": round(frame_bytes / (total_ms * 1e-3) / 1e9, 2),
+                                "frac": round(frame_bytes / (total_ms * 1e-3) / 1e9 / peak, 4)},
+                "kernels": kernels,
+                "note": "algorithmic bytes = closest-hit rays x %.0f B (SURVEY 8d) over k_wf_trace's own launch time; "
+                        "whole_frame adds shadow rays, 300 B per closest hit and 32 B per pixel over the frame time. "
+                        "The BVH fits L2 (traffic = measured DRAM bytes per launch, profiles/), so the kernel is "
+                        "latency/issue bound rather than DRAM bound" % b_ray}
 
     # ---- e2e through the host API: host inputs, D2H of the frame, wall clock -----------------------------------
     e2e = None

@@ -126,6 +126,25 @@ int rt_set_trace_mode(rt_context *ctx, int mode);
 /* Tuning knobs that never change results: "trace_mode" (0/1), "traversal_variant" (0..2, traverse.cuh),
  * "blocks_per_sm" (persistent grid size of the wavefront kernels). */
 int rt_set_option(rt_context *ctx, const char *key, int value);
+/* Per-kernel-class device timing (bench.py's roofline of the dominant kernel). While enabled, the library records
+ * a CUDA event on the context's stream after each of its launches; rt_kernel_timing_read synchronises, returns the
+ * summed milliseconds and launch counts per class since the last read and resets them. Classes: */
+enum {
+  RT_KERNEL_GENERATE = 0, /* camera rays / sample bookkeeping */
+  RT_KERNEL_TRACE = 1,    /* closest-hit traversal (dominant) */
+  RT_KERNEL_SHADE = 2,    /* material + light sampling + next ray */
+  RT_KERNEL_SHADOW = 3,   /* any-hit traversal */
+  RT_KERNEL_RESOLVE = 4,  /* sample mean + EMA + image writes */
+  RT_KERNEL_SKIN = 5,
+  RT_KERNEL_REFIT = 6,
+  RT_KERNEL_BUILD = 7,    /* BLAS / TLAS builds */
+  RT_KERNEL_MEGAKERNEL = 8,
+  RT_KERNEL_OTHER = 9,
+  RT_KERNEL_CLASS_COUNT = 10
+};
+int rt_kernel_timing_enable(rt_context *ctx, int enable);
+int rt_kernel_timing_read(rt_context *ctx, float msByClass[RT_KERNEL_CLASS_COUNT],
+                          uint32_t launchesByClass[RT_KERNEL_CLASS_COUNT]);
 /* Device self-test: for raysPerNode pseudo-random rays per wide node of an acceleration structure, the fast child-box
  * test must report every child the plain-conversion form reports. out[0] = missed children (must be 0), out[1] = extra
  * (allowed: the fast form is slightly more conservative), out[2] = tests run, out[3..10] = first failure details. */

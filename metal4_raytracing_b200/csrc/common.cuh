@@ -116,6 +116,17 @@ struct AccelObject {
 
 } // namespace rtb
 
+namespace rtb {
+// Per-kernel-class device timing (rt_kernel_timing_*): when enabled, an event is recorded after every launch and
+// the interval since the previous event is attributed to that launch's class. Off by default (no events at all).
+struct KernelTimer {
+  bool enabled = false;
+  std::vector<cudaEvent_t> pool;
+  std::vector<int> klass; // class of the interval that ends at event i; -1 = not attributed (sequence start)
+  size_t used = 0;
+};
+} // namespace rtb
+
 struct rt_context {
   int device = 0;
   cudaStream_t ownStream = nullptr;
@@ -134,6 +145,9 @@ struct rt_context {
   // wavefront state (trace_wavefront.cu)
   void *wfState = nullptr;
   size_t wfBytes = 0;
+  rtb::KernelTimer timer;
+  // records an event on the stream (only when timing is enabled); klass < 0 starts a new sequence
+  void mark(int klass);
 };
 
 namespace rtb {

@@ -25,6 +25,19 @@ int ensureScratch(rt_context *ctx, size_t bytes) {
 
 } // namespace rtb
 
+void rt_context::mark(int klass) {
+  if (!timer.enabled) return;
+  if (timer.used == timer.pool.size()) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    timer.pool.push_back(e);
+    timer.klass.push_back(-1);
+  }
+  timer.klass[timer.used] = klass;
+  cudaEventRecord(timer.pool[timer.used], stream);
+  ++timer.used;
+}
+
 using namespace rtb;
 
 #define RT_CTX(ctx)                             \
@@ -88,6 +101,7 @@ int rt_destroy(rt_context *ctx) {
   cudaFree(ctx->wfState);
   cudaEventDestroy(ctx->evBegin);
   cudaEventDestroy(ctx->evEnd);
+  for (cudaEvent_t e : ctx->timer.pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->ownStream);
   delete ctx;
   return 0;
@@ -194,7 +208,9 @@ int rt_blas_build(rt_context *ctx, const rt_triangle_geometry *geoms, uint32_t g
   RT_CHECK(outId != nullptr, "rt_blas_build: null out pointer");
   RT_CHECK(geometryCount == 0 || geoms != nullptr, "rt_blas_build: null geometry array");
   AccelObject *as = nullptr;
+  ctx->mark(-1);
   RT_TRY(buildBlas(ctx, geoms, geometryCount, flags, &as));
+  ctx->mark(RT_KERNEL_BUILD);
   uint64_t id = uint64_t(reinterpret_cast<uintptr_t>(as->headerDev));
   ctx->accels[id] = as;
   *outId = id;
@@ -213,7 +229,10 @@ int rt_blas_refit(rt_context *ctx, uint64_t id, const rt_triangle_geometry *geom
   RT_CTX(ctx);
   AccelObject *as = nullptr;
   RT_TRY(findAccel(ctx, id, false, &as));
-  return refitBlas(ctx, as, geoms, geometryCount);
+  ctx->mark(-1);
+  const int rc = refitBlas(ctx, as, geoms, geometryCount);
+  ctx->mark(RT_KERNEL_REFIT);
+  return rc;
 }
 
 int rt_blas_destroy(rt_context *ctx, uint64_t id) {
@@ -231,7 +250,9 @@ int rt_tlas_build(rt_context *ctx, const rt_instance_descriptor *descriptorsDev,
   RT_CHECK(outId != nullptr, "rt_tlas_build: null out pointer");
   AccelObject *as = new AccelObject();
   as->isTlas = true;
+  ctx->mark(-1);
   int rc = buildTlas(ctx, as, descriptorsDev, count);
+  ctx->mark(RT_KERNEL_BUILD);
   if (rc) {
     destroyAccel(as);
     return rc;
@@ -246,7 +267,10 @@ int rt_tlas_update(rt_context *ctx, uint64_t id, const rt_instance_descriptor *d
   RT_CTX(ctx);
   AccelObject *as = nullptr;
   RT_TRY(findAccel(ctx, id, true, &as));
-  return buildTlas(ctx, as, descriptorsDev, count);
+  ctx->mark(-1);
+  const int rc = buildTlas(ctx, as, descriptorsDev, count);
+  ctx->mark(RT_KERNEL_BUILD);
+  return rc;
 }
 
 int rt_tlas_destroy(rt_context *ctx, uint64_t id) {
@@ -280,7 +304,10 @@ int rt_as_get_info(rt_context *ctx, uint64_t id, rt_as_info *out) {
 
 int rt_skin(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], uint32_t vertexCount) {
   RT_CTX(ctx);
-  return launchSkin(ctx, buffers, vertexCount);
+  ctx->mark(-1);
+  const int rc = launchSkin(ctx, buffers, vertexCount);
+  ctx->mark(RT_KERNEL_SKIN);
+  return rc;
 }
 
 int rt_trace(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], const rt_image textures[RT_TEXTURE_COUNT],
@@ -360,6 +387,36 @@ int rt_set_trace_mode(rt_context *ctx, int mode) {
   RT_CTX(ctx);
   RT_CHECK(mode == 0 || mode == 1, "rt_set_trace_mode: 0 = megakernel, 1 = wavefront");
   ctx->traceMode = mode;
+  return 0;
+}
+
+int rt_kernel_timing_enable(rt_context *ctx, int enable) {
+  RT_CTX(ctx);
+  RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->timer.enabled = enable != 0;
+  ctx->timer.used = 0;
+  return 0;
+}
+
+int rt_kernel_timing_read(rt_context *ctx, float msByClass[RT_KERNEL_CLASS_COUNT],
+                          uint32_t launchesByClass[RT_KERNEL_CLASS_COUNT]) {
+  RT_CTX(ctx);
+  RT_CHECK(msByClass != nullptr, "rt_kernel_timing_read: null output");
+  RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < RT_KERNEL_CLASS_COUNT; ++k) {
+    msByClass[k] = 0.0f;
+    if (launchesByClass) launchesByClass[k] = 0;
+  }
+  KernelTimer &T = ctx->timer;
+  for (size_t i = 1; i < T.used; ++i) {
+    const int k = T.klass[i];
+    if (k < 0 || k >= RT_KERNEL_CLASS_COUNT) continue;
+    float ms = 0.0f;
+    RT_CUDA(cudaEventElapsedTime(&ms, T.pool[i - 1], T.pool[i]));
+    msByClass[k] += ms;
+    if (launchesByClass) ++launchesByClass[k];
+  }
+  T.used = 0;
   return 0;
 }
 

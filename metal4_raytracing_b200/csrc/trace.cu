@@ -139,7 +139,9 @@ int launchTrace(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], con
   const int owned = (tileCount - P.tileRemainder + P.tileModulo - 1) / P.tileModulo;
   if (owned <= 0) return 0;
   if (ctx->traceMode == 1) return launchTraceWavefront(ctx, P);
+  ctx->mark(-1);
   k_trace_megakernel<<<owned, 256, 0, ctx->stream>>>(P);
+  ctx->mark(RT_KERNEL_MEGAKERNEL);
   ++ctx->launches;
   RT_CUDA(cudaGetLastError());
   return 0;

@@ -140,7 +140,15 @@ __global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ 
 // rays ended early are refilled instead of idling until the warp's longest ray finishes; ballot + popc give each
 // idle lane its rank in the claimed range (warp-level ray compaction). kRefill == 0 claims 32 rays at a time only
 // when the whole warp is idle.
-constexpr int kStepsPerCheck = 4;
+#ifndef RT_STEPS_PER_CHECK
+#define RT_STEPS_PER_CHECK 4
+#endif
+constexpr int kStepsPerCheck = RT_STEPS_PER_CHECK;
+// RT_FUSED_PRIMS > 0: fused pop -> node -> primitive iterations (LaneTraversal::stepFused) with that many primitive
+// tests per iteration; 0: one unit of work per iteration (LaneTraversal::step)
+#ifndef RT_FUSED_PRIMS
+#define RT_FUSED_PRIMS 1
+#endif
 
 template <bool kAny, int kRefill, typename Finish>
 __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t *__restrict__ queue, uint32_t count,
@@ -174,7 +182,11 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
     }
 #pragma unroll 1
     for (int k = 0; k < kStepsPerCheck; ++k) {
+#if RT_FUSED_PRIMS > 0
+      if (active && !t.template stepFused<RT_FUSED_PRIMS>(stack)) {
+#else
       if (active && !t.step(stack)) {
+#endif
         finish(slot, t);
         active = false;
       }
@@ -384,7 +396,9 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
   const int traceGrid = ctx->smCount * std::max(1, ctx->blocksPerSm);
   for (int s = 0; s < sampleLoopBound; ++s) {
     RT_CUDA(cudaMemsetAsync(W.counts, 0, 32, st));
+    ctx->mark(-1);
     k_wf_generate<<<persistent, kBlock, 0, st>>>(P, W, s, baseSamples, maxExtraSamples);
+    ctx->mark(RT_KERNEL_GENERATE);
     ++ctx->launches;
     int qin = 0;
     for (int segment = 0; segment < maxSegments; ++segment) {
@@ -393,6 +407,7 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
         RT_CUDA(cudaMemcpyAsync(&remaining, W.counts + qin, 4, cudaMemcpyDeviceToHost, st));
         RT_CUDA(cudaStreamSynchronize(st));
         if (remaining == 0) break;
+        ctx->mark(-1);
       }
       const int first = (s == 0 && segment == 0) ? 1 : 0;
       switch (ctx->traversalVariant) {
@@ -401,18 +416,23 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
         case 3: k_wf_trace<24><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
         default: k_wf_trace<0><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
       }
+      ctx->mark(RT_KERNEL_TRACE);
       k_wf_shade<<<persistent, kBlock, 0, st>>>(P, W, qin, s);
+      ctx->mark(RT_KERNEL_SHADE);
       switch (ctx->traversalVariant) {
         case 1: k_wf_shadow<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
         case 2: k_wf_shadow<16><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
         case 3: k_wf_shadow<24><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
         default: k_wf_shadow<0><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
       }
+      ctx->mark(RT_KERNEL_SHADOW);
       ctx->launches += 3;
       qin ^= 1;
     }
   }
+  ctx->mark(-1);
   k_wf_resolve<<<persistent, kBlock, 0, st>>>(P, W, sampleLoopBound);
+  ctx->mark(RT_KERNEL_RESOLVE);
   ++ctx->launches;
   RT_CUDA(cudaGetLastError());
   return 0;

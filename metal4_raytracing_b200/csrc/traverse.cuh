@@ -371,6 +371,29 @@ struct LaneTraversal {
     return true;
   }
 
+  // One fused iteration: a lane with nothing pending pops, a lane with a pending child (and no pending primitives)
+  // tests that node, and a lane with pending primitives tests up to kPrims of them — each stage falls through
+  // into the next, so a lane does up to three units of work per iteration while the warp still executes each stage
+  // once. Primitives of a node are still all tested before any of its children is entered (hit.t shrinks first).
+  // Returns false when the traversal has finished.
+  template <int kPrims>
+  __device__ __forceinline__ bool stepFused(uint2 *stack) {
+    if (tgroup.y == 0u && ngroup.y <= 0x00FFFFFFu) {
+      if (!popStep(stack)) return false;
+    }
+    if (tgroup.y == 0u && ngroup.y > 0x00FFFFFFu) nodeStep(stack);
+#pragma unroll
+    for (int k = 0; k < kPrims; ++k) {
+      if (tgroup.y != 0u) {
+        if (primitiveStep(stack)) {
+          found = true;
+          return false;
+        }
+      }
+    }
+    return true;
+  }
+
   // One unit of work. Returns false when the traversal has finished (result in `hit` / `found`).
   __device__ __forceinline__ bool step(uint2 *stack) {
     if (tgroup.y != 0u) {

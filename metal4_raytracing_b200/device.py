@@ -37,7 +37,7 @@ EXPORTS = [
     "rt_malloc", "rt_free", "rt_malloc_host", "rt_free_host", "rt_upload", "rt_download", "rt_copy", "rt_memset",
     "rt_blas_build", "rt_blas_refit", "rt_blas_destroy", "rt_tlas_build", "rt_tlas_update", "rt_tlas_destroy",
     "rt_as_get_info", "rt_skin", "rt_trace", "rt_texture_create", "rt_texture_destroy", "rt_launch_count",
-    "rt_set_trace_mode", "rt_set_option",
+    "rt_set_trace_mode", "rt_set_option", "rt_kernel_timing_enable", "rt_kernel_timing_read",
     "rtr_last_error", "rtr_create", "rtr_destroy", "rtr_set_seeds", "rtr_update", "rtr_draw", "rtr_read_image",
     "rtr_image_info", "rtr_reset_accumulation", "rtr_read_mesh_streams", "rtr_get_blas_id", "rtr_get_tlas_id",
     "rtr_mesh_count",
@@ -84,6 +84,8 @@ def lib():
     L.rt_launch_count.argtypes = [vp]
     L.rt_set_trace_mode.argtypes = [vp, i32]
     L.rt_set_option.argtypes = [vp, C.c_char_p, i32]
+    L.rt_kernel_timing_enable.argtypes = [vp, i32]
+    L.rt_kernel_timing_read.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u32)]
     L.rtr_create.argtypes = [vp, C.POINTER(A.SceneDesc), i32, i32, u32, C.POINTER(vp)]
     L.rtr_destroy.argtypes = [vp]
     L.rtr_set_seeds.argtypes = [vp, vp]
@@ -190,6 +192,19 @@ class Context:
     @property
     def launches(self):
         return lib().rt_launch_count(self._h)
+
+    KERNEL_CLASSES = ("generate", "trace", "shade", "shadow", "resolve", "skin", "refit", "build", "megakernel", "other")
+
+    def kernel_timing(self, enable=True):
+        """Per-kernel-class CUDA-event timing of the library's own launches (rt_kernel_timing_enable)."""
+        _check(lib().rt_kernel_timing_enable(self._h, 1 if enable else 0))
+
+    def kernel_times(self):
+        """{class: (milliseconds, launches)} since the last read; synchronises the stream."""
+        ms = (C.c_float * len(self.KERNEL_CLASSES))()
+        n = (C.c_uint32 * len(self.KERNEL_CLASSES))()
+        _check(lib().rt_kernel_timing_read(self._h, ms, n))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNEL_CLASSES) if n[i]}
 
     # -- acceleration structures -----------------------------------------------------------------------------
     def blas_build(self, geoms, flags=A.AS_FLAG_COMPACT):
