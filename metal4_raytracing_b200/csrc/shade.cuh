@@ -95,24 +95,60 @@ __device__ __forceinline__ f3 mulPoint(const M34 &m, f3 v) { return ((m.c0 * v.x
 __device__ __forceinline__ f3 mulDir(const M34 &m, f3 v) { return (m.c0 * v.x + m.c1 * v.y) + m.c2 * v.z; }
 
 // ---- Halton (Raytracing.metal:28-57) -------------------------------------------------------------------------
-__constant__ short c_primes[100] = {
-    2,   3,   5,   7,   11,  13,  17,  19,  23,  29,  31,  37,  41,  43,  47,  53,  59,  61,  67,  71,
-    73,  79,  83,  89,  97,  101, 103, 107, 109, 113, 127, 131, 137, 139, 149, 151, 157, 163, 167, 173,
-    179, 181, 191, 193, 197, 199, 211, 223, 227, 229, 233, 239, 241, 251, 257, 263, 269, 271, 277, 281,
-    283, 293, 307, 311, 313, 317, 331, 337, 347, 349, 353, 359, 367, 373, 379, 383, 389, 397, 401, 409,
-    419, 421, 431, 433, 439, 443, 449, 457, 461, 463, 467, 479, 487, 491, 499, 503, 509, 521, 523, 541};
+// {prime, magic, shift, bits of 1.0f / float(prime)}: i / prime == __umulhi(i, magic) >> shift for 0 <= i < 2^31
+// (round-up reciprocal, Granlund & Montgomery 1994; generated and checked by the script in the comment of halton())
+__constant__ uint4 c_haltonBase[100] = {
+    {2u, 0x80000001u, 0u, 0x3F000000u}, {3u, 0xAAAAAAABu, 1u, 0x3EAAAAABu}, {5u, 0xCCCCCCCDu, 2u, 0x3E4CCCCDu},
+    {7u, 0x92492493u, 2u, 0x3E124925u}, {11u, 0xBA2E8BA3u, 3u, 0x3DBA2E8Cu}, {13u, 0x9D89D89Eu, 3u, 0x3D9D89D9u},
+    {17u, 0xF0F0F0F1u, 4u, 0x3D70F0F1u}, {19u, 0xD79435E6u, 4u, 0x3D579436u}, {23u, 0xB21642C9u, 4u, 0x3D321643u},
+    {29u, 0x8D3DCB09u, 4u, 0x3D0D3DCBu}, {31u, 0x84210843u, 4u, 0x3D042108u}, {37u, 0xDD67C8A7u, 5u, 0x3CDD67C9u},
+    {41u, 0xC7CE0C7Du, 5u, 0x3CC7CE0Cu}, {43u, 0xBE82FA0Cu, 5u, 0x3CBE82FAu}, {47u, 0xAE4C415Du, 5u, 0x3CAE4C41u},
+    {53u, 0x9A90E7DAu, 5u, 0x3C9A90E8u}, {59u, 0x8AD8F2FCu, 5u, 0x3C8AD8F3u}, {61u, 0x864B8A7Eu, 5u, 0x3C864B8Au},
+    {67u, 0xF4898D60u, 6u, 0x3C74898Du}, {71u, 0xE6C2B449u, 6u, 0x3C66C2B4u}, {73u, 0xE070381Du, 6u, 0x3C607038u},
+    {79u, 0xCF6474A9u, 6u, 0x3C4F6475u}, {83u, 0xC565C87Cu, 6u, 0x3C4565C8u}, {89u, 0xB81702E1u, 6u, 0x3C381703u},
+    {97u, 0xA8E83F58u, 6u, 0x3C28E83Fu}, {101u, 0xA237C32Cu, 6u, 0x3C2237C3u}, {103u, 0x9F1165E8u, 6u, 0x3C1F1166u},
+    {107u, 0x991F1A52u, 6u, 0x3C191F1Au}, {109u, 0x964FDA6Du, 6u, 0x3C164FDAu}, {113u, 0x90FDBC0Au, 6u, 0x3C10FDBCu},
+    {127u, 0x81020409u, 6u, 0x3C010204u}, {131u, 0xFA232CF3u, 7u, 0x3BFA232Du}, {137u, 0xEF2EB720u, 7u, 0x3BEF2EB7u},
+    {139u, 0xEBBDB2A6u, 7u, 0x3BEBBDB3u}, {149u, 0xDBEB61EFu, 7u, 0x3BDBEB62u}, {151u, 0xD901B204u, 7u, 0x3BD901B2u},
+    {157u, 0xD0B69FCCu, 7u, 0x3BD0B6A0u}, {163u, 0xC907DA4Fu, 7u, 0x3BC907DAu}, {167u, 0xC4372F86u, 7u, 0x3BC43730u},
+    {173u, 0xBD691048u, 7u, 0x3BBD6910u}, {179u, 0xB70FBB5Bu, 7u, 0x3BB70FBBu}, {181u, 0xB509E68Bu, 7u, 0x3BB509E7u},
+    {191u, 0xAB8F69E3u, 7u, 0x3BAB8F6Au}, {193u, 0xA9C84A48u, 7u, 0x3BA9C84Au}, {197u, 0xA655C43Au, 7u, 0x3BA655C4u},
+    {199u, 0xA4A9CF1Eu, 7u, 0x3BA4A9CFu}, {211u, 0x9B4C6F9Fu, 7u, 0x3B9B4C70u}, {223u, 0x92F11385u, 7u, 0x3B92F114u},
+    {227u, 0x905A3864u, 7u, 0x3B905A38u}, {229u, 0x8F1779DAu, 7u, 0x3B8F177Au}, {233u, 0x8CA29C05u, 7u, 0x3B8CA29Cu},
+    {239u, 0x891AC73Bu, 7u, 0x3B891AC7u}, {241u, 0x87F78088u, 7u, 0x3B87F781u}, {251u, 0x828CBFBFu, 7u, 0x3B828CC0u},
+    {257u, 0xFF00FF01u, 8u, 0x3B7F00FFu}, {263u, 0xF92FB222u, 8u, 0x3B792FB2u}, {269u, 0xF3A0D52Du, 8u, 0x3B73A0D5u},
+    {271u, 0xF1D48BCFu, 8u, 0x3B71D48Cu}, {277u, 0xEC979119u, 8u, 0x3B6C9791u}, {281u, 0xE9396520u, 8u, 0x3B693965u},
+    {283u, 0xE79372E3u, 8u, 0x3B679373u}, {293u, 0xDFAC1F75u, 8u, 0x3B5FAC1Fu}, {307u, 0xD578E97Du, 8u, 0x3B5578E9u},
+    {311u, 0xD2BA083Cu, 8u, 0x3B52BA08u}, {313u, 0xD161543Fu, 8u, 0x3B516154u}, {317u, 0xCEBCF8BCu, 8u, 0x3B4EBCF9u},
+    {331u, 0xC5FE7404u, 8u, 0x3B45FE74u}, {337u, 0xC2780614u, 8u, 0x3B427806u}, {347u, 0xBCDD535Eu, 8u, 0x3B3CDD53u},
+    {349u, 0xBBC8408Du, 8u, 0x3B3BC841u}, {353u, 0xB9A7862Bu, 8u, 0x3B39A786u}, {359u, 0xB68D3135u, 8u, 0x3B368D31u},
+    {367u, 0xB2927C2Au, 8u, 0x3B32927Cu}, {373u, 0xAFB321A2u, 8u, 0x3B2FB322u}, {379u, 0xACEB0F8Au, 8u, 0x3B2CEB10u},
+    {383u, 0xAB1CBDD4u, 8u, 0x3B2B1CBEu}, {389u, 0xA8791709u, 8u, 0x3B287917u}, {397u, 0xA513FD6Cu, 8u, 0x3B2513FDu},
+    {401u, 0xA36E71A3u, 8u, 0x3B236E72u}, {409u, 0xA03C1689u, 8u, 0x3B203C17u}, {419u, 0x9C69169Cu, 8u, 0x3B1C6917u},
+    {421u, 0x9BAADE8Fu, 8u, 0x3B1BAADFu}, {431u, 0x980E4157u, 8u, 0x3B180E41u}, {433u, 0x975A7510u, 8u, 0x3B175A75u},
+    {439u, 0x9548E498u, 8u, 0x3B1548E5u}, {443u, 0x93EFD1C6u, 8u, 0x3B13EFD2u}, {449u, 0x91F5BCB9u, 8u, 0x3B11F5BDu},
+    {457u, 0x8F67A1E4u, 8u, 0x3B0F67A2u}, {461u, 0x8E2917E1u, 8u, 0x3B0E2918u}, {463u, 0x8D8BE340u, 8u, 0x3B0D8BE3u},
+    {467u, 0x8C55841Du, 8u, 0x3B0C5584u}, {479u, 0x88D180CEu, 8u, 0x3B08D181u}, {487u, 0x869222B2u, 8u, 0x3B069223u},
+    {491u, 0x85797B92u, 8u, 0x3B05797Cu}, {499u, 0x8355ACE4u, 8u, 0x3B0355ADu}, {503u, 0x824A4E61u, 8u, 0x3B024A4Eu},
+    {509u, 0x80C121B3u, 8u, 0x3B00C122u}, {521u, 0xFB93E673u, 9u, 0x3AFB93E6u}, {523u, 0xFA9D9D20u, 9u, 0x3AFA9D9Du},
+    {541u, 0xF246FACCu, 9u, 0x3AF246FBu}};
 
+// Same value, bit for bit, as the reference loop `f *= 1/b; r += f * (i % b); i /= b` (Raytracing.metal:42-57): the
+// quotient comes from a multiply-high with a per-prime reciprocal instead of an integer division by a runtime
+// divisor (the dominant cost of the shading kernel before), the float accumulation is unchanged.
+// Table: tools/gen_halton_table.py.
 __device__ __forceinline__ float halton(int i, int d) {
-  const int b = c_primes[((d % 100) + 100) % 100]; // the reference indexes past the table for d > 99 (F9)
+  const uint4 base = c_haltonBase[((d % 100) + 100) % 100]; // the reference indexes past the table for d > 99 (F9)
+  const float invB = __uint_as_float(base.w);
   float f = 1.0f;
-  const float invB = 1.0f / float(b);
   float r = 0.0f;
-  while (i > 0) {
-    const int q = i / b;
-    const int digit = i - q * b;
+  uint32_t n = i > 0 ? uint32_t(i) : 0u;
+  while (n != 0u) {
+    const uint32_t q = __umulhi(n, base.y) >> base.z;
+    const uint32_t digit = n - q * base.x;
     f = f * invB;
     r = r + f * float(digit);
-    i = q;
+    n = q;
   }
   return r;
 }

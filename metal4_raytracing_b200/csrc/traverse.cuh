@@ -27,8 +27,19 @@ constexpr int kStackSize = 48;
 
 __device__ __forceinline__ float pick3(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
 
+// Component selection without branches or predicates: m0 / m1 are all-ones when the wanted axis is 0 / 1. Two LOP3
+// per pick (ncu showed the `?:` form compiled to divergent branches, 10 % of the traversal kernel's instructions).
+struct AxisMask {
+  uint32_t m0, m1;
+};
+__device__ __forceinline__ AxisMask axisMask(int k) { return {k == 0 ? 0xFFFFFFFFu : 0u, k == 1 ? 0xFFFFFFFFu : 0u}; }
+__device__ __forceinline__ float pickMasked(float x, float y, float z, const AxisMask &m) {
+  const uint32_t yz = (__float_as_uint(y) & m.m1) | (__float_as_uint(z) & ~m.m1);
+  return __uint_as_float((__float_as_uint(x) & m.m0) | (yz & ~m.m0));
+}
+
 struct TriSetup { // Woop et al. per-ray constants in the current space
-  int kx, ky, kz;
+  AxisMask kx, ky, kz;
   float Sx, Sy, Sz;
   float ox, oy, oz; // origin permuted to (kx, ky, kz)
 };
@@ -36,21 +47,20 @@ struct TriSetup { // Woop et al. per-ray constants in the current space
 __device__ __forceinline__ TriSetup makeTriSetup(float ox, float oy, float oz, float dx, float dy, float dz) {
   TriSetup s;
   float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
-  s.kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
-  s.kx = s.kz + 1 == 3 ? 0 : s.kz + 1;
-  s.ky = s.kx + 1 == 3 ? 0 : s.kx + 1;
-  float dkz = pick3(dx, dy, dz, s.kz);
-  if (dkz < 0.0f) {
-    int tmp = s.kx;
-    s.kx = s.ky;
-    s.ky = tmp;
-  }
-  s.Sx = pick3(dx, dy, dz, s.kx) / dkz;
-  s.Sy = pick3(dx, dy, dz, s.ky) / dkz;
+  const int kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
+  const int k1 = kz == 2 ? 0 : kz + 1;
+  const int k2 = k1 == 2 ? 0 : k1 + 1;
+  s.kz = axisMask(kz);
+  const float dkz = pickMasked(dx, dy, dz, s.kz);
+  const bool swap = dkz < 0.0f; // keeps the winding
+  s.kx = axisMask(swap ? k2 : k1);
+  s.ky = axisMask(swap ? k1 : k2);
+  s.Sx = pickMasked(dx, dy, dz, s.kx) / dkz;
+  s.Sy = pickMasked(dx, dy, dz, s.ky) / dkz;
   s.Sz = 1.0f / dkz;
-  s.ox = pick3(ox, oy, oz, s.kx);
-  s.oy = pick3(ox, oy, oz, s.ky);
-  s.oz = pick3(ox, oy, oz, s.kz);
+  s.ox = pickMasked(ox, oy, oz, s.kx);
+  s.oy = pickMasked(ox, oy, oz, s.ky);
+  s.oz = pickMasked(ox, oy, oz, s.kz);
   return s;
 }
 
@@ -58,12 +68,12 @@ __device__ __forceinline__ TriSetup makeTriSetup(float ox, float oy, float oz, f
 __device__ __forceinline__ bool intersectTriangle(const TriSetup &s, const float4 &v0, const float4 &v1,
                                                   const float4 &v2, float tmin, float tmax, float &tOut, float &uOut,
                                                   float &vOut) {
-  const float Akx = pick3(v0.x, v0.y, v0.z, s.kx) - s.ox, Aky = pick3(v0.x, v0.y, v0.z, s.ky) - s.oy,
-              Akz = pick3(v0.x, v0.y, v0.z, s.kz) - s.oz;
-  const float Bkx = pick3(v1.x, v1.y, v1.z, s.kx) - s.ox, Bky = pick3(v1.x, v1.y, v1.z, s.ky) - s.oy,
-              Bkz = pick3(v1.x, v1.y, v1.z, s.kz) - s.oz;
-  const float Ckx = pick3(v2.x, v2.y, v2.z, s.kx) - s.ox, Cky = pick3(v2.x, v2.y, v2.z, s.ky) - s.oy,
-              Ckz = pick3(v2.x, v2.y, v2.z, s.kz) - s.oz;
+  const float Akx = pickMasked(v0.x, v0.y, v0.z, s.kx) - s.ox, Aky = pickMasked(v0.x, v0.y, v0.z, s.ky) - s.oy,
+              Akz = pickMasked(v0.x, v0.y, v0.z, s.kz) - s.oz;
+  const float Bkx = pickMasked(v1.x, v1.y, v1.z, s.kx) - s.ox, Bky = pickMasked(v1.x, v1.y, v1.z, s.ky) - s.oy,
+              Bkz = pickMasked(v1.x, v1.y, v1.z, s.kz) - s.oz;
+  const float Ckx = pickMasked(v2.x, v2.y, v2.z, s.kx) - s.ox, Cky = pickMasked(v2.x, v2.y, v2.z, s.ky) - s.oy,
+              Ckz = pickMasked(v2.x, v2.y, v2.z, s.kz) - s.oz;
   const float Ax = Akx - s.Sx * Akz, Ay = Aky - s.Sy * Akz;
   const float Bx = Bkx - s.Sx * Bkz, By = Bky - s.Sy * Bkz;
   const float Cx = Ckx - s.Sx * Ckz, Cy = Cky - s.Sy * Ckz;
@@ -96,16 +106,23 @@ struct BoxSetup { // per-ray constants for the quantised child-box tests in the 
   float idx, idy, idz; // 1 / direction (zero components replaced by a tiny value of the same sign)
   float ox, oy, oz;
   uint32_t octinv;     // 7 ^ (sign bits of the direction): permutes slots into front-to-back priority
+  uint32_t one;        // bits of 1.0f held in a register the compiler cannot fold (see byteAsUnitFloat)
 };
 
+// 1 / d for the box tests only: they just have to be conservative, so the single-instruction reciprocal
+// (MUFU.RCP, <= 1 ulp) is enough — its error is covered by the widening `eps` in intersectChildren.
 __device__ __forceinline__ float safeInverse(float d) {
   const float tiny = 1.0e-20f;
   float a = fabsf(d) < tiny ? copysignf(tiny, d) : d;
-  return 1.0f / a;
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
 }
 
-__device__ __forceinline__ BoxSetup makeBoxSetup(float ox, float oy, float oz, float dx, float dy, float dz) {
+__device__ __forceinline__ BoxSetup makeBoxSetup(float ox, float oy, float oz, float dx, float dy, float dz,
+                                                 uint32_t one = 0x3F800000u) {
   BoxSetup b;
+  b.one = one;
   b.idx = safeInverse(dx);
   b.idy = safeInverse(dy);
   b.idz = safeInverse(dz);
@@ -133,7 +150,7 @@ __device__ __forceinline__ uint32_t intersectChildrenLegacy(const uint4 &n0, con
               aoz = (__uint_as_float(n0.z) - b.oz) * b.idz;
   // conservative widening: |t| <= |ao| + 255 |ai| along each axis; a few ulp of that covers the rounding of the
   // two products and the fma below, so a box is never missed because of float error
-  const float eps = 4.8e-7f;
+  const float eps = 6.0e-7f;
   const float wx = eps * (fabsf(aox) + 255.0f * fabsf(aix)), wy = eps * (fabsf(aoy) + 255.0f * fabsf(aiy)),
               wz = eps * (fabsf(aoz) + 255.0f * fabsf(aiz));
   const float nox = aox - wx, noy = aoy - wy, noz = aoz - wz; // near-plane offsets
@@ -170,9 +187,11 @@ __device__ __forceinline__ uint32_t intersectChildrenLegacy(const uint4 &n0, con
 
 // Quantised byte -> float without an integer conversion: PRMT drops the byte into mantissa bits 8..15 of 1.0f,
 // giving 1 + q * 2^-15 exactly; the 2^15 is folded into the per-axis scale and the 1 into the offset.
+// `one` must live in a register: PRMT takes a single immediate, and with a literal 1.0f the compiler spends it on
+// that and moves the selector into a register before every PRMT (43 extra instructions per node in ncu's SASS view).
 template <int k>
-__device__ __forceinline__ float byteAsUnitFloat(uint32_t word) {
-  return __uint_as_float(__byte_perm(word, 0x3F800000u, 0x7604u | (uint32_t(k) << 4)));
+__device__ __forceinline__ float byteAsUnitFloat(uint32_t word, uint32_t one) {
+  return __uint_as_float(__byte_perm(word, one, 0x7604u | (uint32_t(k) << 4)));
 }
 
 // Tests the eight children of one node; returns the hit mask: bits 24..31 internal children in traversal
@@ -189,7 +208,7 @@ __device__ __forceinline__ uint32_t intersectChildren(const uint4 &n0, const uin
   // plane distance t = (1 + q 2^-15) * ai + (ao - ai). Conservative widening: a few ulp of |ao| + |ai| covers
   // the rounding of both products, the difference and the fma, so no box is missed because of float error
   // (in units of one quantisation step this is < 0.02, far below the outward rounding of the boxes themselves).
-  const float eps = 4.8e-7f;
+  const float eps = 6.0e-7f; // 5 ulp: products, difference, fma and the approximate reciprocal of the direction
   const float wx = eps * (fabsf(aox) + fabsf(aix)), wy = eps * (fabsf(aoy) + fabsf(aiy)), wz = eps * (fabsf(aoz) + fabsf(aiz));
   const float cx = aox - aix, cy = aoy - aiy, cz = aoz - aiz;
   const float nox = cx - wx, noy = cy - wy, noz = cz - wz; // near-plane offsets
@@ -216,9 +235,9 @@ __device__ __forceinline__ uint32_t intersectChildren(const uint4 &n0, const uin
     const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u; // empty slots contribute no bits
 #define RT_CHILD(k)                                                                                                  \
   {                                                                                                                  \
-    const float tnx = fmaf(byteAsUnitFloat<k>(nearx), aix, nox), tfx = fmaf(byteAsUnitFloat<k>(farx), aix, fox);     \
-    const float tny = fmaf(byteAsUnitFloat<k>(neary), aiy, noy), tfy = fmaf(byteAsUnitFloat<k>(fary), aiy, foy);     \
-    const float tnz = fmaf(byteAsUnitFloat<k>(nearz), aiz, noz), tfz = fmaf(byteAsUnitFloat<k>(farz), aiz, foz);     \
+    const float tnx = fmaf(byteAsUnitFloat<k>(nearx, b.one), aix, nox), tfx = fmaf(byteAsUnitFloat<k>(farx, b.one), aix, fox); \
+    const float tny = fmaf(byteAsUnitFloat<k>(neary, b.one), aiy, noy), tfy = fmaf(byteAsUnitFloat<k>(fary, b.one), aiy, foy); \
+    const float tnz = fmaf(byteAsUnitFloat<k>(nearz, b.one), aiz, noz), tfz = fmaf(byteAsUnitFloat<k>(farz, b.one), aiz, foz); \
     const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                                       \
     const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                                       \
     if (tn <= tf) {                                                                                                  \
@@ -272,10 +291,12 @@ struct LaneTraversal {
     leafInstance = tlas->leafInstance;
     nodes = tlasNodes;
     tris = nullptr;
-    box = makeBoxSetup(ox, oy, oz, dx, dy, dz);
-    tri = TriSetup{};
     // an empty TLAS has nothing pending: the first step() pops an empty stack and finishes
-    ngroup = make_uint2(0u, tlas->nodeCount != 0 ? 0x80000000u : 0u);
+    const uint32_t nodeCount = tlas->nodeCount;
+    // 1.0f, but derived from a loaded value so that it stays in a register (nodeCount < 2^31 always)
+    box = makeBoxSetup(ox, oy, oz, dx, dy, dz, 0x3F800000u | (nodeCount >> 31));
+    tri = TriSetup{};
+    ngroup = make_uint2(0u, nodeCount != 0 ? 0x80000000u : 0u);
     tgroup = make_uint2(0u, 0u);
   }
 
@@ -319,7 +340,7 @@ struct LaneTraversal {
         const float ldx = (r0.x * dx + r0.y * dy) + r0.z * dz;
         const float ldy = (r1.x * dx + r1.y * dy) + r1.z * dz;
         const float ldz = (r2.x * dx + r2.y * dy) + r2.z * dz;
-        box = makeBoxSetup(lox, loy, loz, ldx, ldy, ldz);
+        box = makeBoxSetup(lox, loy, loz, ldx, ldy, ldz, box.one);
         tri = makeTriSetup(lox, loy, loz, ldx, ldy, ldz);
         nodes = reinterpret_cast<const uint4 *>(bn);
         tris = reinterpret_cast<const float4 *>(rec->tris);
@@ -357,7 +378,7 @@ struct LaneTraversal {
   __device__ __forceinline__ bool popStep(uint2 *stack) {
     if (sp == instanceSp) {
       instanceSp = -1;
-      box = makeBoxSetup(ox, oy, oz, dx, dy, dz);
+      box = makeBoxSetup(ox, oy, oz, dx, dy, dz, box.one);
       nodes = tlasNodes;
     }
     if (sp == 0) return false;
