@@ -157,6 +157,11 @@ __global__ void k_instance_bounds(const rt_instance_descriptor *desc, uint32_t n
     bool empty = blas == nullptr || blas->triCount == 0;
     r.nodes = empty ? nullptr : blas->nodes;
     r.tris = empty ? nullptr : blas->tris;
+    // a BLAS that is a single leaf-only node (a quad, a small prop): the traversal tests its <= 24 triangles
+    // directly after entering the instance instead of testing the node's child boxes first; the count travels in
+    // the low bits of the (256-byte aligned) triangle pointer
+    if (!empty && blas->nodeCount == 1 && blas->triCount <= 24)
+      r.tris = reinterpret_cast<const TriRecord *>(reinterpret_cast<uintptr_t>(blas->tris) | uintptr_t(blas->triCount));
     records[i] = r;
     if (!empty) {
       lo = make_float3(FLT_MAX, FLT_MAX, FLT_MAX);

@@ -74,7 +74,7 @@ struct BlasHeader {
 struct alignas(16) InstanceRecord {
   float4 row0, row1, row2; // object = row_r . (world, 1)
   const WideNode *nodes;
-  const TriRecord *tris;
+  const TriRecord *tris; // low 5 bits: triangle count of a single-leaf-node BLAS (tested directly), else 0
 };
 static_assert(sizeof(InstanceRecord) == 64, "instance record is 64 bytes");
 
@@ -145,6 +145,9 @@ struct rt_context {
   // wavefront state (trace_wavefront.cu)
   void *wfState = nullptr;
   size_t wfBytes = 0;
+  // per-light constants derived once per rt_trace (trace.cu k_prepare_lights)
+  float4 *lightDerivedDev = nullptr;
+  int lightDerivedCap = 0;
   rtb::KernelTimer timer;
   // records an event on the stream (only when timing is enabled); klass < 0 starts a new sequence
   void mark(int klass);

@@ -23,6 +23,7 @@ struct TraceParams {
   const rt_instance_descriptor *instances;
   const rt_instance_descriptor *prevInstances;
   const rt_light *lights;
+  const float4 *lightDerived; // per light: normalize(direction).xyz, cos(coneAngle) — hoisted out of the per-hit code
   rt_image images[RT_TEXTURE_COUNT];
   const float *srgbLut;
   int maxSubmeshes;
@@ -342,9 +343,10 @@ __device__ __forceinline__ bool shadeSegment(const TraceParams &P, PathState &s,
     const float inv = 1.0f / fmaxf(lightDistance, 1e-3f);
     L *= inv;
     lightColor = mk3(0.0f);
-    const f3 coneDirection = normalize(mk3(light->direction));
+    const float4 ld = __ldg(P.lightDerived + lightIndex);
+    const f3 coneDirection = mk3(ld.x, ld.y, ld.z);
     const float spotResult = dot(-L, coneDirection);
-    if (spotResult > cosDet(light->coneAngle)) lightColor = mk3(light->color) * inv * inv;
+    if (spotResult > ld.w) lightColor = mk3(light->color) * inv * inv;
   } else if (lightType == RT_LIGHT_POINT) {
     L = mk3(light->position) - hitPoint;
     lightDistance = length(L);
@@ -352,7 +354,8 @@ __device__ __forceinline__ bool shadeSegment(const TraceParams &P, PathState &s,
     L *= inv;
     lightColor = mk3(light->color) * inv * inv;
   } else { // sun
-    L = -normalize(mk3(light->direction));
+    const float4 ld = __ldg(P.lightDerived + lightIndex);
+    L = -mk3(ld.x, ld.y, ld.z);
     lightDistance = INFINITY;
     lightColor = mk3(light->color);
   }

@@ -99,6 +99,7 @@ int rt_destroy(rt_context *ctx) {
   cudaFree(ctx->scratch);
   cudaFree(ctx->srgbLutDev);
   cudaFree(ctx->wfState);
+  cudaFree(ctx->lightDerivedDev);
   cudaEventDestroy(ctx->evBegin);
   cudaEventDestroy(ctx->evEnd);
   for (cudaEvent_t e : ctx->timer.pool) cudaEventDestroy(e);

@@ -9,6 +9,7 @@
 // ncu (profiles/r1_megakernel_*.md) shows this layout is divergence-bound — 11.4 of 32 threads active per
 // instruction, 128 registers, instruction-cache stalls — which is why trace_wavefront.cu is the default.
 // Compile with -fmad=false (numeric contract).
+#include <algorithm>
 #include <cstring>
 
 #include "path_step.cuh"
@@ -83,6 +84,15 @@ __global__ void __launch_bounds__(256) k_trace_megakernel(const __grid_constant_
   }
 }
 
+// normalize(direction) and cos(coneAngle) of every light, evaluated once per dispatch with the same functions the
+// per-hit code used (Raytracing.metal:620-636 evaluates them per hit), so results are unchanged.
+__global__ void k_prepare_lights(const rt_light *lights, int count, float4 *derived) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const f3 d = normalize(mk3(lights[i].direction));
+  derived[i] = make_float4(d.x, d.y, d.z, cosDet(lights[i].coneAngle));
+}
+
 int fillTraceParams(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], const rt_image textures[RT_TEXTURE_COUNT],
                     int maxSubmeshes, const rt_trace_options *opt, TraceParams &P) {
   RT_CHECK(buffers != nullptr && textures != nullptr, "rt_trace: null argument table");
@@ -114,6 +124,16 @@ int fillTraceParams(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT],
   RT_CHECK(textures[RT_TEXTURE_MOTION].data && textures[RT_TEXTURE_DEPTH].data, "rt_trace: depth/motion images are not bound");
   RT_CHECK(P.uniforms.frameIndex == 0 || textures[RT_TEXTURE_ACCUMULATION].data, "rt_trace: texture 0 (history) is not bound");
   P.srgbLut = ctx->srgbLutDev;
+  if (ctx->lightDerivedCap < P.uniforms.lightCount) {
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->lightDerivedDev) cudaFree(ctx->lightDerivedDev);
+    ctx->lightDerivedDev = nullptr;
+    ctx->lightDerivedCap = 0;
+    const int cap = std::max(16, P.uniforms.lightCount);
+    RT_CUDA(cudaMalloc(&ctx->lightDerivedDev, size_t(cap) * sizeof(float4)));
+    ctx->lightDerivedCap = cap;
+  }
+  P.lightDerived = ctx->lightDerivedDev;
   P.maxSubmeshes = maxSubmeshes;
   P.tileModulo = (opt && opt->tileModulo > 1) ? opt->tileModulo : 1;
   P.tileRemainder = (opt && opt->tileModulo > 1) ? opt->tileRemainder : 0;
@@ -138,6 +158,9 @@ int launchTrace(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], con
   const int tileCount = P.tilesX * P.tilesY;
   const int owned = (tileCount - P.tileRemainder + P.tileModulo - 1) / P.tileModulo;
   if (owned <= 0) return 0;
+  k_prepare_lights<<<(P.uniforms.lightCount + 63) / 64, 64, 0, ctx->stream>>>(P.lights, P.uniforms.lightCount,
+                                                                               ctx->lightDerivedDev);
+  ++ctx->launches;
   if (ctx->traceMode == 1) return launchTraceWavefront(ctx, P);
   ctx->mark(-1);
   k_trace_megakernel<<<owned, 256, 0, ctx->stream>>>(P);

@@ -56,7 +56,7 @@ struct WfState {
   uint4 *hitB;  // instance, geometry, primitive, 0
   float4 *shO, *shD, *shC; // shadow origin + tmax, direction, contribution
   uint32_t *queue[2], *shadowQueue;
-  uint32_t *counts; // [0], [1] path queues, [2] shadow queue
+  uint32_t *counts; // [0], [1] path queues, [2] shadow queue, [3] trace cursor, [4] shadow cursor
 };
 
 __device__ __forceinline__ void slotPixel(const TraceParams &P, uint32_t slot, int &px, int &py, bool &valid) {
@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_trace(co
   traceQueue<false, kRefill>(P, W.queue[qin], count, W.counts + 3, W.rayO, W.rayD,
                              [&](uint32_t slot, const LaneTraversal<false> &t) {
                                RT_STS(W.hitA + slot, make_float4(t.hit.t, t.hit.u, t.hit.v, t.found ? 1.0f : 0.0f));
-                               RT_STS(W.hitB + slot, make_uint4(t.hit.instance, t.hit.geometry, t.hit.primitive, 0u));
+                               if (t.found)
+                                 RT_STS(W.hitB + slot, make_uint4(t.hit.instance, t.hit.geometry, t.hit.primitive, 0u));
                                if (firstSegment && P.primaryIds != nullptr) {
                                  int px, py;
                                  bool valid;
@@ -219,7 +220,10 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_trace(co
   if (P.rayCounters != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.rayCounters + 0, (unsigned long long)count);
 }
 
-__global__ void __launch_bounds__(kBlock) k_wf_shade(const __grid_constant__ TraceParams P, const WfState W, int qin,
+#ifndef RT_SHADE_MINBLOCKS
+#define RT_SHADE_MINBLOCKS 4 // 64 registers: measured faster than 128 (the kernel is bound by gather latency; more warps hide it)
+#endif
+__global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const __grid_constant__ TraceParams P, const WfState W, int qin,
                                                      int sampleIndex) {
   if (blockIdx.x == 0 && threadIdx.x == 0) W.counts[3] = 0u; // cursor of the next trace kernel
   const uint32_t count = W.counts[qin];
@@ -229,10 +233,15 @@ __global__ void __launch_bounds__(kBlock) k_wf_shade(const __grid_constant__ Tra
   for (uint32_t round = 0; round < rounds; ++round, j += gridDim.x * blockDim.x) { // whole warps stay in the loop
     bool pushPath = false, pushShadow = false, isHit = false;
     uint32_t slot = 0;
+    float4 ha = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (j < count) {
       slot = queue[j];
-      const float4 ha = RT_LDS(W.hitA + slot);
-      if (ha.w != 0.0f) {
+      ha = RT_LDS(W.hitA + slot);
+    }
+    // (compacting the hits of a CTA through shared memory before shading was measured slower: the kernel is bound
+    // by the latency of its dependent gathers, not by issue slots, and compaction removes warps that hide it)
+    if (ha.w != 0.0f) {
+      {
         isHit = true;
         const uint4 hb = RT_LDS(W.hitB + slot);
         RayHit hit;
@@ -240,8 +249,15 @@ __global__ void __launch_bounds__(kBlock) k_wf_shade(const __grid_constant__ Tra
         hit.instance = hb.x, hit.geometry = hb.y, hit.primitive = hb.z;
         const float4 o = RT_LDS(W.rayO + slot), d = RT_LDS(W.rayD + slot), th = RT_LDS(W.thr + slot), ra = RT_LDS(W.rad + slot);
         const int4 c = RT_LDS(W.ctr + slot);
-        const float4 m4 = RT_LDS(W.mot + slot);
-        const float4 mi = RT_LDS(W.misc + slot);
+        // per-pixel primary outputs are only touched by sample 0 (first segment, or until the G-buffer is written)
+        const bool primarySegment = (c.x == 0 && sampleIndex == 0);
+        const bool needPrimary = primarySegment || (sampleIndex == 0 && P.uniforms.enableDenoiseGBuffer != 0) ||
+                                 P.uniforms.debugTextureMode == RT_DEBUG_MOTION;
+        float4 m4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), mi = m4;
+        if (needPrimary) {
+          m4 = RT_LDS(W.mot + slot);
+          mi = RT_LDS(W.misc + slot);
+        }
         PathState s;
         s.origin = mk3(o.x, o.y, o.z);
         s.dir = mk3(d.x, d.y, d.z);
@@ -255,7 +271,6 @@ __global__ void __launch_bounds__(kBlock) k_wf_shade(const __grid_constant__ Tra
         prim.motion = mk2(m4.x, m4.y);
         prim.hadPrimaryHit = (flags & 1u) != 0u;
         prim.wroteGBuffer = (flags & 2u) != 0u;
-        const bool primarySegment = (s.bounce == 0 && sampleIndex == 0);
         const bool hadGBuffer = prim.wroteGBuffer;
         ShadowRequest shadow;
         pushPath = shadeSegment(P, s, hit, hIndex, sampleIndex, mk2(m4.z, m4.w), prim, shadow);

@@ -343,9 +343,18 @@ struct LaneTraversal {
         box = makeBoxSetup(lox, loy, loz, ldx, ldy, ldz, box.one);
         tri = makeTriSetup(lox, loy, loz, ldx, ldy, ldz);
         nodes = reinterpret_cast<const uint4 *>(bn);
-        tris = reinterpret_cast<const float4 *>(rec->tris);
+        const uintptr_t tagged = reinterpret_cast<uintptr_t>(rec->tris);
+#ifdef RT_NO_DIRECT_TRIS
+        const uint32_t direct = 0u;
+#else
+        const uint32_t direct = uint32_t(tagged) & 31u; // single-leaf-node BLAS: its triangle count (bvh_build.cu)
+#endif
+        tris = reinterpret_cast<const float4 *>(tagged & ~uintptr_t(31));
         instanceSp = sp;
-        ngroup = make_uint2(0u, 0x80000000u);
+        if (direct != 0u)
+          tgroup = make_uint2(0u, 0xFFFFFFFFu >> (32u - direct));
+        else
+          ngroup = make_uint2(0u, 0x80000000u);
       }
       return false;
     }

@@ -28,8 +28,13 @@ def timeit(name, w, h, spp, mb, opts, frames=4):
         ctx.timer_begin(); rnd.draw(u, count_rays="accumulate" if f else True); ts.append(ctx.timer_end())
     rays = rnd.read_ray_counters()["rays"] / frames
     img = rnd.read_image(0)
+    ctx.kernel_timing(True)
+    for f in range(frames, frames + 2):
+        u.frameIndex = f
+        rnd.draw(u)
+    kt = {k: round(v[0] / 2, 3) for k, v in ctx.kernel_times().items()}
     rnd.close(); ctx.close()
-    return min(ts[1:]), rays, img
+    return min(ts[1:]), rays, img, kt
 
 if __name__ == "__main__":
     grid = [dict(trace_mode=0)] + [dict(trace_mode=1, traversal_variant=v, blocks_per_sm=b) for v in (0, 1, 2) for b in (2, 4, 8)]
@@ -38,8 +43,8 @@ if __name__ == "__main__":
     for opts in grid:
         row = {"opts": opts, "parity": parity(opts)}
         for (name, spp, mb) in (("K3", 1, 2), ("K3", 4, 3), ("K2", 4, 2)):
-            ms, rays, img = timeit(name, 1920, 1080, spp, mb, opts)
+            ms, rays, img, kt = timeit(name, 1920, 1080, spp, mb, opts)
             key = (name, spp, mb)
             if key not in ref: ref[key] = img
-            row[f"{name}_{spp}_{mb}"] = {"ms": round(ms, 3), "mrays": round(rays / ms / 1e3), "same": bool(np.array_equal(img.view(np.uint16), ref[key].view(np.uint16)))}
+            row[f"{name}_{spp}_{mb}"] = {"ms": round(ms, 3), "mrays": round(rays / ms / 1e3), "same": bool(np.array_equal(img.view(np.uint16), ref[key].view(np.uint16))), "k": kt}
         print(json.dumps(row), flush=True)

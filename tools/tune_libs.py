@@ -7,4 +7,4 @@ for sp in specs:
     env = dict(os.environ, RT_B200_LIBNAME=f"librt_b200_{tag}.so" if tag != "default" else "librt_b200.so")
     opts = json.dumps({"trace_mode": 1, "traversal_variant": variant, "blocks_per_sm": bps})
     out = subprocess.run([sys.executable, "tools/tune.py", opts], env=env, capture_output=True, text=True)
-    print(tag, bps, out.stdout.strip()[-330:] if out.returncode == 0 else out.stderr[-500:], flush=True)
+    print(tag, bps, out.stdout.strip()[-900:] if out.returncode == 0 else out.stderr[-500:], flush=True)
