@@ -49,8 +49,10 @@ def load_traffic(workload):
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(p):
         with open(p) as f:
-            return json.load(f).get(workload)
-    return None
+            t = json.load(f).get(workload.replace("headline", ""))
+            if t:
+                return int(t["dram_bytes_per_launch"]), t["source"]
+    return None, None
 
 
 def load_peaks():
@@ -281,8 +283,10 @@ def main():
         kernels["shadow"]["achieved_gbs"] = round(shadow_rays * b_ray / (ktimes["shadow"][0] * 1e-3) / 1e9, 1)
     if "shade" in ktimes:
         kernels["shade"]["achieved_gbs"] = round(hits * B_HIT / (ktimes["shade"][0] * 1e-3) / 1e9, 1)
+    traffic, traffic_src = load_traffic(args.workload)
     roofline = {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": load_traffic(args.workload), "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_unit": "DRAM bytes per launch",
+                "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel": dominant, "launches": int(trace_launches),
                 "avg_launch_ms": round(trace_ms / max(1, trace_launches), 4),
                 "bytes_per_launch": round(dom_rays * b_ray / max(1, trace_launches)),
