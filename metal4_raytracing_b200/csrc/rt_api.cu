@@ -440,6 +440,11 @@ int rt_set_option(rt_context *ctx, const char *key, int value) {
     ctx->traversalVariant = value;
     return 0;
   }
+  if (k == "sample_batch") {
+    RT_CHECK(value >= 1 && value <= 64, "rt_set_option: sample_batch is 1..64");
+    ctx->sampleBatch = value;
+    return 0;
+  }
   if (k == "blocks_per_sm") {
     RT_CHECK(value >= 1 && value <= 32, "rt_set_option: blocks_per_sm is 1..32");
     ctx->blocksPerSm = value;

@@ -3,8 +3,10 @@
 // Same contract as trace.cu (the reference's raytracingKernel, MetalRaytracing/Raytracing.metal:220-831, behind
 // its argument table) but split by phase so that every kernel runs converged and small:
 //
-//   for each sample index s (the reference's sample loop, :269):
-//     generate      finish sample s-1 of every owned pixel, start sample s: camera ray -> path state, queue
+//   for each batch of sample indices [s0, s0 + n) (the reference's sample loop, :269; up to 16 samples of every
+//   owned pixel are in flight at once so that each launch has enough rays to amortise its tail):
+//     generate      fold the previous batch into the pixel sums in sample order, start the batch: camera rays ->
+//                   path state, queue
 //     repeat for each path segment (the reference's bounce loop, :311):
 //       trace       closest hit for every queued path                       (traverse.cuh, ~64 registers)
 //       shade       one shadeSegment() per hit: emission, light sample, BRDF, next ray; emits a shadow
@@ -43,18 +45,23 @@ constexpr int kTraceBlock = RT_TRACE_BLOCK;
 #define RT_STS(ptr, v) __stcs(ptr, v)
 #endif
 
+// Path slot = b * capacity + pixelSlot for sample b of the batch in flight: sample-major, so a warp (32 pixels of
+// one tile, same sample) touches consecutive state records.
 struct WfState {
-  uint32_t capacity; // slots = owned tiles * 256
+  uint32_t capacity; // pixel slots = owned tiles * 256
+  uint32_t batch;    // samples of a pixel in flight at once; path slots = capacity * batch
+  // per path slot
   float4 *rayO, *rayD;
   float4 *thr;  // throughput.xyz, w = halton index bits
   float4 *rad;  // radiance.xyz
   int4 *ctr;    // bounce, step, transparencyPasses, unused
-  float4 *tot;  // totalColor.xyz, w = totalSamples bits
-  float4 *mot;  // motion.xy, prevMotion.xy
-  float4 *misc; // depth, flags bits (1 = hadPrimaryHit, 2 = wroteGBuffer), seed offset bits, unused
   float4 *hitA; // t, u, v, valid
   uint4 *hitB;  // instance, geometry, primitive, 0
   float4 *shO, *shD, *shC; // shadow origin + tmax, direction, contribution
+  // per pixel slot
+  float4 *tot;  // totalColor.xyz, w = totalSamples bits
+  float4 *mot;  // motion.xy, prevMotion.xy
+  float4 *misc; // depth, flags bits (1 = hadPrimaryHit, 2 = wroteGBuffer), seed offset bits, unused
   uint32_t *queue[2], *shadowQueue;
   uint32_t *counts; // [0], [1] path queues, [2] shadow queue, [3] trace cursor, [4] shadow cursor
 };
@@ -76,27 +83,42 @@ __device__ __forceinline__ void queuePush(uint32_t *queue, uint32_t *count, bool
   if (push) queue[base + __popc(votes & ((1u << lane) - 1u))] = slot;
 }
 
-__global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ TraceParams P, const WfState W,
-                                                        int sampleIndex, int baseSamples, int maxExtraSamples) {
+// Folds the radiances of the batch [s0, s0 + n) into the pixel sum, in sample order (float addition order is part of
+// the result), exactly where the reference does `totalColor += accumulatedColor` (Raytracing.metal:776-777).
+__device__ __forceinline__ void foldBatch(const WfState &W, uint32_t pixelSlot, int s0, int n, int totalSamples, f3 &total) {
+  for (int b = 0; b < n; ++b) {
+    if (s0 + b < totalSamples) {
+      const float4 r4 = RT_LDS(W.rad + size_t(b) * W.capacity + pixelSlot);
+      total += mk3(r4.x, r4.y, r4.z);
+    }
+  }
+}
+
+// Starts the samples [s0, s0 + n) of every owned pixel after folding the previous batch [prevS0, prevS0 + prevN).
+// The first batch never extends past baseSamples, so whether one of its samples exists does not depend on the
+// motion-adaptive count, which is evaluated right after sample 0 has been folded (Raytracing.metal:779-789).
+__global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ TraceParams P, const WfState W, int s0,
+                                                        int n, int prevS0, int prevN, int baseSamples,
+                                                        int maxExtraSamples) {
   const rt_uniforms &U = P.uniforms;
   const int sampleStride = baseSamples + maxExtraSamples;
-  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < W.capacity; slot += gridDim.x * blockDim.x) {
+  for (uint32_t pixelSlot = blockIdx.x * blockDim.x + threadIdx.x; pixelSlot < W.capacity;
+       pixelSlot += gridDim.x * blockDim.x) { // whole warps stay in the loop (capacity is a multiple of 256)
     int px, py;
     bool valid;
-    slotPixel(P, slot, px, py, valid);
-    bool push = false;
+    slotPixel(P, pixelSlot, px, py, valid);
+    int totalSamples = 0;
+    uint32_t offset = 0;
     if (valid) {
       const size_t pixelIndex = size_t(py) * size_t(U.width) + size_t(px);
       f3 total;
-      int totalSamples;
-      uint32_t offset;
-      if (sampleIndex == 0) {
+      if (s0 == 0) {
         offset = reinterpret_cast<const uint32_t *>(P.images[RT_TEXTURE_RANDOM].data)[pixelIndex];
         const f4 pm = readImage(P.images[RT_TEXTURE_MOTION], px, py);
         total = mk3(0.0f);
         totalSamples = baseSamples;
-        RT_STS(W.mot + slot, make_float4(0.0f, 0.0f, pm.x, pm.y));
-        RT_STS(W.misc + slot, make_float4(1.0e8f, __uint_as_float(0u), __uint_as_float(offset), 0.0f));
+        RT_STS(W.mot + pixelSlot, make_float4(0.0f, 0.0f, pm.x, pm.y));
+        RT_STS(W.misc + pixelSlot, make_float4(1.0e8f, __uint_as_float(0u), __uint_as_float(offset), 0.0f));
         if (U.enableDenoiseGBuffer != 0) { // a pixel whose first segment misses keeps zeros (Raytracing.metal:257-260)
           const f4 z = {0.0f, 0.0f, 0.0f, 0.0f};
           writeImage(P.images[RT_TEXTURE_DIFFUSE_ALBEDO], px, py, z);
@@ -105,21 +127,23 @@ __global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ 
           writeImage(P.images[RT_TEXTURE_ROUGHNESS], px, py, z);
         }
       } else {
-        const float4 t4 = RT_LDS(W.tot + slot);
+        const float4 t4 = RT_LDS(W.tot + pixelSlot);
         total = mk3(t4.x, t4.y, t4.z);
         totalSamples = int(__float_as_uint(t4.w));
-        offset = __float_as_uint(RT_LDS(W.misc + slot).z);
-        if (sampleIndex - 1 < totalSamples) { // finish the previous sample in sample order
-          const float4 r4 = RT_LDS(W.rad + slot);
-          total += mk3(r4.x, r4.y, r4.z);
-        }
-        if (sampleIndex == 1 && maxExtraSamples > 0) {
-          const float4 m4 = RT_LDS(W.mot + slot);
+        offset = __float_as_uint(RT_LDS(W.misc + pixelSlot).z);
+        foldBatch(W, pixelSlot, prevS0, prevN, totalSamples, total);
+        if (prevS0 == 0 && maxExtraSamples > 0) {
+          const float4 m4 = RT_LDS(W.mot + pixelSlot);
           totalSamples = adaptiveSampleCount(U, baseSamples, maxExtraSamples, mk2(m4.x, m4.y), mk2(m4.z, m4.w));
         }
       }
-      RT_STS(W.tot + slot, make_float4(total.x, total.y, total.z, __uint_as_float(uint32_t(totalSamples))));
-      if (sampleIndex < totalSamples) {
+      RT_STS(W.tot + pixelSlot, make_float4(total.x, total.y, total.z, __uint_as_float(uint32_t(totalSamples))));
+    }
+    for (int b = 0; b < n; ++b) {
+      const int sampleIndex = s0 + b;
+      const uint32_t slot = uint32_t(b) * W.capacity + pixelSlot;
+      bool push = false;
+      if (valid && sampleIndex < totalSamples) {
         const int hIndex = haltonIndex(U, offset, sampleStride, sampleIndex);
         PathState s;
         startPath(U, px, py, hIndex, s);
@@ -130,8 +154,8 @@ __global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ 
         RT_STS(W.ctr + slot, make_int4(0, 0, 0, 0));
         push = U.maxBounces > 0;
       }
+      queuePush(W.queue[0], W.counts + 0, push, slot);
     }
-    queuePush(W.queue[0], W.counts + 0, push, slot);
   }
 }
 
@@ -208,7 +232,7 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_trace(co
                                RT_STS(W.hitA + slot, make_float4(t.hit.t, t.hit.u, t.hit.v, t.found ? 1.0f : 0.0f));
                                if (t.found)
                                  RT_STS(W.hitB + slot, make_uint4(t.hit.instance, t.hit.geometry, t.hit.primitive, 0u));
-                               if (firstSegment && P.primaryIds != nullptr) {
+                               if (firstSegment && P.primaryIds != nullptr && slot < W.capacity) { // sample 0
                                  int px, py;
                                  bool valid;
                                  slotPixel(P, slot, px, py, valid);
@@ -223,8 +247,8 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_trace(co
 #ifndef RT_SHADE_MINBLOCKS
 #define RT_SHADE_MINBLOCKS 4 // 64 registers: measured faster than 128 (the kernel is bound by gather latency; more warps hide it)
 #endif
-__global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const __grid_constant__ TraceParams P, const WfState W, int qin,
-                                                     int sampleIndex) {
+__global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const __grid_constant__ TraceParams P,
+                                                                         const WfState W, int qin, int s0) {
   if (blockIdx.x == 0 && threadIdx.x == 0) W.counts[3] = 0u; // cursor of the next trace kernel
   const uint32_t count = W.counts[qin];
   const uint32_t *queue = W.queue[qin];
@@ -243,6 +267,9 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
     if (ha.w != 0.0f) {
       {
         isHit = true;
+        const uint32_t b = slot / W.capacity; // sample of the batch, pixel slot
+        const uint32_t pixelSlot = slot - b * W.capacity;
+        const int sampleIndex = s0 + int(b);
         const uint4 hb = RT_LDS(W.hitB + slot);
         RayHit hit;
         hit.t = ha.x, hit.u = ha.y, hit.v = ha.z;
@@ -255,8 +282,8 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
                                  P.uniforms.debugTextureMode == RT_DEBUG_MOTION;
         float4 m4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), mi = m4;
         if (needPrimary) {
-          m4 = RT_LDS(W.mot + slot);
-          mi = RT_LDS(W.misc + slot);
+          m4 = RT_LDS(W.mot + pixelSlot);
+          mi = RT_LDS(W.misc + pixelSlot);
         }
         PathState s;
         s.origin = mk3(o.x, o.y, o.z);
@@ -281,13 +308,13 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
         RT_STS(W.ctr + slot, make_int4(s.bounce, s.step, s.transparencyPasses, 0));
         if (primarySegment || (prim.wroteGBuffer && !hadGBuffer)) {
           const uint32_t nf = (prim.hadPrimaryHit ? 1u : 0u) | (prim.wroteGBuffer ? 2u : 0u);
-          RT_STS(W.mot + slot, make_float4(prim.motion.x, prim.motion.y, m4.z, m4.w));
-          RT_STS(W.misc + slot, make_float4(prim.depth, __uint_as_float(nf), mi.z, 0.0f));
+          RT_STS(W.mot + pixelSlot, make_float4(prim.motion.x, prim.motion.y, m4.z, m4.w));
+          RT_STS(W.misc + pixelSlot, make_float4(prim.depth, __uint_as_float(nf), mi.z, 0.0f));
         }
         if (prim.wroteGBuffer && !hadGBuffer) {
           int px, py;
           bool valid;
-          slotPixel(P, slot, px, py, valid);
+          slotPixel(P, pixelSlot, px, py, valid);
           writeImage(P.images[RT_TEXTURE_DIFFUSE_ALBEDO], px, py, prim.gDiffuse);
           writeImage(P.images[RT_TEXTURE_SPECULAR_ALBEDO], px, py, prim.gSpecular);
           writeImage(P.images[RT_TEXTURE_NORMAL], px, py, prim.gNormal);
@@ -327,7 +354,7 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_shadow(c
 }
 
 __global__ void __launch_bounds__(kBlock) k_wf_resolve(const __grid_constant__ TraceParams P, const WfState W,
-                                                       int sampleLoopBound) {
+                                                       int lastS0, int lastN) {
   for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < W.capacity; slot += gridDim.x * blockDim.x) {
     int px, py;
     bool valid;
@@ -336,10 +363,7 @@ __global__ void __launch_bounds__(kBlock) k_wf_resolve(const __grid_constant__ T
     const float4 t4 = RT_LDS(W.tot + slot);
     f3 total = mk3(t4.x, t4.y, t4.z);
     const int totalSamples = int(__float_as_uint(t4.w));
-    if (sampleLoopBound - 1 < totalSamples) {
-      const float4 r4 = RT_LDS(W.rad + slot);
-      total += mk3(r4.x, r4.y, r4.z);
-    }
+    foldBatch(W, slot, lastS0, lastN, totalSamples, total);
     const float4 m4 = RT_LDS(W.mot + slot);
     const float4 mi = RT_LDS(W.misc + slot);
     PrimaryOutputs prim = emptyPrimaryOutputs();
@@ -350,12 +374,14 @@ __global__ void __launch_bounds__(kBlock) k_wf_resolve(const __grid_constant__ T
   }
 }
 
-int ensureState(rt_context *ctx, uint32_t capacity, WfState &out) {
-  const size_t need = 256 + 13 * (size_t(capacity) * 16 + 256) + 3 * (size_t(capacity) * 4 + 256);
+int ensureState(rt_context *ctx, uint32_t capacity, uint32_t batch, WfState &out) {
+  const size_t paths = size_t(capacity) * batch;
+  const size_t need = 256 + 10 * (paths * 16 + 256) + 3 * (size_t(capacity) * 16 + 256) + 3 * (paths * 4 + 256);
   if (ctx->wfState == nullptr || ctx->wfBytes < need) {
     RT_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->wfState) cudaFree(ctx->wfState);
     ctx->wfState = nullptr;
+    ctx->wfBytes = 0;
     RT_CUDA(cudaMalloc(&ctx->wfState, need));
     ctx->wfBytes = need;
   }
@@ -367,24 +393,25 @@ int ensureState(rt_context *ctx, uint32_t capacity, WfState &out) {
   };
   WfState s{};
   s.capacity = capacity;
-  const size_t v = size_t(capacity) * 16;
+  s.batch = batch;
+  const size_t v = paths * 16, pv = size_t(capacity) * 16;
   s.counts = static_cast<uint32_t *>(take(256));
   s.rayO = static_cast<float4 *>(take(v));
   s.rayD = static_cast<float4 *>(take(v));
   s.thr = static_cast<float4 *>(take(v));
   s.rad = static_cast<float4 *>(take(v));
   s.ctr = static_cast<int4 *>(take(v));
-  s.tot = static_cast<float4 *>(take(v));
-  s.mot = static_cast<float4 *>(take(v));
-  s.misc = static_cast<float4 *>(take(v));
   s.hitA = static_cast<float4 *>(take(v));
   s.hitB = static_cast<uint4 *>(take(v));
   s.shO = static_cast<float4 *>(take(v));
   s.shD = static_cast<float4 *>(take(v));
   s.shC = static_cast<float4 *>(take(v));
-  s.queue[0] = static_cast<uint32_t *>(take(size_t(capacity) * 4));
-  s.queue[1] = static_cast<uint32_t *>(take(size_t(capacity) * 4));
-  s.shadowQueue = static_cast<uint32_t *>(take(size_t(capacity) * 4));
+  s.tot = static_cast<float4 *>(take(pv));
+  s.mot = static_cast<float4 *>(take(pv));
+  s.misc = static_cast<float4 *>(take(pv));
+  s.queue[0] = static_cast<uint32_t *>(take(paths * 4));
+  s.queue[1] = static_cast<uint32_t *>(take(paths * 4));
+  s.shadowQueue = static_cast<uint32_t *>(take(paths * 4));
   RT_CHECK(size_t(p - static_cast<uint8_t *>(ctx->wfState)) <= ctx->wfBytes, "internal: wavefront state overflow");
   out = s;
   return 0;
@@ -396,8 +423,7 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
   const rt_uniforms &U = P.uniforms;
   const int tileCount = P.tilesX * P.tilesY;
   const int owned = (tileCount - P.tileRemainder + P.tileModulo - 1) / P.tileModulo;
-  WfState W;
-  RT_TRY(ensureState(ctx, uint32_t(owned) * 256u, W));
+  const uint32_t capacity = uint32_t(owned) * 256u;
   cudaStream_t st = ctx->stream;
   const int baseSamples = std::max(U.samplesPerPixel, 1);
   const int maxExtraSamples = (U.enableMotionAdaptiveSampling != 0) ? std::max(U.motionSamplingMaxExtraSamples, 0) : 0;
@@ -405,14 +431,24 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
   const int maxBounces = std::max(U.maxBounces, 0);
   // a refraction does not consume a bounce until transparencyPasses > maxBounces (Raytracing.metal:563-575)
   const int maxSegments = maxBounces * (maxBounces + 1);
+  // samples in flight per pixel: as many as the option allows while the path state stays under ~48 M paths
+  // (10.6 GB); the motion debug view reads what sample 0 wrote for its pixel, so it keeps one sample at a time
+  int batch = std::max(1, std::min(ctx->sampleBatch, sampleLoopBound));
+  batch = std::min<int>(batch, std::max<uint32_t>(1u, (48u << 20) / std::max(capacity, 1u)));
+  if (U.debugTextureMode == RT_DEBUG_MOTION) batch = 1;
+  WfState W;
+  RT_TRY(ensureState(ctx, capacity, uint32_t(batch), W));
   const int slotBlocks = (int(W.capacity) + kBlock - 1) / kBlock;
   const int persistent = std::min(slotBlocks, ctx->smCount * 8);
   // traversal kernels: exactly the resident CTA count (they pull work from a cursor), blocks_per_sm overrides
   const int traceGrid = ctx->smCount * std::max(1, ctx->blocksPerSm);
-  for (int s = 0; s < sampleLoopBound; ++s) {
+  int prevS0 = 0, prevN = 0;
+  for (int s0 = 0; s0 < sampleLoopBound;) {
+    // the first batch stays within the base samples (see k_wf_generate)
+    const int n = std::min(batch, (s0 < baseSamples ? baseSamples : sampleLoopBound) - s0);
     RT_CUDA(cudaMemsetAsync(W.counts, 0, 32, st));
     ctx->mark(-1);
-    k_wf_generate<<<persistent, kBlock, 0, st>>>(P, W, s, baseSamples, maxExtraSamples);
+    k_wf_generate<<<persistent, kBlock, 0, st>>>(P, W, s0, n, prevS0, prevN, baseSamples, maxExtraSamples);
     ctx->mark(RT_KERNEL_GENERATE);
     ++ctx->launches;
     int qin = 0;
@@ -424,7 +460,7 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
         if (remaining == 0) break;
         ctx->mark(-1);
       }
-      const int first = (s == 0 && segment == 0) ? 1 : 0;
+      const int first = (s0 == 0 && segment == 0) ? 1 : 0;
       switch (ctx->traversalVariant) {
         case 1: k_wf_trace<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
         case 2: k_wf_trace<16><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
@@ -432,7 +468,7 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
         default: k_wf_trace<0><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
       }
       ctx->mark(RT_KERNEL_TRACE);
-      k_wf_shade<<<persistent, kBlock, 0, st>>>(P, W, qin, s);
+      k_wf_shade<<<persistent, kBlock, 0, st>>>(P, W, qin, s0);
       ctx->mark(RT_KERNEL_SHADE);
       switch (ctx->traversalVariant) {
         case 1: k_wf_shadow<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
@@ -444,9 +480,12 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
       ctx->launches += 3;
       qin ^= 1;
     }
+    prevS0 = s0;
+    prevN = n;
+    s0 += n;
   }
   ctx->mark(-1);
-  k_wf_resolve<<<persistent, kBlock, 0, st>>>(P, W, sampleLoopBound);
+  k_wf_resolve<<<persistent, kBlock, 0, st>>>(P, W, prevS0, prevN);
   ctx->mark(RT_KERNEL_RESOLVE);
   ++ctx->launches;
   RT_CUDA(cudaGetLastError());
