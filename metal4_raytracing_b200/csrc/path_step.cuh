@@ -18,7 +18,7 @@ namespace rtb {
 
 struct TraceParams {
   rt_uniforms uniforms;
-  const TlasHeader *tlas;
+  TlasHeader tlas; // by value: the traversal reads its pointers from the constant bank
   const rt_resource *resources;
   const rt_instance_descriptor *instances;
   const rt_instance_descriptor *prevInstances;

@@ -110,7 +110,12 @@ int fillTraceParams(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT],
   uint64_t tlasId = uint64_t(reinterpret_cast<uintptr_t>(buffers[RT_BUFFER_ACCELERATION_STRUCTURE]));
   auto it = ctx->accels.find(tlasId);
   RT_CHECK(it != ctx->accels.end() && it->second->isTlas, "rt_trace: buffer 8 is not a TLAS id from rt_tlas_build");
-  P.tlas = static_cast<const TlasHeader *>(it->second->headerDev);
+  const AccelObject *tl = it->second;
+  P.tlas.nodes = tl->nodes;
+  P.tlas.instances = tl->instances;
+  P.tlas.leafInstance = tl->leafPrim;
+  P.tlas.instanceCount = tl->primCount;
+  P.tlas.nodeCount = tl->primCount ? tl->nodeCount : 0u;
   P.resources = static_cast<const rt_resource *>(buffers[RT_BUFFER_RESOURCES]);
   P.instances = static_cast<const rt_instance_descriptor *>(buffers[RT_BUFFER_INSTANCE_DESCRIPTORS]);
   P.prevInstances = static_cast<const rt_instance_descriptor *>(buffers[RT_BUFFER_PREVIOUS_INSTANCE_DESCRIPTORS]);

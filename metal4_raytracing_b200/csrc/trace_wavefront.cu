@@ -207,9 +207,9 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
 #pragma unroll 1
     for (int k = 0; k < kStepsPerCheck; ++k) {
 #if RT_FUSED_PRIMS > 0
-      if (active && !t.template stepFused<RT_FUSED_PRIMS>(stack)) {
+      if (active && !t.template stepFused<RT_FUSED_PRIMS>(P.tlas, stack)) {
 #else
-      if (active && !t.step(stack)) {
+      if (active && !t.step(P.tlas, stack)) {
 #endif
         finish(slot, t);
         active = false;
@@ -465,6 +465,8 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
         case 1: k_wf_trace<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
         case 2: k_wf_trace<16><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
         case 3: k_wf_trace<24><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
+        case 4: k_wf_trace<4><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
+        case 5: k_wf_trace<2><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
         default: k_wf_trace<0><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
       }
       ctx->mark(RT_KERNEL_TRACE);
@@ -474,6 +476,8 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
         case 1: k_wf_shadow<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
         case 2: k_wf_shadow<16><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
         case 3: k_wf_shadow<24><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
+        case 4: k_wf_shadow<4><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
+        case 5: k_wf_shadow<2><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
         default: k_wf_shadow<0><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
       }
       ctx->mark(RT_KERNEL_SHADOW);

@@ -261,9 +261,8 @@ __device__ __forceinline__ uint32_t intersectChildren(const uint4 &n0, const uin
 template <bool kAny>
 struct LaneTraversal {
   float ox, oy, oz, dx, dy, dz, tmin, tmax; // world-space ray
-  const uint4 *tlasNodes;
-  const InstanceRecord *instanceRecords;
-  const uint32_t *leafInstance;
+  // the TLAS arrays are not kept here: every step takes the TlasHeader that sits in the kernel's parameter space, so
+  // those uniform pointers cost constant-bank operands instead of six registers per lane
   const uint4 *nodes;
   const float4 *tris;
   BoxSetup box;
@@ -276,7 +275,7 @@ struct LaneTraversal {
   // the traversal stack lives outside (a plain local array passed to every step) so that the compiler keeps the
   // scalar members above in registers instead of placing the whole object in local memory
 
-  __device__ __forceinline__ void begin(const TlasHeader *__restrict__ tlas, float ox_, float oy_, float oz_, float dx_,
+  __device__ __forceinline__ void begin(const TlasHeader &tlas, float ox_, float oy_, float oz_, float dx_,
                                         float dy_, float dz_, float tmin_, float tmax_) {
     ox = ox_, oy = oy_, oz = oz_, dx = dx_, dy = dy_, dz = dz_, tmin = tmin_, tmax = tmax_;
     hit.t = tmax_;
@@ -286,14 +285,11 @@ struct LaneTraversal {
     sp = 0;
     instanceSp = -1;
     instance = 0;
-    tlasNodes = reinterpret_cast<const uint4 *>(tlas->nodes);
-    instanceRecords = tlas->instances;
-    leafInstance = tlas->leafInstance;
-    nodes = tlasNodes;
+    nodes = reinterpret_cast<const uint4 *>(tlas.nodes);
     tris = nullptr;
     // an empty TLAS has nothing pending: the first step() pops an empty stack and finishes
-    const uint32_t nodeCount = tlas->nodeCount;
-    // 1.0f, but derived from a loaded value so that it stays in a register (nodeCount < 2^31 always)
+    const uint32_t nodeCount = tlas.nodeCount;
+    // 1.0f, but derived from a kernel parameter so that it is not folded into an immediate (nodeCount < 2^31 always)
     box = makeBoxSetup(ox, oy, oz, dx, dy, dz, 0x3F800000u | (nodeCount >> 31));
     tri = TriSetup{};
     ngroup = make_uint2(0u, nodeCount != 0 ? 0x80000000u : 0u);
@@ -320,15 +316,15 @@ struct LaneTraversal {
   }
 
   // one primitive of tgroup. Returns true when an any-hit query is satisfied.
-  __device__ __forceinline__ bool primitiveStep(uint2 *stack) {
+  __device__ __forceinline__ bool primitiveStep(const TlasHeader &tlas, uint2 *stack) {
     const uint32_t bit = uint32_t(__ffs(int(tgroup.y))) - 1u;
     tgroup.y &= ~(1u << bit);
     if (instanceSp < 0) {
       // TLAS leaf: enter the instance. Pending world-space work goes to the stack first.
       if (tgroup.y != 0u && sp < kStackSize) stack[sp++] = tgroup;
       if (ngroup.y > 0x00FFFFFFu && sp < kStackSize) stack[sp++] = ngroup;
-      instance = __ldg(leafInstance + tgroup.x + bit);
-      const InstanceRecord *rec = instanceRecords + instance;
+      instance = __ldg(tlas.leafInstance + tgroup.x + bit);
+      const InstanceRecord *rec = tlas.instances + instance;
       const float4 r0 = __ldg(&rec->row0), r1 = __ldg(&rec->row1), r2 = __ldg(&rec->row2);
       const WideNode *bn = rec->nodes;
       tgroup.y = 0u;
@@ -384,11 +380,11 @@ struct LaneTraversal {
 
   // nothing pending in registers: leave the instance if its subtree is exhausted, then pop.
   // Returns false when the traversal is complete.
-  __device__ __forceinline__ bool popStep(uint2 *stack) {
+  __device__ __forceinline__ bool popStep(const TlasHeader &tlas, uint2 *stack) {
     if (sp == instanceSp) {
       instanceSp = -1;
       box = makeBoxSetup(ox, oy, oz, dx, dy, dz, box.one);
-      nodes = tlasNodes;
+      nodes = reinterpret_cast<const uint4 *>(tlas.nodes);
     }
     if (sp == 0) return false;
     const uint2 e = stack[--sp];
@@ -407,15 +403,15 @@ struct LaneTraversal {
   // once. Primitives of a node are still all tested before any of its children is entered (hit.t shrinks first).
   // Returns false when the traversal has finished.
   template <int kPrims>
-  __device__ __forceinline__ bool stepFused(uint2 *stack) {
+  __device__ __forceinline__ bool stepFused(const TlasHeader &tlas, uint2 *stack) {
     if (tgroup.y == 0u && ngroup.y <= 0x00FFFFFFu) {
-      if (!popStep(stack)) return false;
+      if (!popStep(tlas, stack)) return false;
     }
     if (tgroup.y == 0u && ngroup.y > 0x00FFFFFFu) nodeStep(stack);
 #pragma unroll
     for (int k = 0; k < kPrims; ++k) {
       if (tgroup.y != 0u) {
-        if (primitiveStep(stack)) {
+        if (primitiveStep(tlas, stack)) {
           found = true;
           return false;
         }
@@ -425,9 +421,9 @@ struct LaneTraversal {
   }
 
   // One unit of work. Returns false when the traversal has finished (result in `hit` / `found`).
-  __device__ __forceinline__ bool step(uint2 *stack) {
+  __device__ __forceinline__ bool step(const TlasHeader &tlas, uint2 *stack) {
     if (tgroup.y != 0u) {
-      if (primitiveStep(stack)) {
+      if (primitiveStep(tlas, stack)) {
         found = true;
         return false;
       }
@@ -437,19 +433,19 @@ struct LaneTraversal {
       nodeStep(stack);
       return true;
     }
-    return popStep(stack);
+    return popStep(tlas, stack);
   }
 };
 
 // Runs one ray to completion. Closest hit: `hit` holds the result (hit.t == tmax and false when nothing was
 // hit). kAny: true at the first accepted triangle.
 template <bool kAny>
-__device__ __forceinline__ bool traverseScene(const TlasHeader *__restrict__ tlas, float ox, float oy, float oz,
+__device__ __forceinline__ bool traverseScene(const TlasHeader &tlas, float ox, float oy, float oz,
                                               float dx, float dy, float dz, float tmin, float tmax, RayHit &hit) {
   LaneTraversal<kAny> t;
   uint2 stack[kStackSize];
   t.begin(tlas, ox, oy, oz, dx, dy, dz, tmin, tmax);
-  while (t.step(stack)) {
+  while (t.step(tlas, stack)) {
   }
   hit = t.hit;
   return t.found;
