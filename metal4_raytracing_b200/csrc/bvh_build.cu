@@ -11,6 +11,7 @@
 // Compiled with -fmad=false: the instance-matrix inverse must round exactly like the host double arithmetic the
 // oracle uses (DESIGN.md "numeric contract").
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cfloat>
@@ -299,6 +300,89 @@ __global__ void k_bvh2_bounds(const float4 *primLo, const float4 *primHi, const 
     __threadfence();
     node = t.parent[node];
   }
+}
+
+// ---- PLOC: parallel locally-ordered clustering (Meister & Bittner 2018) --------------------------------------
+// Builds the binary hierarchy bottom-up over the Morton-sorted primitives: every cluster looks `radius` places to
+// either side for the neighbour whose union with it has the smallest surface area; mutual nearest neighbours merge;
+// the survivors are compacted in order and the round repeats until one cluster is left. The tree has SAH quality
+// close to a top-down binned builder at a fraction of the cost, and replaces the Karras hierarchy for everything
+// that is not rebuilt every frame. Node ids come from a prefix sum, so the tree is deterministic.
+struct PlocClusters {
+  uint32_t *ref;  // leaf (sorted index | kLeafBit) or internal node id
+  float4 *lo, *hi;
+};
+
+__global__ void k_ploc_init(const float4 *primLo, const float4 *primHi, const uint32_t *sorted, uint32_t n,
+                            PlocClusters c) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t p = sorted[i];
+  c.ref[i] = i | kLeafBit;
+  c.lo[i] = primLo[p];
+  c.hi[i] = primHi[p];
+}
+
+__global__ void k_ploc_nearest(PlocClusters c, uint32_t count, int radius, uint32_t *nearest) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float4 lo = c.lo[i], hi = c.hi[i];
+  const int first = max(0, int(i) - radius), last = min(int(count) - 1, int(i) + radius);
+  float best = FLT_MAX;
+  uint32_t bestJ = i;
+  for (int j = first; j <= last; ++j) {
+    if (j == int(i)) continue;
+    const float4 l = c.lo[j], h = c.hi[j];
+    const float dx = fmaxf(hi.x, h.x) - fminf(lo.x, l.x), dy = fmaxf(hi.y, h.y) - fminf(lo.y, l.y),
+                dz = fmaxf(hi.z, h.z) - fminf(lo.z, l.z);
+    const float area = dx * dy + dy * dz + dz * dx;
+    if (area < best) { // ties keep the smaller index: the relation stays symmetric enough for mutual pairs to exist
+      best = area;
+      bestJ = uint32_t(j);
+    }
+  }
+  nearest[i] = bestJ;
+}
+
+// flags[i]: low word 1 when cluster i survives the round (alone or as the merged pair), high word 1 when it is the
+// lower index of a mutual pair (it creates a node)
+__global__ void k_ploc_flags(const uint32_t *nearest, uint32_t count, unsigned long long *flags) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t j = nearest[i];
+  const bool mutual = j != i && nearest[j] == i;
+  const bool merges = mutual && i < j, dies = mutual && i > j;
+  flags[i] = (dies ? 0ull : 1ull) | (merges ? (1ull << 32) : 0ull);
+}
+
+__global__ void k_ploc_merge(PlocClusters in, PlocClusters out, const uint32_t *nearest, const unsigned long long *scan,
+                             uint32_t count, uint32_t nodeBase, Bvh2 t) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t j = nearest[i];
+  const bool mutual = j != i && nearest[j] == i;
+  if (mutual && i > j) return;
+  // inclusive scan: position = (survivors up to and including i) - 1
+  const unsigned long long inc = scan[i];
+  const uint32_t pos = uint32_t(inc & 0xFFFFFFFFull) - 1u;
+  float4 lo = in.lo[i], hi = in.hi[i];
+  uint32_t ref = in.ref[i];
+  if (mutual) {
+    const uint32_t node = nodeBase + uint32_t(inc >> 32) - 1u;
+    const float4 l = in.lo[j], h = in.hi[j];
+    const uint32_t rj = in.ref[j];
+    lo = make_float4(fminf(lo.x, l.x), fminf(lo.y, l.y), fminf(lo.z, l.z), 0.0f);
+    hi = make_float4(fmaxf(hi.x, h.x), fmaxf(hi.y, h.y), fmaxf(hi.z, h.z), 0.0f);
+    t.left[node] = ref;
+    t.right[node] = rj;
+    t.lo[node] = lo;
+    t.hi[node] = hi;
+    t.count[node] = ((ref & kLeafBit) ? 1u : t.count[ref]) + ((rj & kLeafBit) ? 1u : t.count[rj]);
+    ref = node;
+  }
+  out.ref[pos] = ref;
+  out.lo[pos] = lo;
+  out.hi[pos] = hi;
 }
 
 // ---- quantisation of one wide node ---------------------------------------------------------------------------
@@ -639,7 +723,8 @@ struct Bump {
 
 size_t scratchNeed(uint32_t n, size_t cubBytes) {
   size_t per = 16 + 16 + 8 + 8 + 4 + 4 + (4 + 4 + 8 + 16 + 16 + 4 + 4) + 4 + 4 + 4;
-  return size_t(n) * per + cubBytes + 64 * 1024;
+  per += 2 * (4 + 16 + 16) + 4 + 8 + 8; // PLOC: two cluster arrays, nearest, flags, scan
+  return size_t(n) * per + 2 * cubBytes + 128 * 1024;
 }
 
 inline uint32_t gridFor(uint32_t n, uint32_t block) { return (n + block - 1) / block; }
@@ -649,7 +734,7 @@ inline uint32_t gridFor(uint32_t n, uint32_t block) { return (n + block - 1) / b
 // Builds the wide tree over `n` primitives whose boxes are already in primLo/primHi (scratch). Fills as->nodes,
 // as->nodeBox, as->levelStart, as->nodeCount and leafPrim (device array of n primitive ids in leaf order).
 static int buildWideTree(rt_context *ctx, AccelObject *as, uint32_t n, const float4 *primLo, const float4 *primHi,
-                         BoundsAtomics *bounds, Bump &bump, uint32_t *leafPrim) {
+                         BoundsAtomics *bounds, Bump &bump, uint32_t *leafPrim, int plocRadius) {
   cudaStream_t st = ctx->stream;
   const uint32_t B = 256;
   uint64_t *keysA = bump.take<uint64_t>(n), *keysB = bump.take<uint64_t>(n);
@@ -674,7 +759,38 @@ static int buildWideTree(rt_context *ctx, AccelObject *as, uint32_t n, const flo
   t.hi = bump.take<float4>(ni);
   t.count = bump.take<uint32_t>(ni);
   t.flag = bump.take<uint32_t>(ni);
-  if (n > 1) {
+  uint32_t rootRef = n > 1 ? 0u : kLeafBit;
+  if (n > 1 && plocRadius > 0) {
+    PlocClusters ca{bump.take<uint32_t>(n), bump.take<float4>(n), bump.take<float4>(n)};
+    PlocClusters cb{bump.take<uint32_t>(n), bump.take<float4>(n), bump.take<float4>(n)};
+    uint32_t *nearest = bump.take<uint32_t>(n);
+    unsigned long long *flags = bump.take<unsigned long long>(n), *scan = bump.take<unsigned long long>(n);
+    size_t scanBytes = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, scanBytes, flags, scan, int(n), st);
+    void *scanTemp = bump.take<uint8_t>(scanBytes);
+    RT_CHECK(bump.offset <= bump.capacity, "internal: build scratch overflow (PLOC)");
+    k_ploc_init<<<gridFor(n, B), B, 0, st>>>(primLo, primHi, sorted, n, ca);
+    ++ctx->launches;
+    uint32_t count = n, nodeBase = 0;
+    PlocClusters *cur = &ca, *nxt = &cb;
+    while (count > 1) {
+      k_ploc_nearest<<<gridFor(count, B), B, 0, st>>>(*cur, count, plocRadius, nearest);
+      k_ploc_flags<<<gridFor(count, B), B, 0, st>>>(nearest, count, flags);
+      RT_CUDA(cub::DeviceScan::InclusiveSum(scanTemp, scanBytes, flags, scan, int(count), st));
+      k_ploc_merge<<<gridFor(count, B), B, 0, st>>>(*cur, *nxt, nearest, scan, count, nodeBase, t);
+      ctx->launches += 5;
+      unsigned long long totals = 0;
+      RT_CUDA(cudaMemcpyAsync(&totals, scan + (count - 1), sizeof totals, cudaMemcpyDeviceToHost, st));
+      RT_CUDA(cudaStreamSynchronize(st));
+      const uint32_t survivors = uint32_t(totals & 0xFFFFFFFFull), merges = uint32_t(totals >> 32);
+      RT_CHECK(merges > 0 && survivors == count - merges, "internal: PLOC round made no progress");
+      nodeBase += merges;
+      count = survivors;
+      std::swap(cur, nxt);
+    }
+    RT_CHECK(nodeBase == n - 1, "internal: PLOC node count");
+    rootRef = n - 2; // the last node created
+  } else if (n > 1) {
     k_karras<<<gridFor(n - 1, B), B, 0, st>>>(keys, t);
     k_bvh2_bounds<<<gridFor(n, B), B, 0, st>>>(primLo, primHi, sorted, t);
     ctx->launches += 2;
@@ -685,8 +801,8 @@ static int buildWideTree(rt_context *ctx, AccelObject *as, uint32_t n, const flo
 
   CollapseCounters init{1u, 0u};
   RT_CUDA(cudaMemcpyAsync(counters, &init, sizeof init, cudaMemcpyHostToDevice, st));
-  uint32_t rootRef = n > 1 ? 0u : kLeafBit;
   RT_CUDA(cudaMemcpyAsync(queueA, &rootRef, 4, cudaMemcpyHostToDevice, st));
+  RT_CUDA(cudaStreamSynchronize(st)); // rootRef / init are stack variables
   as->levelStart.clear();
   uint32_t levelStart = 0, levelCount = 1;
   uint32_t *qin = queueA, *qout = queueB;
@@ -837,7 +953,7 @@ int buildBlas(rt_context *ctx, const rt_triangle_geometry *geoms, uint32_t geomC
   k_init_bounds<<<1, 32, 0, st>>>(bounds);
   k_triangle_bounds<<<gridFor(n, 256), 256, 0, st>>>(table, geomCount, n, primLo, primHi, bounds);
   ctx->launches += 2;
-  RT_TRYF(buildWideTree(ctx, as, n, primLo, primHi, bounds, bump, leafPrim));
+  RT_TRYF(buildWideTree(ctx, as, n, primLo, primHi, bounds, bump, leafPrim, ctx->plocRadius));
   k_emit_triangles<<<gridFor(n, 256), 256, 0, st>>>(table, geomCount, leafPrim, n, as->tris, as->triSource);
   ++ctx->launches;
   RT_CUDAF(cudaStreamSynchronize(st));
@@ -919,7 +1035,8 @@ int buildTlas(rt_context *ctx, AccelObject *as, const rt_instance_descriptor *de
   k_init_bounds<<<1, 32, 0, st>>>(bounds);
   k_instance_bounds<<<gridFor(count, 128), 128, 0, st>>>(descDev, count, as->instances, primLo, primHi, bounds);
   ctx->launches += 2;
-  RT_TRY(buildWideTree(ctx, as, count, primLo, primHi, bounds, bump, as->leafPrim));
+  // the TLAS is rebuilt every frame: PLOC only when there are enough instances for tree quality to matter
+  RT_TRY(buildWideTree(ctx, as, count, primLo, primHi, bounds, bump, as->leafPrim, count >= 64 ? ctx->plocRadius : 0));
   k_write_tlas_header<<<1, 32, 0, st>>>(static_cast<TlasHeader *>(as->headerDev), as->nodes, as->instances,
                                         as->leafPrim, count, as->nodeCount);
   ++ctx->launches;

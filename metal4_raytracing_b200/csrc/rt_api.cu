@@ -2,6 +2,7 @@
 // Thin: argument validation, handle bookkeeping, stream plumbing. No CPU fallback anywhere: every compute entry
 // point enqueues CUDA kernels or fails with an error code.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -87,6 +88,23 @@ int rt_create(int device, rt_context **out) {
   RT_CUDA(cudaMalloc(&ctx->srgbLutDev, sizeof lut));
   RT_CUDA(cudaMemcpy(ctx->srgbLutDev, lut, sizeof lut, cudaMemcpyHostToDevice));
   *out = ctx;
+  // tuning overrides for experiments: RT_B200_OPTIONS="key=value,key=value" (same keys as rt_set_option)
+  if (const char *env = std::getenv("RT_B200_OPTIONS")) {
+    std::string all(env);
+    size_t pos = 0;
+    while (pos < all.size()) {
+      size_t end = all.find(',', pos);
+      if (end == std::string::npos) end = all.size();
+      const std::string item = all.substr(pos, end - pos);
+      const size_t eq = item.find('=');
+      if (eq != std::string::npos && rt_set_option(ctx, item.substr(0, eq).c_str(), std::atoi(item.c_str() + eq + 1)) != 0) {
+        rt_destroy(ctx);
+        *out = nullptr;
+        return 2;
+      }
+      pos = end + 1;
+    }
+  }
   return 0;
 }
 
@@ -438,6 +456,11 @@ int rt_set_option(rt_context *ctx, const char *key, int value) {
   if (k == "traversal_variant") {
     RT_CHECK(value >= 0 && value <= 5, "rt_set_option: traversal_variant is 0..5 (refill at 0/8/16/24/4/2 idle lanes)");
     ctx->traversalVariant = value;
+    return 0;
+  }
+  if (k == "ploc_radius") {
+    RT_CHECK(value >= 0 && value <= 256, "rt_set_option: ploc_radius is 0 (LBVH) .. 256");
+    ctx->plocRadius = value;
     return 0;
   }
   if (k == "sample_batch") {

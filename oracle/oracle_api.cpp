@@ -86,7 +86,8 @@ extern "C" {
 
 oracle_ctx *oracle_create(const rt_scene_desc *scene, int threads) {
   oracle_ctx *c = new oracle_ctx();
-  c->threads = threads > 0 ? threads : omp_get_max_threads();
+  // all processors by default, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its children)
+  c->threads = threads > 0 ? threads : omp_get_num_procs();
   c->maxSubmeshes = int(scene->maxSubmeshes);
   c->textures.resize(scene->textureCount);
   for (uint32_t i = 0; i < scene->textureCount; ++i)

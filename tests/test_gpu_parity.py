@@ -343,6 +343,46 @@ def test_bvh_invariants(gpu_ctx):
     rnd.close()
 
 
+@pytest.mark.parametrize("options", [
+    {"ploc_radius": 0}, {"ploc_radius": 4}, {"ploc_radius": 64},           # LBVH vs PLOC hierarchies
+    {"sample_batch": 1}, {"sample_batch": 3},                              # samples in flight per pixel
+    {"traversal_variant": 0}, {"traversal_variant": 3}, {"blocks_per_sm": 2}, {"trace_mode": 0},
+])
+def test_tuning_options_never_change_results(options):
+    """Builder choice (LBVH / PLOC radius), sample batching, lane-refill threshold, grid size and kernel layout are
+    performance knobs: ids, radiance, depth and ray counts must equal the oracle's bit for bit under each of them.
+    5 spp with batch 3 exercises a ragged last batch; adaptive sampling adds per-pixel extra samples."""
+    w, h = 160, 160
+    sc, u, seed = scene.Scene.named("K5small", w, h, assets=None)  # skinned + animated: real motion vectors
+    u.samplesPerPixel, u.maxBounces = 5, 3
+    u.enableMotionAdaptiveSampling, u.motionSamplingMaxExtraSamples = 1, 2
+    u.motionSamplingLowThresholdPixels, u.motionSamplingHighThresholdPixels = 0.05, 1.0
+    ctx = device.Context(0)
+    try:
+        for k, v in options.items():
+            ctx.set_option(k, v)
+        res = check_frames(ctx, sc, u, scene.seed_image(w, h, seed), frames=3, animate=True)
+        assert res[2]["exact"] == 1.0
+        assert res[2]["rays"]["closest"] > res[0]["rays"]["closest"]  # moving pixels took extra samples
+        res[0]["renderer"].close()
+    finally:
+        ctx.close()
+
+
+def test_ploc_tree_is_not_worse_than_lbvh():
+    """SAH cost reported by rt_as_get_info: the PLOC hierarchy must not cost more than the plain LBVH one."""
+    costs = {}
+    for radius in (0, 16):
+        sc, u, seed = scene.Scene.named("K3small", 64, 64, assets=None)
+        ctx = device.Context(0)
+        ctx.set_option("ploc_radius", radius)
+        rnd = device.Renderer(ctx, sc, 64, 64, seeds=scene.seed_image(64, 64, seed))
+        costs[radius] = ctx.as_info(rnd.blas_id(0)).sahCost
+        rnd.close()
+        ctx.close()
+    assert costs[16] <= costs[0] * 1.02, costs
+
+
 def test_full_size_headline_frame(gpu_ctx):
     """BASELINE config 3 at its real size (871,200 triangles, 1920x1080), headline variant 1 spp / maxBounces 2:
     ids and radiance against the oracle, determinism, and ray-count identities."""
