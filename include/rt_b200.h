@@ -81,6 +81,19 @@ int rt_as_get_info(rt_context *ctx, uint64_t id, rt_as_info *out);
  * device pointers. Index 0 (vertexCount in the reference) is passed by value. */
 int rt_skin(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], uint32_t vertexCount);
 
+/* Environment light — an EXTENSION, off unless bound. The reference's kernel ends a path that misses with no
+ * contribution (Raytracing.metal:320-322) and never loads the vulture_hide_4k.hdr it ships; BASELINE's north_star
+ * asks for an "HDR environment lookup", so it is specified here (and in the oracle): a closest-hit ray that
+ * misses adds throughput * intensity * bilinear(texels, u, v) with the equirectangular mapping
+ *   u = atan2(d.z, d.x) / (2 pi) + 0.5,  v = acos(d.y) / pi   (row 0 = straight up, columns wrap, rows clamp),
+ * texel centres at (i + 0.5) / size, then the path ends as before. */
+typedef struct rt_environment {
+  const float *texelsDev; /* RGBA32F, width * height texels in device memory (host memory for the oracle) */
+  int32_t width, height;
+  float intensity;
+  float _pad;
+} rt_environment;
+
 /* Optional extras of rt_trace that have no counterpart in the reference's binding table. Zero-initialise. */
 typedef struct rt_trace_options {
   int32_t tileModulo;    /* multi-GPU ownership: this call renders 16x16 tiles with tile % tileModulo == */
@@ -91,6 +104,7 @@ typedef struct rt_trace_options {
   void *const *peerAccumulation; /* multi-GPU: tileModulo device pointers to every rank's destination
                                     accumulation image (same format/size); owned tiles are also stored there
                                     through NVLink peer mappings. NULL = local only */
+  const rt_environment *environment; /* HOST pointer; NULL = the reference's behaviour (a miss is black) */
 } rt_trace_options;
 
 /* rt_trace: raytracingKernel dispatch (Raytracing.metal:220-831; binding block Renderer.swift:1453-1490).

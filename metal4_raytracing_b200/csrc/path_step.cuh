@@ -33,6 +33,7 @@ struct TraceParams {
   unsigned long long *rayCounters;
   void *peerAccumulation[8];
   int peerCount;
+  rt_environment env; // texelsDev == nullptr: off (reference behaviour)
 };
 
 // Pixel owned by slot `ownedIndex * 256 + t`: CTA-sized 16x16 tiles, eight 8x4-pixel warps per tile.
@@ -413,6 +414,12 @@ __device__ __forceinline__ bool shadeSegment(const TraceParams &P, PathState &s,
   ++s.bounce;
   s.transparencyPasses = 0;
   return s.bounce < U.maxBounces;
+}
+
+// Extension (rt_b200.h rt_environment): what a path that leaves the scene picks up. Returns black when no
+// environment is bound, which is the reference's behaviour.
+__device__ __forceinline__ void shadeMiss(const TraceParams &P, PathState &s) {
+  if (P.env.texelsDev != nullptr) s.radiance += s.throughput * sampleEnvironment(P.env, s.dir);
 }
 
 // Motion-adaptive sample count, evaluated after sample 0 (Raytracing.metal:779-789).

@@ -153,6 +153,31 @@ __device__ __forceinline__ float halton(int i, int d) {
   return r;
 }
 
+// ---- environment (extension, rt_b200.h rt_environment) -----------------------------------------------------------
+// atan2 / acos are evaluated in double and rounded once, like sin / cos above, so the CPU oracle gets the same
+// floats; the bilinear blend uses the same a + (b - a) t form as the material textures.
+constexpr float kInvTwoPi = 0.15915494309189535f, kInvPi = 0.3183098861837907f;
+__device__ __forceinline__ f3 sampleEnvironment(const rt_environment &env, f3 d) {
+  const float phi = float(atan2(double(d.z), double(d.x)));
+  const float theta = float(acos(double(clampf(d.y, -1.0f, 1.0f))));
+  const float u = phi * kInvTwoPi + 0.5f, v = theta * kInvPi;
+  const float x = u * float(env.width) - 0.5f, y = v * float(env.height) - 0.5f;
+  const float fx = floorf(x), fy = floorf(y);
+  const float tx = x - fx, ty = y - fy;
+  int x0 = int(fx), y0 = int(fy);
+  int x1 = x0 + 1, y1 = y0 + 1;
+  x0 = ((x0 % env.width) + env.width) % env.width;
+  x1 = ((x1 % env.width) + env.width) % env.width;
+  y0 = min(max(y0, 0), env.height - 1);
+  y1 = min(max(y1, 0), env.height - 1);
+  const float4 *t = reinterpret_cast<const float4 *>(env.texelsDev);
+  const float4 a = __ldg(t + size_t(y0) * env.width + x0), b = __ldg(t + size_t(y0) * env.width + x1);
+  const float4 c = __ldg(t + size_t(y1) * env.width + x0), e = __ldg(t + size_t(y1) * env.width + x1);
+  const f3 top = mix(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), tx);
+  const f3 bottom = mix(mk3(c.x, c.y, c.z), mk3(e.x, e.y, e.z), tx);
+  return mix(top, bottom, ty) * env.intensity;
+}
+
 // ---- material textures: bilinear, repeat, LOD 0 (Raytracing.metal:421) ---------------------------------------
 __device__ __forceinline__ f4 fetchTexel(const rt_texture2d &t, int x, int y, const float *__restrict__ srgbLut) {
   const uchar4 p = __ldg(reinterpret_cast<const uchar4 *>(t.texels) + (size_t(y) * size_t(t.width) + size_t(x)));

@@ -50,7 +50,10 @@ __global__ void __launch_bounds__(256) k_trace_megakernel(const __grid_constant_
                                : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
         reinterpret_cast<uint4 *>(P.primaryIds)[pixelIndex] = id;
       }
-      if (!found) break;
+      if (!found) {
+        shadeMiss(P, s);
+        break;
+      }
       ++nHits;
       ShadowRequest shadow;
       alive = shadeSegment(P, s, hit, hIndex, sampleIndex, prevMotion, prim, shadow);
@@ -147,6 +150,10 @@ int fillTraceParams(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT],
   P.tilesY = (P.uniforms.height + 15) / 16;
   P.primaryIds = opt ? opt->primaryIdsDev : nullptr;
   P.rayCounters = opt ? reinterpret_cast<unsigned long long *>(opt->rayCountersDev) : nullptr;
+  if (opt && opt->environment && opt->environment->texelsDev) {
+    P.env = *opt->environment;
+    RT_CHECK(P.env.width > 0 && P.env.height > 0, "rt_trace: environment has no texels");
+  }
   P.peerCount = 0;
   if (opt && opt->peerAccumulation) {
     RT_CHECK(P.tileModulo <= 8, "rt_trace: at most 8 peers");

@@ -327,6 +327,14 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
           RT_STS(W.shC + slot, make_float4(shadow.contribution.x, shadow.contribution.y, shadow.contribution.z, 0.0f));
         }
       }
+    } else if (j < count && P.env.texelsDev != nullptr) { // extension: a miss picks up the environment
+      const float4 d = RT_LDS(W.rayD + slot), th = RT_LDS(W.thr + slot), ra = RT_LDS(W.rad + slot);
+      PathState s;
+      s.dir = mk3(d.x, d.y, d.z);
+      s.throughput = mk3(th.x, th.y, th.z);
+      s.radiance = mk3(ra.x, ra.y, ra.z);
+      shadeMiss(P, s);
+      RT_STS(W.rad + slot, make_float4(s.radiance.x, s.radiance.y, s.radiance.z, 0.0f));
     }
     queuePush(W.shadowQueue, W.counts + 2, pushShadow, slot);
     queuePush(W.queue[qin ^ 1], W.counts + (qin ^ 1), pushPath, slot);

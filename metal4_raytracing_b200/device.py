@@ -20,9 +20,16 @@ RTR_FLAG_FP32_IMAGES = 1
 RTR_FLAG_REBUILD_SKINNED = 2
 
 
+class Environment(C.Structure):
+    """rt_environment (include/rt_b200.h): RGBA32F equirectangular texels + intensity. An extension, off by default."""
+    _fields_ = [("texelsDev", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("intensity", C.c_float),
+                ("_pad", C.c_float)]
+
+
 class TraceOptions(C.Structure):
     _fields_ = [("tileModulo", C.c_int32), ("tileRemainder", C.c_int32), ("primaryIdsDev", C.c_void_p),
-                ("rayCountersDev", C.c_void_p), ("peerAccumulation", C.POINTER(C.c_void_p))]
+                ("rayCountersDev", C.c_void_p), ("peerAccumulation", C.POINTER(C.c_void_p)),
+                ("environment", C.POINTER(Environment))]
 
 
 class AsInfo(C.Structure):
@@ -301,6 +308,18 @@ class Renderer:
         desc = self.scene.desc()
         _check(lib().rtr_update(self._h, C.byref(desc)), True)
 
+    def set_environment(self, texels, intensity=1.0):
+        """Binds an (H, W, 4) float32 equirectangular environment for the following draws; None unbinds it
+        (the reference's behaviour: a miss contributes nothing)."""
+        if getattr(self, "_env_dev", None):
+            self.ctx.free(self._env_dev)
+        self._env_dev, self._env = None, None
+        if texels is not None:
+            t = np.ascontiguousarray(texels, np.float32)
+            assert t.ndim == 3 and t.shape[2] == 4
+            self._env_dev = self.ctx.upload(t)
+            self._env = Environment(self._env_dev, t.shape[1], t.shape[0], float(intensity), 0.0)
+
     def draw(self, uniforms, want_ids=False, count_rays=False, tile_modulo=1, tile_remainder=0, peers=None):
         opt = TraceOptions()
         opt.tileModulo, opt.tileRemainder = tile_modulo, tile_remainder
@@ -319,6 +338,8 @@ class Renderer:
         if peers is not None:
             arr = (C.c_void_p * len(peers))(*peers)
             opt.peerAccumulation = arr
+        if getattr(self, "_env", None) is not None:
+            opt.environment = C.pointer(self._env)
         _check(lib().rtr_draw(self._h, C.byref(uniforms), C.byref(opt)), True)
 
     def read_ids(self):

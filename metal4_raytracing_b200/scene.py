@@ -224,3 +224,24 @@ def make_light(kind, position=(0, 0, 0), color=(1, 1, 1), direction=(0, -1, 0), 
     l.right.set(*right)
     l.up.set(*up)
     return l
+
+
+def procedural_sky(width=1024, height=512, sun_dir=(0.35, 0.8, -0.45), sun_radiance=40.0):
+    """Deterministic HDR equirectangular sky (float32 RGBA, row 0 = straight up) standing in for the reference's
+    vulture_hide_4k.hdr, which is absent from the mount: horizon-to-zenith gradient, a darker ground
+    half and a soft sun disc. Same layout as rt_environment: u = atan2(z, x) / 2pi + 0.5, v = acos(y) / pi."""
+    v = (np.arange(height, dtype=np.float64) + 0.5) / height
+    u = (np.arange(width, dtype=np.float64) + 0.5) / width
+    theta, phi = np.pi * v[:, None], 2.0 * np.pi * (u[None, :] - 0.5)
+    d = np.stack([np.sin(theta) * np.cos(phi), np.cos(theta) * np.ones_like(phi), np.sin(theta) * np.sin(phi)], -1)
+    up = np.clip(d[..., 1], 0.0, 1.0)[..., None]
+    sky = (1.0 - up) * np.array([0.9, 0.95, 1.0]) + up * np.array([0.25, 0.45, 0.9])
+    ground = np.array([0.18, 0.16, 0.14]) * np.ones_like(sky)
+    img = np.where(d[..., 1:2] >= 0.0, sky, ground)
+    s = np.asarray(sun_dir, np.float64)
+    s = s / np.linalg.norm(s)
+    cosang = np.clip((d * s).sum(-1), -1.0, 1.0)
+    img = img + sun_radiance * np.exp(-((1.0 - cosang) / 0.0015))[..., None] * np.array([1.0, 0.93, 0.8])
+    out = np.ones((height, width, 4), np.float32)
+    out[..., :3] = img.astype(np.float32)
+    return out

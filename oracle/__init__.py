@@ -49,6 +49,8 @@ def lib():
     L.oracle_trace_ray.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float,
                                    C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
     L.oracle_thread_count.argtypes = [C.c_void_p]
+    L.oracle_set_environment.argtypes = [C.c_void_p, C.c_void_p]
+    L.oracle_sample_environment.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -117,6 +119,19 @@ class Oracle:
     @property
     def threads(self):
         return lib().oracle_thread_count(self._h)
+
+    def set_environment(self, texels, intensity=1.0):
+        """Environment extension (include/rt_b200.h rt_environment); texels (H, W, 4) float32 or None."""
+        from metal4_raytracing_b200.device import Environment
+        if texels is None:
+            self._env_texels = None
+            lib().oracle_set_environment(self._h, None)
+            return
+        self._env_texels = np.ascontiguousarray(texels, np.float32)  # kept alive: the oracle reads it in place
+        env = Environment(self._env_texels.ctypes.data, self._env_texels.shape[1], self._env_texels.shape[0],
+                          float(intensity), 0.0)
+        if lib().oracle_set_environment(self._h, C.byref(env)) != 0:
+            raise RuntimeError("oracle_set_environment failed")
 
     def update(self):
         self._desc = self.scene.desc()
@@ -196,3 +211,14 @@ def skin(rest_pos4, rest_nrm4, joint_idx, joint_w, matrices):
     bufs[A.BUFFER_SKINNED_NORMALS] = on.ctypes.data
     lib().oracle_skin(bufs, n)
     return op, on
+
+
+def sample_environment(texels, direction, intensity=1.0):
+    """KAT probe of the environment extension's equirectangular lookup (include/rt_b200.h rt_environment)."""
+    from metal4_raytracing_b200.device import Environment
+    t = np.ascontiguousarray(texels, np.float32)
+    env = Environment(t.ctypes.data, t.shape[1], t.shape[0], float(intensity), 0.0)
+    d = (C.c_float * 3)(*[float(x) for x in direction])
+    out = (C.c_float * 3)()
+    lib().oracle_sample_environment(C.byref(env), d, out)
+    return np.array(out[:], np.float32)

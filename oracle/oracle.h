@@ -9,6 +9,7 @@
 #ifndef ORACLE_H
 #define ORACLE_H
 #include "../include/rt_scene.h"
+#include "../include/rt_b200.h"
 #include "../include/rt_types.h"
 #ifdef __cplusplus
 extern "C" {
@@ -29,6 +30,9 @@ int oracle_update(oracle_ctx *c, const rt_scene_desc *scene);
  * 4 x u32 per pixel. stats (optional) receives {closest rays, any-hit rays, closest hits}. */
 int oracle_render(oracle_ctx *c, const rt_uniforms *uniforms, const rt_image textures[9], uint32_t *primaryIds,
                   uint64_t stats[3], int tileModulo, int tileRemainder);
+/* Environment extension (include/rt_b200.h rt_environment; texels in HOST memory here). NULL switches it off. */
+int oracle_set_environment(oracle_ctx *c, const rt_environment *env);
+void oracle_sample_environment(const rt_environment *env, const float dir[3], float out_rgb[3]); /* KAT probe */
 /* Current skinned streams of a mesh (float4 per vertex). */
 int oracle_get_mesh_streams(oracle_ctx *c, int mesh, float *positions4, float *normals4, float *prevPositions4);
 

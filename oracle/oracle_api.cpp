@@ -32,6 +32,7 @@ struct oracle_ctx {
   std::vector<rt_light> lights;
   Tlas tlas;
   int maxSubmeshes = 1;
+  rt_environment env{};
 };
 
 static void packDescriptor(const float m[16], uint64_t asId, rt_instance_descriptor &d) {
@@ -163,6 +164,7 @@ int oracle_render(oracle_ctx *c, const rt_uniforms *uniforms, const rt_image tex
   for (int i = 0; i < RT_TEXTURE_COUNT; ++i) a.textures[i] = textures[i];
   a.maxSubmeshes = c->maxSubmeshes;
   a.primaryIds = primaryIds;
+  a.env = c->env;
   if (!textures[RT_TEXTURE_RANDOM].data || !textures[RT_TEXTURE_PREVIOUS_ACCUMULATION].data) return -1;
   if (tileModulo < 1) tileModulo = 1;
   int tilesX = (uniforms->width + 15) / 16, tilesY = (uniforms->height + 15) / 16;
@@ -242,5 +244,20 @@ int oracle_trace_ray(oracle_ctx *c, const float origin[3], const float dir[3], f
 }
 
 int oracle_thread_count(oracle_ctx *c) { return c->threads; }
+
+void oracle_sample_environment(const rt_environment *env, const float dir[3], float out_rgb[3]) {
+  const float3 c = sampleEnvironment(*env, make3(dir[0], dir[1], dir[2]));
+  out_rgb[0] = c.x, out_rgb[1] = c.y, out_rgb[2] = c.z;
+}
+
+int oracle_set_environment(oracle_ctx *c, const rt_environment *env) {
+  if (!c) return -1;
+  c->env = rt_environment{};
+  if (env && env->texelsDev) {
+    if (env->width <= 0 || env->height <= 0) return -1;
+    c->env = *env;
+  }
+  return 0;
+}
 
 } // extern "C"

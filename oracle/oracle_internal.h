@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdint>
 
+#include "../include/rt_b200.h"
 #include "../include/rt_types.h"
 #include "oracle_bvh.h"
 #include "oracle_math.h"
@@ -20,6 +21,7 @@ struct KernelArgs {
   rt_image textures[RT_TEXTURE_COUNT];    // textures 0..8
   int maxSubmeshes;                       // function constant 1
   uint32_t *primaryIds;                   // optional probe: 4 x u32 per pixel (instance, geometry, primitive, t bits)
+  rt_environment env{};                   // extension (rt_b200.h): texelsDev == nullptr means off (reference behaviour)
 };
 
 struct PixelStats {
@@ -28,6 +30,7 @@ struct PixelStats {
 
 float halton(int i, int d);
 float4 sampleTexture(const rt_texture2d *t, float2 uv);
+float3 sampleEnvironment(const rt_environment &env, float3 d);
 void raytracingKernelPixel(int tidx, int tidy, const KernelArgs &a, PixelStats &stats);
 void skinningKernelVertex(uint32_t vertexID, const void *const *buffers, uint32_t vertexCount);
 

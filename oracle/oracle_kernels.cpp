@@ -251,6 +251,31 @@ static inline float4x4 instanceMatrix(const rt_instance_descriptor &d) {
 static inline float3 f3(const rt_float3 &v) { return {v.x, v.y, v.z}; }
 
 // ---- raytracingKernel, one thread (Raytracing.metal:220-831) ----------------------------------------------
+// Environment extension: equirectangular lookup with the arithmetic spelled out in include/rt_b200.h; mirrors
+// sampleEnvironment() in csrc/shade.cuh operation for operation.
+float3 sampleEnvironment(const rt_environment &env, float3 d) {
+  const float kInvTwoPi = 0.15915494309189535f, kInvPi = 0.3183098861837907f;
+  const float phi = static_cast<float>(std::atan2(static_cast<double>(d.z), static_cast<double>(d.x)));
+  const float theta = static_cast<float>(std::acos(static_cast<double>(clampf(d.y, -1.0f, 1.0f))));
+  const float u = phi * kInvTwoPi + 0.5f, v = theta * kInvPi;
+  const float x = u * float(env.width) - 0.5f, y = v * float(env.height) - 0.5f;
+  const float fx = std::floor(x), fy = std::floor(y);
+  const float tx = x - fx, ty = y - fy;
+  int x0 = int(fx), y0 = int(fy);
+  int x1 = x0 + 1, y1 = y0 + 1;
+  x0 = ((x0 % env.width) + env.width) % env.width;
+  x1 = ((x1 % env.width) + env.width) % env.width;
+  y0 = std::min(std::max(y0, 0), env.height - 1);
+  y1 = std::min(std::max(y1, 0), env.height - 1);
+  auto texel = [&](int xx, int yy) {
+    const float *t = env.texelsDev + (size_t(yy) * env.width + xx) * 4;
+    return make3(t[0], t[1], t[2]);
+  };
+  const float3 top = mix(texel(x0, y0), texel(x1, y0), tx);
+  const float3 bottom = mix(texel(x0, y1), texel(x1, y1), tx);
+  return mix(top, bottom, ty) * env.intensity;
+}
+
 void raytracingKernelPixel(int tidx, int tidy, const KernelArgs &a, PixelStats &stats) {
   const rt_uniforms &uniforms = *a.uniforms;
   if (!(tidx < uniforms.width && tidy < uniforms.height)) return;
@@ -304,7 +329,11 @@ void raytracingKernelPixel(int tidx, int tidy, const KernelArgs &a, PixelStats &
           pid[0] = pid[1] = pid[2] = pid[3] = 0xFFFFFFFFu;
         }
       }
-      if (!intersection.valid) break;
+      if (!intersection.valid) {
+        // extension (include/rt_b200.h rt_environment); the reference only breaks here (Raytracing.metal:320-322)
+        if (a.env.texelsDev) accumulatedColor = accumulatedColor + color * sampleEnvironment(a.env, rayDirection);
+        break;
+      }
       ++stats.hits;
 
       int instanceIndex = int(intersection.instance);

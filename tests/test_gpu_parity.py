@@ -343,6 +343,41 @@ def test_bvh_invariants(gpu_ctx):
     rnd.close()
 
 
+@pytest.mark.parametrize("mode", [1, 0])
+def test_environment_extension(mode):
+    """rt_environment (an extension; the reference has no environment lookup): with a sky bound, rays
+    that leave the scene pick it up on both sides identically; unbound, the frame equals the reference behaviour."""
+    w, h = 192, 128
+    sc, u, seed = scene.Scene.named("K3small", w, h, assets=None)
+    u.samplesPerPixel, u.maxBounces = 2, 3
+    seeds = scene.seed_image(w, h, seed)
+    sky = scene.procedural_sky(256, 128)
+    ctx = device.Context(0)
+    ctx.set_trace_mode(mode)
+    rnd = device.Renderer(ctx, sc, w, h, seeds=seeds)
+    orc = oracle.Oracle(sc)
+    imgs = oracle.FrameImages(w, h, seeds)
+    rnd.draw(u)
+    orc.render(u, imgs)
+    plain = rnd.read_image(0).copy()
+    assert np.array_equal(plain.view(np.uint16), imgs.output.view(np.uint16))
+    rnd.set_environment(sky, 0.75)
+    orc.set_environment(sky, 0.75)
+    rnd.reset_accumulation()
+    rnd.draw(u)
+    orc.render(u, imgs)
+    lit = rnd.read_image(0)
+    assert rel_rmse(lit, imgs.output) < RMSE_TOL
+    assert float((lit.view(np.uint16) == imgs.output.view(np.uint16)).all(-1).mean()) >= 0.999
+    assert float(lit[..., :3].astype(np.float32).sum()) > 1.5 * float(plain[..., :3].astype(np.float32).sum())
+    rnd.set_environment(None)
+    rnd.reset_accumulation()
+    rnd.draw(u)
+    assert np.array_equal(rnd.read_image(0).view(np.uint16), plain.view(np.uint16))
+    rnd.close()
+    ctx.close()
+
+
 @pytest.mark.parametrize("options", [
     {"ploc_radius": 0}, {"ploc_radius": 4}, {"ploc_radius": 64},           # LBVH vs PLOC hierarchies
     {"sample_batch": 1}, {"sample_batch": 3},                              # samples in flight per pixel

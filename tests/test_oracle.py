@@ -272,3 +272,37 @@ def test_golden_frame(assets):
     assert np.array_equal(imgs.output.view(np.uint16), g["image"].view(np.uint16))
     assert np.array_equal(imgs.arrays[A.TEXTURE_DEPTH], g["depth"])
     assert [stats["closest"], stats["any"], stats["hits"]] == list(g["stats"])
+
+
+def test_environment_extension_known_answers(assets):
+    """rt_environment (extension): a constant environment makes every escaping primary ray return intensity x value;
+    the equirect mapping puts 'straight up' in row 0 and wraps columns; unbound = black (the reference behaviour)."""
+    from metal4_raytracing_b200 import scene
+    w = h = 32
+    sc, u, seed = scene.Scene.named("K1", w, h, assets=assets)
+    u.samplesPerPixel, u.maxBounces = 1, 1
+    seeds = scene.seed_image(w, h, seed)
+    orc = oracle.Oracle(sc)
+    imgs = oracle.FrameImages(w, h, seeds, fp32=True)
+    _, ids = orc.render(u, imgs, want_ids=True)
+    miss = ids[..., 0] == 0xFFFFFFFF
+    assert miss.any() and not miss.all()
+    assert float(np.abs(imgs.output[miss][:, :3]).max()) == 0.0
+    const = np.full((8, 16, 4), 0.5, np.float32)
+    orc.set_environment(const, 3.0)
+    orc.render(u, imgs)
+    assert np.allclose(imgs.output[miss][:, :3], 1.5, rtol=0, atol=1e-6)
+    # mapping: u = atan2(z, x) / 2pi + 0.5, v = acos(y) / pi; texel centres at (i + 0.5) / size; columns wrap
+    grid = np.zeros((4, 8, 4), np.float32)
+    grid[..., 0] = np.arange(8, dtype=np.float32)[None, :]  # red = column
+    grid[..., 1] = np.arange(4, dtype=np.float32)[:, None]  # green = row
+    probe = lambda d: oracle.sample_environment(grid, d)
+    assert probe((0, 1, 0))[1] == 0.0 and probe((0, -1, 0))[1] == 3.0          # up = row 0, down = last row
+    assert abs(probe((1, 0, 0))[0] - 3.5) < 1e-5 and abs(probe((1, 0, 0))[1] - 1.5) < 1e-5   # +x: u = v = 0.5
+    assert abs(probe((0, 0, 1))[0] - 5.5) < 1e-5                                # +z: u = 0.75
+    assert abs(probe((0, 0, -1))[0] - 1.5) < 1e-5                               # -z: u = 0.25
+    assert abs(probe((-1, 0, 0))[0] - 3.5) < 1e-5                               # -x: u = 1 -> blend of columns 7 and 0
+    assert np.allclose(oracle.sample_environment(grid, (0, 0, 1), 2.0), 2.0 * probe((0, 0, 1)))
+    orc.set_environment(None)
+    orc.render(u, imgs)
+    assert float(np.abs(imgs.output[miss][:, :3]).max()) == 0.0
