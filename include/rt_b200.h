@@ -94,6 +94,17 @@ typedef struct rt_environment {
   float _pad;
 } rt_environment;
 
+/* rt_joint_palette: the joint-palette computation the reference does on the host every animated frame, as one
+ * kernel: local[j] = T * R * S with the rotation quaternion renormalised (Model.update,
+ * Model.swift:207-261, matrix4x4_trs :497-506); global[j] = global[parent[j]] * local[j], parents precede children
+ * (Skeleton hierarchy, Model.swift:379-387); palette[j] = global[j] * inverseBind[j] (SkinningPass.swift:123-157).
+ * localTRS: jointCount x 10 floats {translation xyz, quaternion xyzw (any length), scale xyz}; parents: int32, a
+ * negative or forward index = root; inverseBind / paletteOut: jointCount x float4x4 column-major. All device
+ * pointers; jointCount <= 1024. The products are evaluated in the reference's order, so the palette equals the
+ * host-computed one bit for bit. */
+int rt_joint_palette(rt_context *ctx, const float *localTRSDev, const int32_t *parentsDev, const float *inverseBindDev,
+                     uint32_t jointCount, float *paletteOutDev);
+
 /* Optional extras of rt_trace that have no counterpart in the reference's binding table. Zero-initialise. */
 typedef struct rt_trace_options {
   int32_t tileModulo;    /* multi-GPU ownership: this call renders 16x16 tiles with tile % tileModulo == */
@@ -120,6 +131,15 @@ int rt_trace(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], const 
 int rt_texture_create(rt_context *ctx, const uint8_t *rgba8Host, int width, int height, int srgb,
                       const rt_texture2d **outRecordDev);
 int rt_texture_destroy(rt_context *ctx, const rt_texture2d *recordDev);
+
+/* ---- display transform ---------------------------------------------------------------------
+ * rt_tonemap: the reference's presentation shader, color / (1 + color) (Shaders.metal:38-52), from an rgba16f /
+ * rgba32f image into width*height RGBA8 pixels in device memory. RT_TONEMAP_SRGB applies the sRGB transfer an
+ * *_srgb drawable applies on store; RT_TONEMAP_FLIP_Y writes row 0 = top of the picture (the kernel's row 0 is the
+ * bottom of the view and the reference's quad un-flips it on screen, Shaders.metal:30-35). */
+#define RT_TONEMAP_SRGB 1u
+#define RT_TONEMAP_FLIP_Y 2u
+int rt_tonemap(rt_context *ctx, const rt_image *srcDev, uint8_t *dstRGBA8Dev, uint32_t flags);
 
 /* ---- multi-GPU frame exchange (no counterpart in the single-device reference) ---------------
  * Rank g of N owns 16x16 tiles with tile % N == g. Two ways to assemble the frame:

@@ -25,6 +25,8 @@ const char *rtr_last_error(void);
 
 #define RTR_FLAG_FP32_IMAGES 1u /* accumulation / motion / G-buffer in fp32 instead of the reference's fp16 formats */
 #define RTR_FLAG_REBUILD_SKINNED 2u /* full BLAS rebuild instead of refit after skinning */
+#define RTR_FLAG_GPU_SKELETON 4u    /* joint palettes evaluated on the device from local TRS (rt_joint_palette) instead of
+                                       uploaded from the host scene (SkinningPass.swift:123-157 runs them on the CPU) */
 
 int rtr_create(rt_context *ctx, const rt_scene_desc *scene, int width, int height, uint32_t flags,
                rtr_renderer **out);

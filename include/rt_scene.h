@@ -54,6 +54,10 @@ typedef struct rt_scene_mesh {
   uint32_t _pad;
   const float *jointMatrices;   /* jointCount x float4x4 column-major: current palette (A22) */
   const rt_scene_submesh *submeshes;
+  /* skeleton inputs of that palette, for evaluating it on the device (rt_joint_palette); NULL for a static mesh */
+  const int32_t *jointParents;     /* jointCount; -1 = root; parents precede children */
+  const float *jointInverseBind;   /* jointCount x float4x4 column-major */
+  const float *jointLocalTRS;      /* jointCount x 10: translation xyz, quaternion xyzw, scale xyz (this frame) */
 } rt_scene_mesh;
 
 typedef struct rt_scene_texture {
@@ -137,6 +141,8 @@ rts_scene *rts_scene_create_named(const char *name, const char *assetDir, int wi
 /* Pointers stay valid until the scene is mutated or destroyed. */
 int rts_scene_get_desc(rts_scene *s, rt_scene_desc *out);
 /* seed[y*W+x] = hash32(y*W+x, seed) & 0xFFFFF — range of Renderer.swift:719-726 (arc4random % 2^20). */
+/* Image writer for the post chain: 8-bit RGBA PNG, rows top to bottom. */
+int rts_write_png(const char *path, const uint8_t *rgba8, int width, int height);
 void rts_fill_seed_image(uint32_t *dst, int width, int height, uint32_t seed);
 /* Fills the uniform defaults of Renderer.swift:117-192 for a width x height target (frameIndex 0). */
 void rts_default_uniforms(int width, int height, rt_uniforms *u);

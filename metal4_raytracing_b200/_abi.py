@@ -166,7 +166,9 @@ class SceneMesh(C.Structure):
                 ("positions", C.POINTER(C.c_float)), ("normals", C.POINTER(C.c_float)),
                 ("uvs", C.POINTER(C.c_float)), ("jointIndices", C.POINTER(C.c_uint16)),
                 ("jointWeights", C.POINTER(C.c_float)), ("jointCount", C.c_uint32), ("_pad", C.c_uint32),
-                ("jointMatrices", C.POINTER(C.c_float)), ("submeshes", C.POINTER(SceneSubmesh))]
+                ("jointMatrices", C.POINTER(C.c_float)), ("submeshes", C.POINTER(SceneSubmesh)),
+                ("jointParents", C.POINTER(C.c_int32)), ("jointInverseBind", C.POINTER(C.c_float)),
+                ("jointLocalTRS", C.POINTER(C.c_float))]
 
 
 class SceneTexture(C.Structure):

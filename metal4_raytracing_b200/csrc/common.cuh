@@ -162,6 +162,9 @@ int refitBlas(rt_context *ctx, AccelObject *as, const rt_triangle_geometry *geom
 int buildTlas(rt_context *ctx, AccelObject *as, const rt_instance_descriptor *descDev, uint32_t count);
 void destroyAccel(AccelObject *as);
 int launchSkin(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], uint32_t vertexCount);
+int launchJointPalette(rt_context *ctx, const float *trs, const int32_t *parents, const float *inverseBind,
+                       uint32_t jointCount, float *palette);
+int launchTonemap(rt_context *ctx, const rt_image *src, uint8_t *dst, uint32_t flags);
 int packTiles(rt_context *ctx, const rt_image *image, void *slab, int modulo, int remainder);
 int unpackTiles(rt_context *ctx, const void *slabs, const rt_image *image, int modulo);
 int selftestChildBoxes(rt_context *ctx, AccelObject *as, uint32_t raysPerNode, uint32_t seed, unsigned long long outHost[11]);

@@ -20,6 +20,8 @@ struct DeviceMesh {
   void *positions = nullptr, *prevPositions = nullptr, *normals = nullptr; // live streams the kernel reads
   void *uvs = nullptr;
   void *jointIndices = nullptr, *jointWeights = nullptr, *jointMatrices = nullptr;
+  void *jointParents = nullptr, *jointInverseBind = nullptr, *jointLocalTRS = nullptr; // RTR_FLAG_GPU_SKELETON
+  bool inverseBindUploaded = false;
   std::vector<void *> indices;
   std::vector<uint32_t> triangleCounts;
   void *materials = nullptr; // rt_material per submesh
@@ -149,6 +151,11 @@ int rtr_create(rt_context *ctx, const rt_scene_desc *scene, int width, int heigh
       RTR_TRY(uploadNew(ctx, sm.jointIndices, size_t(sm.vertexCount) * 8, &dm.jointIndices));
       RTR_TRY(uploadNew(ctx, sm.jointWeights, size_t(sm.vertexCount) * 16, &dm.jointWeights));
       RTR_TRY(uploadNew(ctx, sm.jointMatrices, size_t(sm.jointCount) * 64, &dm.jointMatrices));
+      if ((flags & RTR_FLAG_GPU_SKELETON) && sm.jointParents && sm.jointCount <= 1024) {
+        RTR_TRY(uploadNew(ctx, sm.jointParents, size_t(sm.jointCount) * 4, &dm.jointParents));
+        RTR_TRY(rt_malloc(ctx, size_t(sm.jointCount) * 64, &dm.jointInverseBind));
+        RTR_TRY(rt_malloc(ctx, size_t(sm.jointCount) * 40, &dm.jointLocalTRS));
+      }
       RTR_TRY(rt_malloc(ctx, vb, &dm.positions));
       RTR_TRY(rt_malloc(ctx, vb, &dm.prevPositions));
       RTR_TRY(rt_malloc(ctx, vb, &dm.normals));
@@ -262,6 +269,9 @@ int rtr_destroy(rtr_renderer *r) {
       rt_free(ctx, dm.jointIndices);
       rt_free(ctx, dm.jointWeights);
       rt_free(ctx, dm.jointMatrices);
+      rt_free(ctx, dm.jointParents);
+      rt_free(ctx, dm.jointInverseBind);
+      rt_free(ctx, dm.jointLocalTRS);
     }
     for (void *p : dm.indices) rt_free(ctx, p);
     rt_free(ctx, dm.materials);
@@ -312,8 +322,24 @@ int rtr_update(rtr_renderer *r, const rt_scene_desc *scene) {
     size_t vb = size_t(dm.vertexCount) * 16;
     RTR_TRY(rt_copy(ctx, dm.prevPositions, dm.positions, vb));
     RTR_TRY(rt_sync(ctx)); // one shared palette staging buffer
-    std::memcpy(r->stagePalette, sm.jointMatrices, size_t(dm.jointCount) * 64);
-    RTR_TRY(rt_upload(ctx, dm.jointMatrices, r->stagePalette, size_t(dm.jointCount) * 64));
+    if (dm.jointLocalTRS && sm.jointLocalTRS && sm.jointInverseBind) {
+      // palette on the device: 40 B per joint of local TRS go up instead of a 64 B matrix, hierarchy + inverse bind
+      // products run in rt_joint_palette (bit-identical to the host palette)
+      if (!dm.inverseBindUploaded) {
+        std::memcpy(r->stagePalette, sm.jointInverseBind, size_t(dm.jointCount) * 64);
+        RTR_TRY(rt_upload(ctx, dm.jointInverseBind, r->stagePalette, size_t(dm.jointCount) * 64));
+        RTR_TRY(rt_sync(ctx));
+        dm.inverseBindUploaded = true;
+      }
+      std::memcpy(r->stagePalette, sm.jointLocalTRS, size_t(dm.jointCount) * 40);
+      RTR_TRY(rt_upload(ctx, dm.jointLocalTRS, r->stagePalette, size_t(dm.jointCount) * 40));
+      RTR_TRY(rt_joint_palette(ctx, static_cast<const float *>(dm.jointLocalTRS), static_cast<const int32_t *>(dm.jointParents),
+                               static_cast<const float *>(dm.jointInverseBind), dm.jointCount,
+                               static_cast<float *>(dm.jointMatrices)));
+    } else {
+      std::memcpy(r->stagePalette, sm.jointMatrices, size_t(dm.jointCount) * 64);
+      RTR_TRY(rt_upload(ctx, dm.jointMatrices, r->stagePalette, size_t(dm.jointCount) * 64));
+    }
     RTR_TRY(skinMesh(r, dm));
     if (r->flags & RTR_FLAG_REBUILD_SKINNED) {
       uint64_t fresh = 0;

@@ -57,13 +57,22 @@ void Scene::animate(double t) {
     size_t J = sk.parent.size();
     double ct = sk.duration > 0 ? std::fmod(t, sk.duration) : 0.0;
     std::vector<rth::M4> local(sk.rest), global(J);
+    m.jointLocalTRS.resize(J * 10);
+    m.jointInverseBind.resize(J * 16);
     for (size_t j = 0; j < J; ++j) {
       float ang = sk.amplitude[j] * std::sin(float(2.0 * 3.14159265358979323846 * sk.freq[j] * ct) + sk.phase[j]) -
                   sk.amplitude[j] * std::sin(sk.phase[j]); // zero at t = 0 so frame 0 is the bind pose
       rth::V3 ax = rth::normalize(sk.axis[j]);
       float sh = std::sin(ang * 0.5f), ch = std::cos(ang * 0.5f);
       float qx = ax.x * sh, qy = ax.y * sh, qz = ax.z * sh, qw = ch;
-      float ql = std::sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
+      { // the same inputs, as handed to the device-side palette evaluation (rt_joint_palette)
+        float *t = &m.jointLocalTRS[j * 10];
+        t[0] = sk.restOffset[j].x, t[1] = sk.restOffset[j].y, t[2] = sk.restOffset[j].z;
+        t[3] = qx, t[4] = qy, t[5] = qz, t[6] = qw;
+        t[7] = t[8] = t[9] = 1.0f;
+        std::copy(sk.inverseBind[j].m, sk.inverseBind[j].m + 16, &m.jointInverseBind[j * 16]);
+      }
+      float ql = std::sqrt(((qw * qw + qx * qx) + qy * qy) + qz * qz);
       if (ql > 0.0001f) {
         qx /= ql;
         qy /= ql;
@@ -115,6 +124,9 @@ void Scene::flatten(rt_scene_desc *out) {
     fm.jointWeights = m.skinned() ? m.jointWeights.data() : nullptr;
     fm.jointCount = m.skinned() ? uint32_t(m.skeleton.parent.size()) : 0;
     fm.jointMatrices = m.skinned() ? m.jointMatrices.data() : nullptr;
+    fm.jointParents = m.skinned() ? m.skeleton.parent.data() : nullptr;
+    fm.jointInverseBind = m.skinned() && !m.jointInverseBind.empty() ? m.jointInverseBind.data() : nullptr;
+    fm.jointLocalTRS = m.skinned() && !m.jointLocalTRS.empty() ? m.jointLocalTRS.data() : nullptr;
     fm.submeshes = flatSubmeshes[i].data();
   }
   flatTextures.resize(textures.size());

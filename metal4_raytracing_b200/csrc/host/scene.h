@@ -46,6 +46,8 @@ struct Mesh {
   std::vector<Submesh> submeshes;
   Skeleton skeleton;                   // used when jointIndices is non-empty
   std::vector<float> jointMatrices;    // current palette, 16 floats per joint
+  std::vector<float> jointLocalTRS;    // this frame's local transforms: 10 floats per joint (T, quaternion, S)
+  std::vector<float> jointInverseBind; // 16 floats per joint (flat copy of skeleton.inverseBind)
   bool skinned() const { return !jointIndices.empty(); }
 };
 

@@ -329,6 +329,15 @@ int rt_skin(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], uint32_
   return rc;
 }
 
+int rt_joint_palette(rt_context *ctx, const float *localTRSDev, const int32_t *parentsDev, const float *inverseBindDev,
+                     uint32_t jointCount, float *paletteOutDev) {
+  RT_CTX(ctx);
+  ctx->mark(-1);
+  const int rc = launchJointPalette(ctx, localTRSDev, parentsDev, inverseBindDev, jointCount, paletteOutDev);
+  ctx->mark(RT_KERNEL_SKIN);
+  return rc;
+}
+
 int rt_trace(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], const rt_image textures[RT_TEXTURE_COUNT],
              int resourcesStride, int maxSubmeshes, const rt_trace_options *options) {
   RT_CTX(ctx);
@@ -363,6 +372,14 @@ int rt_texture_destroy(rt_context *ctx, const rt_texture2d *recordDev) {
     RT_CUDA(cudaFree(const_cast<rt_texture2d *>(recordDev)));
   }
   return 0;
+}
+
+int rt_tonemap(rt_context *ctx, const rt_image *srcDev, uint8_t *dstRGBA8Dev, uint32_t flags) {
+  RT_CTX(ctx);
+  ctx->mark(-1);
+  const int rc = launchTonemap(ctx, srcDev, dstRGBA8Dev, flags);
+  ctx->mark(RT_KERNEL_OTHER);
+  return rc;
 }
 
 int rt_pack_tiles(rt_context *ctx, const rt_image *imageDev, void *slabDev, int tileModulo, int tileRemainder) {

@@ -103,6 +103,96 @@ int launchSkinImpl(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], 
   return 0;
 }
 
+// ---- joint palette on the device (rt_joint_palette) -------------------------------------------------------------
+struct M4 {
+  float m[16]; // column-major, m[col * 4 + row]
+};
+// r = a * b with the accumulation order of the host helper (csrc/host/hostmath.h mul): s = 0; s += a(k,row) * b(c,k)
+__device__ __forceinline__ void mul44(const M4 &a, const M4 &b, M4 &r) {
+  for (int c = 0; c < 4; ++c)
+    for (int row = 0; row < 4; ++row) {
+      float s = 0.0f;
+      for (int k = 0; k < 4; ++k) s = s + a.m[k * 4 + row] * b.m[c * 4 + k];
+      r.m[c * 4 + row] = s;
+    }
+}
+
+// One CTA, one thread per joint. The hierarchy is resolved level by level (a joint's level = number of ancestors),
+// which applies exactly the products the reference's sequential parents-first loop applies.
+__global__ void __launch_bounds__(1024) k_joint_palette(const float *__restrict__ trs, const int32_t *__restrict__ parents,
+                                                        const float *__restrict__ inverseBind, uint32_t jointCount,
+                                                        float *__restrict__ palette) {
+  extern __shared__ float s_global[]; // jointCount x 16
+  __shared__ int s_maxLevel;
+  const uint32_t j = threadIdx.x;
+  if (j == 0) s_maxLevel = 0;
+  __syncthreads();
+  M4 local{};
+  int parent = -1, level = 0;
+  if (j < jointCount) {
+    const float *t = trs + size_t(j) * 10;
+    float qx = t[3], qy = t[4], qz = t[5], qw = t[6];
+    const float ql = sqrtf(((qw * qw + qx * qx) + qy * qy) + qz * qz);
+    if (ql > 0.0001f) {
+      qx = qx / ql, qy = qy / ql, qz = qz / ql, qw = qw / ql;
+    } else {
+      qx = qy = qz = 0.0f, qw = 1.0f;
+    }
+    M4 T{}, R{}, S{}, TR;
+    T.m[0] = T.m[5] = T.m[10] = T.m[15] = 1.0f;
+    T.m[12] = t[0], T.m[13] = t[1], T.m[14] = t[2];
+    const float xx = qx * qx, yy = qy * qy, zz = qz * qz, xy = qx * qy, xz = qx * qz, yz = qy * qz;
+    const float wx = qw * qx, wy = qw * qy, wz = qw * qz;
+    R.m[15] = 1.0f;
+    R.m[0] = 1 - 2 * (yy + zz), R.m[1] = 2 * (xy + wz), R.m[2] = 2 * (xz - wy);
+    R.m[4] = 2 * (xy - wz), R.m[5] = 1 - 2 * (xx + zz), R.m[6] = 2 * (yz + wx);
+    R.m[8] = 2 * (xz + wy), R.m[9] = 2 * (yz - wx), R.m[10] = 1 - 2 * (xx + yy);
+    S.m[0] = t[7], S.m[5] = t[8], S.m[10] = t[9], S.m[15] = 1.0f;
+    mul44(T, R, TR);
+    mul44(TR, S, local);
+    parent = parents[j];
+    if (parent < 0 || uint32_t(parent) >= j) parent = -1; // the reference composes only with an earlier joint
+    for (int p = parent; p >= 0;) {
+      ++level;
+      const int pp = parents[p];
+      p = (pp >= 0 && pp < p) ? pp : -1;
+    }
+    atomicMax(&s_maxLevel, level);
+    for (int i = 0; i < 16; ++i) s_global[j * 16 + i] = local.m[i];
+  }
+  __syncthreads();
+  const int maxLevel = s_maxLevel;
+  for (int l = 1; l <= maxLevel; ++l) {
+    if (j < jointCount && level == l) {
+      M4 pg, g;
+      for (int i = 0; i < 16; ++i) pg.m[i] = s_global[size_t(parent) * 16 + i];
+      mul44(pg, local, g);
+      for (int i = 0; i < 16; ++i) s_global[j * 16 + i] = g.m[i];
+    }
+    __syncthreads();
+  }
+  if (j < jointCount) {
+    M4 g, ib, skin;
+    for (int i = 0; i < 16; ++i) g.m[i] = s_global[j * 16 + i], ib.m[i] = inverseBind[size_t(j) * 16 + i];
+    mul44(g, ib, skin);
+    for (int i = 0; i < 16; ++i) palette[size_t(j) * 16 + i] = skin.m[i];
+  }
+}
+
+int launchJointPalette(rt_context *ctx, const float *trs, const int32_t *parents, const float *inverseBind,
+                       uint32_t jointCount, float *palette) {
+  RT_CHECK(trs && parents && inverseBind && palette, "rt_joint_palette: null pointer");
+  RT_CHECK(jointCount >= 1 && jointCount <= 1024, "rt_joint_palette: jointCount must be 1..1024");
+  const uint32_t threads = (jointCount + 31u) & ~31u;
+  const size_t smem = size_t(jointCount) * 64;
+  if (smem > 48 * 1024)
+    RT_CUDA(cudaFuncSetAttribute(k_joint_palette, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  k_joint_palette<<<1, threads, smem, ctx->stream>>>(trs, parents, inverseBind, jointCount, palette);
+  ++ctx->launches;
+  RT_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launchSkin(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], uint32_t vertexCount) {
   return launchSkinImpl(ctx, buffers, vertexCount, 0);
 }

@@ -18,6 +18,7 @@ _lib = None
 
 RTR_FLAG_FP32_IMAGES = 1
 RTR_FLAG_REBUILD_SKINNED = 2
+RTR_FLAG_GPU_SKELETON = 4
 
 
 class Environment(C.Structure):
@@ -44,7 +45,8 @@ EXPORTS = [
     "rt_malloc", "rt_free", "rt_malloc_host", "rt_free_host", "rt_upload", "rt_download", "rt_copy", "rt_memset",
     "rt_blas_build", "rt_blas_refit", "rt_blas_destroy", "rt_tlas_build", "rt_tlas_update", "rt_tlas_destroy",
     "rt_as_get_info", "rt_skin", "rt_trace", "rt_texture_create", "rt_texture_destroy", "rt_launch_count",
-    "rt_set_trace_mode", "rt_set_option", "rt_kernel_timing_enable", "rt_kernel_timing_read",
+    "rt_set_trace_mode", "rt_set_option", "rt_kernel_timing_enable", "rt_kernel_timing_read", "rt_joint_palette",
+    "rt_tonemap",
     "rtr_last_error", "rtr_create", "rtr_destroy", "rtr_set_seeds", "rtr_update", "rtr_draw", "rtr_read_image",
     "rtr_image_info", "rtr_reset_accumulation", "rtr_read_mesh_streams", "rtr_get_blas_id", "rtr_get_tlas_id",
     "rtr_mesh_count",
@@ -91,6 +93,8 @@ def lib():
     L.rt_launch_count.argtypes = [vp]
     L.rt_set_trace_mode.argtypes = [vp, i32]
     L.rt_set_option.argtypes = [vp, C.c_char_p, i32]
+    L.rt_joint_palette.argtypes = [vp, vp, vp, vp, u32, vp]
+    L.rt_tonemap.argtypes = [vp, C.POINTER(A.Image), vp, u32]
     L.rt_kernel_timing_enable.argtypes = [vp, i32]
     L.rt_kernel_timing_read.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u32)]
     L.rtr_create.argtypes = [vp, C.POINTER(A.SceneDesc), i32, i32, u32, C.POINTER(vp)]
@@ -200,6 +204,29 @@ class Context:
     def launches(self):
         return lib().rt_launch_count(self._h)
 
+    def tonemap(self, image, srgb=True, flip_y=True):
+        """rt_tonemap of a device image record (A.Image): returns (H, W, 4) uint8, Reinhard [+ sRGB] [+ row flip]."""
+        n = image.width * image.height * 4
+        dst = self.malloc(n)
+        _check(lib().rt_tonemap(self._h, C.byref(image), dst, (1 if srgb else 0) | (2 if flip_y else 0)))
+        out = self.download(dst, (image.height, image.width, 4), np.uint8)
+        self.free(dst)
+        return out
+
+    def joint_palette(self, local_trs, parents, inverse_bind):
+        """rt_joint_palette on numpy inputs; returns the (J, 16) palette."""
+        trs = np.ascontiguousarray(local_trs, np.float32).reshape(-1, 10)
+        par = np.ascontiguousarray(parents, np.int32)
+        ib = np.ascontiguousarray(inverse_bind, np.float32).reshape(-1, 16)
+        n = trs.shape[0]
+        d_trs, d_par, d_ib = self.upload(trs), self.upload(par), self.upload(ib)
+        d_out = self.malloc(n * 64)
+        _check(lib().rt_joint_palette(self._h, d_trs, d_par, d_ib, n, d_out))
+        out = self.download(d_out, (n, 16), np.float32)
+        for p in (d_trs, d_par, d_ib, d_out):
+            self.free(p)
+        return out
+
     KERNEL_CLASSES = ("generate", "trace", "shade", "shadow", "resolve", "skin", "refit", "build", "megakernel", "other")
 
     def kernel_timing(self, enable=True):
@@ -270,11 +297,12 @@ class Context:
 class Renderer:
     """rtr_renderer: scene resident in HBM + per-frame update/draw (Renderer.swift's hot-path half)."""
 
-    def __init__(self, ctx, scene, width, height, seeds=None, fp32=False, rebuild_skinned=False):
+    def __init__(self, ctx, scene, width, height, seeds=None, fp32=False, rebuild_skinned=False, gpu_skeleton=False):
         self.ctx = ctx
         self.scene = scene
         self.width, self.height = width, height
-        flags = (RTR_FLAG_FP32_IMAGES if fp32 else 0) | (RTR_FLAG_REBUILD_SKINNED if rebuild_skinned else 0)
+        flags = ((RTR_FLAG_FP32_IMAGES if fp32 else 0) | (RTR_FLAG_REBUILD_SKINNED if rebuild_skinned else 0) |
+                 (RTR_FLAG_GPU_SKELETON if gpu_skeleton else 0))
         desc = scene.desc()
         h = C.c_void_p()
         _check(lib().rtr_create(ctx._h, C.byref(desc), width, height, flags, C.byref(h)), True)

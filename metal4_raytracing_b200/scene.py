@@ -63,6 +63,7 @@ def lib():
     L.rts_scene_get_desc.argtypes = [C.c_void_p, C.POINTER(A.SceneDesc)]
     L.rts_fill_seed_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32]
     L.rts_default_uniforms.argtypes = [C.c_int, C.c_int, C.POINTER(A.Uniforms)]
+    L.rts_write_png.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
     _lib = L
     return L
 
@@ -245,3 +246,11 @@ def procedural_sky(width=1024, height=512, sun_dir=(0.35, 0.8, -0.45), sun_radia
     out = np.ones((height, width, 4), np.float32)
     out[..., :3] = img.astype(np.float32)
     return out
+
+
+def write_png(path, rgba8):
+    """(H, W, 4) uint8, rows top to bottom -> PNG file (rts_write_png, the post chain's image writer)."""
+    a = np.ascontiguousarray(rgba8, np.uint8)
+    assert a.ndim == 3 and a.shape[2] == 4
+    if lib().rts_write_png(str(path).encode(), a.ctypes.data, a.shape[1], a.shape[0]) != 0:
+        raise RuntimeError(f"rts_write_png failed for {path}")

@@ -160,6 +160,78 @@ def test_skinning_refit_and_rebuild(gpu_ctx):
     res2[0]["renderer"].close()
 
 
+def test_gpu_joint_palette_equals_host_palette(gpu_ctx):
+    """rt_joint_palette: local TRS -> hierarchy -> x inverseBind on the device gives the palette the
+    host scene library computes (Model.swift:207-261, SkinningPass.swift:123-157) bit for bit, and a renderer created
+    with RTR_FLAG_GPU_SKELETON renders the same frames as one fed with host palettes."""
+    w, h = 160, 160
+    sc, u, seed = scene.Scene.named("K5small", w, h, assets=None)
+    seeds = scene.seed_image(w, h, seed)
+    sc.animate(0.37)
+    m = sc.desc().meshes[0]
+    J = m.jointCount
+    trs = np.ctypeslib.as_array(m.jointLocalTRS, (J, 10)).copy()
+    parents = np.ctypeslib.as_array(m.jointParents, (J,)).copy()
+    ib = np.ctypeslib.as_array(m.jointInverseBind, (J, 16)).copy()
+    host = np.ctypeslib.as_array(m.jointMatrices, (J, 16)).copy()
+    assert (parents[1:] < np.arange(1, J)).all() and parents.max() > 0
+    got = gpu_ctx.joint_palette(trs, parents, ib)
+    assert np.array_equal(got.view(np.uint32), host.view(np.uint32))
+    # degenerate quaternion -> identity rotation; forward / negative parent -> root
+    trs2 = trs.copy()
+    trs2[3, 3:7] = 0.0
+    par2 = parents.copy()
+    par2[5] = -7
+    got2 = gpu_ctx.joint_palette(trs2, par2, ib)
+    assert np.isfinite(got2).all() and not np.array_equal(got2[5], got[5])
+    images = []
+    for gpu in (False, True):
+        sc2, u2, _ = scene.Scene.named("K5small", w, h, assets=None)
+        rnd = device.Renderer(gpu_ctx, sc2, w, h, seeds=seeds, gpu_skeleton=gpu)
+        for f in range(3):
+            u2.frameIndex = f
+            if f:
+                sc2.animate(f / 60.0)
+                rnd.update()
+            rnd.draw(u2)
+        images.append(rnd.read_image(0).copy())
+        rnd.close()
+    assert np.array_equal(images[0].view(np.uint16), images[1].view(np.uint16))
+
+
+@pytest.mark.parametrize("fp32", [False, True])
+def test_tonemap_and_png(gpu_ctx, tmp_path, fp32):
+    """rt_tonemap = the reference's presentation shader, color / (1 + color) (Shaders.metal:38-52), + sRGB transfer +
+    row flip, against a numpy restatement; the PNG writer stores exactly those bytes."""
+    from PIL import Image
+    w, h = 200, 120
+    sc, u, seed = scene.Scene.named("K3small", w, h, assets=None)
+    u.samplesPerPixel = 2
+    rnd = device.Renderer(gpu_ctx, sc, w, h, seeds=scene.seed_image(w, h, seed), fp32=fp32)
+    rnd.draw(u)
+    info = rnd.image_info(A.TEXTURE_ACCUMULATION)
+    hdr = rnd.read_image(A.TEXTURE_ACCUMULATION).astype(np.float32)[..., :3]
+    for srgb in (False, True):
+        for flip in (False, True):
+            got = gpu_ctx.tonemap(info, srgb=srgb, flip_y=flip)
+            c = np.maximum(hdr, np.float32(0))
+            c = (c / (np.float32(1) + c)).astype(np.float32)
+            c = np.clip(c, 0, 1)
+            if srgb:
+                x = c.astype(np.float64)
+                c = np.where(x <= 0.0031308, 12.92 * x, 1.055 * np.power(x, 1 / 2.4) - 0.055).astype(np.float32)
+            ref = (c * np.float32(255) + np.float32(0.5)).astype(np.uint8)
+            if flip:
+                ref = ref[::-1]
+            assert (got[..., 3] == 255).all()
+            diff = np.abs(got[..., :3].astype(int) - ref.astype(int))
+            assert diff.max() <= 1 and float((diff == 0).mean()) > 0.9999
+    p = tmp_path / "frame.png"
+    scene.write_png(p, got)
+    assert np.array_equal(np.asarray(Image.open(p)), got)
+    rnd.close()
+
+
 def test_textured_pbr_and_normal_map(gpu_ctx):
     sc, u, seed = scene.Scene.named("K2tex", 320, 180, assets=None)
     u.samplesPerPixel, u.enableDenoiseGBuffer = 2, 1

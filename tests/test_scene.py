@@ -186,3 +186,16 @@ def test_png_decoder(assets):
     t = desc.textures[ti]
     got = np.ctypeslib.as_array(t.texels, shape=(t.height, t.width, 4))
     assert (t.width, t.height) == (ref.shape[1], ref.shape[0]) and np.array_equal(got, ref) and t.srgb == 1
+
+
+def test_png_writer_round_trip(tmp_path):
+    """rts_write_png (post chain image writer): what it writes decodes to the same pixels with an independent
+    decoder (PIL), including a ragged size."""
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    for (h, w) in ((37, 53), (1, 1), (128, 256)):
+        img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        p = tmp_path / f"t_{w}x{h}.png"
+        scene.write_png(p, img)
+        back = np.asarray(Image.open(p))
+        assert back.shape == img.shape and np.array_equal(back, img)
