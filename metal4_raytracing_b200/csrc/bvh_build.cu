@@ -449,7 +449,7 @@ struct CollapseCounters {
 __global__ void k_collapse_level(Bvh2 t, const float4 *primLo, const float4 *primHi, const uint32_t *sorted,
                                  const uint32_t *queueIn, uint32_t *queueOut, uint32_t levelStart,
                                  uint32_t levelCount, uint32_t nextLevelStart, CollapseCounters *counters,
-                                 WideNode *nodes, float4 *nodeBox, uint32_t *leafPrim) {
+                                 WideNode *nodes, float4 *nodeBox, uint32_t *leafPrim, uint32_t maxLeafPrims) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= levelCount) return;
   const uint32_t self = queueIn[i];
@@ -551,7 +551,7 @@ __global__ void k_collapse_level(Bvh2 t, const float4 *primLo, const float4 *pri
   for (int s = 0; s < 8; ++s) {
     if (!present[s]) continue;
     uint32_t c = countOf(refAt[s]);
-    if (c > kMaxLeafPrims) {
+    if (c > maxLeafPrims) {
       imask |= uint8_t(1u << s);
       ++internalCount;
     } else {
@@ -812,7 +812,8 @@ static int buildWideTree(rt_context *ctx, AccelObject *as, uint32_t n, const flo
     RT_CHECK(nextStart <= as->nodeCapacity, "internal: wide node capacity exceeded");
     k_collapse_level<<<gridFor(levelCount, 128), 128, 0, st>>>(t, primLo, primHi, sorted, qin, qout, levelStart,
                                                                 levelCount, nextStart, counters, as->nodes,
-                                                                as->nodeBox, leafPrim);
+                                                                as->nodeBox, leafPrim,
+                                                                uint32_t(std::min(std::max(ctx->leafSize, 1), kMaxLeafPrims)));
     ++ctx->launches;
     CollapseCounters now;
     RT_CUDA(cudaMemcpyAsync(&now, counters, sizeof now, cudaMemcpyDeviceToHost, st));

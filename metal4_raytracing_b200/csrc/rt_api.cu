@@ -475,6 +475,11 @@ int rt_set_option(rt_context *ctx, const char *key, int value) {
     ctx->traversalVariant = value;
     return 0;
   }
+  if (k == "leaf_size") {
+    RT_CHECK(value >= 1 && value <= 3, "rt_set_option: leaf_size is 1..3 primitives per leaf slot");
+    ctx->leafSize = value;
+    return 0;
+  }
   if (k == "ploc_radius") {
     RT_CHECK(value >= 0 && value <= 256, "rt_set_option: ploc_radius is 0 (LBVH) .. 256");
     ctx->plocRadius = value;

@@ -1,6 +1,6 @@
-N=${1:-2}
-for X in peer gather; do
+N=${1:-2}; MODES=${2:-"peer gather"}
+for X in $MODES; do
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 --exchange $X > gpurun_out/bench_n${N}_$X.json 2> gpurun_out/bench_n${N}_$X.err
-echo "rc=$? $X"; tail -1 gpurun_out/bench_n${N}_$X.json | cut -c1-330; tail -3 gpurun_out/bench_n${N}_$X.err
+echo "rc=$? $X"; tail -1 gpurun_out/bench_n${N}_$X.json | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], {k:v['ms_per_step'] for k,v in d['roofline']['kernels'].items()})"
 done
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 2 --warmup 0 2>&1 | tail -1 | cut -c1-400
