@@ -43,6 +43,27 @@ def test_halton_matches_float32_restatement():
     assert 0.0 < min(vals) and max(vals) < 1.0
 
 
+def test_halton_shortcuts_used_by_the_cuda_path_are_identities():
+    """The CUDA kernels evaluate halton() with two shortcuts that must be exact identities of the reference loop
+    (Raytracing.metal:42-57): base 2 as a bit reversal while i < 2^24, and i / p by a multiply-high with the
+    round-up reciprocal of tools/gen_halton_table.py."""
+    rng = np.random.default_rng(3)
+    idx = np.concatenate([np.arange(1, 3000), rng.integers(1, 1 << 24, 4000), [(1 << 24) - 1, 1 << 23, 0xAAAAAA]])
+    for i in idx:
+        i = int(i)
+        brev = int(f"{i:032b}"[::-1], 2)
+        assert oracle.halton(i, 0) == float(np.float32(brev) * np.float32(2.0 ** -32)), i
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen", os.path.join(os.path.dirname(GOLDEN), "..", "tools", "gen_halton_table.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    n = np.concatenate([rng.integers(1, 1 << 31, 50000, dtype=np.uint64), np.array([1, (1 << 31) - 1], np.uint64)])
+    for p in gen.PRIMES:
+        _, magic, shift, inv = gen.entry(p)
+        assert np.array_equal(((n * np.uint64(magic)) >> np.uint64(32)) >> np.uint64(shift), n // np.uint64(p)), p
+        assert inv == int((np.float32(1) / np.float32(p)).view(np.uint32))
+
+
 def test_triangle_barycentric_convention_and_bounds():
     v0, v1, v2 = (0, 0, 0), (1, 0, 0), (0, 1, 0)
     hit, (t, u, v) = oracle.intersect_triangle((0.25, 0.5, 1.0), (0, 0, -1), v0, v1, v2)
