@@ -143,6 +143,9 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
+            for p in getattr(self, "_owned", []):
+                lib().rt_free_host(self._h, p)
+            self._owned = []
             lib().rt_destroy(self._h)
             self._h = None
 
@@ -172,6 +175,15 @@ class Context:
         out = np.empty(shape, dtype)
         _check(lib().rt_download(self._h, out.ctypes.data, ptr, out.nbytes))
         return out
+
+    def pinned_array(self, shape, dtype):
+        """numpy view of page-locked host memory (rt_malloc_host), freed with the context."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _check(lib().rt_malloc_host(self._h, n, C.byref(p)))
+        self._owned.append(p.value)
+        buf = (C.c_uint8 * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
     def memset(self, ptr, value, nbytes):
         _check(lib().rt_memset(self._h, ptr, value, nbytes))
@@ -387,11 +399,14 @@ class Renderer:
         _check(lib().rtr_image_info(self._h, index, C.byref(img)), True)
         return img
 
-    def read_image(self, index=A.TEXTURE_ACCUMULATION):
-        """Host copy of the image bound at `index`; after draw(), index 0 is the frame just rendered."""
+    def read_image(self, index=A.TEXTURE_ACCUMULATION, out=None):
+        """Host copy of the image bound at `index`; after draw(), index 0 is the frame just rendered. `out` may be
+        a pinned array from Context.pinned_array (the copy then runs at full PCIe rate, no staging)."""
         info = self.image_info(index)
         dt, ch = _FORMAT_DTYPE[info.format]
-        out = np.empty((self.height, self.width, ch), dt)
+        if out is None:
+            out = np.empty((self.height, self.width, ch), dt)
+        assert out.dtype == dt and out.shape == (self.height, self.width, ch) and out.flags.c_contiguous
         _check(lib().rtr_read_image(self._h, index, out.ctypes.data, out.nbytes), True)
         return out
 
