@@ -141,6 +141,21 @@ int rt_texture_destroy(rt_context *ctx, const rt_texture2d *recordDev);
 #define RT_TONEMAP_FLIP_Y 2u
 int rt_tonemap(rt_context *ctx, const rt_image *srcDev, uint8_t *dstRGBA8Dev, uint32_t flags);
 
+/* rt_temporal_filter: temporal reprojection of the accumulation image with the kernel's own depth (texture 3), motion
+ * (texture 4) and normal G-buffer (texture 7, needs enableDenoiseGBuffer) — the consumer of those outputs, which the
+ * reference hands to MetalFX's temporal denoiser (FramePresenter.swift:435-521). Per pixel: previous position =
+ * (x - motion.x, y + motion.y); the bilinear history sample is accepted when the nearest history texel agrees in
+ * depth (|dz| <= depthTolerance * z) and normal (dot >= normalThreshold), clamped to the current 3x3 colour range
+ * and blended with historyWeight. history may be NULL (first frame: output = colour). All images device memory. */
+typedef struct rt_denoise_frame {
+  rt_image color;  /* rgba16f / rgba32f */
+  rt_image motion; /* rg16f / rg32f, pixels, +y down (as the kernel writes it) */
+  rt_image depth;  /* r32f, view depth; 1e8 = no primary hit (passed through) */
+  rt_image normal; /* rgba16f / rgba32f, n * 0.5 + 0.5 */
+} rt_denoise_frame;
+int rt_temporal_filter(rt_context *ctx, const rt_denoise_frame *current, const rt_denoise_frame *history,
+                       const rt_image *outColorDev, float historyWeight, float depthTolerance, float normalThreshold);
+
 /* ---- multi-GPU frame exchange (no counterpart in the single-device reference) ---------------
  * Rank g of N owns 16x16 tiles with tile % N == g. Two ways to assemble the frame:
  *  (a) rt_trace with options->peerAccumulation: the kernel stores owned pixels straight into every rank's frame

@@ -165,6 +165,8 @@ void destroyAccel(AccelObject *as);
 int launchSkin(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], uint32_t vertexCount);
 int launchJointPalette(rt_context *ctx, const float *trs, const int32_t *parents, const float *inverseBind,
                        uint32_t jointCount, float *palette);
+int launchTemporalFilter(rt_context *ctx, const rt_denoise_frame *cur, const rt_denoise_frame *hist, const rt_image *out,
+                         float historyWeight, float depthTolerance, float normalThreshold);
 int launchTonemap(rt_context *ctx, const rt_image *src, uint8_t *dst, uint32_t flags);
 int packTiles(rt_context *ctx, const rt_image *image, void *slab, int modulo, int remainder);
 int unpackTiles(rt_context *ctx, const void *slabs, const rt_image *image, int modulo);

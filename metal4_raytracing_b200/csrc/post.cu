@@ -8,7 +8,7 @@
 // Pure streaming: 8 or 16 B read, 4 B written per pixel.
 #include <cuda_fp16.h>
 
-#include "common.cuh"
+#include "shade.cuh"
 
 namespace rtb {
 
@@ -48,7 +48,79 @@ __global__ void k_tonemap(const rt_image src, uchar4 *__restrict__ dst, uint32_t
       make_uchar4(uint8_t(toByte(c.x, srgb)), uint8_t(toByte(c.y, srgb)), uint8_t(toByte(c.z, srgb)), 255);
 }
 
+// ---- temporal reprojection filter -----------------------------------------------------------------------------
+// The consumer of the kernel's depth / motion / normal outputs (Raytracing.metal:341-389, 506-515), the role the
+// reference hands to MetalFX's temporal denoiser (FramePresenter.swift:435-521, closed source). Specified here:
+//   prev = (x - motion.x, y + motion.y)        the kernel stores motion in pixels with +y down, image rows grow upward
+//   history = bilinear(historyColor, prev), taken only if prev is inside the image and the nearest history texel has
+//             |historyDepth - depth| <= depthTolerance * depth and dot(normal, historyNormal) >= normalThreshold
+//   history is clamped to the min / max of the current frame's 3x3 neighbourhood (anti-ghosting)
+//   out = color + (history - color) * historyWeight      (no valid history: out = color)
+// One thread per pixel; reads ~10 texels, writes one. Arithmetic in the association order written (-fmad=false).
+__global__ void k_temporal_filter(const rt_denoise_frame cur, const rt_denoise_frame hist, const rt_image out,
+                                  float historyWeight, float depthTolerance, float normalThreshold) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int w = cur.color.width, h = cur.color.height;
+  if (x >= w || y >= h) return;
+  const f4 c4 = readImage(cur.color, x, y);
+  f3 c = mk3(c4.x, c4.y, c4.z);
+  f3 result = c;
+  const f4 mv = readImage(cur.motion, x, y);
+  const float px = float(x) - mv.x, py = float(y) + mv.y;
+  const float depth = readImage(cur.depth, x, y).x;
+  if (hist.color.data != nullptr && px >= 0.0f && py >= 0.0f && px <= float(w - 1) && py <= float(h - 1) &&
+      depth < 1.0e7f) {
+    const int nx = int(floorf(px + 0.5f)), ny = int(floorf(py + 0.5f));
+    const float hd = readImage(hist.depth, nx, ny).x;
+    const f4 n4 = readImage(cur.normal, x, y), hn4 = readImage(hist.normal, nx, ny);
+    const f3 n = mk3(n4.x, n4.y, n4.z) * 2.0f - mk3(1.0f), hn = mk3(hn4.x, hn4.y, hn4.z) * 2.0f - mk3(1.0f);
+    if (fabsf(hd - depth) <= depthTolerance * depth && dot(n, hn) >= normalThreshold) {
+      const float fx0 = floorf(px), fy0 = floorf(py);
+      const float tx = px - fx0, ty = py - fy0;
+      const int x0 = int(fx0), y0 = int(fy0), x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
+      const f4 a = readImage(hist.color, x0, y0), b = readImage(hist.color, x1, y0);
+      const f4 d = readImage(hist.color, x0, y1), e = readImage(hist.color, x1, y1);
+      const f3 top = mix(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), tx);
+      const f3 bottom = mix(mk3(d.x, d.y, d.z), mk3(e.x, e.y, e.z), tx);
+      f3 history = mix(top, bottom, ty);
+      f3 lo = c, hi = c;
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int qx = min(max(x + dx, 0), w - 1), qy = min(max(y + dy, 0), h - 1);
+          const f4 q = readImage(cur.color, qx, qy);
+          lo = mk3(fminf(lo.x, q.x), fminf(lo.y, q.y), fminf(lo.z, q.z));
+          hi = mk3(fmaxf(hi.x, q.x), fmaxf(hi.y, q.y), fmaxf(hi.z, q.z));
+        }
+      history = mk3(fminf(fmaxf(history.x, lo.x), hi.x), fminf(fmaxf(history.y, lo.y), hi.y),
+                    fminf(fmaxf(history.z, lo.z), hi.z));
+      result = mix(c, history, historyWeight);
+    }
+  }
+  writeImage(out, x, y, {result.x, result.y, result.z, 1.0f});
+}
+
 } // namespace
+
+int launchTemporalFilter(rt_context *ctx, const rt_denoise_frame *cur, const rt_denoise_frame *hist, const rt_image *out,
+                         float historyWeight, float depthTolerance, float normalThreshold) {
+  RT_CHECK(cur && out && cur->color.data && cur->motion.data && cur->depth.data && cur->normal.data && out->data,
+           "rt_temporal_filter: current frame images and the output must be bound");
+  const int w = cur->color.width, h = cur->color.height;
+  auto same = [&](const rt_image &i) { return i.width == w && i.height == h; };
+  RT_CHECK(w > 0 && h > 0 && same(cur->motion) && same(cur->depth) && same(cur->normal) && same(*out),
+           "rt_temporal_filter: image sizes differ");
+  rt_denoise_frame none{};
+  if (hist == nullptr || hist->color.data == nullptr) hist = &none;
+  else
+    RT_CHECK(hist->depth.data && hist->normal.data && same(hist->color) && same(hist->depth) && same(hist->normal),
+             "rt_temporal_filter: history needs colour, depth and normal images of the same size");
+  RT_CHECK(out->data != cur->color.data && out->data != hist->color.data, "rt_temporal_filter: output aliases an input");
+  const dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+  k_temporal_filter<<<grid, block, 0, ctx->stream>>>(*cur, *hist, *out, historyWeight, depthTolerance, normalThreshold);
+  ++ctx->launches;
+  RT_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int launchTonemap(rt_context *ctx, const rt_image *src, uint8_t *dst, uint32_t flags) {
   RT_CHECK(src && src->data && dst, "rt_tonemap: null pointer");

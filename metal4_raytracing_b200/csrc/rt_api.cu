@@ -382,6 +382,15 @@ int rt_tonemap(rt_context *ctx, const rt_image *srcDev, uint8_t *dstRGBA8Dev, ui
   return rc;
 }
 
+int rt_temporal_filter(rt_context *ctx, const rt_denoise_frame *current, const rt_denoise_frame *history,
+                       const rt_image *outColorDev, float historyWeight, float depthTolerance, float normalThreshold) {
+  RT_CTX(ctx);
+  ctx->mark(-1);
+  const int rc = launchTemporalFilter(ctx, current, history, outColorDev, historyWeight, depthTolerance, normalThreshold);
+  ctx->mark(RT_KERNEL_OTHER);
+  return rc;
+}
+
 int rt_pack_tiles(rt_context *ctx, const rt_image *imageDev, void *slabDev, int tileModulo, int tileRemainder) {
   RT_CTX(ctx);
   return packTiles(ctx, imageDev, slabDev, tileModulo, tileRemainder);

@@ -27,6 +27,11 @@ class Environment(C.Structure):
                 ("_pad", C.c_float)]
 
 
+class DenoiseFrame(C.Structure):
+    """rt_denoise_frame: colour, motion, depth, normal image records of one frame."""
+    _fields_ = [("color", A.Image), ("motion", A.Image), ("depth", A.Image), ("normal", A.Image)]
+
+
 class TraceOptions(C.Structure):
     _fields_ = [("tileModulo", C.c_int32), ("tileRemainder", C.c_int32), ("primaryIdsDev", C.c_void_p),
                 ("rayCountersDev", C.c_void_p), ("peerAccumulation", C.POINTER(C.c_void_p)),
@@ -46,7 +51,7 @@ EXPORTS = [
     "rt_blas_build", "rt_blas_refit", "rt_blas_destroy", "rt_tlas_build", "rt_tlas_update", "rt_tlas_destroy",
     "rt_as_get_info", "rt_skin", "rt_trace", "rt_texture_create", "rt_texture_destroy", "rt_launch_count",
     "rt_set_trace_mode", "rt_set_option", "rt_kernel_timing_enable", "rt_kernel_timing_read", "rt_joint_palette",
-    "rt_tonemap",
+    "rt_tonemap", "rt_temporal_filter",
     "rtr_last_error", "rtr_create", "rtr_destroy", "rtr_set_seeds", "rtr_update", "rtr_draw", "rtr_read_image",
     "rtr_image_info", "rtr_reset_accumulation", "rtr_read_mesh_streams", "rtr_get_blas_id", "rtr_get_tlas_id",
     "rtr_mesh_count",
@@ -95,6 +100,8 @@ def lib():
     L.rt_set_option.argtypes = [vp, C.c_char_p, i32]
     L.rt_joint_palette.argtypes = [vp, vp, vp, vp, u32, vp]
     L.rt_tonemap.argtypes = [vp, C.POINTER(A.Image), vp, u32]
+    L.rt_temporal_filter.argtypes = [vp, C.POINTER(DenoiseFrame), C.POINTER(DenoiseFrame), C.POINTER(A.Image),
+                                     C.c_float, C.c_float, C.c_float]
     L.rt_kernel_timing_enable.argtypes = [vp, i32]
     L.rt_kernel_timing_read.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u32)]
     L.rtr_create.argtypes = [vp, C.POINTER(A.SceneDesc), i32, i32, u32, C.POINTER(vp)]
@@ -224,6 +231,18 @@ class Context:
         out = self.download(dst, (image.height, image.width, 4), np.uint8)
         self.free(dst)
         return out
+
+    def image_from_array(self, array, fmt):
+        """Uploads an (H, W[, C]) array and returns its A.Image record (caller frees image.data)."""
+        a = np.ascontiguousarray(array)
+        img = A.Image()
+        img.data, img.width, img.height, img.format = self.upload(a), a.shape[1], a.shape[0], fmt
+        return img
+
+    def temporal_filter(self, current, history, out, history_weight=0.9, depth_tolerance=0.05, normal_threshold=0.9):
+        """rt_temporal_filter on DenoiseFrame records; `history` may be None."""
+        _check(lib().rt_temporal_filter(self._h, C.byref(current), C.byref(history) if history is not None else None,
+                                        C.byref(out), history_weight, depth_tolerance, normal_threshold))
 
     def joint_palette(self, local_trs, parents, inverse_bind):
         """rt_joint_palette on numpy inputs; returns the (J, 16) palette."""

@@ -199,6 +199,85 @@ def test_gpu_joint_palette_equals_host_palette(gpu_ctx):
     assert np.array_equal(images[0].view(np.uint16), images[1].view(np.uint16))
 
 
+def _temporal_filter_numpy(color, motion, depth, normal, hcolor, hdepth, hnormal, wgt, dtol, nthr):
+    """float32 restatement of rt_temporal_filter (include/rt_b200.h), same operation order."""
+    f = np.float32
+    h, w = depth.shape
+    out = color.copy()
+    for y in range(h):
+        for x in range(w):
+            c = color[y, x]
+            px, py = f(f(x) - motion[y, x, 0]), f(f(y) + motion[y, x, 1])
+            if hcolor is None or not (px >= 0 and py >= 0 and px <= w - 1 and py <= h - 1 and depth[y, x] < 1e7):
+                continue
+            nx, ny = int(np.floor(f(px + f(0.5)))), int(np.floor(f(py + f(0.5))))
+            n = f(2) * normal[y, x] - f(1)
+            hn = f(2) * hnormal[ny, nx] - f(1)
+            d = f(f(f(n[0] * hn[0]) + f(n[1] * hn[1])) + f(n[2] * hn[2]))
+            if not (abs(f(hdepth[ny, nx] - depth[y, x])) <= f(dtol * depth[y, x]) and d >= nthr):
+                continue
+            x0, y0 = int(np.floor(px)), int(np.floor(py))
+            tx, ty = f(px - f(x0)), f(py - f(y0))
+            x1, y1 = min(x0 + 1, w - 1), min(y0 + 1, h - 1)
+            mix = lambda a, b, t: (a + (b - a) * t).astype(f)
+            hist = mix(mix(hcolor[y0, x0], hcolor[y0, x1], tx), mix(hcolor[y1, x0], hcolor[y1, x1], tx), ty)
+            nb = color[max(y - 1, 0):y + 2, max(x - 1, 0):x + 2].reshape(-1, 3)
+            hist = np.minimum(np.maximum(hist, nb.min(0)), nb.max(0))
+            out[y, x] = mix(c, hist, f(wgt))
+    return out
+
+
+def test_temporal_filter_on_kernel_outputs(gpu_ctx):
+    """rt_temporal_filter consumes the kernel's own depth / motion / normal outputs of an animated
+    scene: equals a numpy restatement, passes the frame through without history, and pulls a noisy frame toward the
+    previous one where the reprojection is valid."""
+    w, h = 96, 64
+    sc, u, seed = scene.Scene.named("K5small", w, h, assets=None)
+    u.samplesPerPixel, u.maxBounces, u.enableDenoiseGBuffer, u.accumulationWeight = 1, 2, 1, 0.0
+    rnd = device.Renderer(gpu_ctx, sc, w, h, seeds=scene.seed_image(w, h, seed), fp32=True)
+    frames = []
+    for f in range(2):
+        u.frameIndex = f
+        if f:
+            sc.animate(0.05)
+            rnd.update()
+        rnd.draw(u)
+        frames.append({k: rnd.read_image(i).astype(np.float32) for k, i in
+                       (("color", A.TEXTURE_ACCUMULATION), ("motion", A.TEXTURE_MOTION), ("depth", A.TEXTURE_DEPTH),
+                        ("normal", A.TEXTURE_NORMAL))})
+    rnd.close()
+    assert float(np.abs(frames[1]["motion"]).max()) > 0.05
+
+    def record(fr):
+        d = device.DenoiseFrame()
+        d.color = gpu_ctx.image_from_array(np.concatenate([fr["color"][..., :3], np.ones((h, w, 1), np.float32)], -1),
+                                           A.FORMAT_RGBA32_FLOAT)
+        d.motion = gpu_ctx.image_from_array(fr["motion"][..., :2], A.FORMAT_RG32_FLOAT)
+        d.depth = gpu_ctx.image_from_array(fr["depth"][..., 0], A.FORMAT_R32_FLOAT)
+        d.normal = gpu_ctx.image_from_array(fr["normal"], A.FORMAT_RGBA32_FLOAT)
+        return d
+
+    prev, cur = record(frames[0]), record(frames[1])
+    out = gpu_ctx.image_from_array(np.zeros((h, w, 4), np.float32), A.FORMAT_RGBA32_FLOAT)
+    gpu_ctx.temporal_filter(cur, None, out)
+    first = gpu_ctx.download(out.data, (h, w, 4), np.float32)
+    assert np.array_equal(first[..., :3], frames[1]["color"][..., :3])
+    gpu_ctx.temporal_filter(cur, prev, out, 0.8, 0.05, 0.9)
+    got = gpu_ctx.download(out.data, (h, w, 4), np.float32)[..., :3]
+    ref = _temporal_filter_numpy(frames[1]["color"][..., :3], frames[1]["motion"], frames[1]["depth"][..., 0],
+                                 frames[1]["normal"][..., :3], frames[0]["color"][..., :3], frames[0]["depth"][..., 0],
+                                 frames[0]["normal"][..., :3], 0.8, 0.05, 0.9)
+    assert np.abs(got - ref).max() <= 1e-5 * max(1.0, float(np.abs(ref).max()))
+    changed = np.abs(got - frames[1]["color"][..., :3]).max(-1) > 0
+    assert 0.2 < float(changed.mean()) <= 1.0  # history was accepted for a good part of the frame, not blindly
+    with pytest.raises(device.RtError):
+        gpu_ctx.temporal_filter(cur, prev, cur.color)  # output must not alias an input
+    for d in (prev, cur):
+        for img in (d.color, d.motion, d.depth, d.normal):
+            gpu_ctx.free(img.data)
+    gpu_ctx.free(out.data)
+
+
 @pytest.mark.parametrize("fp32", [False, True])
 def test_tonemap_and_png(gpu_ctx, tmp_path, fp32):
     """rt_tonemap = the reference's presentation shader, color / (1 + color) (Shaders.metal:38-52), + sRGB transfer +
