@@ -19,6 +19,7 @@ namespace rtb {
 struct TraceParams {
   rt_uniforms uniforms;
   TlasHeader tlas; // by value: the traversal reads its pointers from the constant bank
+  const float4 *tlasRootBox; // exact box of the TLAS root (lo, hi): grid for the ray-reordering keys
   const rt_resource *resources;
   const rt_instance_descriptor *instances;
   const rt_instance_descriptor *prevInstances;

@@ -119,6 +119,7 @@ int fillTraceParams(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT],
   P.tlas.leafInstance = tl->leafPrim;
   P.tlas.instanceCount = tl->primCount;
   P.tlas.nodeCount = tl->primCount ? tl->nodeCount : 0u;
+  P.tlasRootBox = tl->nodeBox;
   P.resources = static_cast<const rt_resource *>(buffers[RT_BUFFER_RESOURCES]);
   P.instances = static_cast<const rt_instance_descriptor *>(buffers[RT_BUFFER_INSTANCE_DESCRIPTORS]);
   P.prevInstances = static_cast<const rt_instance_descriptor *>(buffers[RT_BUFFER_PREVIOUS_INSTANCE_DESCRIPTORS]);

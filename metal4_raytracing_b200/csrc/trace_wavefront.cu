@@ -19,6 +19,8 @@
 // shared path_step.cuh, so this layout is bit-identical to the megakernel and to the CPU oracle.
 // All kernels are persistent-style: a fixed grid of (SM count x resident CTAs) strides over the queue, whose
 // length is read from device memory, so no host round trip is needed between phases.
+#include <cub/device/device_radix_sort.cuh>
+
 #include <cstring>
 
 #include "path_step.cuh"
@@ -64,6 +66,10 @@ struct WfState {
   float4 *misc; // depth, flags bits (1 = hadPrimaryHit, 2 = wroteGBuffer), seed offset bits, unused
   uint32_t *queue[2], *shadowQueue;
   uint32_t *counts; // [0], [1] path queues, [2] shadow queue, [3] trace cursor, [4] shadow cursor
+  // ray reordering (option sort_rays): key buffers, the sorted copy of a queue and CUB's workspace
+  uint32_t *sortKeys[2], *sortedQueue;
+  void *sortTemp;
+  size_t sortTempBytes;
 };
 
 __device__ __forceinline__ void slotPixel(const TraceParams &P, uint32_t slot, int &px, int &py, bool &valid) {
@@ -156,6 +162,33 @@ __global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ 
       }
       queuePush(W.queue[0], W.counts + 0, push, slot);
     }
+  }
+}
+
+// Ray reordering (option sort_rays, off by default): key = direction octant (3 bits) | Morton code of the origin in
+// a 128^3 grid over the TLAS bounds (21 bits). Rays of one warp then start in the same region and walk the tree in
+// the same child order. Results do not depend on queue order, so this only moves time between kernels.
+__device__ __forceinline__ uint32_t spread7(uint32_t v) { // 7 bits -> every third bit
+  v &= 0x7Fu;
+  v = (v | (v << 8)) & 0x0000700Fu;
+  v = (v | (v << 4)) & 0x000430C3u;
+  v = (v | (v << 2)) & 0x00049249u;
+  return v;
+}
+__global__ void __launch_bounds__(kBlock) k_ray_keys(const uint32_t *__restrict__ queue, uint32_t count,
+                                                     const float4 *__restrict__ rayO, const float4 *__restrict__ rayD,
+                                                     const float4 *__restrict__ rootBox, uint32_t *__restrict__ keys) {
+  const float4 lo = rootBox[0], hi = rootBox[1];
+  const float sx = 128.0f / fmaxf(hi.x - lo.x, 1e-20f), sy = 128.0f / fmaxf(hi.y - lo.y, 1e-20f),
+              sz = 128.0f / fmaxf(hi.z - lo.z, 1e-20f);
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
+    const uint32_t slot = queue[j];
+    const float4 o = RT_LDS(rayO + slot), d = RT_LDS(rayD + slot);
+    const uint32_t cx = uint32_t(fminf(fmaxf((o.x - lo.x) * sx, 0.0f), 127.0f));
+    const uint32_t cy = uint32_t(fminf(fmaxf((o.y - lo.y) * sy, 0.0f), 127.0f));
+    const uint32_t cz = uint32_t(fminf(fmaxf((o.z - lo.z) * sz, 0.0f), 127.0f));
+    const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+    keys[j] = (oct << 21) | (spread7(cx) << 2) | (spread7(cy) << 1) | spread7(cz);
   }
 }
 
@@ -384,7 +417,12 @@ __global__ void __launch_bounds__(kBlock) k_wf_resolve(const __grid_constant__ T
 
 int ensureState(rt_context *ctx, uint32_t capacity, uint32_t batch, WfState &out) {
   const size_t paths = size_t(capacity) * batch;
-  const size_t need = 256 + 10 * (paths * 16 + 256) + 3 * (size_t(capacity) * 16 + 256) + 3 * (paths * 4 + 256);
+  size_t sortTempBytes = 0;
+  if (ctx->sortRays > 0)
+    cub::DeviceRadixSort::SortPairs(nullptr, sortTempBytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, int(paths), 0, 24, ctx->stream);
+  const size_t need = 256 + 10 * (paths * 16 + 256) + 3 * (size_t(capacity) * 16 + 256) + 3 * (paths * 4 + 256) +
+                      (ctx->sortRays > 0 ? 3 * (paths * 4 + 256) + sortTempBytes + 256 : 0);
   if (ctx->wfState == nullptr || ctx->wfBytes < need) {
     RT_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->wfState) cudaFree(ctx->wfState);
@@ -420,8 +458,35 @@ int ensureState(rt_context *ctx, uint32_t capacity, uint32_t batch, WfState &out
   s.queue[0] = static_cast<uint32_t *>(take(paths * 4));
   s.queue[1] = static_cast<uint32_t *>(take(paths * 4));
   s.shadowQueue = static_cast<uint32_t *>(take(paths * 4));
+  if (ctx->sortRays > 0) {
+    s.sortKeys[0] = static_cast<uint32_t *>(take(paths * 4));
+    s.sortKeys[1] = static_cast<uint32_t *>(take(paths * 4));
+    s.sortedQueue = static_cast<uint32_t *>(take(paths * 4));
+    s.sortTemp = take(sortTempBytes);
+    s.sortTempBytes = sortTempBytes;
+  }
   RT_CHECK(size_t(p - static_cast<uint8_t *>(ctx->wfState)) <= ctx->wfBytes, "internal: wavefront state overflow");
   out = s;
+  return 0;
+}
+
+// Sorts `*queue` (count read back from the device) by ray key; the sorted copy takes the queue's place.
+int sortQueue(rt_context *ctx, const TraceParams &P, WfState &W, uint32_t **queue, const uint32_t *countDev,
+              const float4 *rayO, const float4 *rayD) {
+  cudaStream_t st = ctx->stream;
+  uint32_t count = 0;
+  RT_CUDA(cudaMemcpyAsync(&count, countDev, 4, cudaMemcpyDeviceToHost, st));
+  RT_CUDA(cudaStreamSynchronize(st));
+  if (count < 65536u) return 0; // not worth two more launches
+  ctx->mark(-1);
+  const int grid = int(std::min<uint32_t>((count + kBlock - 1) / kBlock, uint32_t(ctx->smCount) * 8u));
+  k_ray_keys<<<grid, kBlock, 0, st>>>(*queue, count, rayO, rayD, P.tlasRootBox, W.sortKeys[0]);
+  size_t bytes = W.sortTempBytes;
+  RT_CUDA(cub::DeviceRadixSort::SortPairs(W.sortTemp, bytes, W.sortKeys[0], W.sortKeys[1], *queue, W.sortedQueue,
+                                          int(count), 0, 24, st));
+  ctx->launches += 4;
+  ctx->mark(RT_KERNEL_OTHER);
+  std::swap(*queue, W.sortedQueue);
   return 0;
 }
 
@@ -469,6 +534,7 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
         ctx->mark(-1);
       }
       const int first = (s0 == 0 && segment == 0) ? 1 : 0;
+      if (ctx->sortRays > 0 && segment > 0) RT_TRY(sortQueue(ctx, P, W, &W.queue[qin], W.counts + qin, W.rayO, W.rayD));
       switch (ctx->traversalVariant) {
         case 1: k_wf_trace<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
         case 2: k_wf_trace<16><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
@@ -480,6 +546,7 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
       ctx->mark(RT_KERNEL_TRACE);
       k_wf_shade<<<persistent, kBlock, 0, st>>>(P, W, qin, s0);
       ctx->mark(RT_KERNEL_SHADE);
+      if (ctx->sortRays > 1) RT_TRY(sortQueue(ctx, P, W, &W.shadowQueue, W.counts + 2, W.shO, W.shD));
       switch (ctx->traversalVariant) {
         case 1: k_wf_shadow<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
         case 2: k_wf_shadow<16><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;

@@ -588,3 +588,36 @@ def test_full_size_headline_frame(gpu_ctx):
     info = gpu_ctx.as_info(rnd.blas_id(0))
     assert info.primitiveCount == 871200
     rnd.close()
+
+
+@pytest.mark.parametrize("name,frames,modulo", [("K2", 1, 6), ("K4", 1, 24), ("K5", 3, 8)])
+def test_full_size_configs_on_a_tile_sample(gpu_ctx, assets, name, frames, modulo):
+    """BASELINE configs 2, 4 and 5 at their real sizes (1080p x 4 spp; 3840x2160 x 8 spp over 4096 instances; the
+    100,000-vertex skinned robot stand-in with skin + refit + TLAS rebuild per frame). The GPU renders whole frames;
+    the oracle renders every `modulo`-th 16x16 tile of the same frames (it would take minutes otherwise) and those
+    pixels must agree bit for bit, ids included."""
+    import bench
+    scene_name, w, h, spp, mb = bench.WORKLOADS[name]
+    if name == "K4" and assets is None:
+        pytest.skip("K4 needs the staged OBJ assets")
+    sc, u, seed = scene.Scene.named(scene_name, w, h, assets=assets)
+    u.samplesPerPixel, u.maxBounces = spp, mb
+    seeds = scene.seed_image(w, h, seed)
+    rnd = device.Renderer(gpu_ctx, sc, w, h, seeds=seeds)
+    orc = oracle.Oracle(sc)
+    imgs = oracle.FrameImages(w, h, seeds)
+    mask = parallel.owner_mask(w, h, modulo, 1)
+    for f in range(frames):
+        u.frameIndex = f
+        if f:
+            sc.animate(f / 60.0)
+            rnd.update()
+            orc.update()
+        rnd.draw(u, want_ids=True)
+        _, ref_ids = orc.render(u, imgs, want_ids=True, tile_modulo=modulo, tile_remainder=1)
+        got, ids = rnd.read_image(A.TEXTURE_ACCUMULATION), rnd.read_ids()
+        assert np.array_equal(ids[mask][:, :3], ref_ids[mask][:, :3]), f"{name} frame {f}: primary ids"
+        assert np.array_equal(got[mask].view(np.uint16), imgs.output[mask].view(np.uint16)), f"{name} frame {f}: radiance"
+        assert np.array_equal(rnd.read_image(A.TEXTURE_DEPTH)[mask], imgs.arrays[A.TEXTURE_DEPTH][mask])
+        imgs.swap()
+    rnd.close()
