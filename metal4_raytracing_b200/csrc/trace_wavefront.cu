@@ -153,12 +153,11 @@ __global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ 
         const int hIndex = haltonIndex(U, offset, sampleStride, sampleIndex);
         PathState s;
         startPath(U, px, py, hIndex, s);
-        RT_STS(W.rayO + slot, make_float4(s.origin.x, s.origin.y, s.origin.z, 0.0f));
-        RT_STS(W.rayD + slot, make_float4(s.dir.x, s.dir.y, s.dir.z, 0.0f));
-        RT_STS(W.thr + slot, make_float4(1.0f, 1.0f, 1.0f, __int_as_float(hIndex)));
-        RT_STS(W.rad + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
-        RT_STS(W.ctr + slot, make_int4(0, 0, 0, 0));
+        // a camera ray's other state is implied (origin = camera, throughput 1, radiance 0, counters 0): the first
+        // segment's trace and shade kernels supply it themselves, so only 16 of the 80 bytes are written here
+        RT_STS(W.rayD + slot, make_float4(s.dir.x, s.dir.y, s.dir.z, __int_as_float(hIndex)));
         push = U.maxBounces > 0;
+        if (!push) RT_STS(W.rad + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f)); // never traced: folds as black
       }
       queuePush(W.queue[0], W.counts + 0, push, slot);
     }
@@ -210,7 +209,7 @@ constexpr int kStepsPerCheck = RT_STEPS_PER_CHECK;
 template <bool kAny, int kRefill, typename Finish>
 __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t *__restrict__ queue, uint32_t count,
                                            uint32_t *cursor, const float4 *__restrict__ rayO,
-                                           const float4 *__restrict__ rayD, Finish finish) {
+                                           const float4 *__restrict__ rayD, bool cameraRays, Finish finish) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   LaneTraversal<kAny> t;
@@ -230,7 +229,12 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
         const uint32_t j = base + uint32_t(__popc(idle & ((1u << lane) - 1u)));
         if (j < count) {
           slot = queue[j];
-          const float4 o = RT_LDS(rayO + slot), d = RT_LDS(rayD + slot);
+          const float4 d = RT_LDS(rayD + slot);
+          float4 o;
+          if (!kAny && cameraRays) // first segment: every ray starts at the camera (k_wf_generate)
+            o = make_float4(P.uniforms.camera.position.x, P.uniforms.camera.position.y, P.uniforms.camera.position.z, 0.0f);
+          else
+            o = RT_LDS(rayO + slot);
           t.begin(P.tlas, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, kAny ? o.w : INFINITY);
           active = true;
         }
@@ -253,14 +257,14 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
 
 template <int kRefill>
 __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_trace(const __grid_constant__ TraceParams P, const WfState W,
-                                                                              int qin, int firstSegment) {
+                                                                              int qin, int firstSegment, int cameraRays) {
   if (blockIdx.x == 0 && threadIdx.x == 0) { // the queues the next two phases append to start empty
     W.counts[qin ^ 1] = 0u;
     W.counts[2] = 0u;
     W.counts[4] = 0u; // cursor of the shadow kernel
   }
   const uint32_t count = W.counts[qin];
-  traceQueue<false, kRefill>(P, W.queue[qin], count, W.counts + 3, W.rayO, W.rayD,
+  traceQueue<false, kRefill>(P, W.queue[qin], count, W.counts + 3, W.rayO, W.rayD, cameraRays != 0,
                              [&](uint32_t slot, const LaneTraversal<false> &t) {
                                RT_STS(W.hitA + slot, make_float4(t.hit.t, t.hit.u, t.hit.v, t.found ? 1.0f : 0.0f));
                                if (t.found)
@@ -281,7 +285,8 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_trace(co
 #define RT_SHADE_MINBLOCKS 4 // 64 registers: measured faster than 128 (the kernel is bound by gather latency; more warps hide it)
 #endif
 __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const __grid_constant__ TraceParams P,
-                                                                         const WfState W, int qin, int s0) {
+                                                                         const WfState W, int qin, int s0,
+                                                                         int cameraRays) {
   if (blockIdx.x == 0 && threadIdx.x == 0) W.counts[3] = 0u; // cursor of the next trace kernel
   const uint32_t count = W.counts[qin];
   const uint32_t *queue = W.queue[qin];
@@ -307,8 +312,18 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
         RayHit hit;
         hit.t = ha.x, hit.u = ha.y, hit.v = ha.z;
         hit.instance = hb.x, hit.geometry = hb.y, hit.primitive = hb.z;
-        const float4 o = RT_LDS(W.rayO + slot), d = RT_LDS(W.rayD + slot), th = RT_LDS(W.thr + slot), ra = RT_LDS(W.rad + slot);
-        const int4 c = RT_LDS(W.ctr + slot);
+        const float4 d = RT_LDS(W.rayD + slot);
+        float4 o, th, ra;
+        int4 c;
+        if (cameraRays) { // first segment: the state k_wf_generate did not write
+          o = make_float4(P.uniforms.camera.position.x, P.uniforms.camera.position.y, P.uniforms.camera.position.z, 0.0f);
+          th = make_float4(1.0f, 1.0f, 1.0f, d.w); // d.w = halton index bits
+          ra = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          c = make_int4(0, 0, 0, 0);
+        } else {
+          o = RT_LDS(W.rayO + slot), th = RT_LDS(W.thr + slot), ra = RT_LDS(W.rad + slot);
+          c = RT_LDS(W.ctr + slot);
+        }
         // per-pixel primary outputs are only touched by sample 0 (first segment, or until the G-buffer is written)
         const bool primarySegment = (c.x == 0 && sampleIndex == 0);
         const bool needPrimary = primarySegment || (sampleIndex == 0 && P.uniforms.enableDenoiseGBuffer != 0) ||
@@ -360,12 +375,19 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
           RT_STS(W.shC + slot, make_float4(shadow.contribution.x, shadow.contribution.y, shadow.contribution.z, 0.0f));
         }
       }
-    } else if (j < count && P.env.texelsDev != nullptr) { // extension: a miss picks up the environment
-      const float4 d = RT_LDS(W.rayD + slot), th = RT_LDS(W.thr + slot), ra = RT_LDS(W.rad + slot);
+    } else if (j < count && (cameraRays || P.env.texelsDev != nullptr)) {
+      // a miss: a camera ray still has to leave radiance 0 behind for the fold (k_wf_generate did not write it);
+      // with the environment extension bound the path picks it up first
       PathState s;
+      s.radiance = mk3(0.0f);
+      s.throughput = mk3(1.0f);
+      const float4 d = RT_LDS(W.rayD + slot);
       s.dir = mk3(d.x, d.y, d.z);
-      s.throughput = mk3(th.x, th.y, th.z);
-      s.radiance = mk3(ra.x, ra.y, ra.z);
+      if (!cameraRays) {
+        const float4 th = RT_LDS(W.thr + slot), ra = RT_LDS(W.rad + slot);
+        s.throughput = mk3(th.x, th.y, th.z);
+        s.radiance = mk3(ra.x, ra.y, ra.z);
+      }
       shadeMiss(P, s);
       RT_STS(W.rad + slot, make_float4(s.radiance.x, s.radiance.y, s.radiance.z, 0.0f));
     }
@@ -382,7 +404,7 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
 template <int kRefill>
 __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_shadow(const __grid_constant__ TraceParams P, const WfState W) {
   const uint32_t count = W.counts[2];
-  traceQueue<true, kRefill>(P, W.shadowQueue, count, W.counts + 4, W.shO, W.shD,
+  traceQueue<true, kRefill>(P, W.shadowQueue, count, W.counts + 4, W.shO, W.shD, false,
                             [&](uint32_t slot, const LaneTraversal<true> &t) {
                               if (!t.found) { // unoccluded: the light sample contributes
                                 const float4 c = RT_LDS(W.shC + slot);
@@ -536,15 +558,15 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
       const int first = (s0 == 0 && segment == 0) ? 1 : 0;
       if (ctx->sortRays > 0 && segment > 0) RT_TRY(sortQueue(ctx, P, W, &W.queue[qin], W.counts + qin, W.rayO, W.rayD));
       switch (ctx->traversalVariant) {
-        case 1: k_wf_trace<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
-        case 2: k_wf_trace<16><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
-        case 3: k_wf_trace<24><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
-        case 4: k_wf_trace<4><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
-        case 5: k_wf_trace<2><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
-        default: k_wf_trace<0><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first); break;
+        case 1: k_wf_trace<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, segment == 0); break;
+        case 2: k_wf_trace<16><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, segment == 0); break;
+        case 3: k_wf_trace<24><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, segment == 0); break;
+        case 4: k_wf_trace<4><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, segment == 0); break;
+        case 5: k_wf_trace<2><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, segment == 0); break;
+        default: k_wf_trace<0><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, segment == 0); break;
       }
       ctx->mark(RT_KERNEL_TRACE);
-      k_wf_shade<<<persistent, kBlock, 0, st>>>(P, W, qin, s0);
+      k_wf_shade<<<persistent, kBlock, 0, st>>>(P, W, qin, s0, segment == 0);
       ctx->mark(RT_KERNEL_SHADE);
       if (ctx->sortRays > 1) RT_TRY(sortQueue(ctx, P, W, &W.shadowQueue, W.counts + 2, W.shO, W.shD));
       switch (ctx->traversalVariant) {
