@@ -349,11 +349,13 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
         const bool hadGBuffer = prim.wroteGBuffer;
         ShadowRequest shadow;
         pushPath = shadeSegment(P, s, hit, hIndex, sampleIndex, mk2(m4.z, m4.w), prim, shadow);
-        RT_STS(W.rayO + slot, make_float4(s.origin.x, s.origin.y, s.origin.z, 0.0f));
-        RT_STS(W.rayD + slot, make_float4(s.dir.x, s.dir.y, s.dir.z, 0.0f));
-        RT_STS(W.thr + slot, make_float4(s.throughput.x, s.throughput.y, s.throughput.z, th.w));
         RT_STS(W.rad + slot, make_float4(s.radiance.x, s.radiance.y, s.radiance.z, 0.0f));
-        RT_STS(W.ctr + slot, make_int4(s.bounce, s.step, s.transparencyPasses, 0));
+        if (pushPath) { // a path that ends here (every path of the last segment) leaves only its radiance behind
+          RT_STS(W.rayO + slot, make_float4(s.origin.x, s.origin.y, s.origin.z, 0.0f));
+          RT_STS(W.rayD + slot, make_float4(s.dir.x, s.dir.y, s.dir.z, 0.0f));
+          RT_STS(W.thr + slot, make_float4(s.throughput.x, s.throughput.y, s.throughput.z, th.w));
+          RT_STS(W.ctr + slot, make_int4(s.bounce, s.step, s.transparencyPasses, 0));
+        }
         if (primarySegment || (prim.wroteGBuffer && !hadGBuffer)) {
           const uint32_t nf = (prim.hadPrimaryHit ? 1u : 0u) | (prim.wroteGBuffer ? 2u : 0u);
           RT_STS(W.mot + pixelSlot, make_float4(prim.motion.x, prim.motion.y, m4.z, m4.w));
