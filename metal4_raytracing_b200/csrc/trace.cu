@@ -174,7 +174,9 @@ int launchTrace(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], con
   k_prepare_lights<<<(P.uniforms.lightCount + 63) / 64, 64, 0, ctx->stream>>>(P.lights, P.uniforms.lightCount,
                                                                                ctx->lightDerivedDev);
   ++ctx->launches;
-  if (ctx->traceMode == 1) return launchTraceWavefront(ctx, P);
+  // the wavefront layout packs (bounce, step, transparency passes) into 10 bits each; deeper paths than that
+  // (maxBounces > 31, far beyond anything the reference's UI offers) run in the megakernel
+  if (ctx->traceMode == 1 && P.uniforms.maxBounces <= 31) return launchTraceWavefront(ctx, P);
   ctx->mark(-1);
   k_trace_megakernel<<<owned, 256, 0, ctx->stream>>>(P);
   ctx->mark(RT_KERNEL_MEGAKERNEL);

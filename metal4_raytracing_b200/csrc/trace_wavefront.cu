@@ -53,13 +53,13 @@ struct WfState {
   uint32_t capacity; // pixel slots = owned tiles * 256
   uint32_t batch;    // samples of a pixel in flight at once; path slots = capacity * batch
   // per path slot
-  float4 *rayO, *rayD;
+  float4 *rayO, *rayD; // rayD.w: sample (halton) index bits on camera rays, packed (bounce, step, transparency
+                       // passes) afterwards; rayO doubles as the origin of the segment's shadow ray
   float4 *thr;  // throughput.xyz, w = halton index bits
   float4 *rad;  // radiance.xyz
-  int4 *ctr;    // bounce, step, transparencyPasses, unused
   float4 *hitA; // t, u, v, valid
   uint4 *hitB;  // instance, geometry, primitive, 0
-  float4 *shO, *shD, *shC; // shadow origin + tmax, direction, contribution
+  float4 *shD, *shC;   // shadow ray direction + tmax, contribution (its origin is rayO)
   // per pixel slot
   float4 *tot;  // totalColor.xyz, w = totalSamples bits
   float4 *mot;  // motion.xy, prevMotion.xy
@@ -235,7 +235,7 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
             o = make_float4(P.uniforms.camera.position.x, P.uniforms.camera.position.y, P.uniforms.camera.position.z, 0.0f);
           else
             o = RT_LDS(rayO + slot);
-          t.begin(P.tlas, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, kAny ? o.w : INFINITY);
+          t.begin(P.tlas, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, kAny ? d.w : INFINITY);
           active = true;
         }
       }
@@ -322,7 +322,8 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
           c = make_int4(0, 0, 0, 0);
         } else {
           o = RT_LDS(W.rayO + slot), th = RT_LDS(W.thr + slot), ra = RT_LDS(W.rad + slot);
-          c = RT_LDS(W.ctr + slot);
+          const uint32_t packed = __float_as_uint(d.w);
+          c = make_int4(int(packed & 1023u), int((packed >> 10) & 1023u), int(packed >> 20), 0);
         }
         // per-pixel primary outputs are only touched by sample 0 (first segment, or until the G-buffer is written)
         const bool primarySegment = (c.x == 0 && sampleIndex == 0);
@@ -351,10 +352,15 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
         pushPath = shadeSegment(P, s, hit, hIndex, sampleIndex, mk2(m4.z, m4.w), prim, shadow);
         RT_STS(W.rad + slot, make_float4(s.radiance.x, s.radiance.y, s.radiance.z, 0.0f));
         if (pushPath) { // a path that ends here (every path of the last segment) leaves only its radiance behind
-          RT_STS(W.rayO + slot, make_float4(s.origin.x, s.origin.y, s.origin.z, 0.0f));
-          RT_STS(W.rayD + slot, make_float4(s.dir.x, s.dir.y, s.dir.z, 0.0f));
+          const uint32_t packed = uint32_t(s.bounce) | (uint32_t(s.step) << 10) | (uint32_t(s.transparencyPasses) << 20);
+          RT_STS(W.rayD + slot, make_float4(s.dir.x, s.dir.y, s.dir.z, __uint_as_float(packed)));
           RT_STS(W.thr + slot, make_float4(s.throughput.x, s.throughput.y, s.throughput.z, th.w));
-          RT_STS(W.ctr + slot, make_int4(s.bounce, s.step, s.transparencyPasses, 0));
+        }
+        // the shadow ray starts where the next segment starts (shadeSegment: both are hit + N * 1e-3), so one origin
+        // record serves both; a path that ends but still has a shadow ray to trace stores it for that alone
+        if (pushPath || shadow.valid) {
+          const f3 org = pushPath ? s.origin : shadow.origin;
+          RT_STS(W.rayO + slot, make_float4(org.x, org.y, org.z, 0.0f));
         }
         if (primarySegment || (prim.wroteGBuffer && !hadGBuffer)) {
           const uint32_t nf = (prim.hadPrimaryHit ? 1u : 0u) | (prim.wroteGBuffer ? 2u : 0u);
@@ -372,8 +378,7 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
         }
         if (shadow.valid) {
           pushShadow = true;
-          RT_STS(W.shO + slot, make_float4(shadow.origin.x, shadow.origin.y, shadow.origin.z, shadow.tmax));
-          RT_STS(W.shD + slot, make_float4(shadow.dir.x, shadow.dir.y, shadow.dir.z, 0.0f));
+          RT_STS(W.shD + slot, make_float4(shadow.dir.x, shadow.dir.y, shadow.dir.z, shadow.tmax));
           RT_STS(W.shC + slot, make_float4(shadow.contribution.x, shadow.contribution.y, shadow.contribution.z, 0.0f));
         }
       }
@@ -406,7 +411,7 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
 template <int kRefill>
 __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_shadow(const __grid_constant__ TraceParams P, const WfState W) {
   const uint32_t count = W.counts[2];
-  traceQueue<true, kRefill>(P, W.shadowQueue, count, W.counts + 4, W.shO, W.shD, false,
+  traceQueue<true, kRefill>(P, W.shadowQueue, count, W.counts + 4, W.rayO, W.shD, false,
                             [&](uint32_t slot, const LaneTraversal<true> &t) {
                               if (!t.found) { // unoccluded: the light sample contributes
                                 const float4 c = RT_LDS(W.shC + slot);
@@ -445,7 +450,7 @@ int ensureState(rt_context *ctx, uint32_t capacity, uint32_t batch, WfState &out
   if (ctx->sortRays > 0)
     cub::DeviceRadixSort::SortPairs(nullptr, sortTempBytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
                                     (uint32_t *)nullptr, int(paths), 0, 24, ctx->stream);
-  const size_t need = 256 + 10 * (paths * 16 + 256) + 3 * (size_t(capacity) * 16 + 256) + 3 * (paths * 4 + 256) +
+  const size_t need = 256 + 8 * (paths * 16 + 256) + 3 * (size_t(capacity) * 16 + 256) + 3 * (paths * 4 + 256) +
                       (ctx->sortRays > 0 ? 3 * (paths * 4 + 256) + sortTempBytes + 256 : 0);
   if (ctx->wfState == nullptr || ctx->wfBytes < need) {
     RT_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -470,10 +475,8 @@ int ensureState(rt_context *ctx, uint32_t capacity, uint32_t batch, WfState &out
   s.rayD = static_cast<float4 *>(take(v));
   s.thr = static_cast<float4 *>(take(v));
   s.rad = static_cast<float4 *>(take(v));
-  s.ctr = static_cast<int4 *>(take(v));
   s.hitA = static_cast<float4 *>(take(v));
   s.hitB = static_cast<uint4 *>(take(v));
-  s.shO = static_cast<float4 *>(take(v));
   s.shD = static_cast<float4 *>(take(v));
   s.shC = static_cast<float4 *>(take(v));
   s.tot = static_cast<float4 *>(take(pv));
@@ -570,7 +573,7 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
       ctx->mark(RT_KERNEL_TRACE);
       k_wf_shade<<<persistent, kBlock, 0, st>>>(P, W, qin, s0, segment == 0);
       ctx->mark(RT_KERNEL_SHADE);
-      if (ctx->sortRays > 1) RT_TRY(sortQueue(ctx, P, W, &W.shadowQueue, W.counts + 2, W.shO, W.shD));
+      if (ctx->sortRays > 1) RT_TRY(sortQueue(ctx, P, W, &W.shadowQueue, W.counts + 2, W.rayO, W.shD));
       switch (ctx->traversalVariant) {
         case 1: k_wf_shadow<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
         case 2: k_wf_shadow<16><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
