@@ -57,8 +57,8 @@ struct WfState {
                        // passes) afterwards; rayO doubles as the origin of the segment's shadow ray
   float4 *thr;  // throughput.xyz, w = halton index bits
   float4 *rad;  // radiance.xyz
-  float4 *hitA; // t, u, v, valid
-  uint4 *hitB;  // instance, geometry, primitive, 0
+  float4 *hitA; // t (+inf = miss), u, v, primitive bits
+  uint2 *hitB;  // instance, geometry (written for hits only)
   float4 *shD, *shC;   // shadow ray direction + tmax, contribution (its origin is rayO)
   // per pixel slot
   float4 *tot;  // totalColor.xyz, w = totalSamples bits
@@ -266,9 +266,10 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_trace(co
   const uint32_t count = W.counts[qin];
   traceQueue<false, kRefill>(P, W.queue[qin], count, W.counts + 3, W.rayO, W.rayD, cameraRays != 0,
                              [&](uint32_t slot, const LaneTraversal<false> &t) {
-                               RT_STS(W.hitA + slot, make_float4(t.hit.t, t.hit.u, t.hit.v, t.found ? 1.0f : 0.0f));
+                               RT_STS(W.hitA + slot, make_float4(t.found ? t.hit.t : INFINITY, t.hit.u, t.hit.v,
+                                                                 __uint_as_float(t.hit.primitive)));
                                if (t.found)
-                                 RT_STS(W.hitB + slot, make_uint4(t.hit.instance, t.hit.geometry, t.hit.primitive, 0u));
+                                 RT_STS(W.hitB + slot, make_uint2(t.hit.instance, t.hit.geometry));
                                if (firstSegment && P.primaryIds != nullptr && slot < W.capacity) { // sample 0
                                  int px, py;
                                  bool valid;
@@ -295,23 +296,23 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
   for (uint32_t round = 0; round < rounds; ++round, j += gridDim.x * blockDim.x) { // whole warps stay in the loop
     bool pushPath = false, pushShadow = false, isHit = false;
     uint32_t slot = 0;
-    float4 ha = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 ha = make_float4(INFINITY, 0.0f, 0.0f, 0.0f);
     if (j < count) {
       slot = queue[j];
       ha = RT_LDS(W.hitA + slot);
     }
     // (compacting the hits of a CTA through shared memory before shading was measured slower: the kernel is bound
     // by the latency of its dependent gathers, not by issue slots, and compaction removes warps that hide it)
-    if (ha.w != 0.0f) {
+    if (ha.x < INFINITY) {
       {
         isHit = true;
         const uint32_t b = slot / W.capacity; // sample of the batch, pixel slot
         const uint32_t pixelSlot = slot - b * W.capacity;
         const int sampleIndex = s0 + int(b);
-        const uint4 hb = RT_LDS(W.hitB + slot);
+        const uint2 hb = RT_LDS(W.hitB + slot);
         RayHit hit;
         hit.t = ha.x, hit.u = ha.y, hit.v = ha.z;
-        hit.instance = hb.x, hit.geometry = hb.y, hit.primitive = hb.z;
+        hit.instance = hb.x, hit.geometry = hb.y, hit.primitive = __float_as_uint(ha.w);
         const float4 d = RT_LDS(W.rayD + slot);
         float4 o, th, ra;
         int4 c;
@@ -476,7 +477,7 @@ int ensureState(rt_context *ctx, uint32_t capacity, uint32_t batch, WfState &out
   s.thr = static_cast<float4 *>(take(v));
   s.rad = static_cast<float4 *>(take(v));
   s.hitA = static_cast<float4 *>(take(v));
-  s.hitB = static_cast<uint4 *>(take(v));
+  s.hitB = static_cast<uint2 *>(take(v / 2));
   s.shD = static_cast<float4 *>(take(v));
   s.shC = static_cast<float4 *>(take(v));
   s.tot = static_cast<float4 *>(take(pv));
