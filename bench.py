@@ -233,13 +233,14 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
+    frame(warmup)  # one more untimed frame: the GPU has idled while the clock sampler started
     launches0 = ctx.launches
     rnd.reset_ray_counters()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     ctx.kernel_timing(True)  # one event after each library launch, on the launching stream, inside the timed region
     barrier()
     total_ms = 0.0
-    for k, i in enumerate(range(warmup, warmup + steps)):
+    for k, i in enumerate(range(warmup + 1, warmup + 1 + steps)):
         flush.fill_(k & 0xFF)  # L2 flush, outside the per-frame events
         ev[k][0].record()
         frame(i, count="accumulate")  # ray counters: three warp-aggregated atomics per warp, always on
@@ -310,7 +311,7 @@ def main():
         e_steps = steps
         barrier()
         t0 = time.perf_counter()
-        for i in range(warmup + steps, warmup + steps + e_steps):
+        for i in range(warmup + 1 + steps, warmup + 1 + steps + e_steps):
             u.frameIndex = i
             if animated:
                 sc.animate(i / 60.0)
