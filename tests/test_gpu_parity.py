@@ -91,6 +91,36 @@ def test_golden_frame_on_gpu(gpu_ctx, assets):
     rnd.close()
 
 
+@pytest.mark.parametrize("name", ["k3small_96x64", "k5small_64", "k2tex_80x48"])
+def test_more_golden_frames_on_gpu(gpu_ctx, name):
+    """The CUDA path reproduces the committed oracle fixtures (tests/golden/make_golden.py CASES) bit for bit."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    scene_name, w, h, spp, mb, frames, animate, gbuffer, adaptive = mg.CASES[name]
+    sc, u, seed = scene.Scene.named(scene_name, w, h, assets=None)
+    C.memmove(C.byref(u), g["uniforms"].tobytes(), C.sizeof(A.Uniforms))
+    rnd = device.Renderer(gpu_ctx, sc, w, h, seeds=scene.seed_image(w, h, int(g["seed"])))
+    for f in range(frames):
+        u.frameIndex = f
+        if animate and f:
+            sc.animate(f / 60.0)
+            rnd.update()
+        rnd.draw(u, want_ids=(f == 0), count_rays=True)
+        if f == 0:
+            assert np.array_equal(rnd.read_ids(), g["ids"])
+        c = rnd.read_ray_counters()
+        assert [c["closest"], c["any"], c["hits"]] == list(g["stats"][f])
+    assert rnd.read_image(A.TEXTURE_ACCUMULATION).tobytes() == g["image"].tobytes()
+    assert rnd.read_image(A.TEXTURE_DEPTH).tobytes() == g["depth"].tobytes()
+    assert rnd.read_image(A.TEXTURE_MOTION).tobytes() == g["motion"].tobytes()
+    if gbuffer:
+        assert rnd.read_image(A.TEXTURE_NORMAL).tobytes() == g["normal"].tobytes()
+    rnd.close()
+
+
 def test_bounces_accumulation_and_adaptive_paths(gpu_ctx):
     """3 bounces, 2 spp, EMA over 4 frames with motion-adaptive accumulation + sampling switched on."""
     sc, u, seed = scene.Scene.named("K3small", 320, 200, assets=None)
