@@ -249,7 +249,8 @@ int addTorusKnot(Scene &s, int nu, int nv, int seed) {
     for (int j = 0; j < nv; ++j) {
       int i1 = (i + 1) % nu, j1 = (j + 1) % nv;
       int a = i * nv + j, b = i1 * nv + j, c = i1 * nv + j1, d = i * nv + j1;
-      sm.indices.insert(sm.indices.end(), {a, b, c, a, c, d});
+      // counter-clockwise seen from outside the tube, so the smooth normals below point outward
+      sm.indices.insert(sm.indices.end(), {a, c, b, a, d, c});
     }
   computeSmoothNormals(m);
   s.meshes.push_back(std::move(m));

@@ -174,3 +174,19 @@ def test_product_does_not_import_oracle():
                 code = "\n".join(l for l in text.splitlines() if not l.lstrip().startswith(("//", "#", "*", "/*")))
                 assert "import oracle" not in code and "liboracle" not in code and '"oracle' not in code, fn
                 assert "../oracle" not in code and "oracle/" not in code, fn
+
+
+def test_cpp_host_program_fails_loudly_without_gpu():
+    """The C++ example client (examples/rt_render.cpp) links both libraries through the C headers; without a CUDA
+    device it exits non-zero with rt_create's message instead of falling back to anything."""
+    import subprocess
+    import torch
+    from metal4_raytracing_b200 import device
+    exe = os.path.join(os.path.dirname(device.LIB_PATH), "rt_render")
+    assert os.path.isfile(exe)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    out = subprocess.run([exe, "K3small", "32", "32", "1", "1", "1", "/tmp/_rt_render_should_not_exist.png"],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode != 0 and "no CPU path" in out.stderr
+    assert not os.path.exists("/tmp/_rt_render_should_not_exist.png")

@@ -651,3 +651,30 @@ def test_full_size_configs_on_a_tile_sample(gpu_ctx, assets, name, frames, modul
         assert np.array_equal(rnd.read_image(A.TEXTURE_DEPTH)[mask], imgs.arrays[A.TEXTURE_DEPTH][mask])
         imgs.swap()
     rnd.close()
+
+
+def test_cpp_host_program_renders_the_same_png(gpu_ctx, tmp_path):
+    """examples/rt_render.cpp drives the same libraries from C++ only (scene -> renderer -> tonemap -> PNG); its
+    output equals the frame the Python client renders and tonemaps."""
+    import subprocess
+    from PIL import Image
+    exe = os.path.join(os.path.dirname(device.LIB_PATH), "rt_render")
+    assert os.path.isfile(exe), "build it with make -C metal4_raytracing_b200/csrc"
+    w, h, spp, mb, frames = 96, 64, 2, 3, 2
+    png = tmp_path / "cpp.png"
+    out = subprocess.run([exe, "K5small", str(w), str(h), str(spp), str(mb), str(frames), str(png)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "mrays_per_s=" in out.stdout
+    sc, u, seed = scene.Scene.named("K5small", w, h, assets=None)
+    u.samplesPerPixel, u.maxBounces = spp, mb
+    rnd = device.Renderer(gpu_ctx, sc, w, h, seeds=scene.seed_image(w, h, seed))
+    for f in range(frames):
+        u.frameIndex = f
+        if f:
+            sc.animate(f / 60.0)
+            rnd.update()
+        rnd.draw(u)
+    ref = gpu_ctx.tonemap(rnd.image_info(A.TEXTURE_ACCUMULATION), srgb=True, flip_y=True)
+    rnd.close()
+    assert np.array_equal(np.asarray(Image.open(png)), ref)

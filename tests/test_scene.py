@@ -199,3 +199,18 @@ def test_png_writer_round_trip(tmp_path):
         scene.write_png(p, img)
         back = np.asarray(Image.open(p))
         assert back.shape == img.shape and np.array_equal(back, img)
+
+
+@pytest.mark.parametrize("name", ["K2", "K3small", "K5small"])
+def test_procedural_stand_ins_face_outward(name):
+    """The closed stand-in meshes (bunny, dragon, robot) must enclose positive volume with their winding and carry
+    vertex normals on the same side — inward normals would send every bounce ray into the mesh and make the
+    benchmark workload unrepresentative (this caught the torus knot being inside out)."""
+    sc, _, _ = scene.Scene.named(name, 64, 64, assets=None)
+    m = sc.mesh_arrays(0)
+    P = m["positions"][:, :3].astype(np.float64)
+    N = m["normals"][:, :3].astype(np.float64)
+    idx = np.concatenate([np.asarray(s_).reshape(-1, 3) for s_ in m["submeshes"]])
+    a, b, c = P[idx[:, 0]], P[idx[:, 1]], P[idx[:, 2]]
+    assert float((a * np.cross(b, c)).sum(1).sum()) > 0.0
+    assert float(((np.cross(b - a, c - a) * N[idx].mean(1)).sum(1) > 0).mean()) > 0.99
