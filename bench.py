@@ -11,8 +11,8 @@ new Halton index, so timed frames are not repeats of cached work; an L2 flush be
   value     whole-job Mrays/s, device-timed, inputs resident in HBM (max over ranks for N > 1)
   e2e       the same metric through the public host API with HOST inputs: per frame rtr_update (pinned H2D of
             instance descriptors + lights, TLAS rebuild) + draw + D2H of the finished frame, wall clock
-  roofline  dominant kernel (k_wf_trace, the closest-hit traversal) vs the measured HBM peak: algorithmic bytes per
-            SURVEY.md §8(d) (closest-hit rays of the timed frames x bytes/ray) over that kernel's own launch time,
+  roofline  dominant kernel (k_wf_traverse, the persistent software traversal) vs the measured HBM peak: algorithmic
+            bytes per SURVEY.md §8(d) (rays of the timed frames x bytes/ray) over that kernel's own launch time,
             measured live with CUDA events the library records around each of its launches during the timed region
   cpu_baseline  the CPU oracle (oracle/, a port of the reference kernels) on a bounded tile sample of the same frame
 
@@ -274,15 +274,19 @@ def main():
     peak, peak_src = load_peaks()
     verts = 100000 if animated else 0
     b_ray = B_RAY[args.workload]
-    trace_ms, trace_launches = ktimes.get("trace", ktimes.get("megakernel", (total_ms, steps)))
-    dominant = "k_wf_trace" if "trace" in ktimes else "k_trace_megakernel"
-    dom_rays = closest_rays if "trace" in ktimes else rays
+    # the persistent traversal kernel k_wf_traverse runs closest-hit rays and (fused into the next segment's launch) the
+    # any-hit shadow rays; the library times its launches in the classes "trace" and "shadow"
+    if "trace" in ktimes:
+        trace_ms = ktimes["trace"][0] + ktimes.get("shadow", (0.0, 0))[0]
+        trace_launches = ktimes["trace"][1] + ktimes.get("shadow", (0.0, 0))[1]
+        dominant, dom_rays = "k_wf_traverse", closest_rays + shadow_rays
+    else:
+        trace_ms, trace_launches = ktimes.get("megakernel", (total_ms, steps))
+        dominant, dom_rays = "k_trace_megakernel", rays
     achieved = dom_rays * b_ray / (trace_ms * 1e-3) / 1e9
     frame_bytes = rays * b_ray + hits * B_HIT + pixels_owned * B_PIXEL * steps + verts * B_VERTEX * steps
     kernels = {k: {"ms_per_step": round(v[0] / steps, 3), "launches_per_step": round(v[1] / steps, 1),
                    "share": round(v[0] / max(1e-9, total_ms), 4)} for k, v in ktimes.items()}
-    if "shadow" in ktimes:
-        kernels["shadow"]["achieved_gbs"] = round(shadow_rays * b_ray / (ktimes["shadow"][0] * 1e-3) / 1e9, 1)
     if "shade" in ktimes:
         kernels["shade"]["achieved_gbs"] = round(hits * B_HIT / (ktimes["shade"][0] * 1e-3) / 1e9, 1)
     traffic, traffic_src = load_traffic(args.workload)
@@ -295,8 +299,10 @@ def main():
                 "whole_frame": {"achieved": round(frame_bytes / (total_ms * 1e-3) / 1e9, 2),
                                 "frac": round(frame_bytes / (total_ms * 1e-3) / 1e9 / peak, 4)},
                 "kernels": kernels,
-                "note": "algorithmic bytes = closest-hit rays x %.0f B (SURVEY 8d) over k_wf_trace's own launch time; "
-                        "whole_frame adds shadow rays, 300 B per closest hit and 32 B per pixel over the frame time. "
+                "note": "algorithmic bytes = rays (closest-hit + any-hit) x %.0f B (SURVEY 8d) over the traversal kernel's "
+                        "own launch time (classes trace + shadow: a launch traces segment k's closest hits and segment "
+                        "k-1's shadow rays); whole_frame adds 300 B per closest hit and 32 B per pixel over the frame "
+                        "time. "
                         "The BVH fits L2 (traffic = measured DRAM bytes per launch, profiles/), so the kernel is "
                         "latency/issue bound rather than DRAM bound" % b_ray}
 

@@ -135,6 +135,7 @@ struct rt_context {
   uint64_t launches = 0;
   int traceMode = 1;        // 0 megakernel, 1 wavefront
   int traversalVariant = 1; // lane refill threshold of the traversal kernels: 0 none, 1 = 8, 2 = 16, 3 = 24 idle lanes
+  int fuseTraversal = 1;    // wavefront: shadow rays of segment k traced in the launch of segment k + 1's closest hits
   int sortRays = 0;         // wavefront: 0 = queues in arrival order, 1 = bounce rays sorted by octant + origin cell
                             // before tracing, 2 = shadow rays too
   int leafSize = 3;         // BVH builder: primitives per leaf slot of a wide node (1..3)

@@ -484,6 +484,11 @@ int rt_set_option(rt_context *ctx, const char *key, int value) {
     ctx->traversalVariant = value;
     return 0;
   }
+  if (k == "fuse_traversal") {
+    RT_CHECK(value == 0 || value == 1, "rt_set_option: fuse_traversal is 0 or 1");
+    ctx->fuseTraversal = value;
+    return 0;
+  }
   if (k == "sort_rays") {
     RT_CHECK(value >= 0 && value <= 2, "rt_set_option: sort_rays is 0 (off), 1 (bounce rays) or 2 (bounce + shadow rays)");
     ctx->sortRays = value;

@@ -65,7 +65,9 @@ struct WfState {
   float4 *mot;  // motion.xy, prevMotion.xy
   float4 *misc; // depth, flags bits (1 = hadPrimaryHit, 2 = wroteGBuffer), seed offset bits, unused
   uint32_t *queue[2], *shadowQueue;
-  uint32_t *counts; // [0], [1] path queues, [2] shadow queue, [3] trace cursor, [4] shadow cursor
+  uint32_t *counts; // [0], [1] path queues, [3] trace cursor, [8 + p] shadow queue length and [10 + p] shadow cursor of
+                    // segment parity p (double-buffered: the shadow rays of segment k are traced in the same launch
+                    // as the closest-hit rays of segment k + 1)
   // ray reordering (option sort_rays): key buffers, the sorted copy of a queue and CUB's workspace
   uint32_t *sortKeys[2], *sortedQueue;
   void *sortTemp;
@@ -255,31 +257,53 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
   }
 }
 
+// One launch of the persistent traversal kernel does up to two jobs: the closest-hit rays of segment k (queue qin)
+// and then the any-hit shadow rays the shade kernel of segment k - 1 emitted (parity shadowParity). Both only depend on
+// that shade kernel, so putting them in one launch lets warps that run out of closest-hit rays go straight on to
+// shadow rays instead of idling through the tail of a separate launch (a persistent launch has a ~50 us tail, which
+// matters once a GPU holds only a slice of the frame). The closest-hit rays go first: they are the longer ones.
 template <int kRefill>
-__global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_trace(const __grid_constant__ TraceParams P, const WfState W,
-                                                                              int qin, int firstSegment, int cameraRays) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) { // the queues the next two phases append to start empty
-    W.counts[qin ^ 1] = 0u;
-    W.counts[2] = 0u;
-    W.counts[4] = 0u; // cursor of the shadow kernel
+__global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse(const __grid_constant__ TraceParams P, const WfState W,
+                                                                                 int qin, int firstSegment, int cameraRays,
+                                                                                 int doClosest, int doShadow, int shadowParity) {
+  if (doClosest) {
+    const int nextParity = doShadow ? (shadowParity ^ 1) : shadowParity; // parity of the segment traced here
+    if (blockIdx.x == 0 && threadIdx.x == 0) { // the queues this segment's shade kernel appends to start empty
+      W.counts[qin ^ 1] = 0u;
+      W.counts[8 + nextParity] = 0u;
+      W.counts[10 + nextParity] = 0u;
+    }
+    const uint32_t count = W.counts[qin];
+    traceQueue<false, kRefill>(P, W.queue[qin], count, W.counts + 3, W.rayO, W.rayD, cameraRays != 0,
+                               [&](uint32_t slot, const LaneTraversal<false> &t) {
+                                 RT_STS(W.hitA + slot, make_float4(t.found ? t.hit.t : INFINITY, t.hit.u, t.hit.v,
+                                                                   __uint_as_float(t.hit.primitive)));
+                                 if (t.found)
+                                   RT_STS(W.hitB + slot, make_uint2(t.hit.instance, t.hit.geometry));
+                                 if (firstSegment && P.primaryIds != nullptr && slot < W.capacity) { // sample 0
+                                   int px, py;
+                                   bool valid;
+                                   slotPixel(P, slot, px, py, valid);
+                                   const uint4 id = t.found ? make_uint4(t.hit.instance, t.hit.geometry, t.hit.primitive, __float_as_uint(t.hit.t))
+                                                            : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                                   reinterpret_cast<uint4 *>(P.primaryIds)[size_t(py) * size_t(P.uniforms.width) + size_t(px)] = id;
+                                 }
+                               });
+    if (P.rayCounters != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.rayCounters + 0, (unsigned long long)count);
   }
-  const uint32_t count = W.counts[qin];
-  traceQueue<false, kRefill>(P, W.queue[qin], count, W.counts + 3, W.rayO, W.rayD, cameraRays != 0,
-                             [&](uint32_t slot, const LaneTraversal<false> &t) {
-                               RT_STS(W.hitA + slot, make_float4(t.found ? t.hit.t : INFINITY, t.hit.u, t.hit.v,
-                                                                 __uint_as_float(t.hit.primitive)));
-                               if (t.found)
-                                 RT_STS(W.hitB + slot, make_uint2(t.hit.instance, t.hit.geometry));
-                               if (firstSegment && P.primaryIds != nullptr && slot < W.capacity) { // sample 0
-                                 int px, py;
-                                 bool valid;
-                                 slotPixel(P, slot, px, py, valid);
-                                 const uint4 id = t.found ? make_uint4(t.hit.instance, t.hit.geometry, t.hit.primitive, __float_as_uint(t.hit.t))
-                                                          : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-                                 reinterpret_cast<uint4 *>(P.primaryIds)[size_t(py) * size_t(P.uniforms.width) + size_t(px)] = id;
-                               }
-                             });
-  if (P.rayCounters != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.rayCounters + 0, (unsigned long long)count);
+  if (doShadow) {
+    const uint32_t count = W.counts[8 + shadowParity];
+    traceQueue<true, kRefill>(P, W.shadowQueue, count, W.counts + 10 + shadowParity, W.rayO, W.shD, false,
+                              [&](uint32_t slot, const LaneTraversal<true> &t) {
+                                if (!t.found) { // unoccluded: the light sample contributes
+                                  const float4 c = RT_LDS(W.shC + slot);
+                                  float4 r = RT_LDS(W.rad + slot);
+                                  r.x = r.x + c.x, r.y = r.y + c.y, r.z = r.z + c.z;
+                                  RT_STS(W.rad + slot, r);
+                                }
+                              });
+    if (P.rayCounters != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.rayCounters + 1, (unsigned long long)count);
+  }
 }
 
 #ifndef RT_SHADE_MINBLOCKS
@@ -287,7 +311,7 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_trace(co
 #endif
 __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const __grid_constant__ TraceParams P,
                                                                          const WfState W, int qin, int s0,
-                                                                         int cameraRays) {
+                                                                         int cameraRays, int shadowParity) {
   if (blockIdx.x == 0 && threadIdx.x == 0) W.counts[3] = 0u; // cursor of the next trace kernel
   const uint32_t count = W.counts[qin];
   const uint32_t *queue = W.queue[qin];
@@ -399,7 +423,7 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
       shadeMiss(P, s);
       RT_STS(W.rad + slot, make_float4(s.radiance.x, s.radiance.y, s.radiance.z, 0.0f));
     }
-    queuePush(W.shadowQueue, W.counts + 2, pushShadow, slot);
+    queuePush(W.shadowQueue, W.counts + 8 + shadowParity, pushShadow, slot);
     queuePush(W.queue[qin ^ 1], W.counts + (qin ^ 1), pushPath, slot);
     if (P.rayCounters != nullptr) {
       const unsigned active = __activemask();
@@ -407,21 +431,6 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
       if ((threadIdx.x & 31) == __ffs(int(active)) - 1 && hits) atomicAdd(P.rayCounters + 2, (unsigned long long)__popc(hits));
     }
   }
-}
-
-template <int kRefill>
-__global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_shadow(const __grid_constant__ TraceParams P, const WfState W) {
-  const uint32_t count = W.counts[2];
-  traceQueue<true, kRefill>(P, W.shadowQueue, count, W.counts + 4, W.rayO, W.shD, false,
-                            [&](uint32_t slot, const LaneTraversal<true> &t) {
-                              if (!t.found) { // unoccluded: the light sample contributes
-                                const float4 c = RT_LDS(W.shC + slot);
-                                float4 r = RT_LDS(W.rad + slot);
-                                r.x = r.x + c.x, r.y = r.y + c.y, r.z = r.z + c.z;
-                                RT_STS(W.rad + slot, r);
-                              }
-                            });
-  if (P.rayCounters != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.rayCounters + 1, (unsigned long long)count);
 }
 
 __global__ void __launch_bounds__(kBlock) k_wf_resolve(const __grid_constant__ TraceParams P, const WfState W,
@@ -547,13 +556,27 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
   for (int s0 = 0; s0 < sampleLoopBound;) {
     // the first batch stays within the base samples (see k_wf_generate)
     const int n = std::min(batch, (s0 < baseSamples ? baseSamples : sampleLoopBound) - s0);
-    RT_CUDA(cudaMemsetAsync(W.counts, 0, 32, st));
+    RT_CUDA(cudaMemsetAsync(W.counts, 0, 64, st));
     ctx->mark(-1);
     k_wf_generate<<<persistent, kBlock, 0, st>>>(P, W, s0, n, prevS0, prevN, baseSamples, maxExtraSamples);
     ctx->mark(RT_KERNEL_GENERATE);
     ++ctx->launches;
     int qin = 0;
+    bool shadowPending = false; // the shadow rays of the previous segment have not been traced yet
+    int pendingParity = 0;
+    auto traverse = [&](int first, int cameraRays, int doClosest, int doShadow, int shadowParity) {
+      switch (ctx->traversalVariant) {
+        case 1: k_wf_traverse<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
+        case 2: k_wf_traverse<16><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
+        case 3: k_wf_traverse<24><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
+        case 4: k_wf_traverse<4><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
+        case 5: k_wf_traverse<2><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
+        default: k_wf_traverse<0><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
+      }
+      ++ctx->launches;
+    };
     for (int segment = 0; segment < maxSegments; ++segment) {
+      const int parity = segment & 1;
       if (segment >= maxBounces) { // only glass paths get here: ask the device whether any are left
         uint32_t remaining = 0;
         RT_CUDA(cudaMemcpyAsync(&remaining, W.counts + qin, 4, cudaMemcpyDeviceToHost, st));
@@ -563,29 +586,31 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
       }
       const int first = (s0 == 0 && segment == 0) ? 1 : 0;
       if (ctx->sortRays > 0 && segment > 0) RT_TRY(sortQueue(ctx, P, W, &W.queue[qin], W.counts + qin, W.rayO, W.rayD));
-      switch (ctx->traversalVariant) {
-        case 1: k_wf_trace<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, segment == 0); break;
-        case 2: k_wf_trace<16><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, segment == 0); break;
-        case 3: k_wf_trace<24><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, segment == 0); break;
-        case 4: k_wf_trace<4><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, segment == 0); break;
-        case 5: k_wf_trace<2><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, segment == 0); break;
-        default: k_wf_trace<0><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, segment == 0); break;
+      if (ctx->fuseTraversal && shadowPending && ctx->sortRays < 2) {
+        traverse(first, segment == 0, 1, 1, pendingParity); // closest hits of this segment + shadow rays of the last
+        shadowPending = false;
+        ctx->mark(RT_KERNEL_TRACE);
+      } else {
+        if (shadowPending) {
+          if (ctx->sortRays > 1) RT_TRY(sortQueue(ctx, P, W, &W.shadowQueue, W.counts + 8 + pendingParity, W.rayO, W.shD));
+          traverse(0, 0, 0, 1, pendingParity);
+          shadowPending = false;
+          ctx->mark(RT_KERNEL_SHADOW);
+        }
+        traverse(first, segment == 0, 1, 0, parity);
+        ctx->mark(RT_KERNEL_TRACE);
       }
-      ctx->mark(RT_KERNEL_TRACE);
-      k_wf_shade<<<persistent, kBlock, 0, st>>>(P, W, qin, s0, segment == 0);
+      k_wf_shade<<<persistent, kBlock, 0, st>>>(P, W, qin, s0, segment == 0, parity);
       ctx->mark(RT_KERNEL_SHADE);
-      if (ctx->sortRays > 1) RT_TRY(sortQueue(ctx, P, W, &W.shadowQueue, W.counts + 2, W.rayO, W.shD));
-      switch (ctx->traversalVariant) {
-        case 1: k_wf_shadow<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
-        case 2: k_wf_shadow<16><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
-        case 3: k_wf_shadow<24><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
-        case 4: k_wf_shadow<4><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
-        case 5: k_wf_shadow<2><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
-        default: k_wf_shadow<0><<<traceGrid, kTraceBlock, 0, st>>>(P, W); break;
-      }
-      ctx->mark(RT_KERNEL_SHADOW);
-      ctx->launches += 3;
+      ++ctx->launches;
+      shadowPending = true;
+      pendingParity = parity;
       qin ^= 1;
+    }
+    if (shadowPending) {
+      if (ctx->sortRays > 1) RT_TRY(sortQueue(ctx, P, W, &W.shadowQueue, W.counts + 8 + pendingParity, W.rayO, W.shD));
+      traverse(0, 0, 0, 1, pendingParity);
+      ctx->mark(RT_KERNEL_SHADOW);
     }
     prevS0 = s0;
     prevN = n;

@@ -18,17 +18,17 @@ units = rows[1]
 agg = {}
 for r in rows[2:]:
     n = r[hdr["Kernel Name"]]
-    k = next((x for x in ("k_wf_trace", "k_wf_shadow", "k_wf_shade", "k_wf_generate", "k_wf_resolve") if x in n), None)
+    k = next((x for x in ("k_wf_traverse", "k_wf_shade", "k_wf_generate", "k_wf_resolve") if x in n), None)
     if not k:
         continue
     def val(m):
         return float(r[hdr[m]].replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[units[hdr[m]]]
     agg.setdefault(k, []).append(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
-traffic = {"K3": {"kernel": "k_wf_trace", "dram_bytes_per_launch": round(sum(agg["k_wf_trace"]) / len(agg["k_wf_trace"])),
-                  "launches_captured": len(agg["k_wf_trace"]),
+traffic = {"K3": {"kernel": "k_wf_traverse", "dram_bytes_per_launch": round(sum(agg["k_wf_traverse"]) / len(agg["k_wf_traverse"])),
+                  "launches_captured": len(agg["k_wf_traverse"]),
                   "source": f"profiles/{out_tag}_bench.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean over "
-                            "the k_wf_trace launches of one timed 16-spp frame)",
-                  "other_kernels": {k: round(sum(v) / len(v)) for k, v in agg.items() if k != "k_wf_trace"}}}
+                            "the k_wf_traverse launches of one timed 16-spp frame)",
+                  "other_kernels": {k: round(sum(v) / len(v)) for k, v in agg.items() if k != "k_wf_traverse"}}}
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 
 import shutil
@@ -40,7 +40,7 @@ ki, vi = lrows[0].index("Kernel Name"), lrows[0].index("Metric Value")
 tot = 0.0
 for r in lrows[1:]:
     t = float(r[vi].replace(",", "")); tot += t
-    for x in ("k_wf_trace", "k_wf_shadow", "k_wf_shade", "k_wf_generate", "k_wf_resolve"):
+    for x in ("k_wf_traverse", "k_wf_shade", "k_wf_generate", "k_wf_resolve"):
         if x in r[ki]:
             shares[x] = shares.get(x, 0.0) + t
 tr = traffic["K3"]["dram_bytes_per_launch"]
@@ -58,12 +58,14 @@ with open(os.path.join(ROOT, "profiles", f"{out_tag}_bench.md"), "w") as f:
     f.write("## Where the frame goes\n\nLive CUDA-event timing inside the timed region (`roofline.kernels`; the library records an event "
             "after each of its launches) against the ncu launch list of the same command (below): the shares agree.\n\n")
     f.write("| kernel | live ms/frame | live share | ncu share (serialised) |\n|---|---|---|---|\n")
-    for name, key in (("k_wf_trace (closest hit)", "trace"), ("k_wf_shadow (any hit)", "shadow"), ("k_wf_shade", "shade"),
-                      ("k_wf_generate", "generate"), ("k_wf_resolve", "resolve")):
+    trav_ms = k["trace"]["ms_per_step"] + k.get("shadow", {"ms_per_step": 0})["ms_per_step"]
+    trav_share = k["trace"]["share"] + k.get("shadow", {"share": 0})["share"]
+    f.write(f"| k_wf_traverse (closest hit + any hit) | {trav_ms:.2f} | {100 * trav_share:.1f} % | {100 * shares.get('k_wf_traverse', 0) / tot:.1f} % |\n")
+    for name, key in (("k_wf_shade", "shade"), ("k_wf_generate", "generate"), ("k_wf_resolve", "resolve")):
         sk = "k_wf_" + key
         f.write(f"| {name} | {k[key]['ms_per_step']:.2f} | {100 * k[key]['share']:.1f} % | {100 * shares.get(sk, 0) / tot:.1f} % |\n")
-    f.write(f"\nRoofline of the dominant kernel: {rl['launches']} k_wf_trace launches, {rl['bytes_per_launch'] / 1e9:.2f} GB of algorithmic "
-            f"node + triangle bytes per launch (672 B per closest-hit ray, SURVEY §8d) in {rl['avg_launch_ms']:.2f} ms = "
+    f.write(f"\nRoofline of the dominant kernel: {rl['launches']} k_wf_traverse launches, {rl['bytes_per_launch'] / 1e9:.2f} GB of algorithmic "
+            f"node + triangle bytes per launch (672 B per ray, SURVEY §8d) in {rl['avg_launch_ms']:.2f} ms = "
             f"**{rl['achieved']:.0f} GB/s = {rl['frac']:.3f} of the measured HBM peak ({rl['peak']} GB/s)**. Measured DRAM traffic of the "
             f"same kernel (ncu capture below, `traffic.json`): **{tr / 1e9:.2f} GB per launch**, {rl['bytes_per_launch'] / tr:.1f}x less than the "
             "algorithmic figure — the BVH (52 MB) stays in L2, and most of what does reach DRAM is the per-path ray/hit state. The kernel is "
@@ -71,7 +73,7 @@ with open(os.path.join(ROOT, "profiles", f"{out_tag}_bench.md"), "w") as f:
             "history of what that analysis led to.\n\n")
     f.write(run(["list", lst, "ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e` (full list: "
                  f"{out_tag}_launches_bench.csv)"]).replace("cub::DeviceRadixSort", "cub::RadixSort"))
-    f.write(run(["rep", rep, "ncu --set full capture: the 11 wavefront launches of one timed frame (generate, 3 x (trace, shade, shadow), resolve)"]))
+    f.write(run(["rep", rep, "ncu --set full capture: the wavefront launches of one timed frame (generate, traverse / shade alternating, resolve)"]))
     f.write("Reading: camera rays (first trace) run at 19 of 32 threads per instruction, bounce and shadow rays at 12–16; issue slots are "
             "61–70 % busy in the traversal kernels at 37 % occupancy (6 CTAs x 4 warps, 80 registers). k_wf_shade is bound by dependent "
             "gathers (long_scoreboard 5–15 cycles per issue) and by its size (6.5 k SASS instructions: no_instruction 3–5); k_wf_generate "
