@@ -1,0 +1,80 @@
+"""Multi-GPU frame assembly on real devices (needs >= 2 GPUs; skipped otherwise): each rank renders only its tiles
+on its own B200 and the frame every rank ends up with — through NVLink peer stores from the resolve kernel, or
+through rt_pack_tiles + NCCL all-gather + rt_unpack_tiles — equals the single-GPU frame bit for bit, over several
+EMA frames of an animated scene."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+W, H, FRAMES = 200, 136, 3
+
+
+def _scene():
+    from metal4_raytracing_b200 import scene
+    sc, u, seed = scene.Scene.named("K5small", W, H, assets=None)
+    u.samplesPerPixel, u.maxBounces = 2, 3
+    return sc, u, scene.seed_image(W, H, seed)
+
+
+def _render(ctx, world, rank, mode, dist=None):
+    from metal4_raytracing_b200 import _abi as A, device, parallel
+    sc, u, seeds = _scene()
+    rnd = device.Renderer(ctx, sc, W, H, seeds=seeds)
+    xchg = parallel.FrameExchange(rnd, world, rank, mode=mode)
+    frames = []
+    for f in range(FRAMES):
+        u.frameIndex = f
+        if f:
+            sc.animate(f / 60.0)
+            rnd.update()
+        rnd.draw(u, tile_modulo=world, tile_remainder=rank, peers=xchg.peers_for_next_draw())
+        xchg.finish_frame()
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+        frames.append(rnd.read_image(A.TEXTURE_ACCUMULATION).copy())
+    rnd.close()
+    return np.stack(frames)
+
+
+def _worker(rank, world, port, mode, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from metal4_raytracing_b200 import device
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    ctx = device.Context(rank)
+    stream = torch.cuda.Stream(device=rank)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    np.save(os.path.join(out_dir, f"{mode}_rank{rank}.npy"), _render(ctx, world, rank, mode, dist))
+    ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["peer", "gather"])
+def test_two_gpu_frame_equals_single_gpu(tmp_path, mode):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    from metal4_raytracing_b200 import device
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, mode, str(tmp_path)), nprocs=2, join=True)
+    ctx = device.Context(0)
+    ref = _render(ctx, 1, 0, mode)
+    ctx.close()
+    for r in range(2):
+        got = np.load(os.path.join(tmp_path, f"{mode}_rank{r}.npy"))
+        assert np.array_equal(got.view(np.uint16), ref.view(np.uint16)), f"{mode}: rank {r} frame differs"

@@ -5,7 +5,8 @@ mode = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 name = sys.argv[2] if len(sys.argv) > 2 else "K3"
 spp = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 mb = int(sys.argv[4]) if len(sys.argv) > 4 else 2
-w, h = 1920, 1080
+w = int(sys.argv[5]) if len(sys.argv) > 5 else 1920
+h = int(sys.argv[6]) if len(sys.argv) > 6 else 1080
 sc, u, seed = scene.Scene.named(name, w, h)
 u.samplesPerPixel, u.maxBounces = spp, mb
 ctx = device.Context(0); ctx.set_trace_mode(mode)
