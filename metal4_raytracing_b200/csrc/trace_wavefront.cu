@@ -207,15 +207,26 @@ constexpr int kStepsPerCheck = RT_STEPS_PER_CHECK;
 #ifndef RT_FUSED_PRIMS
 #define RT_FUSED_PRIMS 1
 #endif
+// entries of each lane's traversal stack kept in shared memory (0 = all in local memory), traverse.cuh SplitStack
+#ifndef RT_SHARED_STACK
+#define RT_SHARED_STACK 0
+#endif
 
 template <bool kAny, int kRefill, typename Finish>
 __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t *__restrict__ queue, uint32_t count,
                                            uint32_t *cursor, const float4 *__restrict__ rayO,
-                                           const float4 *__restrict__ rayD, bool cameraRays, Finish finish) {
+                                           const float4 *__restrict__ rayD, bool cameraRays, uint2 *sharedStack,
+                                           Finish finish) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   LaneTraversal<kAny> t;
-  uint2 stack[kStackSize];
+#if RT_SHARED_STACK > 0
+  SplitStack<RT_SHARED_STACK, kTraceBlock> stack;
+  stack.shared = sharedStack + threadIdx.x;
+#else
+  LocalStack stack;
+  (void)sharedStack;
+#endif
   bool active = false, exhausted = false;
   uint32_t slot = 0;
   while (true) {
@@ -266,6 +277,11 @@ template <int kRefill>
 __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse(const __grid_constant__ TraceParams P, const WfState W,
                                                                                  int qin, int firstSegment, int cameraRays,
                                                                                  int doClosest, int doShadow, int shadowParity) {
+#if RT_SHARED_STACK > 0
+  __shared__ uint2 s_stack[RT_SHARED_STACK * kTraceBlock]; // [entry][thread], used by both phases in turn
+#else
+  uint2 *s_stack = nullptr;
+#endif
   if (doClosest) {
     const int nextParity = doShadow ? (shadowParity ^ 1) : shadowParity; // parity of the segment traced here
     if (blockIdx.x == 0 && threadIdx.x == 0) { // the queues this segment's shade kernel appends to start empty
@@ -274,7 +290,7 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse
       W.counts[10 + nextParity] = 0u;
     }
     const uint32_t count = W.counts[qin];
-    traceQueue<false, kRefill>(P, W.queue[qin], count, W.counts + 3, W.rayO, W.rayD, cameraRays != 0,
+    traceQueue<false, kRefill>(P, W.queue[qin], count, W.counts + 3, W.rayO, W.rayD, cameraRays != 0, s_stack,
                                [&](uint32_t slot, const LaneTraversal<false> &t) {
                                  RT_STS(W.hitA + slot, make_float4(t.found ? t.hit.t : INFINITY, t.hit.u, t.hit.v,
                                                                    __uint_as_float(t.hit.primitive)));
@@ -293,7 +309,7 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse
   }
   if (doShadow) {
     const uint32_t count = W.counts[8 + shadowParity];
-    traceQueue<true, kRefill>(P, W.shadowQueue, count, W.counts + 10 + shadowParity, W.rayO, W.shD, false,
+    traceQueue<true, kRefill>(P, W.shadowQueue, count, W.counts + 10 + shadowParity, W.rayO, W.shD, false, s_stack,
                               [&](uint32_t slot, const LaneTraversal<true> &t) {
                                 if (!t.found) { // unoccluded: the light sample contributes
                                   const float4 c = RT_LDS(W.shC + slot);

@@ -25,6 +25,26 @@ struct RayHit {
 
 constexpr int kStackSize = 48;
 
+// Traversal stack of one lane. LocalStack: a plain array (local memory, served by L1). SplitStack: the first
+// kShared entries — all a ray normally needs — live in shared memory, laid out [entry][thread] so a warp's accesses
+// are conflict-free; deeper entries spill to a local array. Pops then cost a shared-memory load instead of a local
+// load that competes with the BVH nodes for L1 lines.
+struct LocalStack {
+  uint2 e[kStackSize];
+  __device__ __forceinline__ void set(int i, uint2 v) { e[i] = v; }
+  __device__ __forceinline__ uint2 get(int i) const { return e[i]; }
+};
+template <int kShared, int kThreads>
+struct SplitStack {
+  uint2 *shared; // &smem[threadIdx.x]; entry i at shared[i * kThreads]
+  uint2 spill[kStackSize - kShared];
+  __device__ __forceinline__ void set(int i, uint2 v) {
+    if (i < kShared) shared[i * kThreads] = v;
+    else spill[i - kShared] = v;
+  }
+  __device__ __forceinline__ uint2 get(int i) const { return i < kShared ? shared[i * kThreads] : spill[i - kShared]; }
+};
+
 __device__ __forceinline__ float pick3(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
 
 // Component selection without branches or predicates: m0 / m1 are all-ones when the wanted axis is 0 / 1. Two LOP3
@@ -297,11 +317,12 @@ struct LaneTraversal {
   }
 
   // take the nearest pending child of ngroup, test its eight children
-  __device__ __forceinline__ void nodeStep(uint2 *stack) {
+  template <typename Stack>
+  __device__ __forceinline__ void nodeStep(Stack &stack) {
     const uint32_t hits = ngroup.y;
     const uint32_t bit = 31u - uint32_t(__clz(int(hits)));
     ngroup.y &= ~(1u << bit);
-    if (ngroup.y > 0x00FFFFFFu && sp < kStackSize) stack[sp++] = ngroup;
+    if (ngroup.y > 0x00FFFFFFu && sp < kStackSize) stack.set(sp++, ngroup);
     const uint32_t slot = (bit - 24u) ^ (box.octinv & 7u);
     const uint32_t rel = __popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
     const uint4 *np = nodes + size_t(ngroup.x + rel) * 5;
@@ -316,13 +337,14 @@ struct LaneTraversal {
   }
 
   // one primitive of tgroup. Returns true when an any-hit query is satisfied.
-  __device__ __forceinline__ bool primitiveStep(const TlasHeader &tlas, uint2 *stack) {
+  template <typename Stack>
+  __device__ __forceinline__ bool primitiveStep(const TlasHeader &tlas, Stack &stack) {
     const uint32_t bit = uint32_t(__ffs(int(tgroup.y))) - 1u;
     tgroup.y &= ~(1u << bit);
     if (instanceSp < 0) {
       // TLAS leaf: enter the instance. Pending world-space work goes to the stack first.
-      if (tgroup.y != 0u && sp < kStackSize) stack[sp++] = tgroup;
-      if (ngroup.y > 0x00FFFFFFu && sp < kStackSize) stack[sp++] = ngroup;
+      if (tgroup.y != 0u && sp < kStackSize) stack.set(sp++, tgroup);
+      if (ngroup.y > 0x00FFFFFFu && sp < kStackSize) stack.set(sp++, ngroup);
       instance = __ldg(tlas.leafInstance + tgroup.x + bit);
       const InstanceRecord *rec = tlas.instances + instance;
       const float4 r0 = __ldg(&rec->row0), r1 = __ldg(&rec->row1), r2 = __ldg(&rec->row2);
@@ -380,14 +402,15 @@ struct LaneTraversal {
 
   // nothing pending in registers: leave the instance if its subtree is exhausted, then pop.
   // Returns false when the traversal is complete.
-  __device__ __forceinline__ bool popStep(const TlasHeader &tlas, uint2 *stack) {
+  template <typename Stack>
+  __device__ __forceinline__ bool popStep(const TlasHeader &tlas, Stack &stack) {
     if (sp == instanceSp) {
       instanceSp = -1;
       box = makeBoxSetup(ox, oy, oz, dx, dy, dz, box.one);
       nodes = reinterpret_cast<const uint4 *>(tlas.nodes);
     }
     if (sp == 0) return false;
-    const uint2 e = stack[--sp];
+    const uint2 e = stack.get(--sp);
     if (e.y > 0x00FFFFFFu) {
       ngroup = e;
     } else {
@@ -402,8 +425,8 @@ struct LaneTraversal {
   // into the next, so a lane does up to three units of work per iteration while the warp still executes each stage
   // once. Primitives of a node are still all tested before any of its children is entered (hit.t shrinks first).
   // Returns false when the traversal has finished.
-  template <int kPrims>
-  __device__ __forceinline__ bool stepFused(const TlasHeader &tlas, uint2 *stack) {
+  template <int kPrims, typename Stack>
+  __device__ __forceinline__ bool stepFused(const TlasHeader &tlas, Stack &stack) {
     if (tgroup.y == 0u && ngroup.y <= 0x00FFFFFFu) {
       if (!popStep(tlas, stack)) return false;
     }
@@ -421,7 +444,8 @@ struct LaneTraversal {
   }
 
   // One unit of work. Returns false when the traversal has finished (result in `hit` / `found`).
-  __device__ __forceinline__ bool step(const TlasHeader &tlas, uint2 *stack) {
+  template <typename Stack>
+  __device__ __forceinline__ bool step(const TlasHeader &tlas, Stack &stack) {
     if (tgroup.y != 0u) {
       if (primitiveStep(tlas, stack)) {
         found = true;
@@ -443,7 +467,7 @@ template <bool kAny>
 __device__ __forceinline__ bool traverseScene(const TlasHeader &tlas, float ox, float oy, float oz,
                                               float dx, float dy, float dz, float tmin, float tmax, RayHit &hit) {
   LaneTraversal<kAny> t;
-  uint2 stack[kStackSize];
+  LocalStack stack;
   t.begin(tlas, ox, oy, oz, dx, dy, dz, tmin, tmax);
   while (t.step(tlas, stack)) {
   }
