@@ -119,6 +119,16 @@ __global__ void k_triangle_bounds(const GeomEntry *geoms, uint32_t geomCount, ui
     loadTriangle(geoms, geomCount, i, a, b, c, g, p);
     lo = make_float3(fminf(fminf(a.x, b.x), c.x), fminf(fminf(a.y, b.y), c.y), fminf(fminf(a.z, b.z), c.z));
     hi = make_float3(fmaxf(fmaxf(a.x, b.x), c.x), fmaxf(fmaxf(a.y, b.y), c.y), fmaxf(fmaxf(a.z, b.z), c.z));
+    // a triangle with a NaN or infinite coordinate can never be hit (every comparison of the watertight test fails),
+    // but its box must not poison the scene bounds, the Morton keys or PLOC's distances: it becomes a point at the
+    // origin and stays out of the global bounds
+    const float big = 1.0e30f;
+    const bool finite = fabsf(a.x) < big && fabsf(a.y) < big && fabsf(a.z) < big && fabsf(b.x) < big && fabsf(b.y) < big &&
+                        fabsf(b.z) < big && fabsf(c.x) < big && fabsf(c.y) < big && fabsf(c.z) < big;
+    if (!finite) {
+      lo = hi = make_float3(0.0f, 0.0f, 0.0f);
+      valid = false;
+    }
     primLo[i] = make_float4(lo.x, lo.y, lo.z, 0.0f);
     primHi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
   }
@@ -669,6 +679,10 @@ __global__ void k_refit_level(WideNode *nodes, float4 *nodeBox, const TriRecord 
       for (uint32_t k = 0; k < cnt; ++k) {
         TriRecord tr = tris[first + k];
         float v[3][3] = {{tr.v0.x, tr.v0.y, tr.v0.z}, {tr.v1.x, tr.v1.y, tr.v1.z}, {tr.v2.x, tr.v2.y, tr.v2.z}};
+        bool finite = true; // a non-finite triangle cannot be hit and must not blow up the box (see k_triangle_bounds)
+        for (int q = 0; q < 3; ++q)
+          for (int a = 0; a < 3; ++a) finite = finite && fabsf(v[q][a]) < 1.0e30f;
+        if (!finite) continue;
         for (int q = 0; q < 3; ++q)
           for (int a = 0; a < 3; ++a) {
             cb[s].lo[a] = fminf(cb[s].lo[a], v[q][a]);
@@ -676,6 +690,8 @@ __global__ void k_refit_level(WideNode *nodes, float4 *nodeBox, const TriRecord 
           }
       }
     }
+    if (cb[s].lo[0] > cb[s].hi[0]) // only non-finite triangles in this slot: an empty box at the origin
+      for (int a = 0; a < 3; ++a) cb[s].lo[a] = cb[s].hi[a] = 0.0f;
     for (int a = 0; a < 3; ++a) {
       nlo[a] = fminf(nlo[a], cb[s].lo[a]);
       nhi[a] = fmaxf(nhi[a], cb[s].hi[a]);

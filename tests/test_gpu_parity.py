@@ -678,3 +678,40 @@ def test_cpp_host_program_renders_the_same_png(gpu_ctx, tmp_path):
     ref = gpu_ctx.tonemap(rnd.image_info(A.TEXTURE_ACCUMULATION), srgb=True, flip_y=True)
     rnd.close()
     assert np.array_equal(np.asarray(Image.open(png)), ref)
+
+
+def test_non_finite_triangles_do_not_break_the_build(gpu_ctx):
+    """A mesh with NaN / infinite vertices (a skinning blow-up, a broken asset) still builds and refits; the broken
+    triangles are never hit and the rest of the frame is exactly the frame of the mesh without them."""
+    rng = np.random.default_rng(11)
+    n = 400
+    base = rng.uniform(-1, 1, (n, 3, 3)).astype(np.float32) * 0.3 + rng.uniform(-1, 1, (n, 1, 3)).astype(np.float32)
+    bad = base.copy()
+    bad[7, 1, 0] = np.nan
+    bad[100, :, :] = np.inf
+    bad[250, 2, 2] = -np.inf
+    keep = np.ones(n, bool)
+    keep[[7, 100, 250]] = False
+
+    def render(tris):
+        sc = scene.Scene()
+        pos = tris.reshape(-1, 3)
+        m = sc.add_raw(pos, np.arange(len(pos), dtype=np.int32).reshape(-1, 3))
+        sc.add_instance(m, (0, 0, 0), (0, 0, 0), 1.0)
+        sc.default_lights()
+        u = scene.default_uniforms(96, 96)
+        u.samplesPerPixel, u.maxBounces, u.lightCount = 1, 2, sc.desc().lightCount
+        rnd = device.Renderer(gpu_ctx, sc, 96, 96, seeds=scene.seed_image(96, 96, 9))
+        rnd.draw(u, want_ids=True)
+        out = rnd.read_image(0).copy(), rnd.read_ids().copy()
+        rnd.close()
+        return out
+
+    img_bad, ids_bad = render(bad)
+    img_ok, ids_ok = render(base[keep])
+    hit_bad, hit_ok = ids_bad[..., 0] != 0xFFFFFFFF, ids_ok[..., 0] != 0xFFFFFFFF
+    assert np.array_equal(hit_bad, hit_ok) and hit_ok.any()
+    assert not np.isin(ids_bad[..., 2][hit_bad], [7, 100, 250]).any()
+    assert np.array_equal(ids_bad[..., 3], ids_ok[..., 3])  # same hit distances
+    assert np.isfinite(img_bad.astype(np.float32)).all()
+    assert np.array_equal(img_bad.view(np.uint16), img_ok.view(np.uint16))
