@@ -155,6 +155,7 @@ static inline void writeImage(const rt_image &img, int x, int y, float4 v) {
 // ---- helpers (Raytracing.metal:59-218) --------------------------------------------------------------------
 static inline float3 ld3(const rt_float3 *a, unsigned i) { return {a[i].x, a[i].y, a[i].z}; }
 
+// interpolateVertexAttribute<float3> (Raytracing.metal:61-74)
 static inline float3 interpolateFloat3(const rt_float3 *attributes, const Hit &hit, const int32_t *vertexIndices) {
   float3 uvw;
   uvw.x = hit.u;
@@ -168,6 +169,7 @@ static inline float3 interpolateFloat3(const rt_float3 *attributes, const Hit &h
   return uvw.x * T0 + uvw.y * T1 + uvw.z * T2;
 }
 
+// interpolateVertexAttribute<float2> (Raytracing.metal:61-74)
 static inline float2 interpolateFloat2(const float *attributes, const Hit &hit, const int32_t *vertexIndices) {
   float ux = hit.u, uy = hit.v, uz = 1.0f - ux - uy;
   unsigned triangleIndex = hit.primitive;
@@ -179,6 +181,7 @@ static inline float2 interpolateFloat2(const float *attributes, const Hit &hit, 
   return ux * T0 + uy * T1 + uz * T2;
 }
 
+// Raytracing.metal:79-89
 static inline float3 sampleCosineWeightedHemisphere(float2 u) {
   float phi = 2.0f * kPi * u.x;
   float cos_phi = cos_det(phi);
@@ -188,6 +191,7 @@ static inline float3 sampleCosineWeightedHemisphere(float2 u) {
   return {sin_theta * cos_phi, cos_theta, sin_theta * sin_phi};
 }
 
+// Raytracing.metal:95-129
 static inline void sampleAreaLight(const rt_light &light, float2 u, float3 position, float3 &lightDirection,
                                    float3 &lightColor, float &lightDistance) {
   u = u * 2.0f - make2(1.0f, 1.0f);
@@ -203,6 +207,7 @@ static inline void sampleAreaLight(const rt_light &light, float2 u, float3 posit
   lightColor *= saturate(dot(-lightDirection, lf));
 }
 
+// Raytracing.metal:133-148
 static inline float3 alignHemisphereWithNormal(float3 sample, float3 normal) {
   float3 up = normal;
   float3 right = normalize(cross(normal, make3(0.0072f, 1.0f, 0.0034f)));
@@ -210,19 +215,24 @@ static inline float3 alignHemisphereWithNormal(float3 sample, float3 normal) {
   return sample.x * right + sample.y * up + sample.z * forward;
 }
 
+// Raytracing.metal:150-154
 static inline float distributionGGX(float NdotH, float alpha) {
   float a2 = alpha * alpha;
   float denom = (NdotH * NdotH) * (a2 - 1.0f) + 1.0f;
   return a2 / fmaxf(kPi * denom * denom, 1e-7f);
 }
+// Raytracing.metal:156-158
 static inline float geometrySchlickGGX(float NdotV, float k) { return NdotV / fmaxf(NdotV * (1.0f - k) + k, 1e-7f); }
+// Raytracing.metal:160-162
 static inline float geometrySmith(float NdotV, float NdotL, float k) {
   return geometrySchlickGGX(NdotV, k) * geometrySchlickGGX(NdotL, k);
 }
+// Raytracing.metal:164-166
 static inline float3 fresnelSchlick(float cosTheta, float3 F0) {
   return F0 + (1.0f - F0) * pow5(clampf(1.0f - cosTheta, 0.0f, 1.0f));
 }
 
+// Raytracing.metal:185-218
 static inline bool computeTangentBasis(const rt_float3 *positions, const float *uvs, const Hit &hit,
                                        const int32_t *vertexIndices, float3 &tangent, float3 &bitangent) {
   unsigned triangleIndex = hit.primitive;
@@ -242,6 +252,7 @@ static inline bool computeTangentBasis(const rt_float3 *positions, const float *
   return (length(tangent) > 1e-8f) && (length(bitangent) > 1e-8f);
 }
 
+// Raytracing.metal:324-330: 4x4 from the descriptor's packed 4x3 (columns, rows 0..2)
 static inline float4x4 instanceMatrix(const rt_instance_descriptor &d) {
   float4x4 m;
   for (int c = 0; c < 4; ++c) m.c[c] = {d.transformationMatrix[c][0], d.transformationMatrix[c][1],
