@@ -142,7 +142,9 @@ __device__ __forceinline__ bool shadeSegment(const TraceParams &P, PathState &s,
   const int instanceIndex = int(hit.instance);
   const M34 objectToWorld = loadInstanceMatrix(P.instances + instanceIndex);
   const f3 hitPoint = s.origin + s.dir * hit.t;
-  const rt_resource res = P.resources[instanceIndex * P.maxSubmeshes + int(hit.geometry)];
+  // a reference, not a copy: only the pointers a material actually uses are loaded (the 104-byte row has seven
+  // texture slots that an untextured material never touches, and holding all 13 pointers costs 26 registers)
+  const rt_resource &res = P.resources[instanceIndex * P.maxSubmeshes + int(hit.geometry)];
 
   if (s.bounce == 0 && sampleIndex == 0) { // depth + motion vector of the primary hit (Raytracing.metal:341-389)
     const f3 camPos = mk3(U.camera.position), camRight = mk3(U.camera.right), camUp = mk3(U.camera.up),
