@@ -116,7 +116,13 @@ typedef struct rt_trace_options {
                                     accumulation image (same format/size); owned tiles are also stored there
                                     through NVLink peer mappings. NULL = local only */
   const rt_environment *environment; /* HOST pointer; NULL = the reference's behaviour (a miss is black) */
+  uint32_t hints;                    /* RT_TRACE_HINT_* promises of the caller; 0 = none */
+  uint32_t _pad;
 } rt_trace_options;
+/* The caller promises that no Material bound in this dispatch has a textureFlags bit set. The shading kernel is then
+ * a build without the texture paths (about a tenth faster); a material that breaks the promise is shaded as if its
+ * maps were absent. rtr_draw sets the hint by itself from the scene it was given. */
+#define RT_TRACE_HINT_UNTEXTURED 1u
 
 /* rt_trace: raytracingKernel dispatch (Raytracing.metal:220-831; binding block Renderer.swift:1453-1490).
  * buffers[]: 0 Uniforms (HOST pointer; copied into the launch like a `constant` argument), 5 Resource rows (dev),

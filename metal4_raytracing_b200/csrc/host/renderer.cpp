@@ -63,6 +63,7 @@ struct rtr_renderer {
   float *stagePalette = nullptr;
   size_t stagePaletteFloats = 0;
   rt_light *stageLights = nullptr;
+  bool untextured = true; // no submesh material has a textureFlags bit: rtr_draw passes RT_TRACE_HINT_UNTEXTURED
 };
 
 #define RTR_TRY(expr)                  \
@@ -172,6 +173,7 @@ int rtr_create(rt_context *ctx, const rt_scene_desc *scene, int width, int heigh
     dm.triangleCounts.resize(sm.submeshCount);
     for (uint32_t k = 0; k < sm.submeshCount; ++k) {
       mats[k] = sm.submeshes[k].material;
+      if (mats[k].textureFlags != 0u) r->untextured = false;
       dm.triangleCounts[k] = sm.submeshes[k].triangleCount;
       RTR_TRY(uploadNew(ctx, sm.submeshes[k].indices, size_t(sm.submeshes[k].triangleCount) * 12, &dm.indices[k]));
     }
@@ -365,7 +367,10 @@ int rtr_draw(rtr_renderer *r, const rt_uniforms *uniforms, const rt_trace_option
   buffers[RT_BUFFER_ACCELERATION_STRUCTURE] = reinterpret_cast<const void *>(static_cast<uintptr_t>(r->tlas));
   buffers[RT_BUFFER_INSTANCE_DESCRIPTORS] = r->descriptors;
   buffers[RT_BUFFER_PREVIOUS_INSTANCE_DESCRIPTORS] = r->prevDescriptors;
-  RTR_TRY(rt_trace(r->ctx, buffers, r->images, int(sizeof(rt_resource)), int(r->maxSubmeshes), options));
+  rt_trace_options withHints{};
+  if (options) withHints = *options;
+  if (r->untextured) withHints.hints |= RT_TRACE_HINT_UNTEXTURED; // known from the materials uploaded at creation
+  RTR_TRY(rt_trace(r->ctx, buffers, r->images, int(sizeof(rt_resource)), int(r->maxSubmeshes), &withHints));
   std::swap(r->images[RT_TEXTURE_ACCUMULATION], r->images[RT_TEXTURE_PREVIOUS_ACCUMULATION]); // Renderer.swift:1492-1494
   return 0;
 }

@@ -35,6 +35,7 @@ struct TraceParams {
   void *peerAccumulation[8];
   int peerCount;
   rt_environment env; // texelsDev == nullptr: off (reference behaviour)
+  uint32_t hints;     // RT_TRACE_HINT_*
 };
 
 // Pixel owned by slot `ownedIndex * 256 + t`: CTA-sized 16x16 tiles, eight 8x4-pixel warps per tile.
@@ -134,6 +135,10 @@ __device__ __forceinline__ bool tangentBasis(const rt_resource &res, const RayHi
 
 // Shades one closest hit and advances the path. Returns true when the path continues with (s.origin, s.dir).
 // `shadow` is the shadow ray to trace for this segment (valid == false: none).
+// kTextures = false compiles the material-map paths out (RT_TRACE_HINT_UNTEXTURED); kPlain = true compiles the debug
+// views and the Legacy branch out (the launcher checks debugTextureMode == 0 and shadingMode == PBR). The generic
+// instantiation <true, false> is what the megakernel uses.
+template <bool kTextures = true, bool kPlain = false>
 __device__ __forceinline__ bool shadeSegment(const TraceParams &P, PathState &s, const RayHit &hit, int hIndex,
                                              int sampleIndex, const f2 &prevMotion, PrimaryOutputs &prim,
                                              ShadowRequest &shadow) {
@@ -182,7 +187,7 @@ __device__ __forceinline__ bool shadeSegment(const TraceParams &P, PathState &s,
   // material + textures (Raytracing.metal:399-456)
   const rt_material mat = *res.material;
   f3 albedo = mk3(mat.baseColor);
-  const uint32_t flags = mat.textureFlags;
+  const uint32_t flags = kTextures ? mat.textureFlags : 0u;
   const bool hasBase = (flags & RT_MATERIAL_TEXTURE_BASECOLOR) != 0, hasNormalMap = (flags & RT_MATERIAL_TEXTURE_NORMAL) != 0;
   const bool hasRough = (flags & RT_MATERIAL_TEXTURE_ROUGHNESS) != 0, hasMetal = (flags & RT_MATERIAL_TEXTURE_METALLIC) != 0;
   const bool hasOpacityMap = (flags & RT_MATERIAL_TEXTURE_OPACITY) != 0, hasEmissionMap = (flags & RT_MATERIAL_TEXTURE_EMISSION) != 0;
@@ -209,7 +214,7 @@ __device__ __forceinline__ bool shadeSegment(const TraceParams &P, PathState &s,
     emission = mk3(e.x, e.y, e.z);
   }
 
-  if (U.debugTextureMode != RT_DEBUG_NONE) { // debug views end the path (Raytracing.metal:458-490)
+  if (!kPlain && U.debugTextureMode != RT_DEBUG_NONE) { // debug views end the path (Raytracing.metal:458-490)
     f3 dbg = mk3(0.0f);
     switch (U.debugTextureMode) {
       case RT_DEBUG_BASECOLOR: dbg = hasBase ? mk3(baseSample.x, baseSample.y, baseSample.z) : mk3(1.0f, 0.0f, 1.0f); break;
@@ -367,7 +372,7 @@ __device__ __forceinline__ bool shadeSegment(const TraceParams &P, PathState &s,
 
   const f3 shadowOrigin = hitPoint + surfaceNormal * 1e-3f;
 
-  if (U.shadingMode == RT_SHADING_LEGACY) { // Lambert branch (Raytracing.metal:649-690)
+  if (!kPlain && U.shadingMode == RT_SHADING_LEGACY) { // Lambert branch (Raytracing.metal:649-690)
     const f3 Ln = normalize(L);
     const float NdotL = saturatef(dot(shadingNormal, Ln));
     const f3 legacyColor = s.throughput * albedo;

@@ -155,6 +155,7 @@ int fillTraceParams(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT],
     P.env = *opt->environment;
     RT_CHECK(P.env.width > 0 && P.env.height > 0, "rt_trace: environment has no texels");
   }
+  P.hints = opt ? opt->hints : 0u;
   P.peerCount = 0;
   if (opt && opt->peerAccumulation) {
     RT_CHECK(P.tileModulo <= 8, "rt_trace: at most 8 peers");

@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse
 #ifndef RT_SHADE_MINBLOCKS
 #define RT_SHADE_MINBLOCKS 4 // 64 registers: measured faster than 128 (the kernel is bound by gather latency; more warps hide it)
 #endif
+template <bool kTextures, bool kPlain>
 __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const __grid_constant__ TraceParams P,
                                                                          const WfState W, int qin, int s0,
                                                                          int cameraRays, int shadowParity) {
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
         prim.wroteGBuffer = (flags & 2u) != 0u;
         const bool hadGBuffer = prim.wroteGBuffer;
         ShadowRequest shadow;
-        pushPath = shadeSegment(P, s, hit, hIndex, sampleIndex, mk2(m4.z, m4.w), prim, shadow);
+        pushPath = shadeSegment<kTextures, kPlain>(P, s, hit, hIndex, sampleIndex, mk2(m4.z, m4.w), prim, shadow);
         RT_STS(W.rad + slot, make_float4(s.radiance.x, s.radiance.y, s.radiance.z, 0.0f));
         if (pushPath) { // a path that ends here (every path of the last segment) leaves only its radiance behind
           const uint32_t packed = uint32_t(s.bounce) | (uint32_t(s.step) << 10) | (uint32_t(s.transparencyPasses) << 20);
@@ -616,7 +617,14 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
         traverse(first, segment == 0, 1, 0, parity);
         ctx->mark(RT_KERNEL_TRACE);
       }
-      k_wf_shade<<<persistent, kBlock, 0, st>>>(P, W, qin, s0, segment == 0, parity);
+      { // the shade kernel is specialised on what the host knows: texture hint, plain PBR without debug views
+        const bool textures = (P.hints & RT_TRACE_HINT_UNTEXTURED) == 0u;
+        const bool plain = U.debugTextureMode == RT_DEBUG_NONE && U.shadingMode != RT_SHADING_LEGACY;
+        if (textures && plain) k_wf_shade<true, true><<<persistent, kBlock, 0, st>>>(P, W, qin, s0, segment == 0, parity);
+        else if (textures) k_wf_shade<true, false><<<persistent, kBlock, 0, st>>>(P, W, qin, s0, segment == 0, parity);
+        else if (plain) k_wf_shade<false, true><<<persistent, kBlock, 0, st>>>(P, W, qin, s0, segment == 0, parity);
+        else k_wf_shade<false, false><<<persistent, kBlock, 0, st>>>(P, W, qin, s0, segment == 0, parity);
+      }
       ctx->mark(RT_KERNEL_SHADE);
       ++ctx->launches;
       shadowPending = true;

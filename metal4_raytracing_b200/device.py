@@ -35,7 +35,7 @@ class DenoiseFrame(C.Structure):
 class TraceOptions(C.Structure):
     _fields_ = [("tileModulo", C.c_int32), ("tileRemainder", C.c_int32), ("primaryIdsDev", C.c_void_p),
                 ("rayCountersDev", C.c_void_p), ("peerAccumulation", C.POINTER(C.c_void_p)),
-                ("environment", C.POINTER(Environment))]
+                ("environment", C.POINTER(Environment)), ("hints", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class AsInfo(C.Structure):
@@ -379,8 +379,9 @@ class Renderer:
             self._env_dev = self.ctx.upload(t)
             self._env = Environment(self._env_dev, t.shape[1], t.shape[0], float(intensity), 0.0)
 
-    def draw(self, uniforms, want_ids=False, count_rays=False, tile_modulo=1, tile_remainder=0, peers=None):
+    def draw(self, uniforms, want_ids=False, count_rays=False, tile_modulo=1, tile_remainder=0, peers=None, hints=0):
         opt = TraceOptions()
+        opt.hints = hints  # RT_TRACE_HINT_*; rtr_draw adds RT_TRACE_HINT_UNTEXTURED itself when the scene has no maps
         opt.tileModulo, opt.tileRemainder = tile_modulo, tile_remainder
         if want_ids:
             if self._ids_dev is None:

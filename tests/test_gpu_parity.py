@@ -715,3 +715,26 @@ def test_non_finite_triangles_do_not_break_the_build(gpu_ctx):
     assert np.array_equal(ids_bad[..., 3], ids_ok[..., 3])  # same hit distances
     assert np.isfinite(img_bad.astype(np.float32)).all()
     assert np.array_equal(img_bad.view(np.uint16), img_ok.view(np.uint16))
+
+
+def test_untextured_hint(gpu_ctx):
+    """RT_TRACE_HINT_UNTEXTURED selects the shading kernel built without the texture paths. The renderer sets it by
+    itself for scenes without maps (every untextured parity test above runs that kernel) and must not set it for a
+    textured scene; forcing it on a textured scene shades the materials as if their maps were absent."""
+    w, h = 96, 64
+    sc, u, seed = scene.Scene.named("K2tex", w, h, assets=None)
+    u.samplesPerPixel = 2
+    seeds = scene.seed_image(w, h, seed)
+    rnd = device.Renderer(gpu_ctx, sc, w, h, seeds=seeds)
+    orc = oracle.Oracle(sc)
+    imgs = oracle.FrameImages(w, h, seeds)
+    rnd.draw(u)
+    orc.render(u, imgs)
+    textured = rnd.read_image(0).copy()
+    assert np.array_equal(textured.view(np.uint16), imgs.output.view(np.uint16))
+    rnd.reset_accumulation()
+    rnd.draw(u, hints=1)
+    forced = rnd.read_image(0)
+    assert np.isfinite(forced.astype(np.float32)).all()
+    assert not np.array_equal(forced.view(np.uint16), textured.view(np.uint16))
+    rnd.close()
