@@ -43,6 +43,12 @@ int rt_free_host(rt_context *ctx, void *pinnedHost);
 int rt_upload(rt_context *ctx, void *dstDev, const void *srcHost, size_t bytes);   /* stream-ordered */
 int rt_download(rt_context *ctx, void *dstHost, const void *srcDev, size_t bytes); /* stream-ordered + sync */
 int rt_copy(rt_context *ctx, void *dstDev, const void *srcDev, size_t bytes);      /* blit, Renderer.swift:1290-1303 */
+/* Asynchronous read-back for frames in flight (the reference keeps three, Renderer.swift:207,1406-1409): the copy is
+ * ordered after everything enqueued so far but runs on the context's copy stream, so work enqueued afterwards
+ * overlaps it. dstHost should be pinned (rt_malloc_host). rt_download_wait blocks until the copy with that ticket —
+ * and every earlier one — has landed. Up to 8 copies may be outstanding. */
+int rt_download_async(rt_context *ctx, void *dstHost, const void *srcDev, size_t bytes, uint64_t *ticket);
+int rt_download_wait(rt_context *ctx, uint64_t ticket);
 int rt_memset(rt_context *ctx, void *dstDev, int value, size_t bytes);
 
 /* ---- acceleration structures ------------------------------------------------------------------------------

@@ -132,6 +132,11 @@ struct rt_context {
   cudaStream_t ownStream = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t evBegin = nullptr, evEnd = nullptr;
+  // asynchronous read-back (rt_download_async): copy stream, "work so far is done" event, ring of completion events
+  cudaStream_t copyStream = nullptr;
+  cudaEvent_t evReady = nullptr;
+  cudaEvent_t evCopied[8] = {};
+  uint64_t copiesIssued = 0;
   uint64_t launches = 0;
   int traceMode = 1;        // 0 megakernel, 1 wavefront
   int traversalVariant = 1; // lane refill threshold of the traversal kernels: 0 none, 1 = 8, 2 = 16, 3 = 24 idle lanes

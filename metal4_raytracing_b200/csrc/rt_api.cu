@@ -79,6 +79,9 @@ int rt_create(int device, rt_context **out) {
   ctx->stream = ctx->ownStream;
   RT_CUDA(cudaEventCreate(&ctx->evBegin));
   RT_CUDA(cudaEventCreate(&ctx->evEnd));
+  RT_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  RT_CUDA(cudaEventCreateWithFlags(&ctx->evReady, cudaEventDisableTiming));
+  for (cudaEvent_t &e : ctx->evCopied) RT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   // sRGB decode table, evaluated in double and rounded once (same table as the oracle's)
   float lut[256];
   for (int i = 0; i < 256; ++i) {
@@ -120,6 +123,10 @@ int rt_destroy(rt_context *ctx) {
   cudaFree(ctx->lightDerivedDev);
   cudaEventDestroy(ctx->evBegin);
   cudaEventDestroy(ctx->evEnd);
+  cudaStreamSynchronize(ctx->copyStream);
+  cudaEventDestroy(ctx->evReady);
+  for (cudaEvent_t e : ctx->evCopied) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->copyStream);
   for (cudaEvent_t e : ctx->timer.pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->ownStream);
   delete ctx;
@@ -202,6 +209,29 @@ int rt_download(rt_context *ctx, void *dstHost, const void *srcDev, size_t bytes
   RT_CHECK(dstHost && srcDev, "rt_download: null pointer");
   RT_CUDA(cudaMemcpyAsync(dstHost, srcDev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int rt_download_async(rt_context *ctx, void *dstHost, const void *srcDev, size_t bytes, uint64_t *ticket) {
+  RT_CTX(ctx);
+  RT_CHECK(dstHost && srcDev && ticket && bytes, "rt_download_async: null pointer or empty copy");
+  const uint64_t id = ctx->copiesIssued;
+  if (id >= 8) RT_CUDA(cudaEventSynchronize(ctx->evCopied[id % 8])); // the ring slot's previous copy must be done
+  RT_CUDA(cudaEventRecord(ctx->evReady, ctx->stream));
+  RT_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evReady, 0));
+  RT_CUDA(cudaMemcpyAsync(dstHost, srcDev, bytes, cudaMemcpyDeviceToHost, ctx->copyStream));
+  RT_CUDA(cudaEventRecord(ctx->evCopied[id % 8], ctx->copyStream));
+  ctx->copiesIssued = id + 1;
+  *ticket = id + 1;
+  return 0;
+}
+
+int rt_download_wait(rt_context *ctx, uint64_t ticket) {
+  RT_CTX(ctx);
+  RT_CHECK(ticket >= 1 && ticket <= ctx->copiesIssued, "rt_download_wait: unknown ticket");
+  if (ctx->copiesIssued - ticket >= 8) return 0; // older than the ring: finished when its slot was reused
+  // copies complete in issue order on the copy stream, so waiting for this one covers the earlier ones
+  RT_CUDA(cudaEventSynchronize(ctx->evCopied[(ticket - 1) % 8]));
   return 0;
 }
 

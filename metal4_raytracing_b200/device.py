@@ -51,7 +51,7 @@ EXPORTS = [
     "rt_blas_build", "rt_blas_refit", "rt_blas_destroy", "rt_tlas_build", "rt_tlas_update", "rt_tlas_destroy",
     "rt_as_get_info", "rt_skin", "rt_trace", "rt_texture_create", "rt_texture_destroy", "rt_launch_count",
     "rt_set_trace_mode", "rt_set_option", "rt_kernel_timing_enable", "rt_kernel_timing_read", "rt_joint_palette",
-    "rt_tonemap", "rt_temporal_filter",
+    "rt_tonemap", "rt_temporal_filter", "rt_download_async", "rt_download_wait",
     "rtr_last_error", "rtr_create", "rtr_destroy", "rtr_set_seeds", "rtr_update", "rtr_draw", "rtr_read_image",
     "rtr_image_info", "rtr_reset_accumulation", "rtr_read_mesh_streams", "rtr_get_blas_id", "rtr_get_tlas_id",
     "rtr_mesh_count",
@@ -82,6 +82,8 @@ def lib():
     L.rt_upload.argtypes = [vp, vp, vp, sz]
     L.rt_download.argtypes = [vp, vp, vp, sz]
     L.rt_copy.argtypes = [vp, vp, vp, sz]
+    L.rt_download_async.argtypes = [vp, vp, vp, sz, C.POINTER(u64)]
+    L.rt_download_wait.argtypes = [vp, u64]
     L.rt_memset.argtypes = [vp, vp, i32, sz]
     L.rt_blas_build.argtypes = [vp, C.POINTER(A.TriangleGeometry), u32, u32, C.POINTER(u64)]
     L.rt_blas_refit.argtypes = [vp, u64, C.POINTER(A.TriangleGeometry), u32]
@@ -191,6 +193,15 @@ class Context:
         self._owned.append(p.value)
         buf = (C.c_uint8 * n).from_address(p.value)
         return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def download_async(self, ptr, out):
+        """rt_download_async into a (pinned) numpy array; returns the ticket for download_wait."""
+        t = C.c_uint64()
+        _check(lib().rt_download_async(self._h, out.ctypes.data, ptr, out.nbytes, C.byref(t)))
+        return t.value
+
+    def download_wait(self, ticket):
+        _check(lib().rt_download_wait(self._h, ticket))
 
     def memset(self, ptr, value, nbytes):
         _check(lib().rt_memset(self._h, ptr, value, nbytes))
@@ -429,6 +440,14 @@ class Renderer:
         assert out.dtype == dt and out.shape == (self.height, self.width, ch) and out.flags.c_contiguous
         _check(lib().rtr_read_image(self._h, index, out.ctypes.data, out.nbytes), True)
         return out
+
+    def read_image_async(self, index, out):
+        """Starts the read-back of the image bound at `index` into the pinned array `out` without waiting; later draws
+        overlap the copy (they write the other accumulation target). Returns a ticket for Context.download_wait."""
+        info = self.image_info(index)
+        dt, ch = _FORMAT_DTYPE[info.format]
+        assert out.dtype == dt and out.shape == (self.height, self.width, ch) and out.flags.c_contiguous
+        return self.ctx.download_async(info.data, out)
 
     def reset_accumulation(self):
         _check(lib().rtr_reset_accumulation(self._h), True)

@@ -738,3 +738,33 @@ def test_untextured_hint(gpu_ctx):
     assert np.isfinite(forced.astype(np.float32)).all()
     assert not np.array_equal(forced.view(np.uint16), textured.view(np.uint16))
     rnd.close()
+
+
+def test_async_readback_matches_blocking_readback(gpu_ctx):
+    """rt_download_async / rt_download_wait (frames in flight, Renderer.swift:207): the frame copied on the copy stream
+    while the next frame renders equals the frame read back synchronously; tickets complete in order."""
+    w, h = 160, 96
+    sc, u, seed = scene.Scene.named("K3small", w, h, assets=None)
+    u.samplesPerPixel = 2
+    rnd = device.Renderer(gpu_ctx, sc, w, h, seeds=scene.seed_image(w, h, seed))
+    blocking, pinned, tickets = [], [], []
+    for f in range(4):
+        u.frameIndex = f
+        rnd.draw(u)
+        blocking.append(rnd.read_image(A.TEXTURE_ACCUMULATION).copy())
+    rnd.reset_accumulation()
+    for f in range(4):
+        u.frameIndex = f
+        rnd.draw(u)
+        buf = gpu_ctx.pinned_array(blocking[0].shape, blocking[0].dtype)
+        pinned.append(buf)
+        tickets.append(rnd.read_image_async(A.TEXTURE_ACCUMULATION, buf))
+        if f >= 1:
+            gpu_ctx.download_wait(tickets[f - 1])  # one frame in flight
+            assert np.array_equal(pinned[f - 1].view(np.uint16), blocking[f - 1].view(np.uint16))
+    gpu_ctx.download_wait(tickets[-1])
+    assert np.array_equal(pinned[-1].view(np.uint16), blocking[-1].view(np.uint16))
+    assert tickets == sorted(tickets) and len(set(tickets)) == 4
+    with pytest.raises(device.RtError):
+        gpu_ctx.download_wait(tickets[-1] + 100)
+    rnd.close()
