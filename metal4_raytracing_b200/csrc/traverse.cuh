@@ -358,9 +358,7 @@ struct LaneTraversal {
         const float ldx = (r0.x * dx + r0.y * dy) + r0.z * dz;
         const float ldy = (r1.x * dx + r1.y * dy) + r1.z * dz;
         const float ldz = (r2.x * dx + r2.y * dy) + r2.z * dz;
-        box = makeBoxSetup(lox, loy, loz, ldx, ldy, ldz, box.one);
         tri = makeTriSetup(lox, loy, loz, ldx, ldy, ldz);
-        nodes = reinterpret_cast<const uint4 *>(bn);
         const uintptr_t tagged = reinterpret_cast<uintptr_t>(rec->tris);
 #ifdef RT_NO_DIRECT_TRIS
         const uint32_t direct = 0u;
@@ -369,10 +367,15 @@ struct LaneTraversal {
 #endif
         tris = reinterpret_cast<const float4 *>(tagged & ~uintptr_t(31));
         instanceSp = sp;
-        if (direct != 0u)
+        if (direct != 0u) {
+          // no node of this BLAS is ever tested: the world-space box setup (and `nodes`) stay as they are, and
+          // popStep sees from `nodes` that there is nothing to restore when the instance is left
           tgroup = make_uint2(0u, 0xFFFFFFFFu >> (32u - direct));
-        else
+        } else {
+          box = makeBoxSetup(lox, loy, loz, ldx, ldy, ldz, box.one);
+          nodes = reinterpret_cast<const uint4 *>(bn);
           ngroup = make_uint2(0u, 0x80000000u);
+        }
       }
       return false;
     }
@@ -406,8 +409,10 @@ struct LaneTraversal {
   __device__ __forceinline__ bool popStep(const TlasHeader &tlas, Stack &stack) {
     if (sp == instanceSp) {
       instanceSp = -1;
-      box = makeBoxSetup(ox, oy, oz, dx, dy, dz, box.one);
-      nodes = reinterpret_cast<const uint4 *>(tlas.nodes);
+      if (nodes != reinterpret_cast<const uint4 *>(tlas.nodes)) { // a directly-tested BLAS never replaced them
+        box = makeBoxSetup(ox, oy, oz, dx, dy, dz, box.one);
+        nodes = reinterpret_cast<const uint4 *>(tlas.nodes);
+      }
     }
     if (sp == 0) return false;
     const uint2 e = stack.get(--sp);
