@@ -7,12 +7,14 @@
 //   owned pixel are in flight at once so that each launch has enough rays to amortise its tail):
 //     generate      fold the previous batch into the pixel sums in sample order, start the batch: camera rays ->
 //                   path state, queue
-//     repeat for each path segment (the reference's bounce loop, :311):
-//       trace       closest hit for every queued path                       (traverse.cuh, ~64 registers)
+//     repeat for each path segment k (the reference's bounce loop, :311):
+//       traverse    persistent software traversal (traverse.cuh, 80 registers): closest hit for every queued path
+//                   of segment k, then — in the same launch — any-hit for the shadow requests of segment k - 1;
+//                   unoccluded shadow rays add their contribution
 //       shade       one shadeSegment() per hit: emission, light sample, BRDF, next ray; emits a shadow
 //                   request and re-queues surviving paths (warp-aggregated queue appends = ray compaction)
-//       shadow      any-hit for every shadow request; unoccluded ones add their contribution
-//   resolve         sample mean, EMA with history, image writes (+ NVLink peer stores for multi-GPU)
+//     traverse      the shadow requests of the last segment
+//   resolve         fold the last batch, sample mean, EMA with history, image writes (+ NVLink peer stores)
 //
 // Paths that miss or die leave the queue, so later segments run on dense warps instead of the megakernel's
 // 11-of-32 active threads (profiles/). Per-pixel results do not depend on queue order, and the arithmetic is the
