@@ -47,6 +47,11 @@ int rt_copy(rt_context *ctx, void *dstDev, const void *srcDev, size_t bytes);   
  * ordered after everything enqueued so far but runs on the context's copy stream, so work enqueued afterwards
  * overlaps it. dstHost should be pinned (rt_malloc_host). rt_download_wait blocks until the copy with that ticket —
  * and every earlier one — has landed. Up to 8 copies may be outstanding. */
+/* Stream fences for host-side staging rings (the reference triple-buffers its per-frame host data, Renderer.swift:208-212):
+ * rt_fence marks "everything enqueued so far", rt_fence_wait blocks until that point has executed. Up to 16 fences
+ * may be outstanding; older ones count as passed. */
+int rt_fence(rt_context *ctx, uint64_t *ticket);
+int rt_fence_wait(rt_context *ctx, uint64_t ticket);
 int rt_download_async(rt_context *ctx, void *dstHost, const void *srcDev, size_t bytes, uint64_t *ticket);
 int rt_download_wait(rt_context *ctx, uint64_t ticket);
 int rt_memset(rt_context *ctx, void *dstDev, int value, size_t bytes);

@@ -885,14 +885,20 @@ static int uploadGeomTable(rt_context *ctx, AccelObject *as, const rt_triangle_g
                 geoms[g].vertexStride, geoms[g].indexStride, total, geoms[g].triangleCount};
     total += geoms[g].triangleCount;
   }
+  *totalOut = total;
+  const size_t bytes = size_t(n) * sizeof(GeomEntry);
+  if (as->geomTableDev && as->geomCount == n && as->geomTableHost.size() == bytes &&
+      (bytes == 0 || std::memcmp(as->geomTableHost.data(), table.data(), bytes) == 0))
+    return 0; // same buffers as last time (the per-frame refit of a skinned mesh): nothing to upload, no sync
   if (!as->geomTableDev || as->geomCount != n) {
     if (as->geomTableDev) cudaFree(as->geomTableDev);
+    as->geomTableDev = nullptr;
     RT_CUDA(cudaMalloc(&as->geomTableDev, std::max<size_t>(1, n) * sizeof(GeomEntry)));
     as->geomCount = n;
   }
-  if (n) RT_CUDA(cudaMemcpyAsync(as->geomTableDev, table.data(), n * sizeof(GeomEntry), cudaMemcpyHostToDevice, ctx->stream));
+  if (n) RT_CUDA(cudaMemcpyAsync(as->geomTableDev, table.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
   RT_CUDA(cudaStreamSynchronize(ctx->stream)); // `table` is a stack-lifetime staging buffer
-  *totalOut = total;
+  as->geomTableHost.assign(reinterpret_cast<const uint8_t *>(table.data()), reinterpret_cast<const uint8_t *>(table.data()) + bytes);
   return 0;
 }
 

@@ -108,6 +108,7 @@ struct AccelObject {
   uint2 *triSource = nullptr;   // BLAS: per triangle slot (geometry, primitive) — refit source mapping
   // geometry table for refit: device copy of per-geometry (vertex ptr, stride, index ptr, index stride)
   void *geomTableDev = nullptr;
+  std::vector<uint8_t> geomTableHost; // what geomTableDev holds: a refit with the same buffers uploads nothing
   uint32_t geomCount = 0;
   uint64_t bytes = 0;
   float sahCost = 0.0f;
@@ -137,6 +138,8 @@ struct rt_context {
   cudaEvent_t evReady = nullptr;
   cudaEvent_t evCopied[8] = {};
   uint64_t copiesIssued = 0;
+  cudaEvent_t evFence[16] = {}; // rt_fence ring
+  uint64_t fencesIssued = 0;
   uint64_t launches = 0;
   int traceMode = 1;        // 0 megakernel, 1 wavefront
   int traversalVariant = 1; // lane refill threshold of the traversal kernels: 0 none, 1 = 8, 2 = 16, 3 = 24 idle lanes

@@ -58,11 +58,15 @@ struct rtr_renderer {
   uint32_t lightCapacity = 0;
   uint64_t tlas = 0;
   rt_image images[RT_TEXTURE_COUNT]{};
-  // pinned staging for per-frame uploads
-  rt_instance_descriptor *stageDescriptors = nullptr;
-  float *stagePalette = nullptr;
-  size_t stagePaletteFloats = 0;
-  rt_light *stageLights = nullptr;
+  // pinned staging for per-frame uploads: a ring of three arenas (the reference triple-buffers its per-frame host
+  // data, Renderer.swift:208-212), each guarded by a stream fence, so rtr_update never waits for the GPU to drain
+  static constexpr int kStageSlots = 3;
+  uint8_t *stage[kStageSlots] = {};
+  uint64_t stageFence[kStageSlots] = {};
+  size_t stageBytes = 0, stageUsed = 0;
+  uint64_t updates = 0;
+  rt_instance_descriptor *stageDescriptors = nullptr; // inside the current arena
+  size_t stagePaletteFloats = 0;                       // sum over skinned meshes of 16 floats per joint
   bool untextured = true; // no submesh material has a textureFlags bit: rtr_draw passes RT_TRACE_HINT_UNTEXTURED
 };
 
@@ -162,7 +166,7 @@ int rtr_create(rt_context *ctx, const rt_scene_desc *scene, int width, int heigh
       RTR_TRY(rt_malloc(ctx, vb, &dm.normals));
       RTR_TRY(skinMesh(r, dm)); // initial skinning pass (Renderer.swift:470-494)
       RTR_TRY(rt_copy(ctx, dm.prevPositions, dm.positions, vb));
-      r->stagePaletteFloats = std::max(r->stagePaletteFloats, size_t(sm.jointCount) * 16);
+      r->stagePaletteFloats += size_t(sm.jointCount) * 16;
     } else {
       dm.positions = dm.restPositions;
       dm.prevPositions = dm.restPositions; // SubMesh.swift:60: previousPositionBuffer = positionBuffer
@@ -216,7 +220,12 @@ int rtr_create(rt_context *ctx, const rt_scene_desc *scene, int width, int heigh
   RTR_TRY(uploadNew(ctx, rows.data(), rows.size() * sizeof(rt_resource), &r->resources));
   // instance descriptors (current + previous) and TLAS
   size_t descBytes = size_t(scene->instanceCount) * sizeof(rt_instance_descriptor);
-  RTR_TRY(rt_malloc_host(ctx, descBytes, reinterpret_cast<void **>(&r->stageDescriptors)));
+  r->lightCapacity = scene->lightCount ? scene->lightCount : 1;
+  r->stageBytes = ((descBytes + 255) & ~size_t(255)) + ((size_t(r->lightCapacity) * sizeof(rt_light) + 255) & ~size_t(255)) +
+                  r->stagePaletteFloats * 4 + 256 * (scene->meshCount + 2);
+  for (int k = 0; k < rtr_renderer::kStageSlots; ++k)
+    RTR_TRY(rt_malloc_host(ctx, r->stageBytes, reinterpret_cast<void **>(&r->stage[k])));
+  r->stageDescriptors = reinterpret_cast<rt_instance_descriptor *>(r->stage[0]);
   RTR_TRY(rt_malloc(ctx, descBytes, &r->descriptors));
   RTR_TRY(rt_malloc(ctx, descBytes, &r->prevDescriptors));
   for (uint32_t i = 0; i < scene->instanceCount; ++i)
@@ -228,15 +237,12 @@ int rtr_create(rt_context *ctx, const rt_scene_desc *scene, int width, int heigh
   RTR_TRY(rt_upload(ctx, r->descriptors, r->stageDescriptors, descBytes));
   RTR_TRY(rt_tlas_build(ctx, static_cast<const rt_instance_descriptor *>(r->descriptors), scene->instanceCount, &r->tlas));
   // lights
-  r->lightCapacity = scene->lightCount ? scene->lightCount : 1;
-  RTR_TRY(rt_malloc_host(ctx, size_t(r->lightCapacity) * sizeof(rt_light), reinterpret_cast<void **>(&r->stageLights)));
   RTR_TRY(rt_malloc(ctx, size_t(r->lightCapacity) * sizeof(rt_light), &r->lights));
   if (scene->lightCount) {
-    std::memcpy(r->stageLights, scene->lights, size_t(scene->lightCount) * sizeof(rt_light));
-    RTR_TRY(rt_upload(ctx, r->lights, r->stageLights, size_t(scene->lightCount) * sizeof(rt_light)));
+    RTR_TRY(rt_sync(ctx)); // the descriptor upload above still reads arena 0
+    std::memcpy(r->stage[1], scene->lights, size_t(scene->lightCount) * sizeof(rt_light));
+    RTR_TRY(rt_upload(ctx, r->lights, r->stage[1], size_t(scene->lightCount) * sizeof(rt_light)));
   }
-  if (r->stagePaletteFloats)
-    RTR_TRY(rt_malloc_host(ctx, r->stagePaletteFloats * 4, reinterpret_cast<void **>(&r->stagePalette)));
   // images (Renderer.swift:685-799)
   const bool fp32 = (flags & RTR_FLAG_FP32_IMAGES) != 0;
   const int rgba = fp32 ? RT_FORMAT_RGBA32_FLOAT : RT_FORMAT_RGBA16_FLOAT;
@@ -284,9 +290,7 @@ int rtr_destroy(rtr_renderer *r) {
   rt_free(ctx, r->prevDescriptors);
   rt_free(ctx, r->lights);
   for (auto &img : r->images) rt_free(ctx, img.data);
-  rt_free_host(ctx, r->stageDescriptors);
-  rt_free_host(ctx, r->stagePalette);
-  rt_free_host(ctx, r->stageLights);
+  for (uint8_t *p : r->stage) rt_free_host(ctx, p);
   delete r;
   return 0;
 }
@@ -305,42 +309,51 @@ int rtr_update(rtr_renderer *r, const rt_scene_desc *scene) {
   }
   // updateInstanceDescriptors (Renderer.swift:937-973): previous <- current, current <- mesh transforms
   size_t descBytes = size_t(scene->instanceCount) * sizeof(rt_instance_descriptor);
-  RTR_TRY(rt_sync(ctx)); // staging buffers are reused every frame
+  // this update's staging arena: wait only for the uploads that used it three updates ago
+  const int slot = int(r->updates % rtr_renderer::kStageSlots);
+  if (r->stageFence[slot]) RTR_TRY(rt_fence_wait(ctx, r->stageFence[slot]));
+  uint8_t *arena = r->stage[slot];
+  size_t used = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t *p = arena + used;
+    used += (bytes + 255) & ~size_t(255);
+    return p;
+  };
+  r->stageDescriptors = reinterpret_cast<rt_instance_descriptor *>(take(descBytes));
   RTR_TRY(rt_copy(ctx, r->prevDescriptors, r->descriptors, descBytes));
   for (uint32_t i = 0; i < scene->instanceCount; ++i)
     packDescriptor(scene->instances[i].transform, r->meshes[r->instanceMesh[i]].blas, r->stageDescriptors[i]);
   RTR_TRY(rt_upload(ctx, r->descriptors, r->stageDescriptors, descBytes));
   if (scene->lightCount && scene->lightCount <= r->lightCapacity) {
-    std::memcpy(r->stageLights, scene->lights, size_t(scene->lightCount) * sizeof(rt_light));
-    RTR_TRY(rt_upload(ctx, r->lights, r->stageLights, size_t(scene->lightCount) * sizeof(rt_light)));
+    uint8_t *lights = take(size_t(scene->lightCount) * sizeof(rt_light));
+    std::memcpy(lights, scene->lights, size_t(scene->lightCount) * sizeof(rt_light));
+    RTR_TRY(rt_upload(ctx, r->lights, lights, size_t(scene->lightCount) * sizeof(rt_light)));
   }
   // skinned meshes: prev <- cur, new palette, skin, refit (Renderer.swift:1290-1326)
-  size_t paletteOffset = 0;
-  (void)paletteOffset;
   for (uint32_t m = 0; m < scene->meshCount; ++m) {
     DeviceMesh &dm = r->meshes[m];
     if (!dm.skinned) continue;
     const rt_scene_mesh &sm = scene->meshes[m];
     size_t vb = size_t(dm.vertexCount) * 16;
     RTR_TRY(rt_copy(ctx, dm.prevPositions, dm.positions, vb));
-    RTR_TRY(rt_sync(ctx)); // one shared palette staging buffer
+    uint8_t *palette = take(size_t(dm.jointCount) * 64);
     if (dm.jointLocalTRS && sm.jointLocalTRS && sm.jointInverseBind) {
       // palette on the device: 40 B per joint of local TRS go up instead of a 64 B matrix, hierarchy + inverse bind
       // products run in rt_joint_palette (bit-identical to the host palette)
       if (!dm.inverseBindUploaded) {
-        std::memcpy(r->stagePalette, sm.jointInverseBind, size_t(dm.jointCount) * 64);
-        RTR_TRY(rt_upload(ctx, dm.jointInverseBind, r->stagePalette, size_t(dm.jointCount) * 64));
-        RTR_TRY(rt_sync(ctx));
+        std::memcpy(palette, sm.jointInverseBind, size_t(dm.jointCount) * 64);
+        RTR_TRY(rt_upload(ctx, dm.jointInverseBind, palette, size_t(dm.jointCount) * 64));
+        RTR_TRY(rt_sync(ctx)); // once per mesh: the same staging bytes are reused just below
         dm.inverseBindUploaded = true;
       }
-      std::memcpy(r->stagePalette, sm.jointLocalTRS, size_t(dm.jointCount) * 40);
-      RTR_TRY(rt_upload(ctx, dm.jointLocalTRS, r->stagePalette, size_t(dm.jointCount) * 40));
+      std::memcpy(palette, sm.jointLocalTRS, size_t(dm.jointCount) * 40);
+      RTR_TRY(rt_upload(ctx, dm.jointLocalTRS, palette, size_t(dm.jointCount) * 40));
       RTR_TRY(rt_joint_palette(ctx, static_cast<const float *>(dm.jointLocalTRS), static_cast<const int32_t *>(dm.jointParents),
                                static_cast<const float *>(dm.jointInverseBind), dm.jointCount,
                                static_cast<float *>(dm.jointMatrices)));
     } else {
-      std::memcpy(r->stagePalette, sm.jointMatrices, size_t(dm.jointCount) * 64);
-      RTR_TRY(rt_upload(ctx, dm.jointMatrices, r->stagePalette, size_t(dm.jointCount) * 64));
+      std::memcpy(palette, sm.jointMatrices, size_t(dm.jointCount) * 64);
+      RTR_TRY(rt_upload(ctx, dm.jointMatrices, palette, size_t(dm.jointCount) * 64));
     }
     RTR_TRY(skinMesh(r, dm));
     if (r->flags & RTR_FLAG_REBUILD_SKINNED) {
@@ -355,6 +368,12 @@ int rtr_update(rtr_renderer *r, const rt_scene_desc *scene) {
       RTR_TRY(rt_blas_refit(ctx, dm.blas, dm.geoms.data(), uint32_t(dm.geoms.size())));
     }
   }
+  if (used > r->stageBytes) {
+    g_err = "rtr_update: internal staging arena overflow";
+    return 2;
+  }
+  RTR_TRY(rt_fence(ctx, &r->stageFence[slot]));
+  ++r->updates;
   RTR_TRY(rt_tlas_update(ctx, r->tlas, static_cast<const rt_instance_descriptor *>(r->descriptors), scene->instanceCount));
   return 0;
 }

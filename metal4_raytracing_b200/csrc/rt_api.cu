@@ -82,6 +82,7 @@ int rt_create(int device, rt_context **out) {
   RT_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
   RT_CUDA(cudaEventCreateWithFlags(&ctx->evReady, cudaEventDisableTiming));
   for (cudaEvent_t &e : ctx->evCopied) RT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (cudaEvent_t &e : ctx->evFence) RT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   // sRGB decode table, evaluated in double and rounded once (same table as the oracle's)
   float lut[256];
   for (int i = 0; i < 256; ++i) {
@@ -126,6 +127,7 @@ int rt_destroy(rt_context *ctx) {
   cudaStreamSynchronize(ctx->copyStream);
   cudaEventDestroy(ctx->evReady);
   for (cudaEvent_t e : ctx->evCopied) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->evFence) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->copyStream);
   for (cudaEvent_t e : ctx->timer.pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->ownStream);
@@ -209,6 +211,24 @@ int rt_download(rt_context *ctx, void *dstHost, const void *srcDev, size_t bytes
   RT_CHECK(dstHost && srcDev, "rt_download: null pointer");
   RT_CUDA(cudaMemcpyAsync(dstHost, srcDev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int rt_fence(rt_context *ctx, uint64_t *ticket) {
+  RT_CTX(ctx);
+  RT_CHECK(ticket != nullptr, "rt_fence: null ticket");
+  const uint64_t id = ctx->fencesIssued;
+  RT_CUDA(cudaEventRecord(ctx->evFence[id % 16], ctx->stream));
+  ctx->fencesIssued = id + 1;
+  *ticket = id + 1;
+  return 0;
+}
+
+int rt_fence_wait(rt_context *ctx, uint64_t ticket) {
+  RT_CTX(ctx);
+  RT_CHECK(ticket >= 1 && ticket <= ctx->fencesIssued, "rt_fence_wait: unknown ticket");
+  if (ctx->fencesIssued - ticket >= 16) return 0; // its ring slot was re-recorded by a later fence on the same stream
+  RT_CUDA(cudaEventSynchronize(ctx->evFence[(ticket - 1) % 16]));
   return 0;
 }
 

@@ -51,7 +51,7 @@ EXPORTS = [
     "rt_blas_build", "rt_blas_refit", "rt_blas_destroy", "rt_tlas_build", "rt_tlas_update", "rt_tlas_destroy",
     "rt_as_get_info", "rt_skin", "rt_trace", "rt_texture_create", "rt_texture_destroy", "rt_launch_count",
     "rt_set_trace_mode", "rt_set_option", "rt_kernel_timing_enable", "rt_kernel_timing_read", "rt_joint_palette",
-    "rt_tonemap", "rt_temporal_filter", "rt_download_async", "rt_download_wait",
+    "rt_tonemap", "rt_temporal_filter", "rt_download_async", "rt_download_wait", "rt_fence", "rt_fence_wait",
     "rtr_last_error", "rtr_create", "rtr_destroy", "rtr_set_seeds", "rtr_update", "rtr_draw", "rtr_read_image",
     "rtr_image_info", "rtr_reset_accumulation", "rtr_read_mesh_streams", "rtr_get_blas_id", "rtr_get_tlas_id",
     "rtr_mesh_count",
@@ -84,6 +84,8 @@ def lib():
     L.rt_copy.argtypes = [vp, vp, vp, sz]
     L.rt_download_async.argtypes = [vp, vp, vp, sz, C.POINTER(u64)]
     L.rt_download_wait.argtypes = [vp, u64]
+    L.rt_fence.argtypes = [vp, C.POINTER(u64)]
+    L.rt_fence_wait.argtypes = [vp, u64]
     L.rt_memset.argtypes = [vp, vp, i32, sz]
     L.rt_blas_build.argtypes = [vp, C.POINTER(A.TriangleGeometry), u32, u32, C.POINTER(u64)]
     L.rt_blas_refit.argtypes = [vp, u64, C.POINTER(A.TriangleGeometry), u32]
