@@ -649,13 +649,10 @@ __global__ void k_refresh_triangles(const GeomEntry *geoms, uint32_t n, const ui
   tris[i] = r;
 }
 
-// Refit step 2, one level at a time from the deepest: recompute child boxes (triangles or already-refitted child
-// nodes), the exact node box and the quantised boxes. Topology words (w1, imask) are untouched.
-__global__ void k_refit_level(WideNode *nodes, float4 *nodeBox, const TriRecord *tris, uint32_t levelStart,
-                              uint32_t levelCount) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= levelCount) return;
-  uint32_t idx = levelStart + i;
+// Refit of one wide node: recompute child boxes (triangles, or child nodes that are already refitted), the exact node
+// box and the quantised boxes. Topology words (w1, imask) are untouched. Child node boxes are read with ld.cg: they
+// were written by other threads of the same launch.
+__device__ void refitNode(WideNode *nodes, float4 *nodeBox, const TriRecord *tris, uint32_t idx) {
   WideNode node = nodes[idx];
   uint8_t imask = uint8_t(node.w[0].w >> 24);
   uint32_t childBase = node.w[1].x, primBase = node.w[1].y;
@@ -669,7 +666,7 @@ __global__ void k_refit_level(WideNode *nodes, float4 *nodeBox, const TriRecord 
     if (!m) continue;
     if (imask & (1u << s)) {
       uint32_t c = childBase + rank++;
-      float4 l = nodeBox[2 * c], h = nodeBox[2 * c + 1];
+      float4 l = __ldcg(nodeBox + 2 * c), h = __ldcg(nodeBox + 2 * c + 1);
       cb[s].lo[0] = l.x, cb[s].lo[1] = l.y, cb[s].lo[2] = l.z;
       cb[s].hi[0] = h.x, cb[s].hi[1] = h.y, cb[s].hi[2] = h.z;
     } else {
@@ -701,6 +698,36 @@ __global__ void k_refit_level(WideNode *nodes, float4 *nodeBox, const TriRecord 
   nodes[idx] = node;
   nodeBox[2 * idx] = make_float4(nlo[0], nlo[1], nlo[2], 0.0f);
   nodeBox[2 * idx + 1] = make_float4(nhi[0], nhi[1], nhi[2], 0.0f);
+}
+
+// parent[] of every wide node (built once for a refittable BLAS) and the per-refit count of internal children
+__global__ void k_node_parents(const WideNode *nodes, uint32_t nodeCount, uint32_t *parent) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nodeCount) return;
+  if (i == 0) parent[0] = 0xFFFFFFFFu;
+  const uint32_t internal = uint32_t(__popc(nodes[i].w[0].w >> 24)), childBase = nodes[i].w[1].x;
+  for (uint32_t k = 0; k < internal; ++k) parent[childBase + k] = i;
+}
+__global__ void k_refit_pending(const WideNode *nodes, uint32_t nodeCount, uint32_t *pending) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nodeCount) pending[i] = uint32_t(__popc(nodes[i].w[0].w >> 24));
+}
+
+// Refit step 2 in one launch: threads start at the nodes that have no internal children and walk up; the thread that
+// delivers a node's last child refits that node (the other deliverers stop). Replaces one launch per tree level —
+// on a 100 k-vertex mesh the level launches were latency-bound and cost 0.15 ms per frame.
+__global__ void k_refit_bottom_up(WideNode *nodes, float4 *nodeBox, const TriRecord *tris, uint32_t nodeCount,
+                                  const uint32_t *parent, uint32_t *pending) {
+  uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= nodeCount || (nodes[node].w[0].w >> 24) != 0u) return;
+  while (true) {
+    refitNode(nodes, nodeBox, tris, node);
+    __threadfence();
+    const uint32_t p = parent[node];
+    if (p == 0xFFFFFFFFu) return;
+    if (atomicSub(pending + p, 1u) != 1u) return; // a sibling subtree is still being refitted
+    node = p;
+  }
 }
 
 __global__ void k_write_blas_header(BlasHeader *h, const WideNode *nodes, const TriRecord *tris,
@@ -1019,6 +1046,12 @@ int buildBlas(rt_context *ctx, const rt_triangle_geometry *geoms, uint32_t geomC
   if (!(flags & RT_AS_FLAG_REFITTABLE)) { // compaction: drop what only a refit needs
     cudaFree(as->triSource);
     as->triSource = nullptr;
+  } else { // refit walks the tree bottom-up in one launch: parent links + a per-refit counter per node
+    RT_CUDAF(cudaMalloc(&as->nodeParent, size_t(as->nodeCount) * sizeof(uint32_t)));
+    RT_CUDAF(cudaMalloc(&as->nodePending, size_t(as->nodeCount) * sizeof(uint32_t)));
+    k_node_parents<<<gridFor(as->nodeCount, 256), 256, 0, st>>>(as->nodes, as->nodeCount, as->nodeParent);
+    ++ctx->launches;
+    RT_CUDAF(cudaGetLastError());
   }
   as->bytes = sizeof(BlasHeader) + size_t(as->nodeCapacity) * (sizeof(WideNode) + 2 * sizeof(float4)) +
               size_t(n) * sizeof(TriRecord) + (as->triSource ? size_t(n) * sizeof(uint2) : 0);
@@ -1040,12 +1073,10 @@ int refitBlas(rt_context *ctx, AccelObject *as, const rt_triangle_geometry *geom
   k_refresh_triangles<<<gridFor(n, 256), 256, 0, st>>>(static_cast<const GeomEntry *>(as->geomTableDev), n,
                                                         as->triSource, as->tris);
   ++ctx->launches;
-  for (int level = int(as->levelStart.size()) - 2; level >= 0; --level) {
-    uint32_t start = as->levelStart[level], count = as->levelStart[level + 1] - start;
-    if (!count) continue;
-    k_refit_level<<<gridFor(count, 128), 128, 0, st>>>(as->nodes, as->nodeBox, as->tris, start, count);
-    ++ctx->launches;
-  }
+  k_refit_pending<<<gridFor(as->nodeCount, 256), 256, 0, st>>>(as->nodes, as->nodeCount, as->nodePending);
+  k_refit_bottom_up<<<gridFor(as->nodeCount, 128), 128, 0, st>>>(as->nodes, as->nodeBox, as->tris, as->nodeCount,
+                                                                  as->nodeParent, as->nodePending);
+  ctx->launches += 2;
   k_write_blas_header<<<1, 32, 0, st>>>(static_cast<BlasHeader *>(as->headerDev), as->nodes, as->tris, as->nodeBox, n,
                                         as->nodeCount);
   ++ctx->launches;
@@ -1115,6 +1146,8 @@ void destroyAccel(AccelObject *as) {
   cudaFree(as->leafPrim);
   cudaFree(as->triSource);
   cudaFree(as->geomTableDev);
+  cudaFree(as->nodeParent);
+  cudaFree(as->nodePending);
   delete as;
 }
 

@@ -106,6 +106,7 @@ struct AccelObject {
   InstanceRecord *instances = nullptr; // TLAS (in descriptor order)
   uint32_t *leafPrim = nullptr; // TLAS: leaf slot -> instance index (the node's primBase + offset indexes this)
   uint2 *triSource = nullptr;   // BLAS: per triangle slot (geometry, primitive) — refit source mapping
+  uint32_t *nodeParent = nullptr, *nodePending = nullptr; // refittable BLAS: parent links, per-refit child counters
   // geometry table for refit: device copy of per-geometry (vertex ptr, stride, index ptr, index stride)
   void *geomTableDev = nullptr;
   std::vector<uint8_t> geomTableHost; // what geomTableDev holds: a refit with the same buffers uploads nothing
