@@ -134,6 +134,11 @@ typedef struct rt_trace_options {
  * a build without the texture paths (about a tenth faster); a material that breaks the promise is shaded as if its
  * maps were absent. rtr_draw sets the hint by itself from the scene it was given. */
 #define RT_TRACE_HINT_UNTEXTURED 1u
+/* The caller promises that no Material bound in this dispatch takes the glass branch (opacity >= 0.999 and
+ * refractionIndex <= 1.01, Raytracing.metal:517-519). A path then has at most maxBounces segments, so the dispatch
+ * needs no device->host read-back of the surviving-path count between segments and stays fully asynchronous; a
+ * material that breaks the promise has its paths cut after maxBounces segments. rtr_draw sets it from the scene. */
+#define RT_TRACE_HINT_NO_GLASS 2u
 
 /* rt_trace: raytracingKernel dispatch (Raytracing.metal:220-831; binding block Renderer.swift:1453-1490).
  * buffers[]: 0 Uniforms (HOST pointer; copied into the launch like a `constant` argument), 5 Resource rows (dev),

@@ -68,6 +68,7 @@ struct rtr_renderer {
   rt_instance_descriptor *stageDescriptors = nullptr; // inside the current arena
   size_t stagePaletteFloats = 0;                       // sum over skinned meshes of 16 floats per joint
   bool untextured = true; // no submesh material has a textureFlags bit: rtr_draw passes RT_TRACE_HINT_UNTEXTURED
+  bool noGlass = true;    // no submesh material can take the glass branch: rtr_draw passes RT_TRACE_HINT_NO_GLASS
 };
 
 #define RTR_TRY(expr)                  \
@@ -178,6 +179,11 @@ int rtr_create(rt_context *ctx, const rt_scene_desc *scene, int width, int heigh
     for (uint32_t k = 0; k < sm.submeshCount; ++k) {
       mats[k] = sm.submeshes[k].material;
       if (mats[k].textureFlags != 0u) r->untextured = false;
+      // the kernel's test is clamp(opacity [* map]) < 0.999 || max(ior, 1) > 1.01 (Raytracing.metal:517-519); an
+      // opacity map can only lower opacity, so a bound one counts as possible glass
+      const float opacity = std::min(std::max(mats[k].opacity, 0.0f), 1.0f);
+      if (!(opacity >= 0.999f) || mats[k].refractionIndex > 1.01f || (mats[k].textureFlags & RT_MATERIAL_TEXTURE_OPACITY))
+        r->noGlass = false;
       dm.triangleCounts[k] = sm.submeshes[k].triangleCount;
       RTR_TRY(uploadNew(ctx, sm.submeshes[k].indices, size_t(sm.submeshes[k].triangleCount) * 12, &dm.indices[k]));
     }
@@ -389,6 +395,7 @@ int rtr_draw(rtr_renderer *r, const rt_uniforms *uniforms, const rt_trace_option
   rt_trace_options withHints{};
   if (options) withHints = *options;
   if (r->untextured) withHints.hints |= RT_TRACE_HINT_UNTEXTURED; // known from the materials uploaded at creation
+  if (r->noGlass) withHints.hints |= RT_TRACE_HINT_NO_GLASS;
   RTR_TRY(rt_trace(r->ctx, buffers, r->images, int(sizeof(rt_resource)), int(r->maxSubmeshes), &withHints));
   std::swap(r->images[RT_TEXTURE_ACCUMULATION], r->images[RT_TEXTURE_PREVIOUS_ACCUMULATION]); // Renderer.swift:1492-1494
   return 0;

@@ -559,7 +559,8 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
   const int sampleLoopBound = baseSamples + maxExtraSamples;
   const int maxBounces = std::max(U.maxBounces, 0);
   // a refraction does not consume a bounce until transparencyPasses > maxBounces (Raytracing.metal:563-575)
-  const int maxSegments = maxBounces * (maxBounces + 1);
+  // without glass (RT_TRACE_HINT_NO_GLASS) every segment consumes a bounce: exactly maxBounces segments, no read-back
+  const int maxSegments = (P.hints & RT_TRACE_HINT_NO_GLASS) ? maxBounces : maxBounces * (maxBounces + 1);
   // samples in flight per pixel: as many as the option allows while the path state stays under ~48 M paths
   // (10.6 GB); the motion debug view reads what sample 0 wrote for its pixel, so it keeps one sample at a time
   int batch = std::max(1, std::min(ctx->sampleBatch, sampleLoopBound));
