@@ -201,13 +201,19 @@ __global__ void __launch_bounds__(kBlock) k_ray_keys(const uint32_t *__restrict_
 // idle lane its rank in the claimed range (warp-level ray compaction). kRefill == 0 claims 32 rays at a time only
 // when the whole warp is idle.
 #ifndef RT_STEPS_PER_CHECK
-#define RT_STEPS_PER_CHECK 4
+#define RT_STEPS_PER_CHECK 2
 #endif
 constexpr int kStepsPerCheck = RT_STEPS_PER_CHECK;
 // RT_FUSED_PRIMS > 0: fused pop -> node -> primitive iterations (LaneTraversal::stepFused) with that many primitive
 // tests per iteration; 0: one unit of work per iteration (LaneTraversal::step)
 #ifndef RT_FUSED_PRIMS
 #define RT_FUSED_PRIMS 1
+#endif
+// RT_CONVERGED: LaneTraversal::stepConverged; bit 0 = an entry stage before the node stage, bit 2 = one after it,
+// bit 1 = early finish, bit 3 = entry and triangle share one stage as in stepFused, bits 4-5 = extra triangle stages
+// Default 22: entry after the node stage, early finish, two triangle stages (measured best of the combinations, tune34-38)
+#ifndef RT_CONVERGED
+#define RT_CONVERGED 22
 #endif
 // entries of each lane's traversal stack kept in shared memory (0 = all in local memory), traverse.cuh SplitStack
 #ifndef RT_SHARED_STACK
@@ -258,7 +264,9 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
     }
 #pragma unroll 1
     for (int k = 0; k < kStepsPerCheck; ++k) {
-#if RT_FUSED_PRIMS > 0
+#if RT_CONVERGED > 0
+      if (t.template stepConverged<(RT_CONVERGED & 1) != 0, (RT_CONVERGED & 4) != 0, (RT_CONVERGED & 2) != 0, (RT_CONVERGED & 8) != 0, 1 + ((RT_CONVERGED >> 4) & 3)>(P.tlas, stack, active)) {
+#elif RT_FUSED_PRIMS > 0
       if (active && !t.template stepFused<RT_FUSED_PRIMS>(P.tlas, stack)) {
 #else
       if (active && !t.step(P.tlas, stack)) {

@@ -339,9 +339,19 @@ struct LaneTraversal {
   // one primitive of tgroup. Returns true when an any-hit query is satisfied.
   template <typename Stack>
   __device__ __forceinline__ bool primitiveStep(const TlasHeader &tlas, Stack &stack) {
+    if (instanceSp < 0) {
+      enterInstance(tlas, stack);
+      return false;
+    }
+    return triangleStep();
+  }
+
+  // tgroup holds TLAS leaf entries (instanceSp < 0): enter the next instance
+  template <typename Stack>
+  __device__ __forceinline__ void enterInstance(const TlasHeader &tlas, Stack &stack) {
     const uint32_t bit = uint32_t(__ffs(int(tgroup.y))) - 1u;
     tgroup.y &= ~(1u << bit);
-    if (instanceSp < 0) {
+    {
       // TLAS leaf: enter the instance. Pending world-space work goes to the stack first.
       if (tgroup.y != 0u && sp < kStackSize) stack.set(sp++, tgroup);
       if (ngroup.y > 0x00FFFFFFu && sp < kStackSize) stack.set(sp++, ngroup);
@@ -377,8 +387,14 @@ struct LaneTraversal {
           ngroup = make_uint2(0u, 0x80000000u);
         }
       }
-      return false;
     }
+  }
+
+  // tgroup holds triangles of the current BLAS (instanceSp >= 0): test the next one.
+  // Returns true when an any-hit query is satisfied.
+  __device__ __forceinline__ bool triangleStep() {
+    const uint32_t bit = uint32_t(__ffs(int(tgroup.y))) - 1u;
+    tgroup.y &= ~(1u << bit);
     const float4 *tp = tris + size_t(tgroup.x + bit) * 3;
     const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
     float t, u, v;
@@ -446,6 +462,49 @@ struct LaneTraversal {
       }
     }
     return true;
+  }
+
+  // The iteration the wavefront kernel runs (trace_wavefront.cu, RT_CONVERGED): every lane of the warp calls it
+  // (`active` = the lane holds a ray) and the stages pop -> [entry] -> node -> [entry] -> triangle x kTriangles are
+  // separated by __syncwarp(). With the instance entry as a stage of its own a lane can test a node, enter the
+  // instance a TLAS leaf names and test that instance's first triangles in one iteration; kEarlyFinish ends a ray at
+  // the end of the iteration that emptied it instead of at the pop of the next one. The __syncwarp()s are what makes
+  // this pay: written as plain consecutive `if`s (and with the extra exit) the compiler left the lanes that took an
+  // earlier stage running apart from those that did not — ncu showed the same thread instructions in 1.3-1.5x the
+  // warp instructions (profiles/r1_traversal.md, step 12). Per lane the order of node, entry and triangle tests is
+  // the one stepFused has, so results are unchanged. Returns true when this lane's ray has just finished.
+  template <bool kEntryBefore, bool kEntryAfter, bool kEarlyFinish, bool kCombined, int kTriangles, typename Stack>
+  __device__ __forceinline__ bool stepConverged(const TlasHeader &tlas, Stack &stack, bool active) {
+    bool alive = active;
+    if (alive && tgroup.y == 0u && ngroup.y <= 0x00FFFFFFu) alive = popStep(tlas, stack);
+    __syncwarp();
+    if (kEntryBefore && !kCombined) {
+      if (alive && tgroup.y != 0u && instanceSp < 0) enterInstance(tlas, stack);
+      __syncwarp();
+    }
+    if (alive && tgroup.y == 0u && ngroup.y > 0x00FFFFFFu) nodeStep(stack);
+    __syncwarp();
+    if (kEntryAfter && !kCombined) {
+      if (alive && tgroup.y != 0u && instanceSp < 0) enterInstance(tlas, stack);
+      __syncwarp();
+    }
+    bool satisfied = false;
+    if (kCombined) {
+      if (alive && tgroup.y != 0u) satisfied = primitiveStep(tlas, stack);
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int k = 0; k < kTriangles; ++k) {
+        if (alive && !satisfied && tgroup.y != 0u && instanceSp >= 0) satisfied = triangleStep();
+        __syncwarp();
+      }
+    }
+    if (satisfied) {
+      found = true;
+      alive = false;
+    }
+    if (kEarlyFinish && sp == 0 && tgroup.y == 0u && ngroup.y <= 0x00FFFFFFu) alive = false;
+    return active && !alive;
   }
 
   // One unit of work. Returns false when the traversal has finished (result in `hit` / `found`).

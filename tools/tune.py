@@ -42,7 +42,7 @@ if __name__ == "__main__":
     ref = {}
     for opts in grid:
         row = {"opts": opts, "parity": parity(opts)}
-        for (name, spp, mb) in (("K3", 1, 2), ("K3", 4, 3), ("K2", 4, 2)):
+        for (name, spp, mb) in (("K3", 1, 2), ("K3", 4, 3), ("K2", 4, 2), ("K4", 2, 2)):
             ms, rays, img, kt = timeit(name, 1920, 1080, spp, mb, opts)
             key = (name, spp, mb)
             if key not in ref: ref[key] = img
