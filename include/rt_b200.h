@@ -197,7 +197,8 @@ int rt_set_trace_mode(rt_context *ctx, int mode);
 /* Tuning knobs that never change results: "trace_mode" (0/1), "traversal_variant" (0..2, traverse.cuh),
  * "blocks_per_sm" (persistent grid size of the wavefront kernels), "sample_batch" (1..64, samples of a pixel the
  * wavefront layout keeps in flight at once; default 16), "ploc_radius" (builder: PLOC neighbour search radius for
- * acceleration structures built after the call, default 16; 0 = plain LBVH). */
+ * acceleration structures built after the call, default 16; 0 = plain LBVH), "leaf_size" / "tlas_leaf_size" (1..3
+ * triangles / instances per leaf slot of a wide node, defaults 3 / 1). */
 int rt_set_option(rt_context *ctx, const char *key, int value);
 /* Per-kernel-class device timing (bench.py's roofline of the dominant kernel). While enabled, the library records
  * a CUDA event on the context's stream after each of its launches; rt_kernel_timing_read synchronises, returns the

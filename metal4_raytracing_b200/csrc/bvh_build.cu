@@ -886,7 +886,7 @@ static int buildWideTree(rt_context *ctx, AccelObject *as, uint32_t n, const flo
     k_collapse_level<<<gridFor(levelCount, 128), 128, 0, st>>>(t, primLo, primHi, sorted, qin, qout, levelStart,
                                                                 levelCount, nextStart, counters, as->nodes,
                                                                 as->nodeBox, leafPrim,
-                                                                uint32_t(std::min(std::max(ctx->leafSize, 1), kMaxLeafPrims)));
+                                                                uint32_t(std::min(std::max(as->isTlas ? ctx->tlasLeafSize : ctx->leafSize, 1), kMaxLeafPrims)));
     ++ctx->launches;
     CollapseCounters now;
     RT_CUDA(cudaMemcpyAsync(&now, counters, sizeof now, cudaMemcpyDeviceToHost, st));

@@ -549,6 +549,11 @@ int rt_set_option(rt_context *ctx, const char *key, int value) {
     ctx->leafSize = value;
     return 0;
   }
+  if (k == "tlas_leaf_size") {
+    RT_CHECK(value >= 1 && value <= 3, "rt_set_option: tlas_leaf_size is 1..3 instances per leaf slot");
+    ctx->tlasLeafSize = value;
+    return 0;
+  }
   if (k == "ploc_radius") {
     RT_CHECK(value >= 0 && value <= 256, "rt_set_option: ploc_radius is 0 (LBVH) .. 256");
     ctx->plocRadius = value;
