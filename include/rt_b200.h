@@ -97,13 +97,34 @@ int rt_skin(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], uint32_
  * asks for an "HDR environment lookup", so it is specified here (and in the oracle): a closest-hit ray that
  * misses adds throughput * intensity * bilinear(texels, u, v) with the equirectangular mapping
  *   u = atan2(d.z, d.x) / (2 pi) + 0.5,  v = acos(d.y) / pi   (row 0 = straight up, columns wrap, rows clamp),
- * texel centres at (i + 0.5) / size, then the path ends as before. */
+ * texel centres at (i + 0.5) / size, then the path ends as before.
+ *
+ * RT_ENV_IMPORTANCE additionally samples the environment as a light. With the flag set and a
+ * table from rt_environment_cdf bound, the uniform light pick of Raytracing.metal:587-590 chooses among
+ * lightCount + 1 lights, the last one being the environment: the two Halton dimensions of the area-light sample
+ * (2 + 6 step + 1, + 2) pick a row from the marginal and a column from that row's conditional distribution
+ * (piecewise constant over texels, proportional to luminance * sin(theta)), a point inside the texel, and with it a
+ * direction L; its solid-angle density is p_env = p_row * p_col * width * height / (2 pi^2 sin(theta)). The
+ * environment's radiance along L (the bilinear lookup above) is combined with the cosine-hemisphere bounce by the
+ * balance heuristic: the light sample carries radiance / (p_env / n + p_bsdf) with p_bsdf = max(N.L, 0) / pi and
+ * n = lightCount + 1 (this replaces the `* lightCount` of the other lights), its shadow ray has no far end, and a
+ * bounce ray that misses picks the environment up with weight p_bsdf / (p_bsdf + p_env / n). Camera rays and glass
+ * reflections / refractions are not sampled by the light and keep weight 1. All of it is evaluated in fp32 with
+ * the operation order of csrc/shade.cuh, which the oracle repeats. */
+#define RT_ENV_IMPORTANCE 1u
 typedef struct rt_environment {
   const float *texelsDev; /* RGBA32F, width * height texels in device memory (host memory for the oracle) */
   int32_t width, height;
   float intensity;
-  float _pad;
+  uint32_t flags;         /* RT_ENV_* */
+  const float *cdfDev;    /* rt_environment_cdf's table in device memory (host memory for the oracle), or NULL */
 } rt_environment;
+/* Builds the sampling table of RT_ENV_IMPORTANCE on the host: (height + 1) marginal values followed by height rows
+ * of (width + 1) conditional values, each a running sum normalised to [0, 1] (accumulated in double in row / column
+ * order, stored as float; weight = (0.2126 r + 0.7152 g + 0.0722 b) * sin(pi (row + 0.5) / height); a row or a map
+ * without weight becomes uniform). cdfOut: rt_environment_cdf_floats(width, height) floats. Needs no context. */
+size_t rt_environment_cdf_floats(int32_t width, int32_t height);
+int rt_environment_cdf(const float *texelsHost, int32_t width, int32_t height, float *cdfOutHost);
 
 /* rt_joint_palette: the joint-palette computation the reference does on the host every animated frame, as one
  * kernel: local[j] = T * R * S with the rotation quaternion renormalised (Model.update,

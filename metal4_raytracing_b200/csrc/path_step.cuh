@@ -54,7 +54,13 @@ struct PathState { // registers of one path (one sample of one pixel)
   f3 throughput; // `color` in the reference
   f3 radiance;   // `accumulatedColor`
   int bounce, step, transparencyPasses;
+  float bsdfPdf; // RT_ENV_IMPORTANCE: density the current direction was drawn with by the cosine bounce; 0 = camera ray
+                 // or glass (not sampled by the environment light, so a miss takes the environment at full weight)
 };
+
+__host__ __device__ __forceinline__ bool environmentIsLight(const TraceParams &P) {
+  return (P.env.flags & RT_ENV_IMPORTANCE) != 0u && P.env.cdfDev != nullptr && P.env.texelsDev != nullptr;
+}
 
 struct PrimaryOutputs { // per pixel, filled by the first hit of sample 0
   float depth;
@@ -87,6 +93,7 @@ __device__ __forceinline__ void startPath(const rt_uniforms &U, int px, int py, 
   s.throughput = mk3(1.0f);
   s.radiance = mk3(0.0f);
   s.bounce = s.step = s.transparencyPasses = 0;
+  s.bsdfPdf = 0.0f;
 }
 
 __device__ __forceinline__ f3 interpolate3(const rt_float3 *attr, const int32_t *indices, const RayHit &h) {
@@ -307,6 +314,7 @@ __device__ __forceinline__ bool shadeSegment(const TraceParams &P, PathState &s,
       s.throughput *= totalWeight * albedo;
       consumeBounce = false;
     }
+    s.bsdfPdf = 0.0f;
     ++s.step;
     if (consumeBounce) {
       ++s.bounce;
@@ -330,12 +338,23 @@ __device__ __forceinline__ bool shadeSegment(const TraceParams &P, PathState &s,
 
   // one light, picked uniformly (Raytracing.metal:587-647)
   const float lightSample = halton(hIndex, 2 + s.step * 6 + 0);
-  const int lightIndex = min(int(lightSample * float(U.lightCount)), U.lightCount - 1);
-  const rt_light *light = P.lights + lightIndex;
-  const int lightType = light->type;
+  // extension: the environment is light number lightCount. Only the general build of the shade kernel carries the
+  // code (the launcher routes dispatches with RT_ENV_IMPORTANCE to it), the plain-PBR build stays as small as it was
+  const bool envLight = !kPlain && environmentIsLight(P);
+  const int pickCount = U.lightCount + (envLight ? 1 : 0);
+  const int lightIndex = min(int(lightSample * float(pickCount)), pickCount - 1);
+  const bool pickedEnvironment = envLight && lightIndex == U.lightCount;
+  const rt_light *light = P.lights + (pickedEnvironment ? 0 : lightIndex);
+  const int lightType = pickedEnvironment ? -1 : light->type;
   f3 L, lightColor;
   float lightDistance;
-  if (lightType == RT_LIGHT_AREA) {
+  if (pickedEnvironment) { // rt_b200.h RT_ENV_IMPORTANCE
+    const f2 r = mk2(halton(hIndex, 2 + s.step * 6 + 1), halton(hIndex, 2 + s.step * 6 + 2));
+    const float envPdf = sampleEnvironmentDirection(P.env, r, L);
+    lightDistance = INFINITY;
+    const float bouncePdf = saturatef(dot(shadingNormal, L)) * kInvPi;
+    lightColor = sampleEnvironment(P.env, L) / (envPdf / float(pickCount) + bouncePdf);
+  } else if (lightType == RT_LIGHT_AREA) {
     const f2 r = mk2(halton(hIndex, 2 + s.step * 6 + 1), halton(hIndex, 2 + s.step * 6 + 2));
     const f2 sq = r * 2.0f - mk2(1.0f, 1.0f);
     const f3 samplePosition = mk3(light->position) + mk3(light->right) * sq.x + mk3(light->up) * sq.y;
@@ -368,7 +387,7 @@ __device__ __forceinline__ bool shadeSegment(const TraceParams &P, PathState &s,
     lightDistance = INFINITY;
     lightColor = mk3(light->color);
   }
-  lightColor *= float(U.lightCount);
+  if (!pickedEnvironment) lightColor *= float(pickCount);
 
   const f3 shadowOrigin = hitPoint + surfaceNormal * 1e-3f;
 
@@ -417,6 +436,7 @@ __device__ __forceinline__ bool shadeSegment(const TraceParams &P, PathState &s,
   const f2 r = mk2(halton(hIndex, 2 + s.step * 5 + 3), halton(hIndex, 2 + s.step * 5 + 4));
   const f3 local = sampleCosineWeightedHemisphere(r);
   s.dir = alignHemisphereWithNormal(local, shadingNormal);
+  s.bsdfPdf = envLight ? saturatef(dot(shadingNormal, s.dir)) * kInvPi : 0.0f;
   s.origin = shadowOrigin;
   ++s.step;
   ++s.bounce;
@@ -427,7 +447,14 @@ __device__ __forceinline__ bool shadeSegment(const TraceParams &P, PathState &s,
 // Extension (rt_b200.h rt_environment): what a path that leaves the scene picks up. Returns black when no
 // environment is bound, which is the reference's behaviour.
 __device__ __forceinline__ void shadeMiss(const TraceParams &P, PathState &s) {
-  if (P.env.texelsDev != nullptr) s.radiance += s.throughput * sampleEnvironment(P.env, s.dir);
+  if (P.env.texelsDev == nullptr) return;
+  if (environmentIsLight(P) && s.bsdfPdf > 0.0f) { // the light sample of the previous hit covers part of this
+    const float envPdf = environmentPdf(P.env, s.dir) / float(P.uniforms.lightCount + 1);
+    const float weight = s.bsdfPdf / (s.bsdfPdf + envPdf);
+    s.radiance += s.throughput * (sampleEnvironment(P.env, s.dir) * weight);
+  } else {
+    s.radiance += s.throughput * sampleEnvironment(P.env, s.dir);
+  }
 }
 
 // Motion-adaptive sample count, evaluated after sample 0 (Raytracing.metal:779-789).

@@ -524,6 +524,49 @@ int rt_selftest_child_boxes(rt_context *ctx, uint64_t id, uint32_t raysPerNode, 
   return selftestChildBoxes(ctx, it->second, raysPerNode, seed, reinterpret_cast<unsigned long long *>(out));
 }
 
+size_t rt_environment_cdf_floats(int32_t width, int32_t height) {
+  if (width <= 0 || height <= 0) return 0;
+  return size_t(height + 1) + size_t(height) * size_t(width + 1);
+}
+
+// rt_b200.h RT_ENV_IMPORTANCE: marginal over rows + one conditional per row, running sums in double
+int rt_environment_cdf(const float *texelsHost, int32_t width, int32_t height, float *cdfOutHost) {
+  if (!texelsHost || !cdfOutHost || width <= 0 || height <= 0) return 1; // no context to hold an error string
+  const double pi = 3.14159265358979323846;
+  float *marginal = cdfOutHost;
+  float *rows = cdfOutHost + (height + 1);
+  std::vector<double> rowSum(size_t(height), 0.0), weight(size_t(width), 0.0);
+  double total = 0.0;
+  for (int y = 0; y < height; ++y) {
+    const double sinTheta = std::sin(pi * (double(y) + 0.5) / double(height));
+    double sum = 0.0;
+    for (int x = 0; x < width; ++x) {
+      const float *t = texelsHost + (size_t(y) * size_t(width) + size_t(x)) * 4;
+      const double lum = 0.2126 * double(t[0]) + 0.7152 * double(t[1]) + 0.0722 * double(t[2]);
+      weight[size_t(x)] = (lum > 0.0 ? lum : 0.0) * sinTheta;
+      sum += weight[size_t(x)];
+    }
+    rowSum[size_t(y)] = sum;
+    total += sum;
+    float *row = rows + size_t(y) * size_t(width + 1);
+    row[0] = 0.0f;
+    double run = 0.0;
+    for (int x = 0; x < width; ++x) {
+      run += weight[size_t(x)];
+      row[x + 1] = sum > 0.0 ? float(run / sum) : float(double(x + 1) / double(width));
+    }
+    row[width] = 1.0f;
+  }
+  marginal[0] = 0.0f;
+  double run = 0.0;
+  for (int y = 0; y < height; ++y) {
+    run += rowSum[size_t(y)];
+    marginal[y + 1] = total > 0.0 ? float(run / total) : float(double(y + 1) / double(height));
+  }
+  marginal[height] = 1.0f;
+  return 0;
+}
+
 int rt_set_option(rt_context *ctx, const char *key, int value) {
   RT_CTX(ctx);
   RT_CHECK(key != nullptr, "rt_set_option: null key");

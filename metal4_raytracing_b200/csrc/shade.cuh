@@ -187,6 +187,51 @@ __device__ __forceinline__ f3 sampleEnvironment(const rt_environment &env, f3 d)
   return mix(top, bottom, ty) * env.intensity;
 }
 
+// RT_ENV_IMPORTANCE (rt_b200.h): the environment as a light. Table = rt_environment_cdf's output.
+constexpr float kTwoPiSquared = 19.739208802178716f;
+// largest i in [0, n - 1] with c[i] <= xi (c[0] = 0, c[n] = 1 > xi): the selected cell always has weight
+__device__ __forceinline__ int cdfFind(const float *__restrict__ c, int n, float xi) {
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(c + mid) <= xi) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+// solid-angle density of the texel (x, y) at polar sine sinTheta
+__device__ __forceinline__ float environmentTexelPdf(const rt_environment &env, int x, int y, float sinTheta) {
+  const float *marginal = env.cdfDev;
+  const float *row = env.cdfDev + (env.height + 1) + size_t(y) * size_t(env.width + 1);
+  const float pr = (__ldg(marginal + y + 1) - __ldg(marginal + y)) * float(env.height);
+  const float pc = (__ldg(row + x + 1) - __ldg(row + x)) * float(env.width);
+  return (pr * pc) / (kTwoPiSquared * fmaxf(sinTheta, 1e-6f));
+}
+__device__ __forceinline__ float environmentPdf(const rt_environment &env, f3 d) {
+  const float phi = float(atan2(double(d.z), double(d.x)));
+  const float theta = float(acos(double(clampf(d.y, -1.0f, 1.0f))));
+  const float u = phi * kInvTwoPi + 0.5f, v = theta * kInvPi;
+  const int x = min(max(int(floorf(u * float(env.width))), 0), env.width - 1);
+  const int y = min(max(int(floorf(v * float(env.height))), 0), env.height - 1);
+  return environmentTexelPdf(env, x, y, sinDet(theta));
+}
+// direction drawn from the table with (xi.x -> row, xi.y -> column); returns its density
+__device__ __forceinline__ float sampleEnvironmentDirection(const rt_environment &env, f2 xi, f3 &dir) {
+  const float *marginal = env.cdfDev;
+  const int y = cdfFind(marginal, env.height, xi.x);
+  const float m0 = __ldg(marginal + y), m1 = __ldg(marginal + y + 1);
+  const float dy = (xi.x - m0) / (m1 - m0);
+  const float *row = env.cdfDev + (env.height + 1) + size_t(y) * size_t(env.width + 1);
+  const int x = cdfFind(row, env.width, xi.y);
+  const float c0 = __ldg(row + x), c1 = __ldg(row + x + 1);
+  const float dx = (xi.y - c0) / (c1 - c0);
+  const float u = (float(x) + dx) / float(env.width), v = (float(y) + dy) / float(env.height);
+  const float phi = (u - 0.5f) * (2.0f * kPi), theta = v * kPi;
+  const float sinTheta = sinDet(theta), cosTheta = cosDet(theta);
+  dir = mk3(sinTheta * cosDet(phi), cosTheta, sinTheta * sinDet(phi));
+  return environmentTexelPdf(env, x, y, sinTheta);
+}
+
 // ---- material textures: bilinear, repeat, LOD 0 (Raytracing.metal:421) ---------------------------------------
 __device__ __forceinline__ f4 fetchTexel(const rt_texture2d &t, int x, int y, const float *__restrict__ srgbLut) {
   const uchar4 p = __ldg(reinterpret_cast<const uchar4 *>(t.texels) + (size_t(y) * size_t(t.width) + size_t(x)));

@@ -154,6 +154,8 @@ int fillTraceParams(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT],
   if (opt && opt->environment && opt->environment->texelsDev) {
     P.env = *opt->environment;
     RT_CHECK(P.env.width > 0 && P.env.height > 0, "rt_trace: environment has no texels");
+    RT_CHECK((P.env.flags & RT_ENV_IMPORTANCE) == 0u || P.env.cdfDev != nullptr,
+             "rt_trace: RT_ENV_IMPORTANCE needs the table of rt_environment_cdf in cdfDev");
   }
   P.hints = opt ? opt->hints : 0u;
   P.peerCount = 0;

@@ -392,6 +392,7 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
         s.throughput = mk3(th.x, th.y, th.z);
         s.radiance = mk3(ra.x, ra.y, ra.z);
         s.bounce = c.x, s.step = c.y, s.transparencyPasses = c.z;
+        s.bsdfPdf = o.w;
         const int hIndex = __float_as_int(th.w);
         PrimaryOutputs prim = emptyPrimaryOutputs();
         const uint32_t flags = __float_as_uint(mi.y);
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
         // record serves both; a path that ends but still has a shadow ray to trace stores it for that alone
         if (pushPath || shadow.valid) {
           const f3 org = pushPath ? s.origin : shadow.origin;
-          RT_STS(W.rayO + slot, make_float4(org.x, org.y, org.z, 0.0f));
+          RT_STS(W.rayO + slot, make_float4(org.x, org.y, org.z, pushPath ? s.bsdfPdf : 0.0f));
         }
         if (primarySegment || (prim.wroteGBuffer && !hadGBuffer)) {
           const uint32_t nf = (prim.hadPrimaryHit ? 1u : 0u) | (prim.wroteGBuffer ? 2u : 0u);
@@ -442,10 +443,12 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
       s.throughput = mk3(1.0f);
       const float4 d = RT_LDS(W.rayD + slot);
       s.dir = mk3(d.x, d.y, d.z);
+      s.bsdfPdf = 0.0f;
       if (!cameraRays) {
         const float4 th = RT_LDS(W.thr + slot), ra = RT_LDS(W.rad + slot);
         s.throughput = mk3(th.x, th.y, th.z);
         s.radiance = mk3(ra.x, ra.y, ra.z);
+        if (environmentIsLight(P)) s.bsdfPdf = RT_LDS(W.rayO + slot).w;
       }
       shadeMiss(P, s);
       RT_STS(W.rad + slot, make_float4(s.radiance.x, s.radiance.y, s.radiance.z, 0.0f));
@@ -630,7 +633,7 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
       }
       { // the shade kernel is specialised on what the host knows: texture hint, plain PBR without debug views
         const bool textures = (P.hints & RT_TRACE_HINT_UNTEXTURED) == 0u;
-        const bool plain = U.debugTextureMode == RT_DEBUG_NONE && U.shadingMode != RT_SHADING_LEGACY;
+        const bool plain = U.debugTextureMode == RT_DEBUG_NONE && U.shadingMode != RT_SHADING_LEGACY && !environmentIsLight(P);
         if (textures && plain) k_wf_shade<true, true><<<persistent, kBlock, 0, st>>>(P, W, qin, s0, segment == 0, parity);
         else if (textures) k_wf_shade<true, false><<<persistent, kBlock, 0, st>>>(P, W, qin, s0, segment == 0, parity);
         else if (plain) k_wf_shade<false, true><<<persistent, kBlock, 0, st>>>(P, W, qin, s0, segment == 0, parity);

@@ -24,7 +24,24 @@ RTR_FLAG_GPU_SKELETON = 4
 class Environment(C.Structure):
     """rt_environment (include/rt_b200.h): RGBA32F equirectangular texels + intensity. An extension, off by default."""
     _fields_ = [("texelsDev", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("intensity", C.c_float),
-                ("_pad", C.c_float)]
+                ("flags", C.c_uint32), ("cdfDev", C.c_void_p)]
+
+
+ENV_IMPORTANCE = 1  # RT_ENV_IMPORTANCE
+
+
+def environment_cdf(texels):
+    """rt_environment_cdf: the sampling table of RT_ENV_IMPORTANCE for (H, W, 4) float32 texels (host side, no GPU)."""
+    t = np.ascontiguousarray(texels, np.float32)
+    h, w = t.shape[0], t.shape[1]
+    L = lib()
+    L.rt_environment_cdf_floats.restype = C.c_size_t
+    L.rt_environment_cdf_floats.argtypes = [C.c_int32, C.c_int32]
+    L.rt_environment_cdf.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    out = np.empty(L.rt_environment_cdf_floats(w, h), np.float32)
+    if L.rt_environment_cdf(t.ctypes.data, w, h, out.ctypes.data) != 0:
+        raise RuntimeError("rt_environment_cdf failed")
+    return out
 
 
 class DenoiseFrame(C.Structure):
@@ -54,7 +71,7 @@ EXPORTS = [
     "rt_tonemap", "rt_temporal_filter", "rt_download_async", "rt_download_wait", "rt_fence", "rt_fence_wait",
     "rtr_last_error", "rtr_create", "rtr_destroy", "rtr_set_seeds", "rtr_update", "rtr_draw", "rtr_read_image",
     "rtr_image_info", "rtr_reset_accumulation", "rtr_read_mesh_streams", "rtr_get_blas_id", "rtr_get_tlas_id",
-    "rtr_mesh_count",
+    "rtr_mesh_count", "rt_environment_cdf_floats", "rt_environment_cdf",
 ]
 
 
@@ -380,17 +397,23 @@ class Renderer:
         desc = self.scene.desc()
         _check(lib().rtr_update(self._h, C.byref(desc)), True)
 
-    def set_environment(self, texels, intensity=1.0):
+    def set_environment(self, texels, intensity=1.0, importance=False):
         """Binds an (H, W, 4) float32 equirectangular environment for the following draws; None unbinds it
-        (the reference's behaviour: a miss contributes nothing)."""
-        if getattr(self, "_env_dev", None):
-            self.ctx.free(self._env_dev)
-        self._env_dev, self._env = None, None
+        (the reference's behaviour: a miss contributes nothing). importance=True also samples it as a light
+        (RT_ENV_IMPORTANCE)."""
+        for name in ("_env_dev", "_env_cdf_dev"):
+            if getattr(self, name, None):
+                self.ctx.free(getattr(self, name))
+        self._env_dev, self._env_cdf_dev, self._env = None, None, None
         if texels is not None:
             t = np.ascontiguousarray(texels, np.float32)
             assert t.ndim == 3 and t.shape[2] == 4
             self._env_dev = self.ctx.upload(t)
-            self._env = Environment(self._env_dev, t.shape[1], t.shape[0], float(intensity), 0.0)
+            flags = 0
+            if importance:
+                self._env_cdf_dev = self.ctx.upload(environment_cdf(t))
+                flags = ENV_IMPORTANCE
+            self._env = Environment(self._env_dev, t.shape[1], t.shape[0], float(intensity), flags, self._env_cdf_dev)
 
     def draw(self, uniforms, want_ids=False, count_rays=False, tile_modulo=1, tile_remainder=0, peers=None, hints=0):
         opt = TraceOptions()

@@ -120,16 +120,19 @@ class Oracle:
     def threads(self):
         return lib().oracle_thread_count(self._h)
 
-    def set_environment(self, texels, intensity=1.0):
-        """Environment extension (include/rt_b200.h rt_environment); texels (H, W, 4) float32 or None."""
+    def set_environment(self, texels, intensity=1.0, importance=False):
+        """Environment extension (include/rt_b200.h rt_environment); texels (H, W, 4) float32 or None.
+        importance=True: RT_ENV_IMPORTANCE with the oracle's own table."""
         from metal4_raytracing_b200.device import Environment
         if texels is None:
-            self._env_texels = None
+            self._env_texels = self._env_cdf = None
             lib().oracle_set_environment(self._h, None)
             return
         self._env_texels = np.ascontiguousarray(texels, np.float32)  # kept alive: the oracle reads it in place
+        self._env_cdf = environment_cdf(self._env_texels) if importance else None
         env = Environment(self._env_texels.ctypes.data, self._env_texels.shape[1], self._env_texels.shape[0],
-                          float(intensity), 0.0)
+                          float(intensity), 1 if importance else 0,
+                          self._env_cdf.ctypes.data if importance else None)
         if lib().oracle_set_environment(self._h, C.byref(env)) != 0:
             raise RuntimeError("oracle_set_environment failed")
 
@@ -213,11 +216,23 @@ def skin(rest_pos4, rest_nrm4, joint_idx, joint_w, matrices):
     return op, on
 
 
+def environment_cdf(texels):
+    """The oracle's restatement of rt_environment_cdf (include/rt_b200.h): marginal + per-row conditional table."""
+    t = np.ascontiguousarray(texels, np.float32)
+    h, w = t.shape[0], t.shape[1]
+    out = np.empty((h + 1) + h * (w + 1), np.float32)
+    L = lib()
+    L.oracle_environment_cdf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    if L.oracle_environment_cdf(t.ctypes.data, w, h, out.ctypes.data) != 0:
+        raise RuntimeError("oracle_environment_cdf failed")
+    return out
+
+
 def sample_environment(texels, direction, intensity=1.0):
     """KAT probe of the environment extension's equirectangular lookup (include/rt_b200.h rt_environment)."""
     from metal4_raytracing_b200.device import Environment
     t = np.ascontiguousarray(texels, np.float32)
-    env = Environment(t.ctypes.data, t.shape[1], t.shape[0], float(intensity), 0.0)
+    env = Environment(t.ctypes.data, t.shape[1], t.shape[0], float(intensity), 0, None)
     d = (C.c_float * 3)(*[float(x) for x in direction])
     out = (C.c_float * 3)()
     lib().oracle_sample_environment(C.byref(env), d, out)

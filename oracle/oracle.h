@@ -33,6 +33,9 @@ int oracle_render(oracle_ctx *c, const rt_uniforms *uniforms, const rt_image tex
 /* Environment extension (include/rt_b200.h rt_environment; texels in HOST memory here). NULL switches it off. */
 int oracle_set_environment(oracle_ctx *c, const rt_environment *env);
 void oracle_sample_environment(const rt_environment *env, const float dir[3], float out_rgb[3]); /* KAT probe */
+/* RT_ENV_IMPORTANCE's table, (height + 1) + height * (width + 1) floats (the oracle's own restatement of
+ * rt_environment_cdf); bind it through rt_environment.cdfDev (a HOST pointer here). */
+int oracle_environment_cdf(const float *texels, int width, int height, float *out);
 /* Current skinned streams of a mesh (float4 per vertex). */
 int oracle_get_mesh_streams(oracle_ctx *c, int mesh, float *positions4, float *normals4, float *prevPositions4);
 

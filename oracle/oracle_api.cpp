@@ -250,6 +250,44 @@ void oracle_sample_environment(const rt_environment *env, const float dir[3], fl
   out_rgb[0] = c.x, out_rgb[1] = c.y, out_rgb[2] = c.z;
 }
 
+/* The sampling table of RT_ENV_IMPORTANCE as include/rt_b200.h specifies it (rt_environment_cdf): marginal over rows,
+ * then one conditional distribution per row; running sums in double, normalised, stored as float. */
+int oracle_environment_cdf(const float *texels, int width, int height, float *out) {
+  if (!texels || !out || width <= 0 || height <= 0) return -1;
+  const double pi = 3.14159265358979323846;
+  float *marginal = out, *rows = out + (height + 1);
+  std::vector<double> rowSum(static_cast<size_t>(height)), w(static_cast<size_t>(width));
+  double total = 0.0;
+  for (int y = 0; y < height; ++y) {
+    const double sinTheta = std::sin(pi * (double(y) + 0.5) / double(height));
+    double sum = 0.0;
+    for (int x = 0; x < width; ++x) {
+      const float *t = texels + (size_t(y) * width + x) * 4;
+      const double lum = 0.2126 * double(t[0]) + 0.7152 * double(t[1]) + 0.0722 * double(t[2]);
+      w[x] = (lum > 0.0 ? lum : 0.0) * sinTheta;
+      sum += w[x];
+    }
+    rowSum[y] = sum;
+    total += sum;
+    float *row = rows + size_t(y) * (width + 1);
+    row[0] = 0.0f;
+    double run = 0.0;
+    for (int x = 0; x < width; ++x) {
+      run += w[x];
+      row[x + 1] = sum > 0.0 ? float(run / sum) : float(double(x + 1) / double(width));
+    }
+    row[width] = 1.0f;
+  }
+  marginal[0] = 0.0f;
+  double run = 0.0;
+  for (int y = 0; y < height; ++y) {
+    run += rowSum[y];
+    marginal[y + 1] = total > 0.0 ? float(run / total) : float(double(y + 1) / double(height));
+  }
+  marginal[height] = 1.0f;
+  return 0;
+}
+
 int oracle_set_environment(oracle_ctx *c, const rt_environment *env) {
   if (!c) return -1;
   c->env = rt_environment{};

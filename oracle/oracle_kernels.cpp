@@ -287,6 +287,53 @@ float3 sampleEnvironment(const rt_environment &env, float3 d) {
   return mix(top, bottom, ty) * env.intensity;
 }
 
+// RT_ENV_IMPORTANCE (include/rt_b200.h): the environment as one more light; mirrors cdfFind / environmentTexelPdf /
+// environmentPdf / sampleEnvironmentDirection of csrc/shade.cuh operation for operation.
+static inline bool environmentIsLight(const rt_environment &env) {
+  return (env.flags & RT_ENV_IMPORTANCE) != 0u && env.cdfDev != nullptr && env.texelsDev != nullptr;
+}
+static inline int cdfFind(const float *c, int n, float xi) {
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (c[mid] <= xi) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+static inline float environmentTexelPdf(const rt_environment &env, int x, int y, float sinTheta) {
+  const float kTwoPiSquared = 19.739208802178716f;
+  const float *marginal = env.cdfDev;
+  const float *row = env.cdfDev + (env.height + 1) + size_t(y) * size_t(env.width + 1);
+  const float pr = (marginal[y + 1] - marginal[y]) * float(env.height);
+  const float pc = (row[x + 1] - row[x]) * float(env.width);
+  return (pr * pc) / (kTwoPiSquared * fmaxf(sinTheta, 1e-6f));
+}
+static inline float environmentPdf(const rt_environment &env, float3 d) {
+  const float kInvTwoPi = 0.15915494309189535f, kInvPi = 0.3183098861837907f;
+  const float phi = static_cast<float>(std::atan2(static_cast<double>(d.z), static_cast<double>(d.x)));
+  const float theta = static_cast<float>(std::acos(static_cast<double>(clampf(d.y, -1.0f, 1.0f))));
+  const float u = phi * kInvTwoPi + 0.5f, v = theta * kInvPi;
+  const int x = std::min(std::max(int(std::floor(u * float(env.width))), 0), env.width - 1);
+  const int y = std::min(std::max(int(std::floor(v * float(env.height))), 0), env.height - 1);
+  return environmentTexelPdf(env, x, y, sin_det(theta));
+}
+static inline float sampleEnvironmentDirection(const rt_environment &env, float2 xi, float3 &dir) {
+  const float *marginal = env.cdfDev;
+  const int y = cdfFind(marginal, env.height, xi.x);
+  const float m0 = marginal[y], m1 = marginal[y + 1];
+  const float dy = (xi.x - m0) / (m1 - m0);
+  const float *row = env.cdfDev + (env.height + 1) + size_t(y) * size_t(env.width + 1);
+  const int x = cdfFind(row, env.width, xi.y);
+  const float c0 = row[x], c1 = row[x + 1];
+  const float dx = (xi.y - c0) / (c1 - c0);
+  const float u = (float(x) + dx) / float(env.width), v = (float(y) + dy) / float(env.height);
+  const float phi = (u - 0.5f) * (2.0f * kPi), theta = v * kPi;
+  const float sinTheta = sin_det(theta), cosTheta = cos_det(theta);
+  dir = make3(sinTheta * cos_det(phi), cosTheta, sinTheta * sin_det(phi));
+  return environmentTexelPdf(env, x, y, sinTheta);
+}
+
 void raytracingKernelPixel(int tidx, int tidy, const KernelArgs &a, PixelStats &stats) {
   const rt_uniforms &uniforms = *a.uniforms;
   if (!(tidx < uniforms.width && tidy < uniforms.height)) return;
@@ -328,6 +375,9 @@ void raytracingKernelPixel(int tidx, int tidy, const KernelArgs &a, PixelStats &
     int bounce = 0;
     int step = 0;
     int transparencyPasses = 0;
+    const bool envLight = environmentIsLight(a.env); // extension: the environment is light number lightCount
+    const float kInvPi = 0.3183098861837907f;
+    float bsdfPdf = 0.0f; // density of the cosine bounce that produced rayDirection; 0 = camera ray or glass
     while (bounce < uniforms.maxBounces) {
       ++stats.closestRays;
       Hit intersection = traceClosest(*a.tlas, rayOrigin, rayDirection, 0.0f, rayMax);
@@ -342,7 +392,15 @@ void raytracingKernelPixel(int tidx, int tidy, const KernelArgs &a, PixelStats &
       }
       if (!intersection.valid) {
         // extension (include/rt_b200.h rt_environment); the reference only breaks here (Raytracing.metal:320-322)
-        if (a.env.texelsDev) accumulatedColor = accumulatedColor + color * sampleEnvironment(a.env, rayDirection);
+        if (a.env.texelsDev) {
+          if (envLight && bsdfPdf > 0.0f) { // balance heuristic against the light sample of the previous hit
+            const float envPdf = environmentPdf(a.env, rayDirection) / float(uniforms.lightCount + 1);
+            const float weight = bsdfPdf / (bsdfPdf + envPdf);
+            accumulatedColor = accumulatedColor + color * (sampleEnvironment(a.env, rayDirection) * weight);
+          } else {
+            accumulatedColor = accumulatedColor + color * sampleEnvironment(a.env, rayDirection);
+          }
+        }
         break;
       }
       ++stats.hits;
@@ -527,6 +585,7 @@ void raytracingKernelPixel(int tidx, int tidy, const KernelArgs &a, PixelStats &
       }
 
       if (skipLighting) {
+        bsdfPdf = 0.0f;
         step++;
         if (consumeBounce) {
           bounce++;
@@ -550,14 +609,22 @@ void raytracingKernelPixel(int tidx, int tidy, const KernelArgs &a, PixelStats &
       accumulatedColor += color * emission;
 
       float lightSample = halton(haltonIndex, 2 + step * 6 + 0);
-      int lightIndex = std::min(int(lightSample * float(uniforms.lightCount)), uniforms.lightCount - 1);
-      const rt_light &light = a.lights[lightIndex];
+      const int pickCount = uniforms.lightCount + (envLight ? 1 : 0);
+      int lightIndex = std::min(int(lightSample * float(pickCount)), pickCount - 1);
+      const bool pickedEnvironment = envLight && lightIndex == uniforms.lightCount;
+      const rt_light &light = a.lights[pickedEnvironment ? 0 : lightIndex];
 
       float3 worldSpaceLightDirection;
       float lightDistance;
       float3 lightColor;
 
-      if (light.type == RT_LIGHT_AREA) {
+      if (pickedEnvironment) { // include/rt_b200.h RT_ENV_IMPORTANCE
+        r = make2(halton(haltonIndex, 2 + step * 6 + 1), halton(haltonIndex, 2 + step * 6 + 2));
+        const float envPdf = sampleEnvironmentDirection(a.env, r, worldSpaceLightDirection);
+        lightDistance = INFINITY;
+        const float bouncePdf = saturate(dot(shadingNormal, worldSpaceLightDirection)) * kInvPi;
+        lightColor = sampleEnvironment(a.env, worldSpaceLightDirection) / (envPdf / float(pickCount) + bouncePdf);
+      } else if (light.type == RT_LIGHT_AREA) {
         r = make2(halton(haltonIndex, 2 + step * 6 + 1), halton(haltonIndex, 2 + step * 6 + 2));
         sampleAreaLight(light, r, worldSpaceIntersectionPoint, worldSpaceLightDirection, lightColor, lightDistance);
       } else if (light.type == RT_LIGHT_SPOT) {
@@ -580,7 +647,7 @@ void raytracingKernelPixel(int tidx, int tidy, const KernelArgs &a, PixelStats &
         lightDistance = INFINITY;
         lightColor = f3(light.color);
       }
-      lightColor *= float(uniforms.lightCount);
+      if (!pickedEnvironment) lightColor *= float(pickCount);
 
       if (uniforms.shadingMode == RT_SHADING_LEGACY) {
         float3 L = normalize(worldSpaceLightDirection);
@@ -598,6 +665,7 @@ void raytracingKernelPixel(int tidx, int tidy, const KernelArgs &a, PixelStats &
         r = make2(halton(haltonIndex, 2 + step * 5 + 3), halton(haltonIndex, 2 + step * 5 + 4));
         float3 worldSpaceSampleDirection = sampleCosineWeightedHemisphere(r);
         worldSpaceSampleDirection = alignHemisphereWithNormal(worldSpaceSampleDirection, shadingNormal);
+        bsdfPdf = envLight ? saturate(dot(shadingNormal, worldSpaceSampleDirection)) * kInvPi : 0.0f;
         rayOrigin = worldSpaceIntersectionPoint + worldSpaceSurfaceNormal * 1e-3f;
         rayDirection = worldSpaceSampleDirection;
         step++;
@@ -637,6 +705,7 @@ void raytracingKernelPixel(int tidx, int tidy, const KernelArgs &a, PixelStats &
       r = make2(halton(haltonIndex, 2 + step * 5 + 3), halton(haltonIndex, 2 + step * 5 + 4));
       float3 worldSpaceSampleDirection = sampleCosineWeightedHemisphere(r);
       worldSpaceSampleDirection = alignHemisphereWithNormal(worldSpaceSampleDirection, shadingNormal);
+      bsdfPdf = envLight ? saturate(dot(shadingNormal, worldSpaceSampleDirection)) * kInvPi : 0.0f;
       rayOrigin = worldSpaceIntersectionPoint + worldSpaceSurfaceNormal * 1e-3f;
       rayDirection = worldSpaceSampleDirection;
 

@@ -524,6 +524,46 @@ def test_bvh_invariants(gpu_ctx):
     rnd.close()
 
 
+@pytest.mark.parametrize("mode,legacy", [(1, False), (0, False), (1, True)])
+def test_environment_importance_sampling(mode, legacy):
+    """RT_ENV_IMPORTANCE (rt_b200.h): the environment picked as a light through the marginal /
+    conditional table, its shadow ray without a far end and the balance-heuristic weights on both estimators come out
+    the same on the GPU and in the oracle; the table is built by the library on one side and by the oracle on the
+    other."""
+    w, h = 192, 128
+    sc, u, seed = scene.Scene.named("K3small", w, h, assets=None)
+    u.samplesPerPixel, u.maxBounces = 3, 3
+    if legacy:
+        u.shadingMode = A.SHADING_LEGACY
+    seeds = scene.seed_image(w, h, seed)
+    sky = scene.procedural_sky(256, 128)
+    ctx = device.Context(0)
+    ctx.set_trace_mode(mode)
+    rnd = device.Renderer(ctx, sc, w, h, seeds=seeds)
+    orc = oracle.Oracle(sc)
+    imgs = oracle.FrameImages(w, h, seeds)
+    rnd.set_environment(sky, 0.75)
+    orc.set_environment(sky, 0.75)
+    rnd.draw(u)
+    lookup_only = rnd.read_image(0).copy()
+    rnd.set_environment(sky, 0.75, importance=True)
+    orc.set_environment(sky, 0.75, importance=True)
+    for frame in range(2):  # the second frame blends into the first (EMA) with a new sample index
+        u.frameIndex = frame
+        rnd.draw(u, count_rays=True)
+        stats, _ = orc.render(u, imgs)
+        got = rnd.read_image(0)
+        rays = rnd.read_ray_counters()
+        assert rays["closest"] == stats["closest"] and rays["any"] == stats["any"]
+        assert rel_rmse(got, imgs.output) < RMSE_TOL
+        assert float((got.view(np.uint16) == imgs.output.view(np.uint16)).all(-1).mean()) >= 0.999
+        if frame == 0:
+            assert not np.array_equal(got.view(np.uint16), lookup_only.view(np.uint16))
+        imgs.swap()
+    rnd.close()
+    ctx.close()
+
+
 @pytest.mark.parametrize("mode", [1, 0])
 def test_environment_extension(mode):
     """rt_environment (an extension; the reference has no environment lookup): with a sky bound, rays

@@ -329,6 +329,65 @@ def test_environment_extension_known_answers(assets):
     assert float(np.abs(imgs.output[miss][:, :3]).max()) == 0.0
 
 
+def test_environment_importance_tables():
+    """RT_ENV_IMPORTANCE (include/rt_b200.h): the library's table builder and the oracle's restatement agree bit for
+    bit; a constant map gives the sin(theta) marginal and uniform rows; a single bright texel takes all the mass."""
+    from metal4_raytracing_b200 import device, scene
+    sky = scene.procedural_sky(64, 32)
+    a, b = device.environment_cdf(sky), oracle.environment_cdf(sky)
+    assert a.shape == b.shape == ((32 + 1) + 32 * (64 + 1),) and np.array_equal(a, b)
+    h, w = 16, 8
+    t = oracle.environment_cdf(np.full((h, w, 4), 0.25, np.float32))
+    marginal, rows = t[:h + 1], t[h + 1:].reshape(h, w + 1)
+    assert marginal[0] == 0.0 and marginal[-1] == 1.0 and np.all(np.diff(marginal) > 0)
+    edges = (1.0 - np.cos(np.pi * np.arange(h + 1) / h)) / 2.0  # integral of sin over [0, theta] / 2
+    assert np.abs(marginal - edges).max() < 2e-3
+    assert np.allclose(rows, np.arange(w + 1, dtype=np.float32)[None, :] / w, atol=1e-7)
+    one = np.zeros((h, w, 4), np.float32)
+    one[5, 3, :3] = 7.0
+    t = oracle.environment_cdf(one)
+    marginal, rows = t[:h + 1], t[h + 1:].reshape(h, w + 1)
+    assert np.array_equal(marginal, (np.arange(h + 1) > 5).astype(np.float32))
+    assert np.array_equal(rows[5], (np.arange(w + 1) > 3).astype(np.float32))
+    assert np.allclose(rows[0], np.arange(w + 1, dtype=np.float32) / w)  # a row without weight is uniform
+    black = oracle.environment_cdf(np.zeros((h, w, 4), np.float32))    # so is a map without weight
+    assert np.allclose(black[:h + 1], np.arange(h + 1, dtype=np.float32) / h)
+
+
+def test_environment_importance_sampling_converges_to_the_same_image(assets):
+    """Sampling the environment as a light (balance heuristic against the cosine bounce) must not change what the
+    estimator converges to, only its noise: with a small bright sun the two means agree and the light-sampled frame
+    is the less noisy one."""
+    from metal4_raytracing_b200 import scene
+    w = h = 40
+    sc, u, seed = scene.Scene.named("K1", w, h, assets=assets)
+    u.samplesPerPixel, u.maxBounces = 256, 2
+    seeds = scene.seed_image(w, h, seed)
+    sky = scene.procedural_sky(128, 64)
+    orc = oracle.Oracle(sc)
+    imgs = oracle.FrameImages(w, h, seeds, fp32=True)
+    _, ids = orc.render(u, imgs, want_ids=True)
+    hit = ids[..., 0] != 0xFFFFFFFF
+    out = {}
+    for importance in (False, True):
+        orc.set_environment(sky, 1.0, importance=importance)
+        orc.render(u, imgs)
+        out[importance] = imgs.output[..., :3].astype(np.float64).copy()
+    plain, sampled = out[False][hit], out[True][hit]
+    assert not np.array_equal(plain, sampled)
+    assert abs(sampled.mean() - plain.mean()) / plain.mean() < 0.02
+    # noise: difference to the 256-spp mean of a 16-spp frame, light-sampled against not
+    u.samplesPerPixel = 16
+    err = {}
+    for importance in (False, True):
+        orc.set_environment(sky, 1.0, importance=importance)
+        orc.render(u, imgs)
+        ref = out[importance][hit]
+        err[importance] = float(np.sqrt(np.mean((imgs.output[..., :3].astype(np.float64)[hit] - ref) ** 2)))
+    assert err[True] < err[False]
+    orc.set_environment(None)
+
+
 def _golden_module():
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
