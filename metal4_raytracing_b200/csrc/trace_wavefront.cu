@@ -67,7 +67,7 @@ struct WfState {
   float4 *mot;  // motion.xy, prevMotion.xy
   float4 *misc; // depth, flags bits (1 = hadPrimaryHit, 2 = wroteGBuffer), seed offset bits, unused
   uint32_t *queue[2], *shadowQueue;
-  uint32_t *counts; // [0], [1] path queues, [3] trace cursor, [8 + p] shadow queue length and [10 + p] shadow cursor of
+  uint32_t *counts; // [pathCount(q)] path queues, [3] trace cursor, [shadowCount(p)] shadow queue length and [10 + p] shadow cursor of
                     // segment parity p (double-buffered: the shadow rays of segment k are traced in the same launch
                     // as the closest-hit rays of segment k + 1)
   // ray reordering (option sort_rays): key buffers, the sorted copy of a queue and CUB's workspace
@@ -78,6 +78,30 @@ struct WfState {
 
 __device__ __forceinline__ void slotPixel(const TraceParams &P, uint32_t slot, int &px, int &py, bool &valid) {
   valid = ownedPixel(P, int(slot >> 8), int(slot & 255u), px, py);
+}
+
+// Where the queue lengths live in WfState::counts. The shade kernel of a segment appends to path queue qin ^ 1 and to
+// the shadow queue of parity qin, so those two lengths share an aligned 64-bit word and one atomic serves both.
+__host__ __device__ __forceinline__ int pathCount(int q) { return q == 1 ? 16 : 18; }
+__host__ __device__ __forceinline__ int shadowCount(int p) { return p == 0 ? 17 : 19; }
+
+// Appends `slot` to the path queue (lanes with pushPath) and to the shadow queue (lanes with pushShadow) with one
+// 64-bit atomic per warp: low word = path queue length, high word = shadow queue length (`pair` points at both).
+__device__ __forceinline__ void queuePushBoth(uint32_t *pathQueue, uint32_t *shadowQueue, uint32_t *pair, bool pushPath,
+                                              bool pushShadow, uint32_t slot) {
+  const unsigned active = __activemask();
+  const unsigned vp = __ballot_sync(active, pushPath), vs = __ballot_sync(active, pushShadow);
+  if ((vp | vs) == 0u) return;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(int(active)) - 1;
+  unsigned long long base = 0ull;
+  if (lane == leader)
+    base = atomicAdd(reinterpret_cast<unsigned long long *>(pair),
+                     (unsigned long long)__popc(vp) | ((unsigned long long)__popc(vs) << 32));
+  base = __shfl_sync(active, base, leader);
+  const unsigned below = (1u << lane) - 1u;
+  if (pushPath) pathQueue[uint32_t(base) + __popc(vp & below)] = slot;
+  if (pushShadow) shadowQueue[uint32_t(base >> 32) + __popc(vs & below)] = slot;
 }
 
 // Appends `slot` for every lane with `push` set; one atomic per warp.
@@ -163,7 +187,7 @@ __global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ 
         push = U.maxBounces > 0;
         if (!push) RT_STS(W.rad + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f)); // never traced: folds as black
       }
-      queuePush(W.queue[0], W.counts + 0, push, slot);
+      queuePush(W.queue[0], W.counts + pathCount(0), push, slot);
     }
   }
 }
@@ -295,11 +319,11 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse
   if (doClosest) {
     const int nextParity = doShadow ? (shadowParity ^ 1) : shadowParity; // parity of the segment traced here
     if (blockIdx.x == 0 && threadIdx.x == 0) { // the queues this segment's shade kernel appends to start empty
-      W.counts[qin ^ 1] = 0u;
-      W.counts[8 + nextParity] = 0u;
+      W.counts[pathCount(qin ^ 1)] = 0u;
+      W.counts[shadowCount(nextParity)] = 0u;
       W.counts[10 + nextParity] = 0u;
     }
-    const uint32_t count = W.counts[qin];
+    const uint32_t count = W.counts[pathCount(qin)];
     traceQueue<false, kRefill>(P, W.queue[qin], count, W.counts + 3, W.rayO, W.rayD, cameraRays != 0, s_stack,
                                [&](uint32_t slot, const LaneTraversal<false> &t) {
                                  RT_STS(W.hitA + slot, make_float4(t.found ? t.hit.t : INFINITY, t.hit.u, t.hit.v,
@@ -318,7 +342,7 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse
     if (P.rayCounters != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.rayCounters + 0, (unsigned long long)count);
   }
   if (doShadow) {
-    const uint32_t count = W.counts[8 + shadowParity];
+    const uint32_t count = W.counts[shadowCount(shadowParity)];
     traceQueue<true, kRefill>(P, W.shadowQueue, count, W.counts + 10 + shadowParity, W.rayO, W.shD, false, s_stack,
                               [&](uint32_t slot, const LaneTraversal<true> &t) {
                                 if (!t.found) { // unoccluded: the light sample contributes
@@ -340,8 +364,9 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
                                                                          const WfState W, int qin, int s0,
                                                                          int cameraRays, int shadowParity) {
   if (blockIdx.x == 0 && threadIdx.x == 0) W.counts[3] = 0u; // cursor of the next trace kernel
-  const uint32_t count = W.counts[qin];
+  const uint32_t count = W.counts[pathCount(qin)];
   const uint32_t *queue = W.queue[qin];
+  uint32_t hitCount = 0; // this thread's closest hits, added to the probe counter once per warp at the end
   const uint32_t rounds = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   for (uint32_t round = 0; round < rounds; ++round, j += gridDim.x * blockDim.x) { // whole warps stay in the loop
@@ -453,13 +478,13 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
       shadeMiss(P, s);
       RT_STS(W.rad + slot, make_float4(s.radiance.x, s.radiance.y, s.radiance.z, 0.0f));
     }
-    queuePush(W.shadowQueue, W.counts + 8 + shadowParity, pushShadow, slot);
-    queuePush(W.queue[qin ^ 1], W.counts + (qin ^ 1), pushPath, slot);
-    if (P.rayCounters != nullptr) {
-      const unsigned active = __activemask();
-      const unsigned hits = __ballot_sync(active, isHit);
-      if ((threadIdx.x & 31) == __ffs(int(active)) - 1 && hits) atomicAdd(P.rayCounters + 2, (unsigned long long)__popc(hits));
-    }
+    // shadowParity == qin (both are the segment's parity), so the two lengths are the halves of one 64-bit word
+    queuePushBoth(W.queue[qin ^ 1], W.shadowQueue, W.counts + pathCount(qin ^ 1), pushPath, pushShadow, slot);
+    hitCount += isHit ? 1u : 0u;
+  }
+  if (P.rayCounters != nullptr) {
+    const uint32_t warpHits = __reduce_add_sync(0xFFFFFFFFu, hitCount);
+    if ((threadIdx.x & 31) == 0 && warpHits) atomicAdd(P.rayCounters + 2, (unsigned long long)warpHits);
   }
 }
 
@@ -587,7 +612,7 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
   for (int s0 = 0; s0 < sampleLoopBound;) {
     // the first batch stays within the base samples (see k_wf_generate)
     const int n = std::min(batch, (s0 < baseSamples ? baseSamples : sampleLoopBound) - s0);
-    RT_CUDA(cudaMemsetAsync(W.counts, 0, 64, st));
+    RT_CUDA(cudaMemsetAsync(W.counts, 0, 128, st));
     ctx->mark(-1);
     k_wf_generate<<<persistent, kBlock, 0, st>>>(P, W, s0, n, prevS0, prevN, baseSamples, maxExtraSamples);
     ctx->mark(RT_KERNEL_GENERATE);
@@ -610,20 +635,20 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
       const int parity = segment & 1;
       if (segment >= maxBounces) { // only glass paths get here: ask the device whether any are left
         uint32_t remaining = 0;
-        RT_CUDA(cudaMemcpyAsync(&remaining, W.counts + qin, 4, cudaMemcpyDeviceToHost, st));
+        RT_CUDA(cudaMemcpyAsync(&remaining, W.counts + pathCount(qin), 4, cudaMemcpyDeviceToHost, st));
         RT_CUDA(cudaStreamSynchronize(st));
         if (remaining == 0) break;
         ctx->mark(-1);
       }
       const int first = (s0 == 0 && segment == 0) ? 1 : 0;
-      if (ctx->sortRays > 0 && segment > 0) RT_TRY(sortQueue(ctx, P, W, &W.queue[qin], W.counts + qin, W.rayO, W.rayD));
+      if (ctx->sortRays > 0 && segment > 0) RT_TRY(sortQueue(ctx, P, W, &W.queue[qin], W.counts + pathCount(qin), W.rayO, W.rayD));
       if (ctx->fuseTraversal && shadowPending && ctx->sortRays < 2) {
         traverse(first, segment == 0, 1, 1, pendingParity); // closest hits of this segment + shadow rays of the last
         shadowPending = false;
         ctx->mark(RT_KERNEL_TRACE);
       } else {
         if (shadowPending) {
-          if (ctx->sortRays > 1) RT_TRY(sortQueue(ctx, P, W, &W.shadowQueue, W.counts + 8 + pendingParity, W.rayO, W.shD));
+          if (ctx->sortRays > 1) RT_TRY(sortQueue(ctx, P, W, &W.shadowQueue, W.counts + shadowCount(pendingParity), W.rayO, W.shD));
           traverse(0, 0, 0, 1, pendingParity);
           shadowPending = false;
           ctx->mark(RT_KERNEL_SHADOW);
@@ -646,7 +671,7 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
       qin ^= 1;
     }
     if (shadowPending) {
-      if (ctx->sortRays > 1) RT_TRY(sortQueue(ctx, P, W, &W.shadowQueue, W.counts + 8 + pendingParity, W.rayO, W.shD));
+      if (ctx->sortRays > 1) RT_TRY(sortQueue(ctx, P, W, &W.shadowQueue, W.counts + shadowCount(pendingParity), W.rayO, W.shD));
       traverse(0, 0, 0, 1, pendingParity);
       ctx->mark(RT_KERNEL_SHADOW);
     }
