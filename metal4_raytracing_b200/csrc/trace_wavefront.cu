@@ -173,10 +173,10 @@ __global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ 
       }
       RT_STS(W.tot + pixelSlot, make_float4(total.x, total.y, total.z, __uint_as_float(uint32_t(totalSamples))));
     }
+    unsigned long long pushed = 0ull; // bit b: sample b of this pixel has a camera ray to trace (batch <= 64)
     for (int b = 0; b < n; ++b) {
       const int sampleIndex = s0 + b;
       const uint32_t slot = uint32_t(b) * W.capacity + pixelSlot;
-      bool push = false;
       if (valid && sampleIndex < totalSamples) {
         const int hIndex = haltonIndex(U, offset, sampleStride, sampleIndex);
         PathState s;
@@ -184,10 +184,26 @@ __global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ 
         // a camera ray's other state is implied (origin = camera, throughput 1, radiance 0, counters 0): the first
         // segment's trace and shade kernels supply it themselves, so only 16 of the 80 bytes are written here
         RT_STS(W.rayD + slot, make_float4(s.dir.x, s.dir.y, s.dir.z, __int_as_float(hIndex)));
-        push = U.maxBounces > 0;
-        if (!push) RT_STS(W.rad + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f)); // never traced: folds as black
+        if (U.maxBounces > 0) pushed |= 1ull << b;
+        else RT_STS(W.rad + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f)); // never traced: folds as black
       }
-      queuePush(W.queue[0], W.counts + pathCount(0), push, slot);
+    }
+    // one reservation per warp for all of its samples (one atomic instead of n); entries stay sample-major, so 32
+    // consecutive queue entries are still 32 consecutive path slots
+    const unsigned full = 0xFFFFFFFFu;
+    uint32_t total = 0;
+    for (int b = 0; b < n; ++b) total += uint32_t(__popc(__ballot_sync(full, (pushed >> b) & 1ull)));
+    if (total != 0u) {
+      const int lane = threadIdx.x & 31;
+      uint32_t run = 0;
+      if (lane == 0) run = atomicAdd(W.counts + pathCount(0), total);
+      run = __shfl_sync(full, run, 0);
+      for (int b = 0; b < n; ++b) {
+        const bool push = (pushed >> b) & 1ull;
+        const unsigned votes = __ballot_sync(full, push);
+        if (push) W.queue[0][run + uint32_t(__popc(votes & ((1u << lane) - 1u)))] = uint32_t(b) * W.capacity + pixelSlot;
+        run += uint32_t(__popc(votes));
+      }
     }
   }
 }
