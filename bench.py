@@ -181,7 +181,7 @@ def main():
         cb = run_oracle_sample(args.workload, steps, args.warmup, seconds_budget=60.0)
         line = {"metric": "Mrays/s", "value": cb["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps,
                 "warmup": args.warmup, "ms_per_step": round(cb.pop("_ms_per_step"), 3), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "impl": "reference"}
         cb.pop("_modulo")
         line["cpu_baseline"] = cb
