@@ -372,6 +372,10 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse
   }
 }
 
+// RT_SHADE_COMPACT: hits compacted per warp before shading (see k_wf_shade)
+#ifndef RT_SHADE_COMPACT
+#define RT_SHADE_COMPACT 1
+#endif
 #ifndef RT_SHADE_MINBLOCKS
 #define RT_SHADE_MINBLOCKS 4 // 64 registers: measured faster than 128 (the kernel is bound by gather latency; more warps hide it)
 #endif
@@ -383,121 +387,176 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
   const uint32_t count = W.counts[pathCount(qin)];
   const uint32_t *queue = W.queue[qin];
   uint32_t hitCount = 0; // this thread's closest hits, added to the probe counter once per warp at the end
+  // one hit: the path state in, shadeSegment, the state of the next segment and of the shadow ray out
+  auto shadeHit = [&](uint32_t slot, const float4 &ha, bool &pushPath, bool &pushShadow) {
+    const uint32_t b = slot / W.capacity; // sample of the batch, pixel slot
+    const uint32_t pixelSlot = slot - b * W.capacity;
+    const int sampleIndex = s0 + int(b);
+    const uint2 hb = RT_LDS(W.hitB + slot);
+    RayHit hit;
+    hit.t = ha.x, hit.u = ha.y, hit.v = ha.z;
+    hit.instance = hb.x, hit.geometry = hb.y, hit.primitive = __float_as_uint(ha.w);
+    const float4 d = RT_LDS(W.rayD + slot);
+    float4 o, th, ra;
+    int4 c;
+    if (cameraRays) { // first segment: the state k_wf_generate did not write
+      o = make_float4(P.uniforms.camera.position.x, P.uniforms.camera.position.y, P.uniforms.camera.position.z, 0.0f);
+      th = make_float4(1.0f, 1.0f, 1.0f, d.w); // d.w = halton index bits
+      ra = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      c = make_int4(0, 0, 0, 0);
+    } else {
+      o = RT_LDS(W.rayO + slot), th = RT_LDS(W.thr + slot), ra = RT_LDS(W.rad + slot);
+      const uint32_t packed = __float_as_uint(d.w);
+      c = make_int4(int(packed & 1023u), int((packed >> 10) & 1023u), int(packed >> 20), 0);
+    }
+    // per-pixel primary outputs are only touched by sample 0 (first segment, or until the G-buffer is written)
+    const bool primarySegment = (c.x == 0 && sampleIndex == 0);
+    const bool needPrimary = primarySegment || (sampleIndex == 0 && P.uniforms.enableDenoiseGBuffer != 0) ||
+                             P.uniforms.debugTextureMode == RT_DEBUG_MOTION;
+    float4 m4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), mi = m4;
+    if (needPrimary) {
+      m4 = RT_LDS(W.mot + pixelSlot);
+      mi = RT_LDS(W.misc + pixelSlot);
+    }
+    PathState s;
+    s.origin = mk3(o.x, o.y, o.z);
+    s.dir = mk3(d.x, d.y, d.z);
+    s.throughput = mk3(th.x, th.y, th.z);
+    s.radiance = mk3(ra.x, ra.y, ra.z);
+    s.bounce = c.x, s.step = c.y, s.transparencyPasses = c.z;
+    s.bsdfPdf = o.w;
+    const int hIndex = __float_as_int(th.w);
+    PrimaryOutputs prim = emptyPrimaryOutputs();
+    const uint32_t flags = __float_as_uint(mi.y);
+    prim.depth = mi.x;
+    prim.motion = mk2(m4.x, m4.y);
+    prim.hadPrimaryHit = (flags & 1u) != 0u;
+    prim.wroteGBuffer = (flags & 2u) != 0u;
+    const bool hadGBuffer = prim.wroteGBuffer;
+    ShadowRequest shadow;
+    pushPath = shadeSegment<kTextures, kPlain>(P, s, hit, hIndex, sampleIndex, mk2(m4.z, m4.w), prim, shadow);
+    RT_STS(W.rad + slot, make_float4(s.radiance.x, s.radiance.y, s.radiance.z, 0.0f));
+    if (pushPath) { // a path that ends here (every path of the last segment) leaves only its radiance behind
+      const uint32_t packed = uint32_t(s.bounce) | (uint32_t(s.step) << 10) | (uint32_t(s.transparencyPasses) << 20);
+      RT_STS(W.rayD + slot, make_float4(s.dir.x, s.dir.y, s.dir.z, __uint_as_float(packed)));
+      RT_STS(W.thr + slot, make_float4(s.throughput.x, s.throughput.y, s.throughput.z, th.w));
+    }
+    // the shadow ray starts where the next segment starts (shadeSegment: both are hit + N * 1e-3), so one origin
+    // record serves both; a path that ends but still has a shadow ray to trace stores it for that alone
+    if (pushPath || shadow.valid) {
+      const f3 org = pushPath ? s.origin : shadow.origin;
+      RT_STS(W.rayO + slot, make_float4(org.x, org.y, org.z, pushPath ? s.bsdfPdf : 0.0f));
+    }
+    if (primarySegment || (prim.wroteGBuffer && !hadGBuffer)) {
+      const uint32_t nf = (prim.hadPrimaryHit ? 1u : 0u) | (prim.wroteGBuffer ? 2u : 0u);
+      RT_STS(W.mot + pixelSlot, make_float4(prim.motion.x, prim.motion.y, m4.z, m4.w));
+      RT_STS(W.misc + pixelSlot, make_float4(prim.depth, __uint_as_float(nf), mi.z, 0.0f));
+    }
+    if (prim.wroteGBuffer && !hadGBuffer) {
+      int px, py;
+      bool valid;
+      slotPixel(P, pixelSlot, px, py, valid);
+      writeImage(P.images[RT_TEXTURE_DIFFUSE_ALBEDO], px, py, prim.gDiffuse);
+      writeImage(P.images[RT_TEXTURE_SPECULAR_ALBEDO], px, py, prim.gSpecular);
+      writeImage(P.images[RT_TEXTURE_NORMAL], px, py, prim.gNormal);
+      writeImage(P.images[RT_TEXTURE_ROUGHNESS], px, py, prim.gRoughness);
+    }
+    if (shadow.valid) {
+      pushShadow = true;
+      RT_STS(W.shD + slot, make_float4(shadow.dir.x, shadow.dir.y, shadow.dir.z, shadow.tmax));
+      RT_STS(W.shC + slot, make_float4(shadow.contribution.x, shadow.contribution.y, shadow.contribution.z, 0.0f));
+    }
+  };
+  // a miss: a camera ray still has to leave radiance 0 behind for the fold (k_wf_generate did not write it); with the
+  // environment extension bound the path picks it up first
+  auto shadeMissed = [&](uint32_t slot) {
+    PathState s;
+    s.radiance = mk3(0.0f);
+    s.throughput = mk3(1.0f);
+    const float4 d = RT_LDS(W.rayD + slot);
+    s.dir = mk3(d.x, d.y, d.z);
+    s.bsdfPdf = 0.0f;
+    if (!cameraRays) {
+      const float4 th = RT_LDS(W.thr + slot), ra = RT_LDS(W.rad + slot);
+      s.throughput = mk3(th.x, th.y, th.z);
+      s.radiance = mk3(ra.x, ra.y, ra.z);
+      if (environmentIsLight(P)) s.bsdfPdf = RT_LDS(W.rayO + slot).w;
+    }
+    shadeMiss(P, s);
+    RT_STS(W.rad + slot, make_float4(s.radiance.x, s.radiance.y, s.radiance.z, 0.0f));
+  };
+  const bool missesMatter = cameraRays || P.env.texelsDev != nullptr;
+#if RT_SHADE_COMPACT
+  // Hits are compacted per warp before shading: a warp takes 64 queue entries per round (two per lane), appends the
+  // slots of the hits to a list in shared memory and shades 32 of them whenever the list holds that many; what is
+  // left after the last round is the only partial pass. On bounce segments 40 % of the entries are hits: shading
+  // them where they sit keeps ~13 lanes of a warp busy, this keeps 32 — and the number of resident warps, which is
+  // what hides the gather latency, stays what it was (compacting per CTA took warps away and was slower).
+  __shared__ uint32_t s_slots[kBlock / 32][96];
+  uint32_t *mySlots = s_slots[threadIdx.x >> 5];
+  const uint32_t lane = threadIdx.x & 31u;
+  const unsigned below = (1u << lane) - 1u;
+  const uint32_t span = gridDim.x * blockDim.x * 2u;
+  const uint32_t rounds = (count + span - 1u) / span;
+  uint32_t jw = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * 2u;
+  uint32_t listed = 0; // warp-uniform: hits waiting in mySlots (< 32 between rounds)
+  for (uint32_t round = 0; round <= rounds; ++round, jw += span) { // whole warps stay in the loop; the extra trip drains
+    if (round < rounds) {
+      bool hit0 = false, hit1 = false;
+      uint32_t slot0 = 0, slot1 = 0;
+      if (jw + lane < count) {
+        slot0 = queue[jw + lane];
+        hit0 = RT_LDS(reinterpret_cast<const float *>(W.hitA + slot0)) < INFINITY;
+        if (!hit0 && missesMatter) shadeMissed(slot0);
+      }
+      if (jw + 32u + lane < count) {
+        slot1 = queue[jw + 32u + lane];
+        hit1 = RT_LDS(reinterpret_cast<const float *>(W.hitA + slot1)) < INFINITY;
+        if (!hit1 && missesMatter) shadeMissed(slot1);
+      }
+      const unsigned votes0 = __ballot_sync(0xFFFFFFFFu, hit0), votes1 = __ballot_sync(0xFFFFFFFFu, hit1);
+      const uint32_t n0 = uint32_t(__popc(votes0));
+      if (hit0) mySlots[listed + uint32_t(__popc(votes0 & below))] = slot0;
+      if (hit1) mySlots[listed + n0 + uint32_t(__popc(votes1 & below))] = slot1;
+      listed += n0 + uint32_t(__popc(votes1));
+      __syncwarp();
+    }
+    while (listed >= 32u || (round == rounds && listed != 0u)) {
+      const uint32_t take = min(listed, 32u);
+      listed -= take;
+      bool pushPath = false, pushShadow = false;
+      uint32_t slot = 0;
+      if (lane < take) {
+        slot = mySlots[listed + lane];
+        shadeHit(slot, RT_LDS(W.hitA + slot), pushPath, pushShadow);
+        ++hitCount;
+      }
+      // shadowParity == qin (both are the segment's parity), so the two lengths are the halves of one 64-bit word
+      queuePushBoth(W.queue[qin ^ 1], W.shadowQueue, W.counts + pathCount(qin ^ 1), pushPath, pushShadow, slot);
+    }
+    __syncwarp();
+  }
+#else
   const uint32_t rounds = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   for (uint32_t round = 0; round < rounds; ++round, j += gridDim.x * blockDim.x) { // whole warps stay in the loop
-    bool pushPath = false, pushShadow = false, isHit = false;
+    bool pushPath = false, pushShadow = false;
     uint32_t slot = 0;
     float4 ha = make_float4(INFINITY, 0.0f, 0.0f, 0.0f);
     if (j < count) {
       slot = queue[j];
       ha = RT_LDS(W.hitA + slot);
     }
-    // (compacting the hits of a CTA through shared memory before shading was measured slower: the kernel is bound
-    // by the latency of its dependent gathers, not by issue slots, and compaction removes warps that hide it)
     if (ha.x < INFINITY) {
-      {
-        isHit = true;
-        const uint32_t b = slot / W.capacity; // sample of the batch, pixel slot
-        const uint32_t pixelSlot = slot - b * W.capacity;
-        const int sampleIndex = s0 + int(b);
-        const uint2 hb = RT_LDS(W.hitB + slot);
-        RayHit hit;
-        hit.t = ha.x, hit.u = ha.y, hit.v = ha.z;
-        hit.instance = hb.x, hit.geometry = hb.y, hit.primitive = __float_as_uint(ha.w);
-        const float4 d = RT_LDS(W.rayD + slot);
-        float4 o, th, ra;
-        int4 c;
-        if (cameraRays) { // first segment: the state k_wf_generate did not write
-          o = make_float4(P.uniforms.camera.position.x, P.uniforms.camera.position.y, P.uniforms.camera.position.z, 0.0f);
-          th = make_float4(1.0f, 1.0f, 1.0f, d.w); // d.w = halton index bits
-          ra = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-          c = make_int4(0, 0, 0, 0);
-        } else {
-          o = RT_LDS(W.rayO + slot), th = RT_LDS(W.thr + slot), ra = RT_LDS(W.rad + slot);
-          const uint32_t packed = __float_as_uint(d.w);
-          c = make_int4(int(packed & 1023u), int((packed >> 10) & 1023u), int(packed >> 20), 0);
-        }
-        // per-pixel primary outputs are only touched by sample 0 (first segment, or until the G-buffer is written)
-        const bool primarySegment = (c.x == 0 && sampleIndex == 0);
-        const bool needPrimary = primarySegment || (sampleIndex == 0 && P.uniforms.enableDenoiseGBuffer != 0) ||
-                                 P.uniforms.debugTextureMode == RT_DEBUG_MOTION;
-        float4 m4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), mi = m4;
-        if (needPrimary) {
-          m4 = RT_LDS(W.mot + pixelSlot);
-          mi = RT_LDS(W.misc + pixelSlot);
-        }
-        PathState s;
-        s.origin = mk3(o.x, o.y, o.z);
-        s.dir = mk3(d.x, d.y, d.z);
-        s.throughput = mk3(th.x, th.y, th.z);
-        s.radiance = mk3(ra.x, ra.y, ra.z);
-        s.bounce = c.x, s.step = c.y, s.transparencyPasses = c.z;
-        s.bsdfPdf = o.w;
-        const int hIndex = __float_as_int(th.w);
-        PrimaryOutputs prim = emptyPrimaryOutputs();
-        const uint32_t flags = __float_as_uint(mi.y);
-        prim.depth = mi.x;
-        prim.motion = mk2(m4.x, m4.y);
-        prim.hadPrimaryHit = (flags & 1u) != 0u;
-        prim.wroteGBuffer = (flags & 2u) != 0u;
-        const bool hadGBuffer = prim.wroteGBuffer;
-        ShadowRequest shadow;
-        pushPath = shadeSegment<kTextures, kPlain>(P, s, hit, hIndex, sampleIndex, mk2(m4.z, m4.w), prim, shadow);
-        RT_STS(W.rad + slot, make_float4(s.radiance.x, s.radiance.y, s.radiance.z, 0.0f));
-        if (pushPath) { // a path that ends here (every path of the last segment) leaves only its radiance behind
-          const uint32_t packed = uint32_t(s.bounce) | (uint32_t(s.step) << 10) | (uint32_t(s.transparencyPasses) << 20);
-          RT_STS(W.rayD + slot, make_float4(s.dir.x, s.dir.y, s.dir.z, __uint_as_float(packed)));
-          RT_STS(W.thr + slot, make_float4(s.throughput.x, s.throughput.y, s.throughput.z, th.w));
-        }
-        // the shadow ray starts where the next segment starts (shadeSegment: both are hit + N * 1e-3), so one origin
-        // record serves both; a path that ends but still has a shadow ray to trace stores it for that alone
-        if (pushPath || shadow.valid) {
-          const f3 org = pushPath ? s.origin : shadow.origin;
-          RT_STS(W.rayO + slot, make_float4(org.x, org.y, org.z, pushPath ? s.bsdfPdf : 0.0f));
-        }
-        if (primarySegment || (prim.wroteGBuffer && !hadGBuffer)) {
-          const uint32_t nf = (prim.hadPrimaryHit ? 1u : 0u) | (prim.wroteGBuffer ? 2u : 0u);
-          RT_STS(W.mot + pixelSlot, make_float4(prim.motion.x, prim.motion.y, m4.z, m4.w));
-          RT_STS(W.misc + pixelSlot, make_float4(prim.depth, __uint_as_float(nf), mi.z, 0.0f));
-        }
-        if (prim.wroteGBuffer && !hadGBuffer) {
-          int px, py;
-          bool valid;
-          slotPixel(P, pixelSlot, px, py, valid);
-          writeImage(P.images[RT_TEXTURE_DIFFUSE_ALBEDO], px, py, prim.gDiffuse);
-          writeImage(P.images[RT_TEXTURE_SPECULAR_ALBEDO], px, py, prim.gSpecular);
-          writeImage(P.images[RT_TEXTURE_NORMAL], px, py, prim.gNormal);
-          writeImage(P.images[RT_TEXTURE_ROUGHNESS], px, py, prim.gRoughness);
-        }
-        if (shadow.valid) {
-          pushShadow = true;
-          RT_STS(W.shD + slot, make_float4(shadow.dir.x, shadow.dir.y, shadow.dir.z, shadow.tmax));
-          RT_STS(W.shC + slot, make_float4(shadow.contribution.x, shadow.contribution.y, shadow.contribution.z, 0.0f));
-        }
-      }
-    } else if (j < count && (cameraRays || P.env.texelsDev != nullptr)) {
-      // a miss: a camera ray still has to leave radiance 0 behind for the fold (k_wf_generate did not write it);
-      // with the environment extension bound the path picks it up first
-      PathState s;
-      s.radiance = mk3(0.0f);
-      s.throughput = mk3(1.0f);
-      const float4 d = RT_LDS(W.rayD + slot);
-      s.dir = mk3(d.x, d.y, d.z);
-      s.bsdfPdf = 0.0f;
-      if (!cameraRays) {
-        const float4 th = RT_LDS(W.thr + slot), ra = RT_LDS(W.rad + slot);
-        s.throughput = mk3(th.x, th.y, th.z);
-        s.radiance = mk3(ra.x, ra.y, ra.z);
-        if (environmentIsLight(P)) s.bsdfPdf = RT_LDS(W.rayO + slot).w;
-      }
-      shadeMiss(P, s);
-      RT_STS(W.rad + slot, make_float4(s.radiance.x, s.radiance.y, s.radiance.z, 0.0f));
+      shadeHit(slot, ha, pushPath, pushShadow);
+      ++hitCount;
+    } else if (j < count && missesMatter) {
+      shadeMissed(slot);
     }
     // shadowParity == qin (both are the segment's parity), so the two lengths are the halves of one 64-bit word
     queuePushBoth(W.queue[qin ^ 1], W.shadowQueue, W.counts + pathCount(qin ^ 1), pushPath, pushShadow, slot);
-    hitCount += isHit ? 1u : 0u;
   }
+#endif
   if (P.rayCounters != nullptr) {
     const uint32_t warpHits = __reduce_add_sync(0xFFFFFFFFu, hitCount);
     if ((threadIdx.x & 31) == 0 && warpHits) atomicAdd(P.rayCounters + 2, (unsigned long long)warpHits);
