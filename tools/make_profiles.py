@@ -74,8 +74,10 @@ with open(os.path.join(ROOT, "profiles", f"{out_tag}_bench.md"), "w") as f:
     f.write(run(["list", lst, "ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e` (full list: "
                  f"{out_tag}_launches_bench.csv)"]).replace("cub::DeviceRadixSort", "cub::RadixSort"))
     f.write(run(["rep", rep, "ncu --set full capture: the wavefront launches of one timed frame (generate, traverse / shade alternating, resolve)"]))
-    f.write("Reading: camera rays (first trace) run at 19 of 32 threads per instruction, bounce and shadow rays at 12–16; issue slots are "
-            "61–70 % busy in the traversal kernels at 37 % occupancy (6 CTAs x 4 warps, 80 registers). k_wf_shade is bound by dependent "
-            "gathers (long_scoreboard 5–15 cycles per issue) and by its size (6.5 k SASS instructions: no_instruction 3–5); k_wf_generate "
-            "and k_wf_resolve are DRAM-latency bound streaming kernels of 0.3 ms together.\n")
+    f.write("Reading: the traversal launches run at 23 (camera rays) and 15-17 (bounce + shadow rays) of 32 threads per instruction "
+            "with 56-70 % of the issue slots busy at 37 % occupancy (6 CTAs x 4 warps, 80 registers): issue slots x SIMD efficiency "
+            "is what bounds them (r1_traversal.md). k_wf_shade shades compacted hits (24-27 threads per instruction; what is missing "
+            "is divergence inside the light / material code) and is bound by the latency of its dependent gathers: on the bounce "
+            "segments only a third of the issue slots are used. k_wf_generate and k_wf_resolve are streaming kernels of 0.5 ms "
+            "together.\n")
 print("wrote profiles for", out_tag)
