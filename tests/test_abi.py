@@ -23,7 +23,8 @@ PROBE = r"""
 int main(void) {
   S(rt_float3); S(rt_camera); S(rt_light); S(rt_uniforms); S(rt_material); S(rt_instance_descriptor);
   S(rt_texture2d); S(rt_resource); S(rt_image); S(rt_triangle_geometry); S(rt_scene_submesh); S(rt_scene_mesh);
-  S(rt_scene_texture); S(rt_scene_instance); S(rt_scene_desc); S(rt_trace_options); S(rt_as_info);
+  S(rt_scene_texture); S(rt_scene_instance); S(rt_scene_desc); S(rt_trace_options); S(rt_as_info); S(rt_environment);
+  O(rt_environment, intensity); O(rt_environment, flags); O(rt_environment, cdfDev);
   O(rt_camera, right); O(rt_camera, up); O(rt_camera, forward);
   O(rt_light, position); O(rt_light, color); O(rt_light, forward); O(rt_light, right); O(rt_light, up);
   O(rt_light, coneAngle); O(rt_light, direction);
@@ -108,8 +109,11 @@ def test_ctypes_mirror_matches_header(c_layout):
         assert C.sizeof(ctype) == c_layout[f"sizeof {cname}"], cname
     assert C.sizeof(device.TraceOptions) == c_layout["sizeof rt_trace_options"]
     assert C.sizeof(device.AsInfo) == c_layout["sizeof rt_as_info"]
+    assert C.sizeof(device.Environment) == c_layout["sizeof rt_environment"] == 32
+    for field in ("intensity", "flags", "cdfDev"):
+        assert getattr(device.Environment, field).offset == c_layout[f"offsetof rt_environment.{field}"], field
     for key, val in c_layout.items():
-        if not key.startswith("offsetof"):
+        if not key.startswith("offsetof") or key.startswith("offsetof rt_environment"):
             continue
         cname, field = key.split()[1].split(".")
         assert getattr(CTYPES[cname], field).offset == val, key
