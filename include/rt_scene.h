@@ -104,6 +104,25 @@ int rts_add_mesh_procedural(rts_scene *s, const char *kind, int p0, int p1, int 
 /* Raw triangle soup entry point (tests). normals/uvs may be NULL. One submesh. */
 int rts_add_mesh_raw(rts_scene *s, const float *positions3, const float *normals3, const float *uvs2,
                      uint32_t vertexCount, const int32_t *indices, uint32_t triangleCount);
+/* Skinned mesh from caller data — the path for animated assets without USD tooling (the reference
+ * gets the same streams from ModelIO, Model.swift:135-192, 304-341). One submesh. jointIndices4: ushort4 per vertex,
+ * jointWeights4: float4 per vertex, used as authored (Skinning.metal:26-31). parents: -1 = root, parents precede
+ * children (Skeleton.computeGlobalTransforms, Model.swift:379-387). restTRS: jointCount x 10 floats (translation xyz,
+ * rotation quaternion xyzw, scale xyz), the pose without a clip; inverseBind: jointCount x float4x4 column-major.
+ * Returns the mesh index or -1. */
+int rts_add_mesh_skinned(rts_scene *s, const float *positions3, const float *normals3, const float *uvs2,
+                         const uint16_t *jointIndices4, const float *jointWeights4, uint32_t vertexCount,
+                         const int32_t *indices, uint32_t triangleCount, uint32_t jointCount, const int32_t *parents,
+                         const float *restTRS, const float *inverseBind);
+/* Keyed clip of a skinned mesh: keyCount ascending times (seconds) and keyCount x jointCount x 10 floats laid out as
+ * restTRS. rts_animate(t) samples it at times[0] + fmod(t, times[last] - times[0]) (Model.update, Model.swift:207-215):
+ * translation and scale linearly, rotation by normalised linear interpolation along the shorter arc (ModelIO's own
+ * interpolation is not visible in the reference); then the quaternion is renormalised and local = T * R * S,
+ * global = parent * local, palette = global * inverseBind as in Model.swift:226-261. keyCount 0 removes the clip. */
+int rts_set_animation_keys(rts_scene *s, int mesh, uint32_t keyCount, const float *times, const float *trs);
+/* The same data as one little-endian file ("RTSK1", layout in csrc/host/scene.cpp). load returns the mesh index. */
+int rts_save_skinned_mesh(const rts_scene *s, int mesh, const char *path);
+int rts_load_skinned_mesh(rts_scene *s, const char *path);
 int rts_set_material(rts_scene *s, int mesh, int submesh, const rt_material *m);
 int rts_get_material(const rts_scene *s, int mesh, int submesh, rt_material *m);
 /* RGBA8 texture; returns texture index. */

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <string>
 
@@ -51,25 +52,58 @@ int Scene::maxSubmeshes() const {
 // Model.update (Model.swift:207-261) + SkinningPass.updateSkinningJointMatrices (SkinningPass.swift:123-157)
 // at absolute clip time t. geometryBindTransform is identity for the procedural asset.
 void Scene::animate(double t) {
-  for (auto &m : meshes) {
-    if (!m.skinned()) continue;
+  for (auto &m : meshes) animateMesh(m, t);
+}
+
+void Scene::animateMesh(Mesh &m, double t) {
+  {
+    if (!m.skinned()) return;
     const Skeleton &sk = m.skeleton;
     size_t J = sk.parent.size();
     double ct = sk.duration > 0 ? std::fmod(t, sk.duration) : 0.0;
-    std::vector<rth::M4> local(sk.rest), global(J);
+    std::vector<rth::M4> local(J), global(J);
     m.jointLocalTRS.resize(J * 10);
     m.jointInverseBind.resize(J * 16);
+    // keyed clip: the two keys around the clip time (AnimationClip.sample, Model.swift:405-411; ModelIO's
+    // interpolation is not visible in the reference, here: translation and scale linear, rotation normalised-linear
+    // along the shorter arc)
+    const bool keyed = !sk.keyTimes.empty() || !sk.restTRS.empty();
+    size_t k0 = 0, k1 = 0;
+    float blend = 0.0f;
+    if (!sk.keyTimes.empty()) {
+      const size_t K = sk.keyTimes.size();
+      const float ts = sk.keyTimes.front() + float(ct);
+      while (k0 + 1 < K && sk.keyTimes[k0 + 1] <= ts) ++k0;
+      k1 = k0 + 1 < K ? k0 + 1 : k0;
+      const float span = sk.keyTimes[k1] - sk.keyTimes[k0];
+      blend = span > 0.0f ? (ts - sk.keyTimes[k0]) / span : 0.0f;
+    }
     for (size_t j = 0; j < J; ++j) {
-      float ang = sk.amplitude[j] * std::sin(float(2.0 * 3.14159265358979323846 * sk.freq[j] * ct) + sk.phase[j]) -
-                  sk.amplitude[j] * std::sin(sk.phase[j]); // zero at t = 0 so frame 0 is the bind pose
-      rth::V3 ax = rth::normalize(sk.axis[j]);
-      float sh = std::sin(ang * 0.5f), ch = std::cos(ang * 0.5f);
-      float qx = ax.x * sh, qy = ax.y * sh, qz = ax.z * sh, qw = ch;
+      float qx, qy, qz, qw;
+      rth::V3 offset, scl{1, 1, 1};
+      if (keyed) {
+        const float *a = sk.keyTimes.empty() ? &sk.restTRS[j * 10] : &sk.keyTRS[(k0 * J + j) * 10];
+        const float *b = sk.keyTimes.empty() ? a : &sk.keyTRS[(k1 * J + j) * 10];
+        auto lerp = [&](int c) { return a[c] + (b[c] - a[c]) * blend; };
+        offset = {lerp(0), lerp(1), lerp(2)};
+        scl = {lerp(7), lerp(8), lerp(9)};
+        const float d = ((a[3] * b[3] + a[4] * b[4]) + a[5] * b[5]) + a[6] * b[6];
+        const float sgn = d < 0.0f ? -1.0f : 1.0f; // q and -q are the same rotation: take the shorter arc
+        qx = a[3] + (sgn * b[3] - a[3]) * blend, qy = a[4] + (sgn * b[4] - a[4]) * blend;
+        qz = a[5] + (sgn * b[5] - a[5]) * blend, qw = a[6] + (sgn * b[6] - a[6]) * blend;
+      } else {
+        float ang = sk.amplitude[j] * std::sin(float(2.0 * 3.14159265358979323846 * sk.freq[j] * ct) + sk.phase[j]) -
+                    sk.amplitude[j] * std::sin(sk.phase[j]); // zero at t = 0 so frame 0 is the bind pose
+        rth::V3 ax = rth::normalize(sk.axis[j]);
+        float sh = std::sin(ang * 0.5f), ch = std::cos(ang * 0.5f);
+        qx = ax.x * sh, qy = ax.y * sh, qz = ax.z * sh, qw = ch;
+        offset = sk.restOffset[j];
+      }
       { // the same inputs, as handed to the device-side palette evaluation (rt_joint_palette)
         float *t = &m.jointLocalTRS[j * 10];
-        t[0] = sk.restOffset[j].x, t[1] = sk.restOffset[j].y, t[2] = sk.restOffset[j].z;
+        t[0] = offset.x, t[1] = offset.y, t[2] = offset.z;
         t[3] = qx, t[4] = qy, t[5] = qz, t[6] = qw;
-        t[7] = t[8] = t[9] = 1.0f;
+        t[7] = scl.x, t[8] = scl.y, t[9] = scl.z;
         std::copy(sk.inverseBind[j].m, sk.inverseBind[j].m + 16, &m.jointInverseBind[j * 16]);
       }
       float ql = std::sqrt(((qw * qw + qx * qx) + qy * qy) + qz * qz);
@@ -82,9 +116,8 @@ void Scene::animate(double t) {
         qx = qy = qz = 0;
         qw = 1;
       }
-      // matrix4x4_trs (Model.swift:497-506): T * R * S with S = 1
-      local[j] = rth::mul(rth::mul(rth::translate(sk.restOffset[j]), rth::fromQuat(qx, qy, qz, qw)),
-                          rth::scale({1, 1, 1}));
+      // matrix4x4_trs (Model.swift:497-506): T * R * S
+      local[j] = rth::mul(rth::mul(rth::translate(offset), rth::fromQuat(qx, qy, qz, qw)), rth::scale(scl));
     }
     global = local;
     for (size_t j = 0; j < J; ++j) { // Skeleton.computeGlobalTransforms: parents precede children
@@ -228,6 +261,160 @@ int rts_add_mesh_raw(rts_scene *s, const float *positions3, const float *normals
   m.submeshes.back().indices.assign(indices, indices + size_t(triangleCount) * 3);
   s->s.meshes.push_back(std::move(m));
   return int(s->s.meshes.size()) - 1;
+}
+
+// ---- skinned meshes from caller data / from a file (the USD-free path for animated assets) ----
+int rts_add_mesh_skinned(rts_scene *s, const float *positions3, const float *normals3, const float *uvs2,
+                         const uint16_t *jointIndices4, const float *jointWeights4, uint32_t vertexCount,
+                         const int32_t *indices, uint32_t triangleCount, uint32_t jointCount, const int32_t *parents,
+                         const float *restTRS, const float *inverseBind) {
+  if (!jointIndices4 || !jointWeights4 || !jointCount || !parents || !restTRS || !inverseBind) {
+    g_error = "rts_add_mesh_skinned: joint data missing";
+    return -1;
+  }
+  for (uint32_t j = 0; j < jointCount; ++j)
+    if (parents[j] >= int32_t(j)) {
+      g_error = "rts_add_mesh_skinned: parents must precede children (-1 = root)";
+      return -1;
+    }
+  for (size_t i = 0; i < size_t(vertexCount) * 4; ++i)
+    if (jointIndices4[i] >= jointCount) {
+      g_error = "rts_add_mesh_skinned: joint index out of range";
+      return -1;
+    }
+  const int mesh = rts_add_mesh_raw(s, positions3, normals3, uvs2, vertexCount, indices, triangleCount);
+  if (mesh < 0) return -1;
+  Mesh &m = s->s.meshes[size_t(mesh)];
+  m.name = "skinned";
+  m.jointIndices.assign(jointIndices4, jointIndices4 + size_t(vertexCount) * 4);
+  m.jointWeights.assign(jointWeights4, jointWeights4 + size_t(vertexCount) * 4);
+  Skeleton &sk = m.skeleton;
+  sk.parent.assign(parents, parents + jointCount);
+  sk.restTRS.assign(restTRS, restTRS + size_t(jointCount) * 10);
+  sk.inverseBind.resize(jointCount);
+  for (uint32_t j = 0; j < jointCount; ++j) std::copy(inverseBind + 16 * j, inverseBind + 16 * j + 16, sk.inverseBind[j].m);
+  sk.duration = 0.0;
+  s->s.animateMesh(m, 0.0); // palette of the rest pose
+  return mesh;
+}
+
+int rts_set_animation_keys(rts_scene *s, int mesh, uint32_t keyCount, const float *times, const float *trs) {
+  if (mesh < 0 || size_t(mesh) >= s->s.meshes.size() || !s->s.meshes[size_t(mesh)].skinned()) {
+    g_error = "rts_set_animation_keys: not a skinned mesh";
+    return -1;
+  }
+  Skeleton &sk = s->s.meshes[size_t(mesh)].skeleton;
+  if (keyCount == 0) { // back to the rest pose (or the procedural clip of a stand-in)
+    sk.keyTimes.clear();
+    sk.keyTRS.clear();
+    return 0;
+  }
+  if (!times || !trs) {
+    g_error = "rts_set_animation_keys: null arrays";
+    return -1;
+  }
+  for (uint32_t k = 1; k < keyCount; ++k)
+    if (!(times[k] > times[k - 1])) {
+      g_error = "rts_set_animation_keys: key times must ascend";
+      return -1;
+    }
+  const size_t J = sk.parent.size();
+  sk.keyTimes.assign(times, times + keyCount);
+  sk.keyTRS.assign(trs, trs + size_t(keyCount) * J * 10);
+  if (sk.restTRS.empty()) sk.restTRS.assign(trs, trs + J * 10);
+  sk.duration = double(times[keyCount - 1]) - double(times[0]); // AnimationClip.duration, Model.swift:399-401
+  return 0;
+}
+
+// File layout (little endian): "RTSK1\0\0\0", u32 vertexCount, triangleCount, jointCount, keyCount, hasUvs, 3 x u32 zero;
+// positions (3 f32 / vertex), normals (3), [uvs (2)], joint indices (4 u16), joint weights (4 f32), indices (3 i32 /
+// triangle), parents (i32 / joint), rest TRS (10 f32 / joint), inverse bind (16 f32 / joint), key times (f32 / key),
+// key TRS (10 f32 / joint / key).
+int rts_save_skinned_mesh(const rts_scene *s, int mesh, const char *path) {
+  if (mesh < 0 || size_t(mesh) >= s->s.meshes.size() || !s->s.meshes[size_t(mesh)].skinned() || !path) {
+    g_error = "rts_save_skinned_mesh: not a skinned mesh";
+    return -1;
+  }
+  const Mesh &m = s->s.meshes[size_t(mesh)];
+  const Skeleton &sk = m.skeleton;
+  if (sk.restTRS.empty()) {
+    g_error = "rts_save_skinned_mesh: the mesh has a procedural clip, not keys";
+    return -1;
+  }
+  FILE *f = std::fopen(path, "wb");
+  if (!f) {
+    g_error = std::string("rts_save_skinned_mesh: cannot write ") + path;
+    return -1;
+  }
+  std::vector<int32_t> indices;
+  for (const Submesh &sm : m.submeshes) indices.insert(indices.end(), sm.indices.begin(), sm.indices.end());
+  const uint32_t V = uint32_t(m.positions.size()), T = uint32_t(indices.size() / 3), J = uint32_t(sk.parent.size()),
+                 K = uint32_t(sk.keyTimes.size());
+  const uint32_t head[8] = {V, T, J, K, m.uvs.empty() ? 0u : 1u, 0u, 0u, 0u};
+  bool ok = std::fwrite("RTSK1\0\0\0", 1, 8, f) == 8 && std::fwrite(head, 4, 8, f) == 8;
+  auto put = [&](const void *p, size_t bytes) { ok = ok && (bytes == 0 || std::fwrite(p, 1, bytes, f) == bytes); };
+  std::vector<float> p3(size_t(V) * 3), n3(size_t(V) * 3);
+  for (uint32_t i = 0; i < V; ++i) {
+    p3[3 * i] = m.positions[i].x, p3[3 * i + 1] = m.positions[i].y, p3[3 * i + 2] = m.positions[i].z;
+    n3[3 * i] = m.normals[i].x, n3[3 * i + 1] = m.normals[i].y, n3[3 * i + 2] = m.normals[i].z;
+  }
+  put(p3.data(), p3.size() * 4);
+  put(n3.data(), n3.size() * 4);
+  put(m.uvs.data(), m.uvs.size() * 4);
+  put(m.jointIndices.data(), m.jointIndices.size() * 2);
+  put(m.jointWeights.data(), m.jointWeights.size() * 4);
+  put(indices.data(), indices.size() * 4);
+  put(sk.parent.data(), sk.parent.size() * 4);
+  put(sk.restTRS.data(), sk.restTRS.size() * 4);
+  for (uint32_t j = 0; j < J; ++j) put(sk.inverseBind[j].m, 64);
+  put(sk.keyTimes.data(), sk.keyTimes.size() * 4);
+  put(sk.keyTRS.data(), sk.keyTRS.size() * 4);
+  ok = (std::fclose(f) == 0) && ok;
+  if (!ok) g_error = std::string("rts_save_skinned_mesh: write failed: ") + path;
+  return ok ? 0 : -1;
+}
+
+int rts_load_skinned_mesh(rts_scene *s, const char *path) {
+  FILE *f = path ? std::fopen(path, "rb") : nullptr;
+  if (!f) {
+    g_error = std::string("rts_load_skinned_mesh: cannot open ") + (path ? path : "(null)");
+    return -1;
+  }
+  char magic[8];
+  uint32_t head[8];
+  bool ok = std::fread(magic, 1, 8, f) == 8 && std::memcmp(magic, "RTSK1\0\0\0", 8) == 0 && std::fread(head, 4, 8, f) == 8;
+  const uint32_t V = ok ? head[0] : 0, T = ok ? head[1] : 0, J = ok ? head[2] : 0, K = ok ? head[3] : 0;
+  ok = ok && V > 0 && T > 0 && J > 0 && V <= (1u << 26) && T <= (1u << 26) && J <= 1024 && K <= (1u << 20);
+  std::vector<float> p3, n3, uv, w4, rest, bind, times, keys;
+  std::vector<uint16_t> j4;
+  std::vector<int32_t> indices, parents;
+  auto get = [&](auto &v, size_t count) {
+    v.resize(count);
+    ok = ok && (count == 0 || std::fread(v.data(), sizeof(v[0]), count, f) == count);
+  };
+  if (ok) {
+    get(p3, size_t(V) * 3);
+    get(n3, size_t(V) * 3);
+    get(uv, head[4] ? size_t(V) * 2 : 0);
+    get(j4, size_t(V) * 4);
+    get(w4, size_t(V) * 4);
+    get(indices, size_t(T) * 3);
+    get(parents, J);
+    get(rest, size_t(J) * 10);
+    get(bind, size_t(J) * 16);
+    get(times, K);
+    get(keys, size_t(K) * J * 10);
+  }
+  std::fclose(f);
+  if (!ok) {
+    g_error = std::string("rts_load_skinned_mesh: not a skinned-mesh file or truncated: ") + path;
+    return -1;
+  }
+  const int mesh = rts_add_mesh_skinned(s, p3.data(), n3.data(), uv.empty() ? nullptr : uv.data(), j4.data(), w4.data(), V,
+                                        indices.data(), T, J, parents.data(), rest.data(), bind.data());
+  if (mesh < 0) return -1;
+  if (K > 0 && rts_set_animation_keys(s, mesh, K, times.data(), keys.data()) != 0) return -1;
+  return mesh;
 }
 
 static Submesh *findSubmesh(rts_scene *s, int mesh, int submesh) {

@@ -35,6 +35,9 @@ struct Skeleton {
   std::vector<rth::V3> axis;
   std::vector<float> amplitude, freq, phase;
   double duration = 0.0;
+  // keyed clip (rts_set_animation_keys): when keyTimes is non-empty it replaces the procedural one. keyTRS holds
+  // keyCount x jointCount x 10 floats (translation xyz, quaternion xyzw, scale xyz); restTRS is the pose without a clip.
+  std::vector<float> keyTimes, keyTRS, restTRS;
 };
 
 struct Mesh {
@@ -75,6 +78,7 @@ struct Scene {
   void initSubmeshDefaults(Submesh &sm) const;
   int maxSubmeshes() const;
   void animate(double t);
+  void animateMesh(Mesh &m, double t);
   void flatten(rt_scene_desc *out);
 };
 

@@ -42,6 +42,11 @@ def lib():
     L.rts_add_mesh_procedural.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.rts_add_mesh_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                    C.c_uint32]
+    L.rts_add_mesh_skinned.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32,
+                                                                         C.c_void_p, C.c_void_p, C.c_void_p]
+    L.rts_set_animation_keys.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.rts_save_skinned_mesh.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    L.rts_load_skinned_mesh.argtypes = [C.c_void_p, C.c_char_p]
     L.rts_set_material.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(A.Material)]
     L.rts_get_material.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(A.Material)]
     L.rts_add_texture_rgba8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -167,6 +172,39 @@ class Scene:
         self._desc = d
         return d
 
+    def add_skinned(self, positions, indices, joint_indices, joint_weights, parents, rest_trs, inverse_bind,
+                    normals=None, uvs=None):
+        """rts_add_mesh_skinned: a skinned mesh from arrays (joint_indices (V, 4) uint16, joint_weights (V, 4),
+        parents (J,), rest_trs (J, 10), inverse_bind (J, 16) column-major)."""
+        p = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        i = np.ascontiguousarray(indices, np.int32).reshape(-1, 3)
+        n = None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+        t = None if uvs is None else np.ascontiguousarray(uvs, np.float32).reshape(-1, 2)
+        ji = np.ascontiguousarray(joint_indices, np.uint16).reshape(-1, 4)
+        jw = np.ascontiguousarray(joint_weights, np.float32).reshape(-1, 4)
+        par = np.ascontiguousarray(parents, np.int32).reshape(-1)
+        rest = np.ascontiguousarray(rest_trs, np.float32).reshape(-1, 10)
+        bind = np.ascontiguousarray(inverse_bind, np.float32).reshape(-1, 16)
+        assert len(ji) == len(jw) == len(p) and len(rest) == len(bind) == len(par)
+        return self._check(lib().rts_add_mesh_skinned(
+            self._h, p.ctypes.data, n.ctypes.data if n is not None else None, t.ctypes.data if t is not None else None,
+            ji.ctypes.data, jw.ctypes.data, len(p), i.ctypes.data, len(i), len(par), par.ctypes.data, rest.ctypes.data,
+            bind.ctypes.data))
+
+    def set_animation_keys(self, mesh, times, trs):
+        """rts_set_animation_keys: times (K,) ascending seconds, trs (K, J, 10); None / empty removes the clip."""
+        if times is None or len(times) == 0:
+            return self._check(lib().rts_set_animation_keys(self._h, mesh, 0, None, None))
+        tm = np.ascontiguousarray(times, np.float32).reshape(-1)
+        k = np.ascontiguousarray(trs, np.float32).reshape(len(tm), -1, 10)
+        return self._check(lib().rts_set_animation_keys(self._h, mesh, len(tm), tm.ctypes.data, k.ctypes.data))
+
+    def save_skinned(self, mesh, path):
+        return self._check(lib().rts_save_skinned_mesh(self._h, mesh, str(path).encode()))
+
+    def load_skinned(self, path):
+        return self._check(lib().rts_load_skinned_mesh(self._h, str(path).encode()))
+
     # ---- numpy views (copies) for tests ---------------------------------------------------------------
     def mesh_arrays(self, mesh):
         d = self.desc()
@@ -180,6 +218,10 @@ class Scene:
             "jointWeights": np.ctypeslib.as_array(m.jointWeights, shape=(n, 4)).copy() if m.jointWeights else None,
             "jointMatrices": (np.ctypeslib.as_array(m.jointMatrices, shape=(m.jointCount, 16)).copy()
                               if m.jointCount else None),
+            "jointLocalTRS": (np.ctypeslib.as_array(m.jointLocalTRS, shape=(m.jointCount, 10)).copy()
+                              if m.jointCount and m.jointLocalTRS else None),
+            "jointParents": (np.ctypeslib.as_array(m.jointParents, shape=(m.jointCount,)).copy()
+                             if m.jointCount and m.jointParents else None),
             "submeshes": [],
         }
         for k in range(m.submeshCount):

@@ -229,6 +229,36 @@ def test_gpu_joint_palette_equals_host_palette(gpu_ctx):
     assert np.array_equal(images[0].view(np.uint16), images[1].view(np.uint16))
 
 
+@pytest.mark.parametrize("gpu_skeleton", [False, True])
+def test_keyed_skinned_mesh_from_arrays(gpu_ctx, two_joint_arm_scene, gpu_skeleton):
+    """A skinned mesh handed over as arrays with a keyed clip (rts_add_mesh_skinned / rts_set_animation_keys,
+    SURVEY.md §8f N-2) takes the same per-frame path as the stand-in — palette (host or rt_joint_palette), rt_skin,
+    BLAS refit, TLAS rebuild, trace — and matches the oracle bit for bit on every frame of the bend."""
+    sc, u, seeds, w, h = two_joint_arm_scene(96, 96)
+    u.samplesPerPixel, u.maxBounces = 2, 2
+    rnd = device.Renderer(gpu_ctx, sc, w, h, seeds=seeds, gpu_skeleton=gpu_skeleton)
+    orc = oracle.Oracle(sc)
+    imgs = oracle.FrameImages(w, h, seeds)
+    covered = []
+    for f in range(4):
+        u.frameIndex = f
+        if f:
+            sc.animate(0.3 * f)
+            rnd.update()
+            orc.update()
+        rnd.draw(u, want_ids=True)
+        _, ref_ids = orc.render(u, imgs, want_ids=True)
+        ids = rnd.read_ids()
+        assert np.array_equal(ids[..., :3], ref_ids[..., :3]), f"frame {f}: primary ids"
+        assert np.array_equal(rnd.read_image(0).view(np.uint16), imgs.output.view(np.uint16)), f"frame {f}: radiance"
+        assert np.array_equal(rnd.read_image(A.TEXTURE_MOTION).view(np.uint16),
+                              imgs.arrays[A.TEXTURE_MOTION].view(np.uint16)), f"frame {f}: motion"
+        covered.append(ids[..., 0] != 0xFFFFFFFF)
+        imgs.swap()
+    assert covered[0].sum() > 50 and (covered[0] != covered[2]).sum() > 20  # the arm bends
+    rnd.close()
+
+
 def _temporal_filter_numpy(color, motion, depth, normal, hcolor, hdepth, hnormal, wgt, dtol, nthr):
     """float32 restatement of rt_temporal_filter (include/rt_b200.h), same operation order."""
     f = np.float32

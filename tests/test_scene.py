@@ -133,6 +133,74 @@ def test_humanoid_skeleton_and_animation():
     assert np.allclose(m1, m2, atol=2e-3)
 
 
+def test_keyed_skinned_mesh_and_file_round_trip(tmp_path, two_joint_arm):
+    """rts_add_mesh_skinned + rts_set_animation_keys: the sampled clip gives the analytic palette
+    (half way to a 90-degree bend is a 45-degree bend: the normalised-linear midpoint is the slerp midpoint), loops with
+    the clip duration, hands the same TRS to the device-side palette evaluation, and survives the file format."""
+    import oracle
+    pos, tris, nrm, ji, jw, parents, rest, bind, times, keys = two_joint_arm
+    sc = scene.Scene()
+    m = sc.add_skinned(pos, tris, ji, jw, parents, rest, bind, normals=nrm)
+    a = sc.mesh_arrays(m)
+    assert np.allclose(a["jointMatrices"].reshape(2, 4, 4), np.eye(4), atol=1e-6)  # rest pose == bind pose
+    sc.set_animation_keys(m, times, keys)
+    sc.animate(0.5)
+    a = sc.mesh_arrays(m)
+    pal = a["jointMatrices"].reshape(2, 4, 4).transpose(0, 2, 1)  # -> row-major
+    c = np.float32(np.cos(np.pi / 4))
+    want = np.array([[c, -c, 0, c], [c, c, 0, 1 - c], [0, 0, 1, 0], [0, 0, 0, 1]], np.float32)  # T(0,1,0) Rz(45) T(0,-1,0)
+    assert np.allclose(pal[0], np.eye(4), atol=1e-6) and np.allclose(pal[1], want, atol=1e-6)
+    p4 = np.concatenate([pos, np.zeros((len(pos), 1), np.float32)], 1)
+    n4 = np.concatenate([nrm, np.zeros((len(pos), 1), np.float32)], 1)
+    skinned, _ = oracle.skin(p4, n4, ji, jw, a["jointMatrices"])
+    tip = skinned[np.argmax(pos[:, 1] + 0.01 * pos[:, 0])]  # rest (0.1, 2, 0): elbow-local (0.1, 1, 0) turned by 45 degrees
+    assert np.allclose(tip[:3], [0.1 * c - c, 1 + 0.1 * c + c, 0], atol=1e-5)
+    assert np.allclose(skinned[pos[:, 1] <= 1.0][:, :3], pos[pos[:, 1] <= 1.0], atol=1e-7)
+    # the TRS the device-side evaluation (rt_joint_palette) receives is the sampled key, and the clip loops
+    trs = a["jointLocalTRS"]
+    assert np.allclose(trs[1, :3], [0, 1, 0]) and np.allclose(trs[1, 7:], 1.0)
+    q = trs[1, 3:7] / np.linalg.norm(trs[1, 3:7])
+    assert np.allclose(q, [0, 0, np.sin(np.pi / 8), np.cos(np.pi / 8)], atol=1e-6)
+    sc.animate(1.5)
+    assert np.allclose(sc.mesh_arrays(m)["jointMatrices"], a["jointMatrices"], atol=1e-6)
+    sc.animate(0.0)
+    assert np.allclose(sc.mesh_arrays(m)["jointMatrices"].reshape(2, 4, 4), np.eye(4), atol=1e-6)
+    # file round trip
+    path = tmp_path / "arm.rtsk"
+    sc.save_skinned(m, path)
+    sc2 = scene.Scene()
+    m2 = sc2.load_skinned(path)
+    sc2.animate(0.5)
+    b = sc2.mesh_arrays(m2)
+    for key in ("positions", "normals", "jointIndices", "jointWeights", "jointMatrices", "jointLocalTRS", "jointParents"):
+        assert np.array_equal(a[key], b[key]), key
+    assert np.array_equal(a["submeshes"][0], b["submeshes"][0])
+    # errors are reported, not trapped
+    with pytest.raises(RuntimeError):
+        sc.add_skinned(pos, tris, ji, jw, [0, -1], rest, bind)  # a child before its parent
+    with pytest.raises(RuntimeError):
+        sc.set_animation_keys(m, [1.0, 0.5], keys)  # times must ascend
+    (tmp_path / "bad.rtsk").write_bytes(b"RTSK1\0\0\0" + b"\1" * 20)
+    with pytest.raises(RuntimeError):
+        sc2.load_skinned(tmp_path / "bad.rtsk")
+
+
+def test_keyed_skinned_mesh_renders_through_the_oracle(two_joint_arm_scene):
+    """The raw skinned mesh goes through the same per-frame path as the stand-in (skin -> refit -> trace): the bent
+    arm covers different pixels than the straight one."""
+    import oracle
+    sc, u, seeds, w, h = two_joint_arm_scene()
+    orc = oracle.Oracle(sc)
+    imgs = oracle.FrameImages(w, h, seeds)
+    _, ids0 = orc.render(u, imgs, want_ids=True)
+    sc.animate(0.75)  # (the clip lasts 1 s and loops: t = 1 would be the rest pose again)
+    orc.update()
+    _, ids1 = orc.render(u, imgs, want_ids=True)
+    hit0, hit1 = ids0[..., 0] != 0xFFFFFFFF, ids1[..., 0] != 0xFFFFFFFF
+    assert hit0.sum() > 20 and hit1.sum() > 20
+    assert (hit0 != hit1).sum() > 10
+
+
 def test_named_scenes(assets):
     for name, (w, h), tris, inst, spp, mb in [("K1", (512, 512), 4902, 2, 1, 1), ("K2", (1920, 1080), 81922, 2, 4, 2),
                                              ("K4small", (256, 256), 19682, 65, 8, 2),
