@@ -162,6 +162,12 @@ int rts_scene_get_desc(rts_scene *s, rt_scene_desc *out);
 /* seed[y*W+x] = hash32(y*W+x, seed) & 0xFFFFF — range of Renderer.swift:719-726 (arc4random % 2^20). */
 /* Image writer for the post chain: 8-bit RGBA PNG, rows top to bottom. */
 int rts_write_png(const char *path, const uint8_t *rgba8, int width, int height);
+/* Radiance RGBE (.hdr) reader for the environment extension (rt_b200.h rt_environment; BASELINE's K3 names
+ * vulture_hide_4k.hdr, which the reference ships and never loads): "#?RADIANCE" / "#?RGBE" header,
+ * FORMAT=32-bit_rle_rgbe, "-Y h +X w", flat or run-length-encoded scanlines; (r, g, b, e) -> (r, g, b) * 2^(e - 136).
+ * *rgbaOut receives width * height RGBA32F texels (alpha 1, row 0 = top = straight up), to be released with rts_free. */
+int rts_load_hdr(const char *path, int *width, int *height, float **rgbaOut);
+void rts_free(void *p);
 void rts_fill_seed_image(uint32_t *dst, int width, int height, uint32_t seed);
 /* Fills the uniform defaults of Renderer.swift:117-192 for a width x height target (frameIndex 0). */
 void rts_default_uniforms(int width, int height, rt_uniforms *u);

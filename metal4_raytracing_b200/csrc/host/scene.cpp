@@ -4,10 +4,13 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
 namespace rts {
+
+bool decodeHdr(const std::string &path, int &width, int &height, std::vector<float> &rgba, std::string &err); // hdr_decode.cpp
 
 static thread_local std::string g_error;
 
@@ -416,6 +419,28 @@ int rts_load_skinned_mesh(rts_scene *s, const char *path) {
   if (K > 0 && rts_set_animation_keys(s, mesh, K, times.data(), keys.data()) != 0) return -1;
   return mesh;
 }
+
+int rts_load_hdr(const char *path, int *width, int *height, float **rgbaOut) {
+  if (!path || !width || !height || !rgbaOut) {
+    g_error = "rts_load_hdr: null argument";
+    return -1;
+  }
+  std::vector<float> texels;
+  std::string err;
+  if (!rts::decodeHdr(path, *width, *height, texels, err)) {
+    g_error = "rts_load_hdr: " + err;
+    return -1;
+  }
+  *rgbaOut = static_cast<float *>(std::malloc(texels.size() * sizeof(float)));
+  if (!*rgbaOut) {
+    g_error = "rts_load_hdr: out of memory";
+    return -1;
+  }
+  std::memcpy(*rgbaOut, texels.data(), texels.size() * sizeof(float));
+  return 0;
+}
+
+void rts_free(void *p) { std::free(p); }
 
 static Submesh *findSubmesh(rts_scene *s, int mesh, int submesh) {
   if (mesh < 0 || size_t(mesh) >= s->s.meshes.size() || submesh < 0 ||

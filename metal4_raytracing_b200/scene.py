@@ -69,6 +69,8 @@ def lib():
     L.rts_fill_seed_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32]
     L.rts_default_uniforms.argtypes = [C.c_int, C.c_int, C.POINTER(A.Uniforms)]
     L.rts_write_png.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
+    L.rts_load_hdr.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_float))]
+    L.rts_free.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -228,6 +230,17 @@ class Scene:
             sm = m.submeshes[k]
             out["submeshes"].append(np.ctypeslib.as_array(sm.indices, shape=(sm.triangleCount, 3)).copy())
         return out
+
+
+def load_hdr(path):
+    """rts_load_hdr: a Radiance RGBE picture as (H, W, 4) float32 (alpha 1), e.g. for Renderer.set_environment."""
+    w, h, p = C.c_int(), C.c_int(), C.POINTER(C.c_float)()
+    if lib().rts_load_hdr(str(path).encode(), C.byref(w), C.byref(h), C.byref(p)) != 0:
+        raise RuntimeError(_err())
+    try:
+        return np.ctypeslib.as_array(p, shape=(h.value, w.value, 4)).copy()
+    finally:
+        lib().rts_free(p)
 
 
 def default_uniforms(width, height):

@@ -256,6 +256,65 @@ def test_png_decoder(assets):
     assert (t.width, t.height) == (ref.shape[1], ref.shape[0]) and np.array_equal(got, ref) and t.srgb == 1
 
 
+def _rgbe_rows(rng, w, h):
+    px = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    px[..., 3] = rng.integers(120, 140, (h, w), dtype=np.uint8)
+    px[0, :5] = [10, 20, 30, 0]          # exponent 0 decodes to black
+    px[1, 8:40] = [200, 100, 50, 130]    # a long run for the run-length coder
+    return px
+
+
+def _rle_channel(values):
+    out, i, n = bytearray(), 0, len(values)
+    while i < n:
+        run = 1
+        while i + run < n and run < 127 and values[i + run] == values[i]:
+            run += 1
+        if run >= 4:
+            out += bytes([128 + run, values[i]])
+            i += run
+        else:
+            lit = [values[i]]
+            i += 1
+            while i < n and len(lit) < 128 and not (i + 3 < n and values[i] == values[i + 1] == values[i + 2] == values[i + 3]):
+                lit.append(values[i])
+                i += 1
+            out += bytes([len(lit)]) + bytes(lit)
+    return bytes(out)
+
+
+def test_radiance_hdr_reader(tmp_path):
+    """rts_load_hdr: flat and run-length-encoded RGBE files decode to (r, g, b) * 2^(e - 136); malformed files are
+    refused with a message. The texels can go straight into the environment extension's table builder."""
+    rng = np.random.default_rng(11)
+    w, h = 48, 6
+    px = _rgbe_rows(rng, w, h)
+    want = np.ones((h, w, 4), np.float32)
+    scale = np.where(px[..., 3] > 0, np.ldexp(np.float32(1.0), px[..., 3].astype(np.int32) - 136), 0).astype(np.float32)
+    want[..., :3] = px[..., :3].astype(np.float32) * scale[..., None]
+    header = b"#?RADIANCE\n# written by the test\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=1.0\n\n-Y %d +X %d\n" % (h, w)
+    flat = tmp_path / "flat.hdr"
+    flat.write_bytes(header + px.tobytes())
+    assert np.array_equal(scene.load_hdr(flat), want)
+    body = b""
+    for y in range(h):
+        body += bytes([2, 2, w >> 8, w & 255]) + b"".join(_rle_channel(px[y, :, c].tolist()) for c in range(4))
+    rle = tmp_path / "rle.hdr"
+    rle.write_bytes(header.replace(b"#?RADIANCE", b"#?RGBE") + body)
+    assert len(body) < px.nbytes + 4 * h and np.array_equal(scene.load_hdr(rle), want)
+    from metal4_raytracing_b200 import device
+    table = device.environment_cdf(scene.load_hdr(rle))
+    assert table.shape == ((h + 1) + h * (w + 1),) and table[h] == 1.0
+    for name, data in (("magic.hdr", b"P6\n" + px.tobytes()), ("short.hdr", header + px.tobytes()[:100]),
+                       ("format.hdr", header.replace(b"rgbe", b"xyze") + px.tobytes()),
+                       ("run.hdr", header + bytes([2, 2, 0, w, 128 + 100, 7]))):
+        (tmp_path / name).write_bytes(data)
+        with pytest.raises(RuntimeError):
+            scene.load_hdr(tmp_path / name)
+    with pytest.raises(RuntimeError):
+        scene.load_hdr(tmp_path / "absent.hdr")
+
+
 def test_png_writer_round_trip(tmp_path):
     """rts_write_png (post chain image writer): what it writes decodes to the same pixels with an independent
     decoder (PIL), including a ragged size."""
