@@ -3,7 +3,10 @@
 // shape of what the reference's Renderer + FramePresenter do per frame (Renderer.swift:1405-1503) and what a port of
 // the app would look like; the Python package is just another client of the same two libraries.
 //
-//   rt_render <scene> <width> <height> <spp> <maxBounces> <frames> <out.png> [assetDir]
+//   rt_render <scene> <width> <height> <spp> <maxBounces> <frames> <out.png> [assetDir|-] [environment.hdr] [intensity]
+//
+// With a Radiance .hdr file the environment extension is bound (rt_b200.h rt_environment) and sampled as a light
+// (RT_ENV_IMPORTANCE); without one a ray that leaves the scene returns black, as in the reference.
 //
 // Exit code 0 and one line "frames=.. ms_per_frame=.. mrays_per_s=.." on success; errors come back as messages from
 // rt_last_error / rtr_last_error / rts_last_error (the library never aborts).
@@ -27,14 +30,16 @@
 
 int main(int argc, char **argv) {
   if (argc < 8) {
-    std::fprintf(stderr, "usage: %s <scene> <width> <height> <spp> <maxBounces> <frames> <out.png> [assetDir]\n", argv[0]);
+    std::fprintf(stderr, "usage: %s <scene> <width> <height> <spp> <maxBounces> <frames> <out.png> [assetDir|-] [environment.hdr] [intensity]\n", argv[0]);
     return 2;
   }
   const char *name = argv[1];
   const int width = std::atoi(argv[2]), height = std::atoi(argv[3]), spp = std::atoi(argv[4]), bounces = std::atoi(argv[5]);
   const int frames = std::atoi(argv[6]);
   const char *outPath = argv[7];
-  const char *assetDir = argc > 8 ? argv[8] : nullptr;
+  const char *assetDir = (argc > 8 && std::strcmp(argv[8], "-") != 0) ? argv[8] : nullptr;
+  const char *envPath = argc > 9 ? argv[9] : nullptr;
+  const float envIntensity = argc > 10 ? float(std::atof(argv[10])) : 1.0f;
 
   rt_uniforms uniforms{};
   uint32_t seed = 0;
@@ -61,6 +66,33 @@ int main(int argc, char **argv) {
   CHECK(rt_memset(ctx, countersDev, 0, 24), rt_last_error);
   rt_trace_options options{};
   options.rayCountersDev = countersDev;
+
+  // environment extension: texels + importance-sampling table, both built on the host and uploaded once
+  rt_environment environment{};
+  float *envTexelsDev = nullptr, *envCdfDev = nullptr;
+  if (envPath) {
+    int ew = 0, eh = 0;
+    float *texels = nullptr;
+    CHECK(rts_load_hdr(envPath, &ew, &eh, &texels), rts_last_error);
+    std::vector<float> cdf(rt_environment_cdf_floats(ew, eh));
+    if (rt_environment_cdf(texels, ew, eh, cdf.data()) != 0) {
+      std::fprintf(stderr, "rt_environment_cdf failed\n");
+      return 1;
+    }
+    const size_t texelBytes = size_t(ew) * size_t(eh) * 4 * sizeof(float);
+    CHECK(rt_malloc(ctx, texelBytes, reinterpret_cast<void **>(&envTexelsDev)), rt_last_error);
+    CHECK(rt_malloc(ctx, cdf.size() * sizeof(float), reinterpret_cast<void **>(&envCdfDev)), rt_last_error);
+    CHECK(rt_upload(ctx, envTexelsDev, texels, texelBytes), rt_last_error);
+    CHECK(rt_upload(ctx, envCdfDev, cdf.data(), cdf.size() * sizeof(float)), rt_last_error);
+    CHECK(rt_sync(ctx), rt_last_error); // the uploads read host memory that goes away below
+    rts_free(texels);
+    environment.texelsDev = envTexelsDev;
+    environment.width = ew, environment.height = eh;
+    environment.intensity = envIntensity;
+    environment.flags = RT_ENV_IMPORTANCE;
+    environment.cdfDev = envCdfDev;
+    options.environment = &environment;
+  }
 
   CHECK(rt_timer_begin(ctx), rt_last_error);
   for (int f = 0; f < frames; ++f) {
@@ -93,6 +125,8 @@ int main(int argc, char **argv) {
               (unsigned long long)rt_launch_count(ctx), outPath);
   rt_free(ctx, rgbaDev);
   rt_free(ctx, countersDev);
+  if (envTexelsDev) rt_free(ctx, envTexelsDev);
+  if (envCdfDev) rt_free(ctx, envCdfDev);
   rtr_destroy(renderer);
   rt_destroy(ctx);
   rts_scene_destroy(scene);
