@@ -198,6 +198,17 @@ typedef struct rt_denoise_frame {
 } rt_denoise_frame;
 int rt_temporal_filter(rt_context *ctx, const rt_denoise_frame *current, const rt_denoise_frame *history,
                        const rt_image *outColorDev, float historyWeight, float depthTolerance, float normalThreshold);
+/* rt_spatial_filter: one pass of an edge-avoiding a-trous wavelet filter (Dammertz et al. 2010) over frame->color,
+ * guided by the kernel's depth (texture 3) and normal G-buffer (texture 7) — the spatial half of what the reference
+ * leaves to MetalFX's denoiser (FramePresenter.swift:435-521); frame->motion is not read and may be unbound. 5 x 5 taps
+ * spaced `step` pixels apart (call it with step 1, 2, 4, ... ping-ponging two images) with the B3-spline weights
+ * (1, 4, 6, 4, 1) / 16 per axis, each multiplied by
+ *   max(0, n_p . n_q) squared normalSquarings times,   1 / (1 + (|z_p - z_q| / (depthSigma * z_p))^2)   and, when
+ *   colorSigma > 0,   1 / (1 + |c_p - c_q|^2 / colorSigma^2);
+ * taps outside the image or without a primary hit (depth >= 1e7) are skipped, a pixel without a primary hit is passed
+ * through. out = sum(w * c_q) / sum(w), accumulated row by row in fp32. */
+int rt_spatial_filter(rt_context *ctx, const rt_denoise_frame *frame, const rt_image *outColorDev, int step,
+                      float depthSigma, int normalSquarings, float colorSigma);
 
 /* ---- multi-GPU frame exchange (no counterpart in the single-device reference) ---------------
  * Rank g of N owns 16x16 tiles with tile % N == g. Two ways to assemble the frame:

@@ -179,6 +179,8 @@ void destroyAccel(AccelObject *as);
 int launchSkin(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], uint32_t vertexCount);
 int launchJointPalette(rt_context *ctx, const float *trs, const int32_t *parents, const float *inverseBind,
                        uint32_t jointCount, float *palette);
+int launchSpatialFilter(rt_context *ctx, const rt_denoise_frame *fr, const rt_image *out, int step, float depthSigma,
+                        int normalSquarings, float colorSigma);
 int launchTemporalFilter(rt_context *ctx, const rt_denoise_frame *cur, const rt_denoise_frame *hist, const rt_image *out,
                          float historyWeight, float depthTolerance, float normalThreshold);
 int launchTonemap(rt_context *ctx, const rt_image *src, uint8_t *dst, uint32_t flags);

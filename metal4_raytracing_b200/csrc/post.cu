@@ -99,7 +99,71 @@ __global__ void k_temporal_filter(const rt_denoise_frame cur, const rt_denoise_f
   writeImage(out, x, y, {result.x, result.y, result.z, 1.0f});
 }
 
+// rt_spatial_filter (rt_b200.h): one a-trous pass, one thread per pixel
+__global__ void k_spatial_filter(const rt_denoise_frame fr, const rt_image out, int step, float depthSigma,
+                                 int normalSquarings, float colorSigma) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int w = fr.color.width, h = fr.color.height;
+  if (x >= w || y >= h) return;
+  const f4 c4 = readImage(fr.color, x, y);
+  const f3 c = mk3(c4.x, c4.y, c4.z);
+  const float depth = readImage(fr.depth, x, y).x;
+  f3 result = c;
+  if (depth < 1.0e7f) {
+    const f4 n4 = readImage(fr.normal, x, y);
+    const f3 n = mk3(n4.x, n4.y, n4.z) * 2.0f - mk3(1.0f);
+    const float kernel1[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
+    const float depthScale = depthSigma * depth;
+    const float colorScale = colorSigma * colorSigma;
+    f3 sum = mk3(0.0f);
+    float weightSum = 0.0f;
+    for (int dy = -2; dy <= 2; ++dy)
+      for (int dx = -2; dx <= 2; ++dx) {
+        const int qx = x + dx * step, qy = y + dy * step;
+        if (qx < 0 || qy < 0 || qx >= w || qy >= h) continue;
+        const float qd = readImage(fr.depth, qx, qy).x;
+        if (!(qd < 1.0e7f)) continue;
+        const f4 q4 = readImage(fr.color, qx, qy);
+        const f3 q = mk3(q4.x, q4.y, q4.z);
+        const f4 qn4 = readImage(fr.normal, qx, qy);
+        const f3 qn = mk3(qn4.x, qn4.y, qn4.z) * 2.0f - mk3(1.0f);
+        float wn = fmaxf(dot(n, qn), 0.0f);
+        for (int k = 0; k < normalSquarings; ++k) wn = wn * wn;
+        const float dz = fabsf(depth - qd) / depthScale;
+        const float wz = 1.0f / (1.0f + dz * dz);
+        float wc = 1.0f;
+        if (colorSigma > 0.0f) {
+          const f3 dc = c - q;
+          wc = 1.0f / (1.0f + dot(dc, dc) / colorScale);
+        }
+        const float wgt = ((kernel1[dx + 2] * kernel1[dy + 2]) * wn) * (wz * wc);
+        sum = sum + q * wgt;
+        weightSum = weightSum + wgt;
+      }
+    if (weightSum > 0.0f) result = sum / weightSum;
+  }
+  writeImage(out, x, y, {result.x, result.y, result.z, 1.0f});
+}
+
 } // namespace
+
+int launchSpatialFilter(rt_context *ctx, const rt_denoise_frame *fr, const rt_image *out, int step, float depthSigma,
+                        int normalSquarings, float colorSigma) {
+  RT_CHECK(fr && out && fr->color.data && fr->depth.data && fr->normal.data && out->data,
+           "rt_spatial_filter: colour, depth, normal and output images must be bound");
+  const int w = fr->color.width, h = fr->color.height;
+  auto same = [&](const rt_image &i) { return i.width == w && i.height == h; };
+  RT_CHECK(w > 0 && h > 0 && same(fr->depth) && same(fr->normal) && same(*out), "rt_spatial_filter: image sizes differ");
+  RT_CHECK(step >= 1 && step <= 1024, "rt_spatial_filter: step is 1..1024");
+  RT_CHECK(depthSigma > 0.0f && normalSquarings >= 0 && normalSquarings <= 8,
+           "rt_spatial_filter: depthSigma > 0, normalSquarings 0..8");
+  RT_CHECK(out->data != fr->color.data, "rt_spatial_filter: output aliases the input");
+  const dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+  k_spatial_filter<<<grid, block, 0, ctx->stream>>>(*fr, *out, step, depthSigma, normalSquarings, colorSigma);
+  ++ctx->launches;
+  RT_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int launchTemporalFilter(rt_context *ctx, const rt_denoise_frame *cur, const rt_denoise_frame *hist, const rt_image *out,
                          float historyWeight, float depthTolerance, float normalThreshold) {

@@ -441,6 +441,15 @@ int rt_temporal_filter(rt_context *ctx, const rt_denoise_frame *current, const r
   return rc;
 }
 
+int rt_spatial_filter(rt_context *ctx, const rt_denoise_frame *frame, const rt_image *outColorDev, int step,
+                      float depthSigma, int normalSquarings, float colorSigma) {
+  RT_CTX(ctx);
+  ctx->mark(-1);
+  const int rc = launchSpatialFilter(ctx, frame, outColorDev, step, depthSigma, normalSquarings, colorSigma);
+  ctx->mark(RT_KERNEL_OTHER);
+  return rc;
+}
+
 int rt_pack_tiles(rt_context *ctx, const rt_image *imageDev, void *slabDev, int tileModulo, int tileRemainder) {
   RT_CTX(ctx);
   return packTiles(ctx, imageDev, slabDev, tileModulo, tileRemainder);

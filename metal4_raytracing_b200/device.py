@@ -71,7 +71,7 @@ EXPORTS = [
     "rt_tonemap", "rt_temporal_filter", "rt_download_async", "rt_download_wait", "rt_fence", "rt_fence_wait",
     "rtr_last_error", "rtr_create", "rtr_destroy", "rtr_set_seeds", "rtr_update", "rtr_draw", "rtr_read_image",
     "rtr_image_info", "rtr_reset_accumulation", "rtr_read_mesh_streams", "rtr_get_blas_id", "rtr_get_tlas_id",
-    "rtr_mesh_count", "rt_environment_cdf_floats", "rt_environment_cdf",
+    "rtr_mesh_count", "rt_environment_cdf_floats", "rt_environment_cdf", "rt_spatial_filter",
 ]
 
 
@@ -123,6 +123,7 @@ def lib():
     L.rt_tonemap.argtypes = [vp, C.POINTER(A.Image), vp, u32]
     L.rt_temporal_filter.argtypes = [vp, C.POINTER(DenoiseFrame), C.POINTER(DenoiseFrame), C.POINTER(A.Image),
                                      C.c_float, C.c_float, C.c_float]
+    L.rt_spatial_filter.argtypes = [vp, C.POINTER(DenoiseFrame), C.POINTER(A.Image), i32, C.c_float, i32, C.c_float]
     L.rt_kernel_timing_enable.argtypes = [vp, i32]
     L.rt_kernel_timing_read.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u32)]
     L.rtr_create.argtypes = [vp, C.POINTER(A.SceneDesc), i32, i32, u32, C.POINTER(vp)]
@@ -273,6 +274,11 @@ class Context:
         """rt_temporal_filter on DenoiseFrame records; `history` may be None."""
         _check(lib().rt_temporal_filter(self._h, C.byref(current), C.byref(history) if history is not None else None,
                                         C.byref(out), history_weight, depth_tolerance, normal_threshold))
+
+    def spatial_filter(self, frame, out, step=1, depth_sigma=0.02, normal_squarings=5, color_sigma=0.0):
+        """rt_spatial_filter: one a-trous pass over frame.color guided by frame.depth / frame.normal."""
+        _check(lib().rt_spatial_filter(self._h, C.byref(frame), C.byref(out), step, depth_sigma, normal_squarings,
+                                       color_sigma))
 
     def joint_palette(self, local_trs, parents, inverse_bind):
         """rt_joint_palette on numpy inputs; returns the (J, 16) palette."""

@@ -338,6 +338,94 @@ def test_temporal_filter_on_kernel_outputs(gpu_ctx):
     gpu_ctx.free(out.data)
 
 
+def _spatial_filter_numpy(color, depth, normal, step, depth_sigma, squarings, color_sigma):
+    """float32 restatement of rt_spatial_filter (include/rt_b200.h), same operation order."""
+    f = np.float32
+    h, w = depth.shape
+    k1 = [f(0.0625), f(0.25), f(0.375), f(0.25), f(0.0625)]
+    out = color.copy()
+    for y in range(h):
+        for x in range(w):
+            z = depth[y, x]
+            if not z < f(1e7):
+                continue
+            c = color[y, x]
+            n = f(2) * normal[y, x] - f(1)
+            zs, cs = f(depth_sigma) * z, f(color_sigma) * f(color_sigma)
+            acc, wsum = np.zeros(3, f), f(0)
+            for dy in range(-2, 3):
+                for dx in range(-2, 3):
+                    qx, qy = x + dx * step, y + dy * step
+                    if qx < 0 or qy < 0 or qx >= w or qy >= h or not depth[qy, qx] < f(1e7):
+                        continue
+                    q = color[qy, qx]
+                    qn = f(2) * normal[qy, qx] - f(1)
+                    wn = max(f(f(n[0] * qn[0] + n[1] * qn[1]) + n[2] * qn[2]), f(0))
+                    for _ in range(squarings):
+                        wn = f(wn * wn)
+                    dz = f(abs(f(z - depth[qy, qx])) / zs)
+                    wz = f(f(1) / f(f(1) + f(dz * dz)))
+                    wc = f(1)
+                    if color_sigma > 0:
+                        d = c - q
+                        wc = f(f(1) / f(f(1) + f(f(f(d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]) / cs)))
+                    wgt = f(f(f(k1[dx + 2] * k1[dy + 2]) * wn) * f(wz * wc))
+                    acc = (acc + q * wgt).astype(f)
+                    wsum = f(wsum + wgt)
+            if wsum > 0:
+                out[y, x] = acc / wsum
+    return out
+
+
+def test_spatial_filter_consumes_depth_and_normal(gpu_ctx):
+    """rt_spatial_filter (the spatial half of the denoiser role): one pass equals a numpy
+    restatement; three passes (steps 1, 2, 4) bring a 1-spp frame closer to the converged one without bleeding across
+    the depth / normal edges the guides mark; pixels without a primary hit pass through."""
+    w, h = 96, 64
+    images = {}
+    for spp in (1, 64):
+        sc, u, seed = scene.Scene.named("K3small", w, h, assets=None)
+        u.samplesPerPixel, u.maxBounces, u.enableDenoiseGBuffer = spp, 2, 1
+        rnd = device.Renderer(gpu_ctx, sc, w, h, seeds=scene.seed_image(w, h, seed), fp32=True)
+        rnd.draw(u)
+        images[spp] = {k: rnd.read_image(i).astype(np.float32) for k, i in
+                       (("color", A.TEXTURE_ACCUMULATION), ("depth", A.TEXTURE_DEPTH), ("normal", A.TEXTURE_NORMAL))}
+        rnd.close()
+    noisy, clean = images[1], images[64]["color"][..., :3]
+    rgba = np.concatenate([noisy["color"][..., :3], np.ones((h, w, 1), np.float32)], -1)
+    fr = device.DenoiseFrame()
+    fr.color = gpu_ctx.image_from_array(rgba, A.FORMAT_RGBA32_FLOAT)
+    fr.depth = gpu_ctx.image_from_array(noisy["depth"][..., 0], A.FORMAT_R32_FLOAT)
+    fr.normal = gpu_ctx.image_from_array(noisy["normal"], A.FORMAT_RGBA32_FLOAT)
+    out = gpu_ctx.image_from_array(np.zeros((h, w, 4), np.float32), A.FORMAT_RGBA32_FLOAT)
+    for color_sigma in (0.0, 0.5):
+        gpu_ctx.spatial_filter(fr, out, step=1, depth_sigma=0.02, normal_squarings=5, color_sigma=color_sigma)
+        got = gpu_ctx.download(out.data, (h, w, 4), np.float32)[..., :3]
+        ref = _spatial_filter_numpy(noisy["color"][..., :3], noisy["depth"][..., 0], noisy["normal"][..., :3], 1, 0.02, 5,
+                                    color_sigma)
+        assert np.abs(got - ref).max() <= 1e-5 * max(1.0, float(np.abs(ref).max())), color_sigma
+    sky = ~(noisy["depth"][..., 0] < 1e7)
+    assert sky.any() and np.array_equal(got[sky], noisy["color"][..., :3][sky])
+    # three passes, ping-pong between `out` and the frame's own colour image
+    ping, pong = fr.color, out
+    for step in (1, 2, 4):
+        cur = device.DenoiseFrame()
+        cur.color, cur.depth, cur.normal = ping, fr.depth, fr.normal
+        gpu_ctx.spatial_filter(cur, pong, step=step, depth_sigma=0.02, normal_squarings=5)
+        ping, pong = pong, ping
+    filtered = gpu_ctx.download(ping.data, (h, w, 4), np.float32)[..., :3]
+    hitmask = ~sky
+    err_noisy = float(np.sqrt(np.mean((noisy["color"][..., :3][hitmask] - clean[hitmask]) ** 2)))
+    err_filtered = float(np.sqrt(np.mean((filtered[hitmask] - clean[hitmask]) ** 2)))
+    assert err_filtered < 0.8 * err_noisy, (err_filtered, err_noisy)
+    with pytest.raises(device.RtError):
+        gpu_ctx.spatial_filter(cur, cur.color)  # output must not alias the input
+    with pytest.raises(device.RtError):
+        gpu_ctx.spatial_filter(cur, pong, step=0)
+    for img in (fr.color, fr.depth, fr.normal, out):
+        gpu_ctx.free(img.data)
+
+
 @pytest.mark.parametrize("fp32", [False, True])
 def test_tonemap_and_png(gpu_ctx, tmp_path, fp32):
     """rt_tonemap = the reference's presentation shader, color / (1 + color) (Shaders.metal:38-52), + sRGB transfer +
