@@ -168,6 +168,9 @@ int rts_write_png(const char *path, const uint8_t *rgba8, int width, int height)
  * *rgbaOut receives width * height RGBA32F texels (alpha 1, row 0 = top = straight up), to be released with rts_free. */
 int rts_load_hdr(const char *path, int *width, int *height, float **rgbaOut);
 void rts_free(void *p);
+/* The HDR end of the image writers: width * height RGBA32F texels (e.g. a downloaded fp32
+ * accumulation image; alpha ignored, negative values clamped to 0) as a flat Radiance RGBE picture, rows as given. */
+int rts_write_hdr(const char *path, const float *rgba32f, int width, int height);
 void rts_fill_seed_image(uint32_t *dst, int width, int height, uint32_t seed);
 /* Fills the uniform defaults of Renderer.swift:117-192 for a width x height target (frameIndex 0). */
 void rts_default_uniforms(int width, int height, rt_uniforms *u);

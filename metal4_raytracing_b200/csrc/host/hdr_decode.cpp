@@ -103,4 +103,41 @@ bool decodeHdr(const std::string &path, int &width, int &height, std::vector<flo
   return true;
 }
 
+// Writer: flat (not run-length-encoded) RGBE pixels, rows top to bottom; the shared exponent is that of the largest
+// channel, mantissas are truncated (Ward's float2rgbe), so decode(encode(x)) is within 1/128 of the largest channel.
+bool encodeHdr(const std::string &path, int width, int height, const float *rgba, int channels, std::string &err) {
+  if (width <= 0 || height <= 0 || !rgba || (channels != 3 && channels != 4)) {
+    err = "empty image or unsupported channel count";
+    return false;
+  }
+  FILE *f = std::fopen(path.c_str(), "wb");
+  if (!f) {
+    err = "cannot write " + path;
+    return false;
+  }
+  std::fprintf(f, "#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n", height, width);
+  std::vector<uint8_t> row(size_t(width) * 4);
+  bool ok = true;
+  for (int y = 0; y < height && ok; ++y) {
+    for (int x = 0; x < width; ++x) {
+      const float *p = rgba + (size_t(y) * size_t(width) + size_t(x)) * size_t(channels);
+      const float r = p[0] > 0.0f ? p[0] : 0.0f, g = p[1] > 0.0f ? p[1] : 0.0f, b = p[2] > 0.0f ? p[2] : 0.0f;
+      const float m = r > g ? (r > b ? r : b) : (g > b ? g : b);
+      uint8_t *o = row.data() + size_t(x) * 4;
+      if (!(m > 1e-32f) || !std::isfinite(m)) {
+        o[0] = o[1] = o[2] = o[3] = 0;
+      } else {
+        int e = 0;
+        const float scale = std::frexp(m, &e) * 256.0f / m; // m = mantissa * 2^e, mantissa in [0.5, 1)
+        o[0] = uint8_t(r * scale), o[1] = uint8_t(g * scale), o[2] = uint8_t(b * scale);
+        o[3] = uint8_t(e + 128);
+      }
+    }
+    ok = std::fwrite(row.data(), 1, row.size(), f) == row.size();
+  }
+  ok = (std::fclose(f) == 0) && ok;
+  if (!ok) err = "write failed: " + path;
+  return ok;
+}
+
 } // namespace rts

@@ -11,6 +11,7 @@
 namespace rts {
 
 bool decodeHdr(const std::string &path, int &width, int &height, std::vector<float> &rgba, std::string &err); // hdr_decode.cpp
+bool encodeHdr(const std::string &path, int width, int height, const float *rgba, int channels, std::string &err);
 
 static thread_local std::string g_error;
 
@@ -441,6 +442,15 @@ int rts_load_hdr(const char *path, int *width, int *height, float **rgbaOut) {
 }
 
 void rts_free(void *p) { std::free(p); }
+
+int rts_write_hdr(const char *path, const float *rgba32f, int width, int height) {
+  std::string err;
+  if (!path || !rts::encodeHdr(path, width, height, rgba32f, 4, err)) {
+    g_error = "rts_write_hdr: " + (path ? err : std::string("null path"));
+    return -1;
+  }
+  return 0;
+}
 
 static Submesh *findSubmesh(rts_scene *s, int mesh, int submesh) {
   if (mesh < 0 || size_t(mesh) >= s->s.meshes.size() || submesh < 0 ||

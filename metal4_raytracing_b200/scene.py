@@ -71,6 +71,7 @@ def lib():
     L.rts_write_png.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
     L.rts_load_hdr.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_float))]
     L.rts_free.argtypes = [C.c_void_p]
+    L.rts_write_hdr.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
     _lib = L
     return L
 
@@ -241,6 +242,14 @@ def load_hdr(path):
         return np.ctypeslib.as_array(p, shape=(h.value, w.value, 4)).copy()
     finally:
         lib().rts_free(p)
+
+
+def write_hdr(path, rgba):
+    """rts_write_hdr: (H, W, 4) float32 as a Radiance RGBE picture."""
+    a = np.ascontiguousarray(rgba, np.float32)
+    assert a.ndim == 3 and a.shape[2] == 4
+    if lib().rts_write_hdr(str(path).encode(), a.ctypes.data, a.shape[1], a.shape[0]) != 0:
+        raise RuntimeError(_err())
 
 
 def default_uniforms(width, height):

@@ -313,6 +313,16 @@ def test_radiance_hdr_reader(tmp_path):
             scene.load_hdr(tmp_path / name)
     with pytest.raises(RuntimeError):
         scene.load_hdr(tmp_path / "absent.hdr")
+    # writer: decode(encode(x)) within 1/128 of the pixel's largest channel; zero and negative values come back as 0
+    img = np.ones((5, 7, 4), np.float32)
+    img[..., :3] = rng.uniform(0, 1, (5, 7, 3)).astype(np.float32) * np.float32(10.0) ** rng.integers(-3, 4, (5, 7, 1))
+    img[0, 0, :3] = 0.0
+    img[0, 1, :3] = [-1.0, 0.5, 0.25]
+    scene.write_hdr(tmp_path / "out.hdr", img)
+    back = scene.load_hdr(tmp_path / "out.hdr")
+    want = np.maximum(img[..., :3], 0)
+    assert back.shape == img.shape and np.array_equal(back[0, 0, :3], [0, 0, 0])
+    assert (np.abs(back[..., :3] - want) <= want.max(-1, keepdims=True) / 128 + 1e-30).all()
 
 
 def test_png_writer_round_trip(tmp_path):
