@@ -29,6 +29,9 @@ int rt_destroy(rt_context *ctx);
 const char *rt_last_error(void);
 /* Use an external CUDA stream (cudaStream_t as void*), e.g. torch's current stream; NULL = the context's own. */
 int rt_set_stream(rt_context *ctx, void *cudaStream);
+/* The stream the context currently enqueues on (cudaStream_t as void*): lets a caller order its own work — an NCCL
+ * collective, a torch op — against the library's without moving the library onto the caller's stream. */
+int rt_get_stream(rt_context *ctx, void **cudaStreamOut);
 /* commitAndWait (Utilities.swift:122-128,240-246) */
 int rt_sync(rt_context *ctx);
 /* CUDA-event timer on the context's stream: begin/end bracket enqueued work; end synchronises. */
@@ -48,8 +51,8 @@ int rt_copy(rt_context *ctx, void *dstDev, const void *srcDev, size_t bytes);   
  * overlaps it. dstHost should be pinned (rt_malloc_host). rt_download_wait blocks until the copy with that ticket —
  * and every earlier one — has landed. Up to 8 copies may be outstanding. */
 /* Stream fences for host-side staging rings (the reference triple-buffers its per-frame host data, Renderer.swift:208-212):
- * rt_fence marks "everything enqueued so far", rt_fence_wait blocks until that point has executed. Up to 16 fences
- * may be outstanding; older ones count as passed. */
+ * rt_fence marks "everything enqueued so far", rt_fence_wait blocks until that point has executed. The ring holds 16
+ * fences; waiting on an older ticket waits for the newer fence that took its slot (never returns early). */
 int rt_fence(rt_context *ctx, uint64_t *ticket);
 int rt_fence_wait(rt_context *ctx, uint64_t ticket);
 int rt_download_async(rt_context *ctx, void *dstHost, const void *srcDev, size_t bytes, uint64_t *ticket);
@@ -64,13 +67,21 @@ int rt_memset(rt_context *ctx, void *dstDev, int value, size_t bytes);
  * rt_blas_refit: refit of a skinned mesh's BLAS in place (Renderer.swift:1084-1202): same topology, boxes and
  * triangle records recomputed from the current vertex buffer contents.
  * rt_tlas_build / rt_tlas_update: instance AS over `count` 72-byte descriptors in DEVICE memory
- * (Renderer.swift:547-606, 937-973); update = rebuild from the descriptors' current contents. */
+ * (Renderer.swift:547-606, 937-973); update = rebuild from the descriptors' current contents.
+ * rt_tlas_refit: the reference's per-frame path when the device supports refitting (Renderer.swift:1084-1202): same
+ * instance count as the last build, tree topology kept, instance records (transforms, BLAS pointers) and every node
+ * box recomputed from the descriptors' current contents. Results never depend on which of the two is used; a tree
+ * refitted over instances that moved far apart just traverses slower until it is rebuilt.
+ * Neither call blocks the host for up to 65,536 instances: hierarchy, wide nodes and parent links of a rebuild come
+ * from a single resident CTA (<= 8 instances: one node, one thread), node counts stay on the device, and a tree too
+ * deep for the traversal stack is reported by the next call on that TLAS instead of being waited for. */
 int rt_blas_build(rt_context *ctx, const rt_triangle_geometry *geoms, uint32_t geometryCount, uint32_t flags,
                   uint64_t *outId);
 int rt_blas_refit(rt_context *ctx, uint64_t id, const rt_triangle_geometry *geoms, uint32_t geometryCount);
 int rt_blas_destroy(rt_context *ctx, uint64_t id);
 int rt_tlas_build(rt_context *ctx, const rt_instance_descriptor *descriptorsDev, uint32_t count, uint64_t *outId);
 int rt_tlas_update(rt_context *ctx, uint64_t id, const rt_instance_descriptor *descriptorsDev, uint32_t count);
+int rt_tlas_refit(rt_context *ctx, uint64_t id, const rt_instance_descriptor *descriptorsDev, uint32_t count);
 int rt_tlas_destroy(rt_context *ctx, uint64_t id);
 
 typedef struct rt_as_info {
@@ -143,7 +154,9 @@ typedef struct rt_trace_options {
   int32_t tileRemainder; /*   tileRemainder (0/1 and 0 = every tile) */
   uint32_t *primaryIdsDev;   /* probe: 4 x u32 per pixel (instance, geometry, primitive, t bits) of sample 0's
                                 first intersect call; 0xFFFFFFFF x4 on a miss. NULL = off */
-  uint64_t *rayCountersDev;  /* probe: 3 x u64 {closest-hit rays, any-hit rays, closest hits}, accumulated */
+  uint64_t *rayCountersDev;  /* probe: 9 x u64, accumulated: {closest-hit rays, any-hit rays, closest hits} and, filled
+                                only by the counter build of the library (-DRT_COUNT_WORK), {node steps, triangle
+                                tests, instance entries} of the closest-hit rays and the same three of the any-hit rays */
   void *const *peerAccumulation; /* multi-GPU: tileModulo device pointers to every rank's destination
                                     accumulation image (same format/size); owned tiles are also stored there
                                     through NVLink peer mappings. NULL = local only */
@@ -156,10 +169,17 @@ typedef struct rt_trace_options {
  * maps were absent. rtr_draw sets the hint by itself from the scene it was given. */
 #define RT_TRACE_HINT_UNTEXTURED 1u
 /* The caller promises that no Material bound in this dispatch takes the glass branch (opacity >= 0.999 and
- * refractionIndex <= 1.01, Raytracing.metal:517-519). A path then has at most maxBounces segments, so the dispatch
- * needs no device->host read-back of the surviving-path count between segments and stays fully asynchronous; a
- * material that breaks the promise has its paths cut after maxBounces segments. rtr_draw sets it from the scene. */
+ * refractionIndex <= 1.01, Raytracing.metal:517-519). A path then has at most maxBounces segments instead of
+ * maxBounces (maxBounces + 1), and the dispatch launches that many segment passes (without the hint the extra passes
+ * are launched too and end at once when their queue is empty — no device->host read-back either way); a material
+ * that breaks the promise has its paths cut after maxBounces segments. rtr_draw sets it from the scene. */
 #define RT_TRACE_HINT_NO_GLASS 2u
+/* Not a promise but a switch: the reference's compile-time ENABLE_AO (ShaderTypes.h:155-157; 0 in the shipping build).
+ * With it a material whose textureFlags has MATERIAL_TEXTURE_AO samples its ambient-occlusion map (x channel) and the
+ * value scales the throughput of the next bounce (Raytracing.metal:405-409,442-446,672,748); debug view 5 shows it
+ * (:475-479). Ignored under RT_TRACE_HINT_UNTEXTURED. rtr_draw passes it when the renderer was created with
+ * RTR_FLAG_ENABLE_AO. */
+#define RT_TRACE_ENABLE_AO 4u
 
 /* rt_trace: raytracingKernel dispatch (Raytracing.metal:220-831; binding block Renderer.swift:1453-1490).
  * buffers[]: 0 Uniforms (HOST pointer; copied into the launch like a `constant` argument), 5 Resource rows (dev),
@@ -224,11 +244,16 @@ int rt_ipc_close(rt_context *ctx, void *importedDev);
 
 /* Number of kernels this library has launched on the context since creation (bench.py's gpu_launches). */
 uint64_t rt_launch_count(rt_context *ctx);
+/* Number of times the library itself blocked the host on the device outside the calls that exist to wait (rt_sync,
+ * rt_download, rt_timer_end, rt_fence_wait, rt_download_wait, rt_kernel_timing_read): build-time read-backs, scratch
+ * growth, pageable uploads. The per-frame paths (rt_skin, rt_blas_refit, rt_tlas_refit / _update, rt_trace) add none. */
+uint64_t rt_host_sync_count(rt_context *ctx);
 /* Select the trace kernel layout: 0 = megakernel, 1 = wavefront (default). */
 int rt_set_trace_mode(rt_context *ctx, int mode);
 /* Tuning knobs that never change results: "trace_mode" (0/1), "traversal_variant" (0..2, traverse.cuh),
  * "blocks_per_sm" (persistent grid size of the wavefront kernels), "sample_batch" (1..64, samples of a pixel the
- * wavefront layout keeps in flight at once; default 16), "ploc_radius" (builder: PLOC neighbour search radius for
+ * wavefront layout keeps in flight at once; default 16), "pipeline_lanes" (1..4, default 2: independent tile subsets
+ * of a dispatch whose kernel sequences run on separate streams so that launch tails overlap), "ploc_radius" (builder: PLOC neighbour search radius for
  * acceleration structures built after the call, default 16; 0 = plain LBVH), "leaf_size" / "tlas_leaf_size" (1..3
  * triangles / instances per leaf slot of a wide node, defaults 3 / 1). */
 int rt_set_option(rt_context *ctx, const char *key, int value);

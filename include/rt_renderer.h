@@ -4,7 +4,7 @@
  * It is the C++ mirror of the hot-path half of the reference's Renderer (MetalRaytracing/Renderer.swift):
  *   rtr_create   = createBuffers (:342-420) + createTextures (:676-799) + createMTL4AccelerationStructures (:464-606)
  *   rtr_update   = updateSkinningAndBLAS (:1280-1326): descriptors cur->prev, skinned cur->prev, skinning
- *                  dispatch, BLAS refit, TLAS rebuild
+ *                  dispatch, BLAS refit, TLAS refit (or rebuild: RTR_FLAG_TLAS_REBUILD; :1084-1202)
  *   rtr_draw     = the binding block + dispatch + accumulation swap of draw(in:) (:1445-1494)
  * It consumes the flat host scene of rt_scene.h and only ever calls the rt_* entry points; the GUI, presenter
  * and MetalFX parts of Renderer.swift are out of scope. Lives in librt_b200.so.
@@ -27,6 +27,11 @@ const char *rtr_last_error(void);
 #define RTR_FLAG_REBUILD_SKINNED 2u /* full BLAS rebuild instead of refit after skinning */
 #define RTR_FLAG_GPU_SKELETON 4u    /* joint palettes evaluated on the device from local TRS (rt_joint_palette) instead of
                                        uploaded from the host scene (SkinningPass.swift:123-157 runs them on the CPU) */
+
+#define RTR_FLAG_ENABLE_AO 8u       /* the reference's compile-time ENABLE_AO (ShaderTypes.h:155-157): materials with
+                                       MATERIAL_TEXTURE_AO sample their ambient-occlusion map (RT_TRACE_ENABLE_AO) */
+#define RTR_FLAG_TLAS_REBUILD 16u   /* rtr_update rebuilds the TLAS from scratch every frame instead of refitting it
+                                       (the reference refits when the device supports it, Renderer.swift:1084-1202) */
 
 int rtr_create(rt_context *ctx, const rt_scene_desc *scene, int width, int height, uint32_t flags,
                rtr_renderer **out);

@@ -34,6 +34,8 @@ TEXTURE_COUNT = 9
 
 LIGHT_SUN, LIGHT_SPOT, LIGHT_POINT, LIGHT_AREA = 1, 2, 3, 4
 SHADING_PBR, SHADING_LEGACY = 0, 1
+# DebugTextureMode (ShaderTypes.h:159-168)
+DEBUG_NONE, DEBUG_BASECOLOR, DEBUG_NORMAL, DEBUG_ROUGHNESS, DEBUG_METALLIC, DEBUG_AO, DEBUG_EMISSION, DEBUG_MOTION = range(8)
 
 FORMAT_NONE = 0
 FORMAT_R32_UINT = 1

@@ -455,13 +455,11 @@ struct CollapseCounters {
   uint32_t primCount; // next free leaf-primitive slot
 };
 
-// One thread per wide node of the current level. queueIn[i] = BVH2 reference of wide node levelStart + i.
-__global__ void k_collapse_level(Bvh2 t, const float4 *primLo, const float4 *primHi, const uint32_t *sorted,
-                                 const uint32_t *queueIn, uint32_t *queueOut, uint32_t levelStart,
-                                 uint32_t levelCount, uint32_t nextLevelStart, CollapseCounters *counters,
-                                 WideNode *nodes, float4 *nodeBox, uint32_t *leafPrim, uint32_t maxLeafPrims) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= levelCount) return;
+// Wide node levelStart + i of the current level. queueIn[i] = BVH2 reference of that node.
+__device__ void collapseOne(uint32_t i, const Bvh2 &t, const float4 *primLo, const float4 *primHi, const uint32_t *sorted,
+                            const uint32_t *queueIn, uint32_t *queueOut, uint32_t levelStart, uint32_t nextLevelStart,
+                            CollapseCounters *counters, WideNode *nodes, float4 *nodeBox, uint32_t *leafPrim,
+                            uint32_t maxLeafPrims) {
   const uint32_t self = queueIn[i];
   auto boxOf = [&](uint32_t ref, float lo[3], float hi[3]) {
     float4 l, h;
@@ -609,6 +607,17 @@ __global__ void k_collapse_level(Bvh2 t, const float4 *primLo, const float4 *pri
   nodeBox[2 * idx + 1] = make_float4(nhi[0], nhi[1], nhi[2], 0.0f);
 }
 
+// One thread per wide node of the current level (BLAS builds, and TLAS builds too large for the one-CTA builder).
+__global__ void k_collapse_level(Bvh2 t, const float4 *primLo, const float4 *primHi, const uint32_t *sorted,
+                                 const uint32_t *queueIn, uint32_t *queueOut, uint32_t levelStart,
+                                 uint32_t levelCount, uint32_t nextLevelStart, CollapseCounters *counters,
+                                 WideNode *nodes, float4 *nodeBox, uint32_t *leafPrim, uint32_t maxLeafPrims) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= levelCount) return;
+  collapseOne(i, t, primLo, primHi, sorted, queueIn, queueOut, levelStart, nextLevelStart, counters, nodes, nodeBox,
+              leafPrim, maxLeafPrims);
+}
+
 // BLAS leaves: write 48-byte triangle records in leaf order + remember where each came from (for refits).
 __global__ void k_emit_triangles(const GeomEntry *geoms, uint32_t geomCount, const uint32_t *leafPrim, uint32_t n,
                                  TriRecord *tris, uint2 *triSource) {
@@ -649,10 +658,39 @@ __global__ void k_refresh_triangles(const GeomEntry *geoms, uint32_t n, const ui
   tris[i] = r;
 }
 
-// Refit of one wide node: recompute child boxes (triangles, or child nodes that are already refitted), the exact node
-// box and the quantised boxes. Topology words (w1, imask) are untouched. Child node boxes are read with ld.cg: they
-// were written by other threads of the same launch.
-__device__ void refitNode(WideNode *nodes, float4 *nodeBox, const TriRecord *tris, uint32_t idx) {
+// Refit of one wide node: recompute child boxes (leaf primitives, or child nodes that are already refitted), the exact
+// node box and the quantised boxes. Topology words (w1, imask) are untouched. Child node boxes are read with ld.cg: they
+// were written by other threads of the same launch. Leaf primitives are triangles (BLAS: `tris`) or instances (TLAS:
+// the world boxes k_instance_bounds just wrote, through the leaf -> instance table).
+struct TriangleLeaves {
+  const TriRecord *tris;
+  __device__ void grow(uint32_t slot, float lo[3], float hi[3]) const {
+    const TriRecord tr = tris[slot];
+    const float v[3][3] = {{tr.v0.x, tr.v0.y, tr.v0.z}, {tr.v1.x, tr.v1.y, tr.v1.z}, {tr.v2.x, tr.v2.y, tr.v2.z}};
+    bool finite = true; // a non-finite triangle cannot be hit and must not blow up the box (see k_triangle_bounds)
+    for (int q = 0; q < 3; ++q)
+      for (int a = 0; a < 3; ++a) finite = finite && fabsf(v[q][a]) < 1.0e30f;
+    if (!finite) return;
+    for (int q = 0; q < 3; ++q)
+      for (int a = 0; a < 3; ++a) {
+        lo[a] = fminf(lo[a], v[q][a]);
+        hi[a] = fmaxf(hi[a], v[q][a]);
+      }
+  }
+};
+struct InstanceLeaves {
+  const float4 *primLo, *primHi;
+  const uint32_t *leafPrim;
+  __device__ void grow(uint32_t slot, float lo[3], float hi[3]) const {
+    const uint32_t p = leafPrim[slot];
+    const float4 l = primLo[p], h = primHi[p];
+    lo[0] = fminf(lo[0], l.x), lo[1] = fminf(lo[1], l.y), lo[2] = fminf(lo[2], l.z);
+    hi[0] = fmaxf(hi[0], h.x), hi[1] = fmaxf(hi[1], h.y), hi[2] = fmaxf(hi[2], h.z);
+  }
+};
+
+template <typename Leaves>
+__device__ void refitNode(WideNode *nodes, float4 *nodeBox, const Leaves &leaves, uint32_t idx) {
   WideNode node = nodes[idx];
   uint8_t imask = uint8_t(node.w[0].w >> 24);
   uint32_t childBase = node.w[1].x, primBase = node.w[1].y;
@@ -673,19 +711,7 @@ __device__ void refitNode(WideNode *nodes, float4 *nodeBox, const TriRecord *tri
       uint32_t cnt = (m >> 5) == 1 ? 1 : ((m >> 5) == 3 ? 2 : 3);
       uint32_t first = primBase + (m & 31u);
       for (int a = 0; a < 3; ++a) cb[s].lo[a] = FLT_MAX, cb[s].hi[a] = -FLT_MAX;
-      for (uint32_t k = 0; k < cnt; ++k) {
-        TriRecord tr = tris[first + k];
-        float v[3][3] = {{tr.v0.x, tr.v0.y, tr.v0.z}, {tr.v1.x, tr.v1.y, tr.v1.z}, {tr.v2.x, tr.v2.y, tr.v2.z}};
-        bool finite = true; // a non-finite triangle cannot be hit and must not blow up the box (see k_triangle_bounds)
-        for (int q = 0; q < 3; ++q)
-          for (int a = 0; a < 3; ++a) finite = finite && fabsf(v[q][a]) < 1.0e30f;
-        if (!finite) continue;
-        for (int q = 0; q < 3; ++q)
-          for (int a = 0; a < 3; ++a) {
-            cb[s].lo[a] = fminf(cb[s].lo[a], v[q][a]);
-            cb[s].hi[a] = fmaxf(cb[s].hi[a], v[q][a]);
-          }
-      }
+      for (uint32_t k = 0; k < cnt; ++k) leaves.grow(first + k, cb[s].lo, cb[s].hi);
     }
     if (cb[s].lo[0] > cb[s].hi[0]) // only non-finite triangles in this slot: an empty box at the origin
       for (int a = 0; a < 3; ++a) cb[s].lo[a] = cb[s].hi[a] = 0.0f;
@@ -720,8 +746,9 @@ __global__ void k_refit_bottom_up(WideNode *nodes, float4 *nodeBox, const TriRec
                                   const uint32_t *parent, uint32_t *pending) {
   uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
   if (node >= nodeCount || (nodes[node].w[0].w >> 24) != 0u) return;
+  const TriangleLeaves leaves{tris};
   while (true) {
-    refitNode(nodes, nodeBox, tris, node);
+    refitNode(nodes, nodeBox, leaves, node);
     __threadfence();
     const uint32_t p = parent[node];
     if (p == 0xFFFFFFFFu) return;
@@ -780,6 +807,189 @@ __global__ void k_tlas_small(const float4 *primLo, const float4 *primHi, uint32_
   nodes[0] = node;
   nodeBox[0] = make_float4(nlo[0], nlo[1], nlo[2], 0.0f);
   nodeBox[1] = make_float4(nhi[0], nhi[1], nhi[2], 0.0f);
+}
+
+// ---- TLAS built by one CTA, no host round trips ---------------------------------------------------------------
+// The general builder above reads a counter back after every PLOC round and every collapse level (fine for a BLAS,
+// which is built once); a TLAS is updated every frame (Renderer.swift:937-973,1084-1202), so for up to kTlasCtaMax
+// instances the hierarchy (PLOC over the Morton-sorted instance boxes), its collapse into wide nodes and the parent
+// links a later refit needs are produced by a single 1024-thread CTA that iterates on the device: rounds and levels
+// are separated by __syncthreads() instead of launches. 4096 instances take ~25 rounds of 128 box pairs per thread.
+constexpr uint32_t kTlasCtaMax = 1u << 16;
+constexpr int kTlasCtaThreads = 1024;
+constexpr uint32_t kMaxTlasLevels = 20, kMaxBlasLevels = 24; // + 2 for an instance entry must fit kStackSize = 48 (traverse.cuh)
+
+// inclusive scan of one 64-bit value per thread over the CTA (warp shuffles + one shared array); every thread calls it
+__device__ unsigned long long blockInclusiveScan(unsigned long long v, unsigned long long *warpTotals, unsigned long long &total) {
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long up = __shfl_up_sync(full, v, o);
+    if (lane >= o) v += up;
+  }
+  if (lane == 31) warpTotals[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = lane < warps ? warpTotals[lane] : 0ull;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long up = __shfl_up_sync(full, w, o);
+      if (lane >= o) w += up;
+    }
+    warpTotals[lane] = w; // inclusive totals of warps 0..lane
+  }
+  __syncthreads();
+  if (warp > 0) v += warpTotals[warp - 1];
+  total = warpTotals[warps - 1];
+  __syncthreads(); // warpTotals may be reused by the next call
+  return v;
+}
+
+__global__ void __launch_bounds__(kTlasCtaThreads) k_tlas_build_cta(uint32_t n, const float4 *primLo, const float4 *primHi,
+                                                                     const uint32_t *sorted, Bvh2 t, PlocClusters ca,
+                                                                     PlocClusters cb, uint32_t *nearest, int radius,
+                                                                     uint32_t *queueA, uint32_t *queueB,
+                                                                     CollapseCounters *counters, WideNode *nodes,
+                                                                     float4 *nodeBox, uint32_t *leafPrim,
+                                                                     uint32_t maxLeafPrims, uint32_t *parent,
+                                                                     TlasBuildInfo *info) {
+  __shared__ unsigned long long s_warpTotals[32];
+  const uint32_t tid = threadIdx.x, T = blockDim.x;
+  // PLOC (same rounds as k_ploc_nearest / k_ploc_flags / scan / k_ploc_merge, hence the same tree)
+  for (uint32_t i = tid; i < n; i += T) {
+    const uint32_t p = sorted[i];
+    ca.ref[i] = i | kLeafBit;
+    ca.lo[i] = primLo[p];
+    ca.hi[i] = primHi[p];
+  }
+  __syncthreads();
+  uint32_t count = n, nodeBase = 0;
+  PlocClusters cur = ca, nxt = cb;
+  while (count > 1) {
+    for (uint32_t i = tid; i < count; i += T) {
+      const float4 lo = cur.lo[i], hi = cur.hi[i];
+      const int first = max(0, int(i) - radius), last = min(int(count) - 1, int(i) + radius);
+      float best = FLT_MAX;
+      uint32_t bestJ = i;
+      for (int j = first; j <= last; ++j) {
+        if (j == int(i)) continue;
+        const float4 l = cur.lo[j], h = cur.hi[j];
+        const float dx = fmaxf(hi.x, h.x) - fminf(lo.x, l.x), dy = fmaxf(hi.y, h.y) - fminf(lo.y, l.y),
+                    dz = fmaxf(hi.z, h.z) - fminf(lo.z, l.z);
+        const float area = dx * dy + dy * dz + dz * dx;
+        if (area < best) {
+          best = area;
+          bestJ = uint32_t(j);
+        }
+      }
+      nearest[i] = bestJ;
+    }
+    __syncthreads();
+    unsigned long long carry = 0ull; // survivors (low word) and merges (high word) of the tiles before this one
+    for (uint32_t base = 0; base < count; base += T) {
+      const uint32_t i = base + tid;
+      bool mutual = false;
+      uint32_t j = i;
+      unsigned long long flag = 0ull;
+      if (i < count) {
+        j = nearest[i];
+        mutual = j != i && nearest[j] == i;
+        const bool merges = mutual && i < j, dies = mutual && i > j;
+        flag = (dies ? 0ull : 1ull) | (merges ? (1ull << 32) : 0ull);
+      }
+      unsigned long long tileTotal;
+      const unsigned long long inc = carry + blockInclusiveScan(flag, s_warpTotals, tileTotal);
+      carry += tileTotal;
+      if (i < count && !(mutual && i > j)) {
+        const uint32_t pos = uint32_t(inc & 0xFFFFFFFFull) - 1u;
+        float4 lo = cur.lo[i], hi = cur.hi[i];
+        uint32_t ref = cur.ref[i];
+        if (mutual) {
+          const uint32_t node = nodeBase + uint32_t(inc >> 32) - 1u;
+          const float4 l = cur.lo[j], h = cur.hi[j];
+          const uint32_t rj = cur.ref[j];
+          lo = make_float4(fminf(lo.x, l.x), fminf(lo.y, l.y), fminf(lo.z, l.z), 0.0f);
+          hi = make_float4(fmaxf(hi.x, h.x), fmaxf(hi.y, h.y), fmaxf(hi.z, h.z), 0.0f);
+          t.left[node] = ref;
+          t.right[node] = rj;
+          t.lo[node] = lo;
+          t.hi[node] = hi;
+          t.count[node] = ((ref & kLeafBit) ? 1u : t.count[ref]) + ((rj & kLeafBit) ? 1u : t.count[rj]);
+          ref = node;
+        }
+        nxt.ref[pos] = ref;
+        nxt.lo[pos] = lo;
+        nxt.hi[pos] = hi;
+      }
+    }
+    __syncthreads();
+    const uint32_t survivors = uint32_t(carry & 0xFFFFFFFFull), merges = uint32_t(carry >> 32);
+    if (merges == 0u) break; // cannot happen (the globally closest pair is always mutual); never spin
+    nodeBase += merges;
+    count = survivors;
+    const PlocClusters tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  // collapse, one level per trip
+  if (tid == 0) {
+    counters->nodeCount = 1u;
+    counters->primCount = 0u;
+    queueA[0] = n > 1 ? n - 2 : kLeafBit; // the last node PLOC created is the root
+  }
+  __syncthreads();
+  uint32_t levelStart = 0, levelCount = 1, levels = 0;
+  uint32_t *qin = queueA, *qout = queueB;
+  while (levelCount) {
+    const uint32_t nextStart = levelStart + levelCount;
+    for (uint32_t i = tid; i < levelCount; i += T)
+      collapseOne(i, t, primLo, primHi, sorted, qin, qout, levelStart, nextStart, counters, nodes, nodeBox, leafPrim,
+                  maxLeafPrims);
+    __syncthreads();
+    const uint32_t now = *reinterpret_cast<volatile uint32_t *>(&counters->nodeCount);
+    __syncthreads();
+    levelStart = nextStart;
+    levelCount = now - nextStart;
+    ++levels;
+    uint32_t *tmp = qin;
+    qin = qout;
+    qout = tmp;
+  }
+  const uint32_t nodeCount = levelStart;
+  // parent links for refits
+  for (uint32_t i = tid; i < nodeCount; i += T) {
+    if (i == 0) parent[0] = 0xFFFFFFFFu;
+    const uint32_t internal = uint32_t(__popc(nodes[i].w[0].w >> 24)), childBase = nodes[i].w[1].x;
+    for (uint32_t k = 0; k < internal; ++k) parent[childBase + k] = i;
+  }
+  if (tid == 0) {
+    info->nodeCount = nodeCount;
+    info->levelCount = levels;
+    info->status = levels > kMaxTlasLevels ? 1u : 0u;
+    info->builds += 1u;
+  }
+}
+
+// TLAS refit (Renderer.swift:1084-1202 refits the instance AS when the device supports it): topology, leaf order and
+// node count stay; instance records and world boxes come fresh from the descriptors (k_instance_bounds), node boxes are
+// recomputed bottom-up exactly like a BLAS refit. The node count lives on the device (TlasBuildInfo).
+__global__ void k_tlas_refit_pending(const WideNode *nodes, const TlasBuildInfo *info, uint32_t *pending) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < info->nodeCount) pending[i] = uint32_t(__popc(nodes[i].w[0].w >> 24));
+}
+__global__ void k_tlas_refit_bottom_up(WideNode *nodes, float4 *nodeBox, const float4 *primLo, const float4 *primHi,
+                                       const uint32_t *leafPrim, const TlasBuildInfo *info, const uint32_t *parent,
+                                       uint32_t *pending) {
+  uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= info->nodeCount || (nodes[node].w[0].w >> 24) != 0u) return;
+  const InstanceLeaves leaves{primLo, primHi, leafPrim};
+  while (true) {
+    refitNode(nodes, nodeBox, leaves, node);
+    __threadfence();
+    const uint32_t p = parent[node];
+    if (p == 0xFFFFFFFFu) return;
+    if (atomicSub(pending + p, 1u) != 1u) return;
+    node = p;
+  }
 }
 
 struct Bump {
@@ -854,7 +1064,7 @@ static int buildWideTree(rt_context *ctx, AccelObject *as, uint32_t n, const flo
       ctx->launches += 5;
       unsigned long long totals = 0;
       RT_CUDA(cudaMemcpyAsync(&totals, scan + (count - 1), sizeof totals, cudaMemcpyDeviceToHost, st));
-      RT_CUDA(cudaStreamSynchronize(st));
+      RT_CUDA(RT_SYNC_STREAM(ctx, st));
       const uint32_t survivors = uint32_t(totals & 0xFFFFFFFFull), merges = uint32_t(totals >> 32);
       RT_CHECK(merges > 0 && survivors == count - merges, "internal: PLOC round made no progress");
       nodeBase += merges;
@@ -875,7 +1085,7 @@ static int buildWideTree(rt_context *ctx, AccelObject *as, uint32_t n, const flo
   CollapseCounters init{1u, 0u};
   RT_CUDA(cudaMemcpyAsync(counters, &init, sizeof init, cudaMemcpyHostToDevice, st));
   RT_CUDA(cudaMemcpyAsync(queueA, &rootRef, 4, cudaMemcpyHostToDevice, st));
-  RT_CUDA(cudaStreamSynchronize(st)); // rootRef / init are stack variables
+  RT_CUDA(RT_SYNC_STREAM(ctx, st)); // rootRef / init are stack variables
   as->levelStart.clear();
   uint32_t levelStart = 0, levelCount = 1;
   uint32_t *qin = queueA, *qout = queueB;
@@ -890,7 +1100,7 @@ static int buildWideTree(rt_context *ctx, AccelObject *as, uint32_t n, const flo
     ++ctx->launches;
     CollapseCounters now;
     RT_CUDA(cudaMemcpyAsync(&now, counters, sizeof now, cudaMemcpyDeviceToHost, st));
-    RT_CUDA(cudaStreamSynchronize(st));
+    RT_CUDA(RT_SYNC_STREAM(ctx, st));
     levelStart = nextStart;
     levelCount = now.nodeCount - nextStart;
     std::swap(qin, qout);
@@ -924,7 +1134,7 @@ static int uploadGeomTable(rt_context *ctx, AccelObject *as, const rt_triangle_g
     as->geomCount = n;
   }
   if (n) RT_CUDA(cudaMemcpyAsync(as->geomTableDev, table.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
-  RT_CUDA(cudaStreamSynchronize(ctx->stream)); // `table` is a stack-lifetime staging buffer
+  RT_CUDA(RT_SYNC_STREAM(ctx, ctx->stream)); // `table` is a stack-lifetime staging buffer
   as->geomTableHost.assign(reinterpret_cast<const uint8_t *>(table.data()), reinterpret_cast<const uint8_t *>(table.data()) + bytes);
   return 0;
 }
@@ -938,7 +1148,7 @@ static int shrinkNodes(rt_context *ctx, AccelObject *as) {
   RT_CUDA(cudaMalloc(&boxes, size_t(cap) * 2 * sizeof(float4)));
   RT_CUDA(cudaMemcpyAsync(nodes, as->nodes, size_t(cap) * sizeof(WideNode), cudaMemcpyDeviceToDevice, ctx->stream));
   RT_CUDA(cudaMemcpyAsync(boxes, as->nodeBox, size_t(cap) * 2 * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
-  RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  RT_CUDA(RT_SYNC_STREAM(ctx, ctx->stream));
   cudaFree(as->nodes);
   cudaFree(as->nodeBox);
   as->nodes = nodes;
@@ -954,7 +1164,7 @@ static int finishInfo(rt_context *ctx, AccelObject *as) {
   if (as->nodeCount) {
     RT_CUDA(cudaMemcpyAsync(boxes.data(), as->nodeBox, boxes.size() * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(cudaMemcpyAsync(nodes.data(), as->nodes, nodes.size() * sizeof(WideNode), cudaMemcpyDeviceToHost, ctx->stream));
-    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    RT_CUDA(RT_SYNC_STREAM(ctx, ctx->stream));
   }
   auto area = [&](uint32_t i) {
     float dx = boxes[2 * i + 1].x - boxes[2 * i].x, dy = boxes[2 * i + 1].y - boxes[2 * i].y,
@@ -1033,10 +1243,25 @@ int buildBlas(rt_context *ctx, const rt_triangle_geometry *geoms, uint32_t geomC
   k_init_bounds<<<1, 32, 0, st>>>(bounds);
   k_triangle_bounds<<<gridFor(n, 256), 256, 0, st>>>(table, geomCount, n, primLo, primHi, bounds);
   ctx->launches += 2;
-  RT_TRYF(buildWideTree(ctx, as, n, primLo, primHi, bounds, bump, leafPrim, ctx->plocRadius));
+  {
+    // the traversal stack (traverse.cuh kStackSize) holds TLAS levels + 2 + BLAS levels entries: a hierarchy deeper than
+    // kMaxBlasLevels wide levels (PLOC can chain on adversarial input) is rebuilt as a plain LBVH, whose depth is bounded
+    // by the Morton key length; failing that the build is refused instead of dropping subtrees during traversal
+    const Bump saved = bump;
+    RT_TRYF(buildWideTree(ctx, as, n, primLo, primHi, bounds, bump, leafPrim, ctx->plocRadius));
+    if (as->levelStart.size() - 1 > kMaxBlasLevels && ctx->plocRadius > 0) {
+      bump = saved;
+      RT_TRYF(buildWideTree(ctx, as, n, primLo, primHi, bounds, bump, leafPrim, 0));
+    }
+    if (as->levelStart.size() - 1 > kMaxBlasLevels) {
+      setError("rt_blas_build: hierarchy is " + std::to_string(as->levelStart.size() - 1) + " levels deep; the traversal stack holds " +
+               std::to_string(kMaxBlasLevels));
+      return fail(2);
+    }
+  }
   k_emit_triangles<<<gridFor(n, 256), 256, 0, st>>>(table, geomCount, leafPrim, n, as->tris, as->triSource);
   ++ctx->launches;
-  RT_CUDAF(cudaStreamSynchronize(st));
+  RT_CUDAF(RT_SYNC_STREAM(ctx, st));
   RT_TRYF(shrinkNodes(ctx, as));
   k_write_blas_header<<<1, 32, 0, st>>>(static_cast<BlasHeader *>(as->headerDev), as->nodes, as->tris, as->nodeBox, n,
                                         as->nodeCount);
@@ -1084,26 +1309,64 @@ int refitBlas(rt_context *ctx, AccelObject *as, const rt_triangle_geometry *geom
   return 0;
 }
 
-int buildTlas(rt_context *ctx, AccelObject *as, const rt_instance_descriptor *descDev, uint32_t count) {
+// Looks at the result of the last device-side TLAS build once its copy has landed (wait = block for it). A tree deeper
+// than the traversal stack allows is an error reported here — one library call after the build, never silently.
+int checkTlasInfo(rt_context *ctx, AccelObject *as, bool wait) {
+  if (!as->infoPending) return 0;
+  if (wait) {
+    RT_CUDA(RT_SYNC_EVENT(ctx, as->infoEvent));
+  } else {
+    const cudaError_t q = cudaEventQuery(as->infoEvent);
+    if (q == cudaErrorNotReady) return 0;
+    RT_CUDA(q);
+  }
+  as->infoPending = false;
+  as->nodeCount = as->infoHost->nodeCount;
+  RT_CHECK(as->infoHost->status == 0u,
+           "TLAS is " + std::to_string(as->infoHost->levelCount) + " levels deep; the traversal stack holds " +
+               std::to_string(kMaxTlasLevels) + " (rebuild it after rt_set_option(ctx, \"ploc_radius\", 0))");
+  return 0;
+}
+
+// refit = true: keep the topology of the last build (rt_tlas_refit). The per-frame paths — refit, the one-node TLAS of
+// small scenes, the one-CTA build — enqueue kernels only: no device->host read-back, no synchronisation.
+int buildTlas(rt_context *ctx, AccelObject *as, const rt_instance_descriptor *descDev, uint32_t count, bool refit) {
   cudaStream_t st = ctx->stream;
   as->isTlas = true;
+  RT_TRY(checkTlasInfo(ctx, as, false));
   if (!as->headerDev) RT_CUDA(cudaMalloc(&as->headerDev, sizeof(TlasHeader)));
+  if (!as->infoDev) {
+    RT_CUDA(cudaMalloc(&as->infoDev, sizeof(TlasBuildInfo)));
+    RT_CUDA(cudaMemsetAsync(as->infoDev, 0, sizeof(TlasBuildInfo), st));
+    RT_CUDA(cudaMallocHost(&as->infoHost, sizeof(TlasBuildInfo)));
+    std::memset(as->infoHost, 0, sizeof(TlasBuildInfo));
+    RT_CUDA(cudaEventCreateWithFlags(&as->infoEvent, cudaEventDisableTiming));
+  }
   if (count > as->primCapacity) {
+    if (as->primCapacity) RT_CUDA(RT_SYNC_STREAM(ctx, st)); // the old arrays may still be in use
     if (as->instances) cudaFree(as->instances);
     if (as->leafPrim) cudaFree(as->leafPrim);
     if (as->nodes) cudaFree(as->nodes);
     if (as->nodeBox) cudaFree(as->nodeBox);
+    if (as->nodeParent) cudaFree(as->nodeParent);
+    if (as->nodePending) cudaFree(as->nodePending);
     as->instances = nullptr, as->leafPrim = nullptr, as->nodes = nullptr, as->nodeBox = nullptr;
+    as->nodeParent = nullptr, as->nodePending = nullptr;
     RT_CUDA(cudaMalloc(&as->instances, size_t(count) * sizeof(InstanceRecord)));
     RT_CUDA(cudaMalloc(&as->leafPrim, size_t(count) * sizeof(uint32_t)));
     RT_CUDA(cudaMalloc(&as->nodes, size_t(count) * sizeof(WideNode)));
     RT_CUDA(cudaMalloc(&as->nodeBox, size_t(count) * 2 * sizeof(float4)));
+    RT_CUDA(cudaMalloc(&as->nodeParent, size_t(count) * sizeof(uint32_t)));
+    RT_CUDA(cudaMalloc(&as->nodePending, size_t(count) * sizeof(uint32_t)));
     as->primCapacity = count;
     as->nodeCapacity = count;
+    as->treeValid = false;
   }
+  if (count != as->primCount) as->treeValid = false;
   as->primCount = count;
   if (count == 0) {
     as->nodeCount = 0;
+    as->deviceBuilt = false;
     k_write_tlas_header<<<1, 32, 0, st>>>(static_cast<TlasHeader *>(as->headerDev), nullptr, nullptr, nullptr, 0, 0);
     ++ctx->launches;
     return 0;
@@ -1119,20 +1382,79 @@ int buildTlas(rt_context *ctx, AccelObject *as, const rt_instance_descriptor *de
   k_init_bounds<<<1, 32, 0, st>>>(bounds);
   k_instance_bounds<<<gridFor(count, 128), 128, 0, st>>>(descDev, count, as->instances, primLo, primHi, bounds);
   ctx->launches += 2;
-  if (count <= 8) {
+  if (count <= 8) { // one wide node written by one thread: build and refit are the same thing
     k_tlas_small<<<1, 32, 0, st>>>(primLo, primHi, count, as->nodes, as->nodeBox, as->leafPrim);
     ++ctx->launches;
     as->levelStart = {0u, 1u};
     as->nodeCount = 1;
+    as->deviceBuilt = false;
+  } else if (refit && as->treeValid) {
+    // nodes without internal children start, whoever delivers a node's last child refits it (as for a BLAS); the
+    // grids cover the node capacity because the node count of a device-side build is only known on the device
+    TlasBuildInfo *info = as->infoDev;
+    if (!as->deviceBuilt) { // host-driven build: publish its node count where the kernels look for it
+      const TlasBuildInfo known{as->nodeCount, uint32_t(as->levelStart.size() ? as->levelStart.size() - 1 : 0), 0u, 0u};
+      *as->infoHost = known;
+      RT_CUDA(cudaMemcpyAsync(info, as->infoHost, sizeof known, cudaMemcpyHostToDevice, st));
+    }
+    const uint32_t cap = as->deviceBuilt ? as->nodeCapacity : as->nodeCount;
+    k_tlas_refit_pending<<<gridFor(cap, 256), 256, 0, st>>>(as->nodes, info, as->nodePending);
+    k_tlas_refit_bottom_up<<<gridFor(cap, 128), 128, 0, st>>>(as->nodes, as->nodeBox, primLo, primHi, as->leafPrim, info,
+                                                            as->nodeParent, as->nodePending);
+    ctx->launches += 2;
+    RT_CUDA(cudaGetLastError());
+    return 0; // header unchanged: same arrays, same counts
+  } else if (count <= kTlasCtaMax) {
+    // sort by Morton code, then the whole tree in one CTA (k_tlas_build_cta)
+    const uint32_t B = 256;
+    uint64_t *keysA = bump.take<uint64_t>(count), *keysB = bump.take<uint64_t>(count);
+    uint32_t *valsA = bump.take<uint32_t>(count), *valsB = bump.take<uint32_t>(count);
+    k_morton<<<gridFor(count, B), B, 0, st>>>(primLo, primHi, count, bounds, keysA, valsA);
+    void *cubTemp = bump.take<uint8_t>(cubBytes);
+    RT_CUDA(cub::DeviceRadixSort::SortPairs(cubTemp, cubBytes, keysA, keysB, valsA, valsB, int(count), 0, 63, st));
+    ctx->launches += 5;
+    Bvh2 t{};
+    t.n = count;
+    const uint32_t ni = count - 1;
+    t.left = bump.take<uint32_t>(ni);
+    t.right = bump.take<uint32_t>(ni);
+    t.parent = nullptr; // Karras only
+    t.lo = bump.take<float4>(ni);
+    t.hi = bump.take<float4>(ni);
+    t.count = bump.take<uint32_t>(ni);
+    t.flag = nullptr;
+    PlocClusters ca{bump.take<uint32_t>(count), bump.take<float4>(count), bump.take<float4>(count)};
+    PlocClusters cb{bump.take<uint32_t>(count), bump.take<float4>(count), bump.take<float4>(count)};
+    uint32_t *nearest = bump.take<uint32_t>(count);
+    uint32_t *queueA = bump.take<uint32_t>(count), *queueB = bump.take<uint32_t>(count);
+    CollapseCounters *counters = bump.take<CollapseCounters>(1);
+    RT_CHECK(bump.offset <= bump.capacity, "internal: build scratch overflow (TLAS)");
+    const int radius = std::max(1, ctx->plocRadius > 0 ? ctx->plocRadius : 8);
+    k_tlas_build_cta<<<1, kTlasCtaThreads, 0, st>>>(count, primLo, primHi, valsB, t, ca, cb, nearest, radius, queueA, queueB,
+                                                    counters, as->nodes, as->nodeBox, as->leafPrim,
+                                                    uint32_t(std::min(std::max(ctx->tlasLeafSize, 1), kMaxLeafPrims)),
+                                                    as->nodeParent, as->infoDev);
+    ++ctx->launches;
+    RT_CUDA(cudaMemcpyAsync(as->infoHost, as->infoDev, sizeof(TlasBuildInfo), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaEventRecord(as->infoEvent, st));
+    as->infoPending = true;
+    as->deviceBuilt = true;
+    as->levelStart.clear();
+    as->nodeCount = 1; // a lower bound until the info arrives; the traversal only needs "not empty"
   } else {
-    // the TLAS is rebuilt every frame: PLOC only when there are enough instances for tree quality to matter
-    RT_TRY(buildWideTree(ctx, as, count, primLo, primHi, bounds, bump, as->leafPrim, count >= 64 ? ctx->plocRadius : 0));
+    // beyond the one-CTA builder: the general builder, which reads counters back between rounds and levels
+    RT_TRY(buildWideTree(ctx, as, count, primLo, primHi, bounds, bump, as->leafPrim, ctx->plocRadius));
+    RT_CHECK(as->levelStart.size() - 1 <= kMaxTlasLevels, "TLAS too deep for the traversal stack");
+    k_node_parents<<<gridFor(as->nodeCount, 256), 256, 0, st>>>(as->nodes, as->nodeCount, as->nodeParent);
+    ++ctx->launches;
+    as->deviceBuilt = false;
   }
+  as->treeValid = true;
   k_write_tlas_header<<<1, 32, 0, st>>>(static_cast<TlasHeader *>(as->headerDev), as->nodes, as->instances,
                                         as->leafPrim, count, as->nodeCount);
   ++ctx->launches;
   RT_CUDA(cudaGetLastError());
-  as->bytes = sizeof(TlasHeader) + size_t(as->primCapacity) * (sizeof(InstanceRecord) + 4 + sizeof(WideNode) + 32);
+  as->bytes = sizeof(TlasHeader) + size_t(as->primCapacity) * (sizeof(InstanceRecord) + 4 + sizeof(WideNode) + 32 + 8);
   return 0;
 }
 
@@ -1148,6 +1470,9 @@ void destroyAccel(AccelObject *as) {
   cudaFree(as->geomTableDev);
   cudaFree(as->nodeParent);
   cudaFree(as->nodePending);
+  cudaFree(as->infoDev);
+  if (as->infoHost) cudaFreeHost(as->infoHost);
+  if (as->infoEvent) cudaEventDestroy(as->infoEvent);
   delete as;
 }
 

@@ -25,6 +25,9 @@ void setError(const std::string &msg);
       return 1;                                                                                                \
     }                                                                                                          \
   } while (0)
+// every blocking wait of the library goes through these, so tests can assert that a per-frame path has none
+#define RT_SYNC_STREAM(ctx, s) (++(ctx)->hostSyncs, cudaStreamSynchronize(s))
+#define RT_SYNC_EVENT(ctx, e) (++(ctx)->hostSyncs, cudaEventSynchronize(e))
 #define RT_CHECK(cond, msg)          \
   do {                               \
     if (!(cond)) {                   \
@@ -86,6 +89,13 @@ struct TlasHeader {
   uint32_t nodeCount;
 };
 
+// Result of a device-side TLAS build (bvh_build.cu k_tlas_build_cta): lives in device memory, is copied to pinned host
+// memory after every build without waiting, and is looked at one library call later (status != 0 = tree too deep for
+// the traversal stack: reported as an error then, never silently).
+struct TlasBuildInfo {
+  uint32_t nodeCount, levelCount, status, builds;
+};
+
 struct Aabb {
   float lo[3], hi[3];
 };
@@ -106,7 +116,13 @@ struct AccelObject {
   InstanceRecord *instances = nullptr; // TLAS (in descriptor order)
   uint32_t *leafPrim = nullptr; // TLAS: leaf slot -> instance index (the node's primBase + offset indexes this)
   uint2 *triSource = nullptr;   // BLAS: per triangle slot (geometry, primitive) — refit source mapping
-  uint32_t *nodeParent = nullptr, *nodePending = nullptr; // refittable BLAS: parent links, per-refit child counters
+  uint32_t *nodeParent = nullptr, *nodePending = nullptr; // refittable BLAS / TLAS: parent links, per-refit child counters
+  // TLAS built on the device (no host round trip): node / level counts live there
+  TlasBuildInfo *infoDev = nullptr, *infoHost = nullptr; // infoHost: pinned
+  cudaEvent_t infoEvent = nullptr;                        // the copy of infoDev into infoHost has landed
+  bool infoPending = false;                               // a build's info has not been checked yet
+  bool deviceBuilt = false;                               // the current tree came from k_tlas_build_cta
+  bool treeValid = false;                                 // a tree over primCount instances exists (refit possible)
   // geometry table for refit: device copy of per-geometry (vertex ptr, stride, index ptr, index stride)
   void *geomTableDev = nullptr;
   std::vector<uint8_t> geomTableHost; // what geomTableDev holds: a refit with the same buffers uploads nothing
@@ -121,12 +137,19 @@ struct AccelObject {
 namespace rtb {
 // Per-kernel-class device timing (rt_kernel_timing_*): when enabled, an event is recorded after every launch and
 // the interval since the previous event is attributed to that launch's class. Off by default (no events at all).
+// With pipeline lanes (trace_wavefront.cu) launches of different streams overlap at their edges, so an interval is not
+// simply "since the previous event": record i ends a launch of class klass[i] whose stream predecessor is record
+// prev[i]; rt_kernel_timing_read charges it the time from max(predecessor's end, latest end of any other launch before
+// it) to its own end — the machine's busy time is attributed once, to the launch that ended each stretch.
 struct KernelTimer {
   bool enabled = false;
   std::vector<cudaEvent_t> pool;
-  std::vector<int> klass; // class of the interval that ends at event i; -1 = not attributed (sequence start)
+  std::vector<int> klass; // class of the launch that ends at event i; -1 = not attributed (sequence start)
+  std::vector<int> prev;  // record of the previous event on the same stream, -1 = none
   size_t used = 0;
+  int last[1 + 4] = {-1, -1, -1, -1, -1}; // latest record per stream: [0] the context stream, [1 + lane] the lanes
 };
+constexpr int kMaxLanes = 4;
 } // namespace rtb
 
 struct rt_context {
@@ -142,6 +165,7 @@ struct rt_context {
   cudaEvent_t evFence[16] = {}; // rt_fence ring
   uint64_t fencesIssued = 0;
   uint64_t launches = 0;
+  uint64_t hostSyncs = 0; // times the library blocked the host on the device (rt_host_sync_count): per-frame paths keep it 0
   int traceMode = 1;        // 0 megakernel, 1 wavefront
   int traversalVariant = 1; // lane refill threshold of the traversal kernels: 0 none, 1 = 8, 2 = 16, 3 = 24 idle lanes
   int fuseTraversal = 1;    // wavefront: shadow rays of segment k traced in the launch of segment k + 1's closest hits
@@ -159,22 +183,30 @@ struct rt_context {
   size_t scratchBytes = 0;
   float *srgbLutDev = nullptr;
   int smCount = 148;
-  // wavefront state (trace_wavefront.cu)
-  void *wfState = nullptr;
-  size_t wfBytes = 0;
+  // wavefront state (trace_wavefront.cu), one per pipeline lane
+  void *wfState[rtb::kMaxLanes] = {};
+  size_t wfBytes[rtb::kMaxLanes] = {};
+  // pipeline lanes: a dispatch is split into `pipelineLanes` interleaved tile subsets whose kernel sequences run on
+  // their own streams, so that the tail of one lane's persistent launch is filled by the other lane's next launch
+  int pipelineLanes = 2;
+  cudaStream_t laneStream[rtb::kMaxLanes] = {};
+  cudaEvent_t evFork = nullptr, evLaneDone[rtb::kMaxLanes] = {};
   // per-light constants derived once per rt_trace (trace.cu k_prepare_lights)
   float4 *lightDerivedDev = nullptr;
   int lightDerivedCap = 0;
   rtb::KernelTimer timer;
-  // records an event on the stream (only when timing is enabled); klass < 0 starts a new sequence
-  void mark(int klass);
+  // records an event (only when timing is enabled) on the context's stream (lane < 0) or on a lane's stream;
+  // klass < 0 starts a new sequence on that stream. forkFrom >= 0: the stream predecessor is that stream's latest
+  // record (a lane's first launch follows the fork point on the context's stream)
+  void mark(int klass, int lane = -1, bool afterFork = false);
 };
 
 namespace rtb {
 int ensureScratch(rt_context *ctx, size_t bytes);
 int buildBlas(rt_context *ctx, const rt_triangle_geometry *geoms, uint32_t n, uint32_t flags, AccelObject **out);
 int refitBlas(rt_context *ctx, AccelObject *as, const rt_triangle_geometry *geoms, uint32_t n);
-int buildTlas(rt_context *ctx, AccelObject *as, const rt_instance_descriptor *descDev, uint32_t count);
+int buildTlas(rt_context *ctx, AccelObject *as, const rt_instance_descriptor *descDev, uint32_t count, bool refit);
+int checkTlasInfo(rt_context *ctx, AccelObject *as, bool wait);
 void destroyAccel(AccelObject *as);
 int launchSkin(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], uint32_t vertexCount);
 int launchJointPalette(rt_context *ctx, const float *trs, const int32_t *parents, const float *inverseBind,

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 
 #include "scene.h"
 
@@ -19,7 +20,20 @@ int paeth(int a, int b, int c) {
 }
 } // namespace
 
+// The file is untrusted: chunk lengths, the IHDR fields and every size derived from them are checked before use,
+// dimensions are capped (kMaxSide) so that no size computation can wrap, and allocation failure is reported as a
+// decode failure instead of escaping through the extern "C" callers.
+static bool decodePngChecked(const std::string &path, Texture &out);
 bool decodePng(const std::string &path, Texture &out) {
+  try {
+    return decodePngChecked(path, out);
+  } catch (const std::exception &) { // std::bad_alloc / length_error on hostile sizes
+    return false;
+  }
+}
+
+static bool decodePngChecked(const std::string &path, Texture &out) {
+  constexpr uint32_t kMaxSide = 16384; // the reference's largest map is 4096^2
   FILE *f = std::fopen(path.c_str(), "rb");
   if (!f) return false;
   std::fseek(f, 0, SEEK_END);
@@ -32,14 +46,17 @@ bool decodePng(const std::string &path, Texture &out) {
   if (got < 8 || std::memcmp(file.data(), sig, 8) != 0) return false;
   uint32_t w = 0, h = 0;
   int depth = 0, ctype = 0, interlace = 0;
+  bool haveHeader = false;
   std::vector<uint8_t> idat, palette, trns;
   size_t pos = 8;
   while (pos + 12 <= file.size()) {
     uint32_t len = be32(&file[pos]);
     const uint8_t *type = &file[pos + 4];
     const uint8_t *data = &file[pos + 8];
-    if (pos + 12 + len > file.size()) return false;
+    if (len > file.size() || pos + 12 + size_t(len) > file.size()) return false;
     if (!std::memcmp(type, "IHDR", 4)) {
+      if (len != 13 || haveHeader) return false;
+      haveHeader = true;
       w = be32(data);
       h = be32(data + 4);
       depth = data[8];
@@ -56,7 +73,7 @@ bool decodePng(const std::string &path, Texture &out) {
     }
     pos += 12 + len;
   }
-  if (!w || !h || interlace || (depth != 8 && depth != 16)) return false;
+  if (!haveHeader || !w || !h || w > kMaxSide || h > kMaxSide || interlace || (depth != 8 && depth != 16)) return false;
   int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
   if (!channels || (ctype == 3 && depth != 8)) return false;
   size_t bpp = size_t(channels) * (depth / 8), stride = bpp * w;
@@ -69,6 +86,7 @@ bool decodePng(const std::string &path, Texture &out) {
     uint8_t *dst = &img[stride * y];
     const uint8_t *up = y ? &img[stride * (y - 1)] : nullptr;
     int ft = src[0];
+    if (ft > 4) return false;
     ++src;
     for (size_t x = 0; x < stride; ++x) {
       int a = x >= bpp ? dst[x - bpp] : 0, b = up ? up[x] : 0, c = (up && x >= bpp) ? up[x - bpp] : 0;

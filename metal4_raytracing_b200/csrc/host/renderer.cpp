@@ -56,6 +56,7 @@ struct rtr_renderer {
   void *descriptors = nullptr, *prevDescriptors = nullptr;
   void *lights = nullptr;
   uint32_t lightCapacity = 0;
+  uint32_t lightCount = 0; // lights resident in `lights` (what uniforms.lightCount may address)
   uint64_t tlas = 0;
   rt_image images[RT_TEXTURE_COUNT]{};
   // pinned staging for per-frame uploads: a ring of three arenas (the reference triple-buffers its per-frame host
@@ -214,6 +215,13 @@ int rtr_create(rt_context *ctx, const rt_scene_desc *scene, int width, int heigh
       row.material = static_cast<const rt_material *>(dm.materials) + k;
       row.uvs = dm.uvs ? static_cast<const float *>(dm.uvs) : static_cast<const float *>(dm.normals);
       const int32_t *ti = sm.submeshes[k].textureIndex;
+      for (int slot = 0; slot < RT_SLOT_COUNT; ++slot)
+        if (ti[slot] < 0 || uint32_t(ti[slot]) >= scene->textureCount) {
+          g_err = "rtr_create: mesh " + std::to_string(m) + " submesh " + std::to_string(k) + " texture slot " +
+                  std::to_string(slot) + " has index " + std::to_string(ti[slot]) + " outside the scene's " +
+                  std::to_string(scene->textureCount) + " textures (rt_scene.h: every slot names a texture, 1x1 fallbacks included)";
+          return 2;
+        }
       row.baseColorMap = r->textures[ti[RT_SLOT_BASECOLOR]];
       row.normalMap = r->textures[ti[RT_SLOT_NORMAL]];
       row.roughnessMap = r->textures[ti[RT_SLOT_ROUGHNESS]];
@@ -249,6 +257,7 @@ int rtr_create(rt_context *ctx, const rt_scene_desc *scene, int width, int heigh
     std::memcpy(r->stage[1], scene->lights, size_t(scene->lightCount) * sizeof(rt_light));
     RTR_TRY(rt_upload(ctx, r->lights, r->stage[1], size_t(scene->lightCount) * sizeof(rt_light)));
   }
+  r->lightCount = scene->lightCount;
   // images (Renderer.swift:685-799)
   const bool fp32 = (flags & RTR_FLAG_FP32_IMAGES) != 0;
   const int rgba = fp32 ? RT_FORMAT_RGBA32_FLOAT : RT_FORMAT_RGBA16_FLOAT;
@@ -330,7 +339,15 @@ int rtr_update(rtr_renderer *r, const rt_scene_desc *scene) {
   for (uint32_t i = 0; i < scene->instanceCount; ++i)
     packDescriptor(scene->instances[i].transform, r->meshes[r->instanceMesh[i]].blas, r->stageDescriptors[i]);
   RTR_TRY(rt_upload(ctx, r->descriptors, r->stageDescriptors, descBytes));
-  if (scene->lightCount && scene->lightCount <= r->lightCapacity) {
+  if (scene->lightCount > r->lightCapacity) {
+    // more lights than the renderer was created with: the staging arenas and the device array were sized for
+    // lightCapacity (the reference's light list is fixed after Scene.init, Scene.swift:82-93)
+    g_err = "rtr_update: scene has " + std::to_string(scene->lightCount) + " lights, renderer was created for " +
+            std::to_string(r->lightCapacity) + "; create a new renderer";
+    return 2;
+  }
+  r->lightCount = scene->lightCount;
+  if (scene->lightCount) {
     uint8_t *lights = take(size_t(scene->lightCount) * sizeof(rt_light));
     std::memcpy(lights, scene->lights, size_t(scene->lightCount) * sizeof(rt_light));
     RTR_TRY(rt_upload(ctx, r->lights, lights, size_t(scene->lightCount) * sizeof(rt_light)));
@@ -380,11 +397,25 @@ int rtr_update(rtr_renderer *r, const rt_scene_desc *scene) {
   }
   RTR_TRY(rt_fence(ctx, &r->stageFence[slot]));
   ++r->updates;
-  RTR_TRY(rt_tlas_update(ctx, r->tlas, static_cast<const rt_instance_descriptor *>(r->descriptors), scene->instanceCount));
+  // instance AS: refit in place when only transforms / BLAS contents changed — which is all rtr_update allows — as the
+  // reference does on devices that support it, otherwise (or on request) rebuild (Renderer.swift:1084-1202)
+  if (r->flags & RTR_FLAG_TLAS_REBUILD)
+    RTR_TRY(rt_tlas_update(ctx, r->tlas, static_cast<const rt_instance_descriptor *>(r->descriptors), scene->instanceCount));
+  else
+    RTR_TRY(rt_tlas_refit(ctx, r->tlas, static_cast<const rt_instance_descriptor *>(r->descriptors), scene->instanceCount));
   return 0;
 }
 
 int rtr_draw(rtr_renderer *r, const rt_uniforms *uniforms, const rt_trace_options *options) {
+  if (!r || !uniforms) {
+    g_err = "rtr_draw: null argument";
+    return 2;
+  }
+  if (uniforms->lightCount < 0 || uint32_t(uniforms->lightCount) > r->lightCount) {
+    g_err = "rtr_draw: uniforms.lightCount " + std::to_string(uniforms->lightCount) + " exceeds the " +
+            std::to_string(r->lightCount) + " lights resident on the device";
+    return 2;
+  }
   const void *buffers[RT_BUFFER_COUNT] = {};
   buffers[RT_BUFFER_UNIFORMS] = uniforms;
   buffers[RT_BUFFER_RESOURCES] = r->resources;
@@ -396,6 +427,7 @@ int rtr_draw(rtr_renderer *r, const rt_uniforms *uniforms, const rt_trace_option
   if (options) withHints = *options;
   if (r->untextured) withHints.hints |= RT_TRACE_HINT_UNTEXTURED; // known from the materials uploaded at creation
   if (r->noGlass) withHints.hints |= RT_TRACE_HINT_NO_GLASS;
+  if (r->flags & RTR_FLAG_ENABLE_AO) withHints.hints |= RT_TRACE_ENABLE_AO;
   RTR_TRY(rt_trace(r->ctx, buffers, r->images, int(sizeof(rt_resource)), int(r->maxSubmeshes), &withHints));
   std::swap(r->images[RT_TEXTURE_ACCUMULATION], r->images[RT_TEXTURE_PREVIOUS_ACCUMULATION]); // Renderer.swift:1492-1494
   return 0;

@@ -198,8 +198,12 @@ __device__ __forceinline__ bool shadeSegment(const TraceParams &P, PathState &s,
   const bool hasBase = (flags & RT_MATERIAL_TEXTURE_BASECOLOR) != 0, hasNormalMap = (flags & RT_MATERIAL_TEXTURE_NORMAL) != 0;
   const bool hasRough = (flags & RT_MATERIAL_TEXTURE_ROUGHNESS) != 0, hasMetal = (flags & RT_MATERIAL_TEXTURE_METALLIC) != 0;
   const bool hasOpacityMap = (flags & RT_MATERIAL_TEXTURE_OPACITY) != 0, hasEmissionMap = (flags & RT_MATERIAL_TEXTURE_EMISSION) != 0;
+  // the reference's compile-time ENABLE_AO (ShaderTypes.h:155-157, default 0; Raytracing.metal:405-409) is a per-dispatch
+  // switch here (RT_TRACE_ENABLE_AO in rt_trace_options.hints): uniform over the launch, textured build only
+  const bool enableAO = kTextures && (P.hints & RT_TRACE_ENABLE_AO) != 0u;
+  const bool hasAO = enableAO && (flags & RT_MATERIAL_TEXTURE_AO) != 0;
   f2 texCoord = mk2(0.0f, 0.0f);
-  if (hasBase || hasNormalMap || hasRough || hasMetal || hasOpacityMap || hasEmissionMap) {
+  if (hasBase || hasNormalMap || hasRough || hasMetal || hasAO || hasOpacityMap || hasEmissionMap) {
     texCoord = interpolate2(res.uvs, res.indices, hit);
     texCoord.y = 1.0f - texCoord.y;
   }
@@ -212,7 +216,8 @@ __device__ __forceinline__ bool shadeSegment(const TraceParams &P, PathState &s,
   if (hasRough) roughness = sampleTexture(res.roughnessMap, texCoord, P.srgbLut).x;
   float metallic = 0.0f;
   if (hasMetal) metallic = sampleTexture(res.metallicMap, texCoord, P.srgbLut).x;
-  const float ao = 1.0f; // ENABLE_AO == 0 in the reference build (ShaderTypes.h:155-157)
+  float ao = 1.0f;
+  if (hasAO) ao = sampleTexture(res.aoMap, texCoord, P.srgbLut).x; // #if ENABLE_AO (Raytracing.metal:442-446)
   float opacity = clampf(mat.opacity, 0.0f, 1.0f);
   if (hasOpacityMap) opacity *= sampleTexture(res.opacityMap, texCoord, P.srgbLut).x;
   f3 emission = mk3(mat.emission);
@@ -235,7 +240,7 @@ __device__ __forceinline__ bool shadeSegment(const TraceParams &P, PathState &s,
         break;
       case RT_DEBUG_ROUGHNESS: dbg = mk3(roughness); break;
       case RT_DEBUG_METALLIC: dbg = mk3(metallic); break;
-      case RT_DEBUG_AO: dbg = mk3(1.0f, 0.0f, 1.0f); break;
+      case RT_DEBUG_AO: dbg = enableAO ? mk3(ao) : mk3(1.0f, 0.0f, 1.0f); break; // Raytracing.metal:475-479
       case RT_DEBUG_EMISSION: dbg = emission; break;
       case RT_DEBUG_MOTION: {
         const f2 mp = prim.hadPrimaryHit ? prim.motion : prevMotion;

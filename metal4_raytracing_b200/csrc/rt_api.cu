@@ -1,6 +1,7 @@
 // rt_api.cu — extern "C" entry points of librt_b200.so (include/rt_b200.h).
 // Thin: argument validation, handle bookkeeping, stream plumbing. No CPU fallback anywhere: every compute entry
 // point enqueues CUDA kernels or fails with an error code.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -14,7 +15,7 @@ void setError(const std::string &msg) { g_lastError = msg; }
 
 int ensureScratch(rt_context *ctx, size_t bytes) {
   if (bytes <= ctx->scratchBytes) return 0;
-  RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  RT_CUDA(RT_SYNC_STREAM(ctx, ctx->stream));
   if (ctx->scratch) cudaFree(ctx->scratch);
   ctx->scratch = nullptr;
   ctx->scratchBytes = 0;
@@ -26,16 +27,20 @@ int ensureScratch(rt_context *ctx, size_t bytes) {
 
 } // namespace rtb
 
-void rt_context::mark(int klass) {
+void rt_context::mark(int klass, int lane, bool afterFork) {
   if (!timer.enabled) return;
   if (timer.used == timer.pool.size()) {
     cudaEvent_t e = nullptr;
     if (cudaEventCreate(&e) != cudaSuccess) return;
     timer.pool.push_back(e);
     timer.klass.push_back(-1);
+    timer.prev.push_back(-1);
   }
+  const int slot = lane < 0 ? 0 : 1 + lane;
   timer.klass[timer.used] = klass;
-  cudaEventRecord(timer.pool[timer.used], stream);
+  timer.prev[timer.used] = klass < 0 ? -1 : (afterFork ? timer.last[0] : timer.last[slot]);
+  cudaEventRecord(timer.pool[timer.used], lane < 0 ? stream : laneStream[lane]);
+  timer.last[slot] = int(timer.used);
   ++timer.used;
 }
 
@@ -83,6 +88,9 @@ int rt_create(int device, rt_context **out) {
   RT_CUDA(cudaEventCreateWithFlags(&ctx->evReady, cudaEventDisableTiming));
   for (cudaEvent_t &e : ctx->evCopied) RT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (cudaEvent_t &e : ctx->evFence) RT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (cudaStream_t &s : ctx->laneStream) RT_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  RT_CUDA(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
+  for (cudaEvent_t &e : ctx->evLaneDone) RT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   // sRGB decode table, evaluated in double and rounded once (same table as the oracle's)
   float lut[256];
   for (int i = 0; i < 256; ++i) {
@@ -120,7 +128,11 @@ int rt_destroy(rt_context *ctx) {
   ctx->accels.clear();
   cudaFree(ctx->scratch);
   cudaFree(ctx->srgbLutDev);
-  cudaFree(ctx->wfState);
+  for (cudaStream_t s : ctx->laneStream) if (s) cudaStreamSynchronize(s);
+  for (void *p : ctx->wfState) cudaFree(p);
+  for (cudaStream_t s : ctx->laneStream) if (s) cudaStreamDestroy(s);
+  if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+  for (cudaEvent_t e : ctx->evLaneDone) if (e) cudaEventDestroy(e);
   cudaFree(ctx->lightDerivedDev);
   cudaEventDestroy(ctx->evBegin);
   cudaEventDestroy(ctx->evEnd);
@@ -139,6 +151,13 @@ int rt_set_stream(rt_context *ctx, void *cudaStream) {
   RT_CTX(ctx);
   RT_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->stream = cudaStream ? static_cast<cudaStream_t>(cudaStream) : ctx->ownStream;
+  return 0;
+}
+
+int rt_get_stream(rt_context *ctx, void **cudaStreamOut) {
+  RT_CTX(ctx);
+  RT_CHECK(cudaStreamOut != nullptr, "rt_get_stream: null out pointer");
+  *cudaStreamOut = static_cast<void *>(ctx->stream);
   return 0;
 }
 
@@ -201,7 +220,7 @@ int rt_upload(rt_context *ctx, void *dstDev, const void *srcHost, size_t bytes) 
   cudaPointerAttributes attr{};
   bool pinned = cudaPointerGetAttributes(&attr, srcHost) == cudaSuccess && attr.type == cudaMemoryTypeHost;
   cudaGetLastError();
-  if (!pinned) RT_CUDA(cudaStreamSynchronize(ctx->stream)); // pageable source: caller may reuse it right away
+  if (!pinned) RT_CUDA(RT_SYNC_STREAM(ctx, ctx->stream)); // pageable source: caller may reuse it right away
   return 0;
 }
 
@@ -227,7 +246,8 @@ int rt_fence(rt_context *ctx, uint64_t *ticket) {
 int rt_fence_wait(rt_context *ctx, uint64_t ticket) {
   RT_CTX(ctx);
   RT_CHECK(ticket >= 1 && ticket <= ctx->fencesIssued, "rt_fence_wait: unknown ticket");
-  if (ctx->fencesIssued - ticket >= 16) return 0; // its ring slot was re-recorded by a later fence on the same stream
+  // a ticket older than the ring had its slot re-recorded by a later fence of the same stream: waiting for that later
+  // point covers the older one, so the wait below is right in both cases (it never returns before the work is done)
   RT_CUDA(cudaEventSynchronize(ctx->evFence[(ticket - 1) % 16]));
   return 0;
 }
@@ -236,7 +256,7 @@ int rt_download_async(rt_context *ctx, void *dstHost, const void *srcDev, size_t
   RT_CTX(ctx);
   RT_CHECK(dstHost && srcDev && ticket && bytes, "rt_download_async: null pointer or empty copy");
   const uint64_t id = ctx->copiesIssued;
-  if (id >= 8) RT_CUDA(cudaEventSynchronize(ctx->evCopied[id % 8])); // the ring slot's previous copy must be done
+  if (id >= 8) RT_CUDA(RT_SYNC_EVENT(ctx, ctx->evCopied[id % 8])); // the ring slot's previous copy must be done
   RT_CUDA(cudaEventRecord(ctx->evReady, ctx->stream));
   RT_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evReady, 0));
   RT_CUDA(cudaMemcpyAsync(dstHost, srcDev, bytes, cudaMemcpyDeviceToHost, ctx->copyStream));
@@ -320,7 +340,7 @@ int rt_tlas_build(rt_context *ctx, const rt_instance_descriptor *descriptorsDev,
   AccelObject *as = new AccelObject();
   as->isTlas = true;
   ctx->mark(-1);
-  int rc = buildTlas(ctx, as, descriptorsDev, count);
+  int rc = buildTlas(ctx, as, descriptorsDev, count, false);
   ctx->mark(RT_KERNEL_BUILD);
   if (rc) {
     destroyAccel(as);
@@ -337,8 +357,20 @@ int rt_tlas_update(rt_context *ctx, uint64_t id, const rt_instance_descriptor *d
   AccelObject *as = nullptr;
   RT_TRY(findAccel(ctx, id, true, &as));
   ctx->mark(-1);
-  const int rc = buildTlas(ctx, as, descriptorsDev, count);
+  const int rc = buildTlas(ctx, as, descriptorsDev, count, false);
   ctx->mark(RT_KERNEL_BUILD);
+  return rc;
+}
+
+int rt_tlas_refit(rt_context *ctx, uint64_t id, const rt_instance_descriptor *descriptorsDev, uint32_t count) {
+  RT_CTX(ctx);
+  AccelObject *as = nullptr;
+  RT_TRY(findAccel(ctx, id, true, &as));
+  RT_CHECK(as->treeValid && count == as->primCount,
+           "rt_tlas_refit: instance count differs from the last build (rebuild with rt_tlas_update)");
+  ctx->mark(-1);
+  const int rc = buildTlas(ctx, as, descriptorsDev, count, true);
+  ctx->mark(RT_KERNEL_REFIT);
   return rc;
 }
 
@@ -357,11 +389,16 @@ int rt_as_get_info(rt_context *ctx, uint64_t id, rt_as_info *out) {
   RT_CHECK(out != nullptr, "rt_as_get_info: null out pointer");
   auto it = ctx->accels.find(id);
   RT_CHECK(it != ctx->accels.end(), "unknown acceleration structure id");
-  const AccelObject *as = it->second;
+  AccelObject *as = it->second;
   std::memset(out, 0, sizeof *out);
   out->primitiveCount = as->primCount;
   out->wideNodeCount = as->nodeCount;
   out->levelCount = as->levelStart.empty() ? 0 : uint32_t(as->levelStart.size() - 1);
+  if (as->isTlas && as->deviceBuilt) { // counts of a device-side build live on the device: wait for their copy
+    RT_TRY(checkTlasInfo(ctx, as, true));
+    out->wideNodeCount = as->infoHost->nodeCount;
+    out->levelCount = as->infoHost->levelCount;
+  }
   out->bytes = as->bytes;
   for (int a = 0; a < 3; ++a) {
     out->boundsMin[a] = as->bounds.lo[a];
@@ -486,6 +523,7 @@ int rt_ipc_close(rt_context *ctx, void *importedDev) {
 }
 
 uint64_t rt_launch_count(rt_context *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t rt_host_sync_count(rt_context *ctx) { return ctx ? ctx->hostSyncs : 0; }
 
 int rt_set_trace_mode(rt_context *ctx, int mode) {
   RT_CTX(ctx);
@@ -499,6 +537,7 @@ int rt_kernel_timing_enable(rt_context *ctx, int enable) {
   RT_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->timer.enabled = enable != 0;
   ctx->timer.used = 0;
+  for (int &l : ctx->timer.last) l = -1;
   return 0;
 }
 
@@ -511,16 +550,33 @@ int rt_kernel_timing_read(rt_context *ctx, float msByClass[RT_KERNEL_CLASS_COUNT
     msByClass[k] = 0.0f;
     if (launchesByClass) launchesByClass[k] = 0;
   }
+  for (cudaStream_t s : ctx->laneStream) RT_CUDA(cudaStreamSynchronize(s));
   KernelTimer &T = ctx->timer;
-  for (size_t i = 1; i < T.used; ++i) {
-    const int k = T.klass[i];
-    if (k < 0 || k >= RT_KERNEL_CLASS_COUNT) continue;
-    float ms = 0.0f;
-    RT_CUDA(cudaEventElapsedTime(&ms, T.pool[i - 1], T.pool[i]));
-    msByClass[k] += ms;
-    if (launchesByClass) ++launchesByClass[k];
+  if (T.used > 0) {
+    // completion time of every record relative to the first one, then the records in completion order
+    std::vector<double> at(T.used, 0.0);
+    for (size_t i = 1; i < T.used; ++i) {
+      float ms = 0.0f;
+      RT_CUDA(cudaEventElapsedTime(&ms, T.pool[0], T.pool[i]));
+      at[i] = double(ms);
+    }
+    std::vector<uint32_t> order(T.used);
+    for (size_t i = 0; i < T.used; ++i) order[i] = uint32_t(i);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return at[a] < at[b]; });
+    double latestEnd = 0.0; // latest completion seen so far among launches (class >= 0)
+    for (size_t r = 0; r < T.used; ++r) {
+      const uint32_t i = order[r];
+      const int k = T.klass[i];
+      if (k >= 0 && k < RT_KERNEL_CLASS_COUNT && T.prev[i] >= 0) {
+        const double begin = std::max(at[size_t(T.prev[i])], latestEnd);
+        if (at[i] > begin) msByClass[k] += float(at[i] - begin);
+        if (launchesByClass) ++launchesByClass[k];
+      }
+      if (k >= 0) latestEnd = std::max(latestEnd, at[i]);
+    }
   }
   T.used = 0;
+  for (int &l : T.last) l = -1;
   return 0;
 }
 
@@ -614,6 +670,11 @@ int rt_set_option(rt_context *ctx, const char *key, int value) {
   if (k == "sample_batch") {
     RT_CHECK(value >= 1 && value <= 64, "rt_set_option: sample_batch is 1..64");
     ctx->sampleBatch = value;
+    return 0;
+  }
+  if (k == "pipeline_lanes") {
+    RT_CHECK(value >= 1 && value <= rtb::kMaxLanes, "rt_set_option: pipeline_lanes is 1..4");
+    ctx->pipelineLanes = value;
     return 0;
   }
   if (k == "blocks_per_sm") {

@@ -134,7 +134,7 @@ int fillTraceParams(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT],
   RT_CHECK(P.uniforms.frameIndex == 0 || textures[RT_TEXTURE_ACCUMULATION].data, "rt_trace: texture 0 (history) is not bound");
   P.srgbLut = ctx->srgbLutDev;
   if (ctx->lightDerivedCap < P.uniforms.lightCount) {
-    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    RT_CUDA(RT_SYNC_STREAM(ctx, ctx->stream));
     if (ctx->lightDerivedDev) cudaFree(ctx->lightDerivedDev);
     ctx->lightDerivedDev = nullptr;
     ctx->lightDerivedCap = 0;

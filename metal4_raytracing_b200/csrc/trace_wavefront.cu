@@ -260,6 +260,18 @@ constexpr int kStepsPerCheck = RT_STEPS_PER_CHECK;
 #define RT_SHARED_STACK 0
 #endif
 
+#ifdef RT_COUNT_WORK
+// counter build: rayCounters[3..5] (closest-hit rays) and [6..8] (any-hit rays) += node steps, triangle tests, entries
+template <bool kAny>
+__device__ __forceinline__ void countWork(const TraceParams &P, const LaneTraversal<kAny> &t) {
+  if (P.rayCounters == nullptr) return;
+  unsigned long long *c = P.rayCounters + (kAny ? 6 : 3);
+  atomicAdd(c + 0, (unsigned long long)t.nNodes);
+  atomicAdd(c + 1, (unsigned long long)t.nTris);
+  atomicAdd(c + 2, (unsigned long long)t.nEntries);
+}
+#endif
+
 template <bool kAny, int kRefill, typename Finish>
 __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t *__restrict__ queue, uint32_t count,
                                            uint32_t *cursor, const float4 *__restrict__ rayO,
@@ -312,6 +324,9 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
       if (active && !t.step(P.tlas, stack)) {
 #endif
         finish(slot, t);
+#ifdef RT_COUNT_WORK
+        countWork<kAny>(P, t);
+#endif
         active = false;
       }
     }
@@ -584,7 +599,7 @@ __global__ void __launch_bounds__(kBlock) k_wf_resolve(const __grid_constant__ T
   }
 }
 
-int ensureState(rt_context *ctx, uint32_t capacity, uint32_t batch, WfState &out) {
+int ensureState(rt_context *ctx, int lane, uint32_t capacity, uint32_t batch, WfState &out) {
   const size_t paths = size_t(capacity) * batch;
   size_t sortTempBytes = 0;
   if (ctx->sortRays > 0)
@@ -592,15 +607,15 @@ int ensureState(rt_context *ctx, uint32_t capacity, uint32_t batch, WfState &out
                                     (uint32_t *)nullptr, int(paths), 0, 24, ctx->stream);
   const size_t need = 256 + 8 * (paths * 16 + 256) + 3 * (size_t(capacity) * 16 + 256) + 3 * (paths * 4 + 256) +
                       (ctx->sortRays > 0 ? 3 * (paths * 4 + 256) + sortTempBytes + 256 : 0);
-  if (ctx->wfState == nullptr || ctx->wfBytes < need) {
-    RT_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->wfState) cudaFree(ctx->wfState);
-    ctx->wfState = nullptr;
-    ctx->wfBytes = 0;
-    RT_CUDA(cudaMalloc(&ctx->wfState, need));
-    ctx->wfBytes = need;
+  if (ctx->wfState[lane] == nullptr || ctx->wfBytes[lane] < need) {
+    RT_CUDA(RT_SYNC_STREAM(ctx, ctx->stream)); // every lane joined the context's stream at the end of its last dispatch
+    if (ctx->wfState[lane]) cudaFree(ctx->wfState[lane]);
+    ctx->wfState[lane] = nullptr;
+    ctx->wfBytes[lane] = 0;
+    RT_CUDA(cudaMalloc(&ctx->wfState[lane], need));
+    ctx->wfBytes[lane] = need;
   }
-  uint8_t *p = static_cast<uint8_t *>(ctx->wfState);
+  uint8_t *p = static_cast<uint8_t *>(ctx->wfState[lane]);
   auto take = [&](size_t bytes) {
     void *r = p;
     p += (bytes + 255) & ~size_t(255);
@@ -632,7 +647,7 @@ int ensureState(rt_context *ctx, uint32_t capacity, uint32_t batch, WfState &out
     s.sortTemp = take(sortTempBytes);
     s.sortTempBytes = sortTempBytes;
   }
-  RT_CHECK(size_t(p - static_cast<uint8_t *>(ctx->wfState)) <= ctx->wfBytes, "internal: wavefront state overflow");
+  RT_CHECK(size_t(p - static_cast<uint8_t *>(ctx->wfState[lane])) <= ctx->wfBytes[lane], "internal: wavefront state overflow");
   out = s;
   return 0;
 }
@@ -643,7 +658,7 @@ int sortQueue(rt_context *ctx, const TraceParams &P, WfState &W, uint32_t **queu
   cudaStream_t st = ctx->stream;
   uint32_t count = 0;
   RT_CUDA(cudaMemcpyAsync(&count, countDev, 4, cudaMemcpyDeviceToHost, st));
-  RT_CUDA(cudaStreamSynchronize(st));
+  RT_CUDA(RT_SYNC_STREAM(ctx, st));
   if (count < 65536u) return 0; // not worth two more launches
   ctx->mark(-1);
   const int grid = int(std::min<uint32_t>((count + kBlock - 1) / kBlock, uint32_t(ctx->smCount) * 8u));
@@ -659,105 +674,161 @@ int sortQueue(rt_context *ctx, const TraceParams &P, WfState &W, uint32_t **queu
 
 } // namespace
 
-int launchTraceWavefront(rt_context *ctx, const TraceParams &P) {
-  const rt_uniforms &U = P.uniforms;
-  const int tileCount = P.tilesX * P.tilesY;
-  const int owned = (tileCount - P.tileRemainder + P.tileModulo - 1) / P.tileModulo;
-  const uint32_t capacity = uint32_t(owned) * 256u;
-  cudaStream_t st = ctx->stream;
+// One dispatch = `lanes` independent pipelines over interleaved tile subsets (lane l of L on rank r of N renders the
+// tiles with tile % (N L) == r + l N — the multi-GPU tile partition applied once more), each with its own path state,
+// queues and stream. A persistent launch ends with a tail in which ever fewer warps finish the longest rays (50-100 us
+// however small the launch); with two lanes the other lane's next launch moves onto the SMs the tail frees, so the
+// frame pays the tails of its last launches only instead of one per launch. Results do not depend on the partition
+// (tests: tile partition == full frame). Zero device->host read-backs: glass paths, which can take up to
+// maxBounces (maxBounces + 1) segments, are handled by launching that many segments — a launch whose queue turns out
+// to be empty ends after one load.
+int launchTraceWavefront(rt_context *ctx, const TraceParams &P0) {
+  const rt_uniforms &U = P0.uniforms;
+  const int tileCount = P0.tilesX * P0.tilesY;
   const int baseSamples = std::max(U.samplesPerPixel, 1);
   const int maxExtraSamples = (U.enableMotionAdaptiveSampling != 0) ? std::max(U.motionSamplingMaxExtraSamples, 0) : 0;
   const int sampleLoopBound = baseSamples + maxExtraSamples;
   const int maxBounces = std::max(U.maxBounces, 0);
   // a refraction does not consume a bounce until transparencyPasses > maxBounces (Raytracing.metal:563-575)
-  // without glass (RT_TRACE_HINT_NO_GLASS) every segment consumes a bounce: exactly maxBounces segments, no read-back
-  const int maxSegments = (P.hints & RT_TRACE_HINT_NO_GLASS) ? maxBounces : maxBounces * (maxBounces + 1);
-  // samples in flight per pixel: as many as the option allows while the path state stays under ~48 M paths
-  // (10.6 GB); the motion debug view reads what sample 0 wrote for its pixel, so it keeps one sample at a time
-  int batch = std::max(1, std::min(ctx->sampleBatch, sampleLoopBound));
-  batch = std::min<int>(batch, std::max<uint32_t>(1u, (48u << 20) / std::max(capacity, 1u)));
-  if (U.debugTextureMode == RT_DEBUG_MOTION) batch = 1;
-  WfState W;
-  RT_TRY(ensureState(ctx, capacity, uint32_t(batch), W));
-  const int slotBlocks = (int(W.capacity) + kBlock - 1) / kBlock;
-  const int persistent = std::min(slotBlocks, ctx->smCount * 8);
+  // without glass (RT_TRACE_HINT_NO_GLASS) every segment consumes a bounce: exactly maxBounces segments
+  const int maxSegments = (P0.hints & RT_TRACE_HINT_NO_GLASS) ? maxBounces : maxBounces * (maxBounces + 1);
+  const int ownedAll = (tileCount - P0.tileRemainder + P0.tileModulo - 1) / P0.tileModulo;
+  // ray sorting reads queue lengths back (an experiment, off by default): one lane, on the context's stream
+  int lanes = ctx->sortRays > 0 ? 1 : std::max(1, std::min(std::min(ctx->pipelineLanes, kMaxLanes), ownedAll));
+  struct Lane {
+    TraceParams P;
+    WfState W;
+    cudaStream_t st;
+    int id; // -1: the context's own stream (single lane)
+    int persistent;
+    int qin = 0;
+    bool shadowPending = false;
+    int pendingParity = 0;
+    bool first = true; // no launch of this lane has been timed yet
+  };
+  std::vector<Lane> L;
+  L.resize(size_t(lanes));
+  for (int l = 0; l < lanes; ++l) {
+    Lane &ln = L[size_t(l)];
+    ln.P = P0;
+    ln.P.tileModulo = P0.tileModulo * lanes;
+    ln.P.tileRemainder = P0.tileRemainder + l * P0.tileModulo;
+    const int owned = (tileCount - ln.P.tileRemainder + ln.P.tileModulo - 1) / ln.P.tileModulo;
+    const uint32_t capacity = uint32_t(std::max(owned, 0)) * 256u;
+    // samples in flight per pixel: as many as the option allows while the path state stays under ~48 M paths
+    // (10.6 GB) over all lanes; the motion debug view reads what sample 0 wrote for its pixel, so it keeps one sample
+    int batch = std::max(1, std::min(ctx->sampleBatch, sampleLoopBound));
+    batch = std::min<int>(batch, std::max<uint32_t>(1u, ((48u << 20) / uint32_t(lanes)) / std::max(capacity, 1u)));
+    if (U.debugTextureMode == RT_DEBUG_MOTION) batch = 1;
+    RT_TRY(ensureState(ctx, l, std::max(capacity, 256u), uint32_t(batch), ln.W));
+    ln.W.capacity = capacity;
+    ln.id = lanes > 1 ? l : -1;
+    ln.st = lanes > 1 ? ctx->laneStream[l] : ctx->stream;
+    const int slotBlocks = (int(capacity) + kBlock - 1) / kBlock;
+    ln.persistent = std::max(1, std::min(slotBlocks, ctx->smCount * 8));
+  }
+  const int batch = int(L[0].W.batch); // lane 0 owns the most tiles, so its batch is the smallest; all lanes use it
+  for (Lane &ln : L) ln.W.batch = uint32_t(batch);
   // traversal kernels: exactly the resident CTA count (they pull work from a cursor), blocks_per_sm overrides
   const int traceGrid = ctx->smCount * std::max(1, ctx->blocksPerSm);
+  if (lanes > 1) { // fork: the lanes start after everything enqueued on the context's stream so far
+    ctx->mark(-1);
+    RT_CUDA(cudaEventRecord(ctx->evFork, ctx->stream));
+    for (Lane &ln : L) RT_CUDA(cudaStreamWaitEvent(ln.st, ctx->evFork, 0));
+  }
+  auto timed = [&](Lane &ln, int klass) { // the launch just enqueued on this lane belongs to `klass`
+    ctx->mark(klass, ln.id, ln.id >= 0 && ln.first);
+    ln.first = false;
+    ++ctx->launches;
+  };
+  auto traverse = [&](Lane &ln, int first, int cameraRays, int doClosest, int doShadow, int shadowParity) {
+    const TraceParams &P = ln.P;
+    const WfState &W = ln.W;
+    cudaStream_t st = ln.st;
+    const int qin = ln.qin;
+    switch (ctx->traversalVariant) {
+      case 1: k_wf_traverse<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
+      case 2: k_wf_traverse<16><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
+      case 3: k_wf_traverse<24><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
+      case 4: k_wf_traverse<4><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
+      case 5: k_wf_traverse<2><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
+      default: k_wf_traverse<0><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
+    }
+  };
   int prevS0 = 0, prevN = 0;
   for (int s0 = 0; s0 < sampleLoopBound;) {
     // the first batch stays within the base samples (see k_wf_generate)
     const int n = std::min(batch, (s0 < baseSamples ? baseSamples : sampleLoopBound) - s0);
-    RT_CUDA(cudaMemsetAsync(W.counts, 0, 128, st));
-    ctx->mark(-1);
-    k_wf_generate<<<persistent, kBlock, 0, st>>>(P, W, s0, n, prevS0, prevN, baseSamples, maxExtraSamples);
-    ctx->mark(RT_KERNEL_GENERATE);
-    ++ctx->launches;
-    int qin = 0;
-    bool shadowPending = false; // the shadow rays of the previous segment have not been traced yet
-    int pendingParity = 0;
-    auto traverse = [&](int first, int cameraRays, int doClosest, int doShadow, int shadowParity) {
-      switch (ctx->traversalVariant) {
-        case 1: k_wf_traverse<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
-        case 2: k_wf_traverse<16><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
-        case 3: k_wf_traverse<24><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
-        case 4: k_wf_traverse<4><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
-        case 5: k_wf_traverse<2><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
-        default: k_wf_traverse<0><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
-      }
-      ++ctx->launches;
-    };
+    for (Lane &ln : L) {
+      if (ln.W.capacity == 0) continue;
+      RT_CUDA(cudaMemsetAsync(ln.W.counts, 0, 128, ln.st));
+      if (ln.id < 0) ctx->mark(-1);
+      k_wf_generate<<<ln.persistent, kBlock, 0, ln.st>>>(ln.P, ln.W, s0, n, prevS0, prevN, baseSamples, maxExtraSamples);
+      timed(ln, RT_KERNEL_GENERATE);
+      ln.qin = 0;
+      ln.shadowPending = false;
+      ln.pendingParity = 0;
+    }
     for (int segment = 0; segment < maxSegments; ++segment) {
       const int parity = segment & 1;
-      if (segment >= maxBounces) { // only glass paths get here: ask the device whether any are left
-        uint32_t remaining = 0;
-        RT_CUDA(cudaMemcpyAsync(&remaining, W.counts + pathCount(qin), 4, cudaMemcpyDeviceToHost, st));
-        RT_CUDA(cudaStreamSynchronize(st));
-        if (remaining == 0) break;
-        ctx->mark(-1);
-      }
       const int first = (s0 == 0 && segment == 0) ? 1 : 0;
-      if (ctx->sortRays > 0 && segment > 0) RT_TRY(sortQueue(ctx, P, W, &W.queue[qin], W.counts + pathCount(qin), W.rayO, W.rayD));
-      if (ctx->fuseTraversal && shadowPending && ctx->sortRays < 2) {
-        traverse(first, segment == 0, 1, 1, pendingParity); // closest hits of this segment + shadow rays of the last
-        shadowPending = false;
-        ctx->mark(RT_KERNEL_TRACE);
-      } else {
-        if (shadowPending) {
-          if (ctx->sortRays > 1) RT_TRY(sortQueue(ctx, P, W, &W.shadowQueue, W.counts + shadowCount(pendingParity), W.rayO, W.shD));
-          traverse(0, 0, 0, 1, pendingParity);
-          shadowPending = false;
-          ctx->mark(RT_KERNEL_SHADOW);
+      for (Lane &ln : L) {
+        if (ln.W.capacity == 0) continue;
+        const TraceParams &P = ln.P;
+        WfState &W = ln.W;
+        if (ctx->sortRays > 0 && segment > 0) RT_TRY(sortQueue(ctx, P, W, &W.queue[ln.qin], W.counts + pathCount(ln.qin), W.rayO, W.rayD));
+        if (ctx->fuseTraversal && ln.shadowPending && ctx->sortRays < 2) {
+          traverse(ln, first, segment == 0, 1, 1, ln.pendingParity); // closest hits of this segment + shadow rays of the last
+          ln.shadowPending = false;
+          timed(ln, RT_KERNEL_TRACE);
+        } else {
+          if (ln.shadowPending) {
+            if (ctx->sortRays > 1) RT_TRY(sortQueue(ctx, P, W, &W.shadowQueue, W.counts + shadowCount(ln.pendingParity), W.rayO, W.shD));
+            traverse(ln, 0, 0, 0, 1, ln.pendingParity);
+            ln.shadowPending = false;
+            timed(ln, RT_KERNEL_SHADOW);
+          }
+          traverse(ln, first, segment == 0, 1, 0, parity);
+          timed(ln, RT_KERNEL_TRACE);
         }
-        traverse(first, segment == 0, 1, 0, parity);
-        ctx->mark(RT_KERNEL_TRACE);
+        { // the shade kernel is specialised on what the host knows: texture hint, plain PBR without debug views
+          const bool textures = (P.hints & RT_TRACE_HINT_UNTEXTURED) == 0u;
+          const bool plain = U.debugTextureMode == RT_DEBUG_NONE && U.shadingMode != RT_SHADING_LEGACY && !environmentIsLight(P);
+          const int qin = ln.qin, cam = segment == 0;
+          if (textures && plain) k_wf_shade<true, true><<<ln.persistent, kBlock, 0, ln.st>>>(P, W, qin, s0, cam, parity);
+          else if (textures) k_wf_shade<true, false><<<ln.persistent, kBlock, 0, ln.st>>>(P, W, qin, s0, cam, parity);
+          else if (plain) k_wf_shade<false, true><<<ln.persistent, kBlock, 0, ln.st>>>(P, W, qin, s0, cam, parity);
+          else k_wf_shade<false, false><<<ln.persistent, kBlock, 0, ln.st>>>(P, W, qin, s0, cam, parity);
+        }
+        timed(ln, RT_KERNEL_SHADE);
+        ln.shadowPending = true;
+        ln.pendingParity = parity;
+        ln.qin ^= 1;
       }
-      { // the shade kernel is specialised on what the host knows: texture hint, plain PBR without debug views
-        const bool textures = (P.hints & RT_TRACE_HINT_UNTEXTURED) == 0u;
-        const bool plain = U.debugTextureMode == RT_DEBUG_NONE && U.shadingMode != RT_SHADING_LEGACY && !environmentIsLight(P);
-        if (textures && plain) k_wf_shade<true, true><<<persistent, kBlock, 0, st>>>(P, W, qin, s0, segment == 0, parity);
-        else if (textures) k_wf_shade<true, false><<<persistent, kBlock, 0, st>>>(P, W, qin, s0, segment == 0, parity);
-        else if (plain) k_wf_shade<false, true><<<persistent, kBlock, 0, st>>>(P, W, qin, s0, segment == 0, parity);
-        else k_wf_shade<false, false><<<persistent, kBlock, 0, st>>>(P, W, qin, s0, segment == 0, parity);
-      }
-      ctx->mark(RT_KERNEL_SHADE);
-      ++ctx->launches;
-      shadowPending = true;
-      pendingParity = parity;
-      qin ^= 1;
     }
-    if (shadowPending) {
-      if (ctx->sortRays > 1) RT_TRY(sortQueue(ctx, P, W, &W.shadowQueue, W.counts + shadowCount(pendingParity), W.rayO, W.shD));
-      traverse(0, 0, 0, 1, pendingParity);
-      ctx->mark(RT_KERNEL_SHADOW);
+    for (Lane &ln : L) {
+      if (ln.W.capacity == 0 || !ln.shadowPending) continue;
+      if (ctx->sortRays > 1) RT_TRY(sortQueue(ctx, ln.P, ln.W, &ln.W.shadowQueue, ln.W.counts + shadowCount(ln.pendingParity), ln.W.rayO, ln.W.shD));
+      traverse(ln, 0, 0, 0, 1, ln.pendingParity);
+      timed(ln, RT_KERNEL_SHADOW);
+      ln.shadowPending = false;
     }
     prevS0 = s0;
     prevN = n;
     s0 += n;
   }
-  ctx->mark(-1);
-  k_wf_resolve<<<persistent, kBlock, 0, st>>>(P, W, prevS0, prevN);
-  ctx->mark(RT_KERNEL_RESOLVE);
-  ++ctx->launches;
+  for (Lane &ln : L) {
+    if (ln.W.capacity == 0) continue;
+    k_wf_resolve<<<ln.persistent, kBlock, 0, ln.st>>>(ln.P, ln.W, prevS0, prevN);
+    timed(ln, RT_KERNEL_RESOLVE);
+  }
+  if (lanes > 1) { // join: the context's stream continues after every lane
+    for (int l = 0; l < lanes; ++l) {
+      RT_CUDA(cudaEventRecord(ctx->evLaneDone[l], L[size_t(l)].st));
+      RT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evLaneDone[l], 0));
+    }
+    ctx->mark(-1);
+  }
   RT_CUDA(cudaGetLastError());
   return 0;
 }

@@ -292,6 +292,14 @@ struct LaneTraversal {
   uint32_t instance;
   RayHit hit;
   bool found;
+#ifdef RT_COUNT_WORK
+  // counter build (tools/count_work.py): work done for this ray — node steps, triangle tests, instance entries.
+  // bench.py turns them into counted bytes per ray (80 B per node, 48 B per triangle, 64 B per instance record)
+  uint32_t nNodes, nTris, nEntries;
+#define RT_COUNT(x) (++(x))
+#else
+#define RT_COUNT(x) ((void)0)
+#endif
   // the traversal stack lives outside (a plain local array passed to every step) so that the compiler keeps the
   // scalar members above in registers instead of placing the whole object in local memory
 
@@ -302,6 +310,9 @@ struct LaneTraversal {
     hit.u = hit.v = 0.0f;
     hit.instance = hit.geometry = hit.primitive = 0u;
     found = false;
+#ifdef RT_COUNT_WORK
+    nNodes = nTris = nEntries = 0u;
+#endif
     sp = 0;
     instanceSp = -1;
     instance = 0;
@@ -319,6 +330,7 @@ struct LaneTraversal {
   // take the nearest pending child of ngroup, test its eight children
   template <typename Stack>
   __device__ __forceinline__ void nodeStep(Stack &stack) {
+    RT_COUNT(nNodes);
     const uint32_t hits = ngroup.y;
     const uint32_t bit = 31u - uint32_t(__clz(int(hits)));
     ngroup.y &= ~(1u << bit);
@@ -349,6 +361,7 @@ struct LaneTraversal {
   // tgroup holds TLAS leaf entries (instanceSp < 0): enter the next instance
   template <typename Stack>
   __device__ __forceinline__ void enterInstance(const TlasHeader &tlas, Stack &stack) {
+    RT_COUNT(nEntries);
     const uint32_t bit = uint32_t(__ffs(int(tgroup.y))) - 1u;
     tgroup.y &= ~(1u << bit);
     {
@@ -393,6 +406,7 @@ struct LaneTraversal {
   // tgroup holds triangles of the current BLAS (instanceSp >= 0): test the next one.
   // Returns true when an any-hit query is satisfied.
   __device__ __forceinline__ bool triangleStep() {
+    RT_COUNT(nTris);
     const uint32_t bit = uint32_t(__ffs(int(tgroup.y))) - 1u;
     tgroup.y &= ~(1u << bit);
     const float4 *tp = tris + size_t(tgroup.x + bit) * 3;

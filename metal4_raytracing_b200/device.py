@@ -19,6 +19,8 @@ _lib = None
 RTR_FLAG_FP32_IMAGES = 1
 RTR_FLAG_REBUILD_SKINNED = 2
 RTR_FLAG_GPU_SKELETON = 4
+RTR_FLAG_ENABLE_AO = 8
+RTR_FLAG_TLAS_REBUILD = 16
 
 
 class Environment(C.Structure):
@@ -63,9 +65,10 @@ class AsInfo(C.Structure):
 
 # every symbol include/rt_b200.h and include/rt_renderer.h declare (tests/test_abi.py checks the library exports them)
 EXPORTS = [
-    "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_sync", "rt_timer_begin", "rt_timer_end",
+    "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_get_stream", "rt_sync", "rt_timer_begin", "rt_timer_end",
     "rt_malloc", "rt_free", "rt_malloc_host", "rt_free_host", "rt_upload", "rt_download", "rt_copy", "rt_memset",
-    "rt_blas_build", "rt_blas_refit", "rt_blas_destroy", "rt_tlas_build", "rt_tlas_update", "rt_tlas_destroy",
+    "rt_blas_build", "rt_blas_refit", "rt_blas_destroy", "rt_tlas_build", "rt_tlas_update", "rt_tlas_refit",
+    "rt_tlas_destroy", "rt_host_sync_count",
     "rt_as_get_info", "rt_skin", "rt_trace", "rt_texture_create", "rt_texture_destroy", "rt_launch_count",
     "rt_set_trace_mode", "rt_set_option", "rt_kernel_timing_enable", "rt_kernel_timing_read", "rt_joint_palette",
     "rt_tonemap", "rt_temporal_filter", "rt_download_async", "rt_download_wait", "rt_fence", "rt_fence_wait",
@@ -89,6 +92,7 @@ def lib():
     L.rt_create.argtypes = [i32, C.POINTER(vp)]
     L.rt_destroy.argtypes = [vp]
     L.rt_set_stream.argtypes = [vp, vp]
+    L.rt_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.rt_sync.argtypes = [vp]
     L.rt_timer_begin.argtypes = [vp]
     L.rt_timer_end.argtypes = [vp, C.POINTER(C.c_float)]
@@ -109,6 +113,9 @@ def lib():
     L.rt_blas_destroy.argtypes = [vp, u64]
     L.rt_tlas_build.argtypes = [vp, vp, u32, C.POINTER(u64)]
     L.rt_tlas_update.argtypes = [vp, u64, vp, u32]
+    L.rt_tlas_refit.argtypes = [vp, u64, vp, u32]
+    L.rt_host_sync_count.restype = u64
+    L.rt_host_sync_count.argtypes = [vp]
     L.rt_tlas_destroy.argtypes = [vp, u64]
     L.rt_as_get_info.argtypes = [vp, u64, C.POINTER(AsInfo)]
     L.rt_skin.argtypes = [vp, C.POINTER(vp), u32]
@@ -235,6 +242,13 @@ class Context:
     def set_stream(self, cuda_stream):
         _check(lib().rt_set_stream(self._h, cuda_stream))
 
+    @property
+    def stream(self):
+        """cudaStream_t (int) the context enqueues on (rt_get_stream)."""
+        out = C.c_void_p()
+        _check(lib().rt_get_stream(self._h, C.byref(out)))
+        return out.value or 0
+
     def set_trace_mode(self, mode):
         """0 = megakernel, 1 = wavefront (default). Both produce identical images."""
         _check(lib().rt_set_trace_mode(self._h, int(mode)))
@@ -253,6 +267,11 @@ class Context:
     @property
     def launches(self):
         return lib().rt_launch_count(self._h)
+
+    @property
+    def host_syncs(self):
+        """rt_host_sync_count: implicit host<->device synchronisations inside the library so far."""
+        return lib().rt_host_sync_count(self._h)
 
     def tonemap(self, image, srgb=True, flip_y=True):
         """rt_tonemap of a device image record (A.Image): returns (H, W, 4) uint8, Reinhard [+ sRGB] [+ row flip]."""
@@ -329,6 +348,9 @@ class Context:
     def tlas_update(self, tlas, descriptors_dev, count):
         _check(lib().rt_tlas_update(self._h, tlas, descriptors_dev, count))
 
+    def tlas_refit(self, tlas, descriptors_dev, count):
+        _check(lib().rt_tlas_refit(self._h, tlas, descriptors_dev, count))
+
     def tlas_destroy(self, tlas):
         _check(lib().rt_tlas_destroy(self._h, tlas))
 
@@ -364,12 +386,14 @@ class Context:
 class Renderer:
     """rtr_renderer: scene resident in HBM + per-frame update/draw (Renderer.swift's hot-path half)."""
 
-    def __init__(self, ctx, scene, width, height, seeds=None, fp32=False, rebuild_skinned=False, gpu_skeleton=False):
+    def __init__(self, ctx, scene, width, height, seeds=None, fp32=False, rebuild_skinned=False, gpu_skeleton=False,
+                 enable_ao=False, tlas_rebuild=False):
         self.ctx = ctx
         self.scene = scene
         self.width, self.height = width, height
         flags = ((RTR_FLAG_FP32_IMAGES if fp32 else 0) | (RTR_FLAG_REBUILD_SKINNED if rebuild_skinned else 0) |
-                 (RTR_FLAG_GPU_SKELETON if gpu_skeleton else 0))
+                 (RTR_FLAG_GPU_SKELETON if gpu_skeleton else 0) | (RTR_FLAG_ENABLE_AO if enable_ao else 0) |
+                 (RTR_FLAG_TLAS_REBUILD if tlas_rebuild else 0))
         desc = scene.desc()
         h = C.c_void_p()
         _check(lib().rtr_create(ctx._h, C.byref(desc), width, height, flags, C.byref(h)), True)
@@ -432,10 +456,10 @@ class Renderer:
             opt.primaryIdsDev = self._ids_dev
         if count_rays:  # True: reset then count this frame; "accumulate": keep adding to the counters
             if self._counters_dev is None:
-                self._counters_dev = self.ctx.malloc(24)
-                self.ctx.memset(self._counters_dev, 0, 24)
+                self._counters_dev = self.ctx.malloc(72)
+                self.ctx.memset(self._counters_dev, 0, 72)
             if count_rays is True:
-                self.ctx.memset(self._counters_dev, 0, 24)
+                self.ctx.memset(self._counters_dev, 0, 72)
             opt.rayCountersDev = self._counters_dev
         if peers is not None:
             arr = (C.c_void_p * len(peers))(*peers)
@@ -449,12 +473,16 @@ class Renderer:
 
     def reset_ray_counters(self):
         if self._counters_dev is None:
-            self._counters_dev = self.ctx.malloc(24)
-        self.ctx.memset(self._counters_dev, 0, 24)
+            self._counters_dev = self.ctx.malloc(72)
+        self.ctx.memset(self._counters_dev, 0, 72)
 
     def read_ray_counters(self):
-        c = self.ctx.download(self._counters_dev, (3,), np.uint64)
-        return {"closest": int(c[0]), "any": int(c[1]), "hits": int(c[2]), "rays": int(c[0] + c[1])}
+        c = self.ctx.download(self._counters_dev, (9,), np.uint64)
+        out = {"closest": int(c[0]), "any": int(c[1]), "hits": int(c[2]), "rays": int(c[0] + c[1])}
+        if c[3:].any():  # counter build of the library (RT_COUNT_WORK, tools/count_work.py)
+            out["work"] = {"closest": {"nodes": int(c[3]), "triangles": int(c[4]), "entries": int(c[5])},
+                           "any": {"nodes": int(c[6]), "triangles": int(c[7]), "entries": int(c[8])}}
+        return out
 
     def image_info(self, index):
         img = A.Image()

@@ -82,7 +82,12 @@ def gather_frame_host(local_image, world_size, rank, dist):
 
 
 class FrameExchange:
-    """Device-side frame assembly for a `device.Renderer` under torch.distributed (NCCL)."""
+    """Device-side frame assembly for a `device.Renderer` under torch.distributed (NCCL).
+
+    Stream ordering: the library enqueues on the context's own stream (rt_get_stream), which need not be torch's
+    current stream. Every collective here is issued with that stream made current (a torch ExternalStream over the
+    same cudaStream_t), so pack -> all-gather -> unpack, and peer stores -> barrier, are ordered on the one stream the
+    kernels run on, whatever stream the caller's torch code uses. `close()` unmaps the imported peer images."""
 
     def __init__(self, renderer, world_size, rank, mode="peer"):
         import torch
@@ -94,11 +99,13 @@ class FrameExchange:
         self.ctx = renderer.ctx
         self._flag = torch.zeros(1, device=f"cuda:{self.ctx.device}")
         self._peers = None  # [image slot][rank] -> device pointer
+        self._imported = []  # peer mappings this rank opened (rt_ipc_close at close())
         L = D.lib()
         L.rt_pack_tiles.argtypes = [C.c_void_p, C.POINTER(A.Image), C.c_void_p, C.c_int, C.c_int]
         L.rt_unpack_tiles.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(A.Image), C.c_int]
         L.rt_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
         L.rt_ipc_import.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        L.rt_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
         if world_size > 1 and mode == "peer":
             self._open_peers()
         if world_size > 1 and mode == "gather":
@@ -130,7 +137,24 @@ class FrameExchange:
                     out = C.c_void_p()
                     D._check(L.rt_ipc_import(self.ctx._h, everyone[rk][slot][1], C.byref(out)))
                     ptrs.append(out.value)
+                    self._imported.append(out.value)
             self._peers[ptr] = ptrs
+
+    def _library_stream(self):
+        """torch view of the stream the library enqueues on right now (it may have been changed with set_stream)."""
+        return self.torch.cuda.ExternalStream(self.ctx.stream, device=self.ctx.device)
+
+    def close(self):
+        """Unmaps the peer images (collective: every rank must have finished using them)."""
+        if self._imported:
+            self.ctx.sync()
+            if self.dist.is_initialized():
+                self.dist.barrier()
+            L = self.D.lib()
+            for p in self._imported:
+                L.rt_ipc_close(self.ctx._h, p)
+            self._imported = []
+        self._peers = None
 
     def peers_for_next_draw(self):
         """Peer pointers matching the image the next draw writes (TextureIndexPreviousAccumulation)."""
@@ -144,11 +168,12 @@ class FrameExchange:
         if self.world == 1:
             return
         A, L = self.A, self.D.lib()
-        if self.mode == "gather":
-            img = self.r.image_info(A.TEXTURE_ACCUMULATION)
-            self.D._check(L.rt_pack_tiles(self.ctx._h, C.byref(img), self._slab.data_ptr(), self.world, self.rank))
-            self.dist.all_gather_into_tensor(self._all, self._slab)
-            self.D._check(L.rt_unpack_tiles(self.ctx._h, self._all.data_ptr(), C.byref(img), self.world))
-        else:
-            # peer stores are complete when every rank's kernel has finished: stream-ordered barrier
-            self.dist.all_reduce(self._flag)
+        with self.torch.cuda.stream(self._library_stream()):  # NCCL orders itself against the *current* stream
+            if self.mode == "gather":
+                img = self.r.image_info(A.TEXTURE_ACCUMULATION)
+                self.D._check(L.rt_pack_tiles(self.ctx._h, C.byref(img), self._slab.data_ptr(), self.world, self.rank))
+                self.dist.all_gather_into_tensor(self._all, self._slab)
+                self.D._check(L.rt_unpack_tiles(self.ctx._h, self._all.data_ptr(), C.byref(img), self.world))
+            else:
+                # peer stores are complete when every rank's kernel has finished: stream-ordered barrier
+                self.dist.all_reduce(self._flag)

@@ -136,6 +136,13 @@ class Oracle:
         if lib().oracle_set_environment(self._h, C.byref(env)) != 0:
             raise RuntimeError("oracle_set_environment failed")
 
+    def set_enable_ao(self, enable=True):
+        """The reference's compile-time ENABLE_AO switch (ShaderTypes.h:155-157), off by default."""
+        L = lib()
+        L.oracle_set_enable_ao.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_set_enable_ao.restype = None
+        L.oracle_set_enable_ao(self._h, 1 if enable else 0)
+
     def update(self):
         self._desc = self.scene.desc()
         if lib().oracle_update(self._h, C.byref(self._desc)) != 0:

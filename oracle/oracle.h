@@ -30,6 +30,10 @@ int oracle_update(oracle_ctx *c, const rt_scene_desc *scene);
  * 4 x u32 per pixel. stats (optional) receives {closest rays, any-hit rays, closest hits}. */
 int oracle_render(oracle_ctx *c, const rt_uniforms *uniforms, const rt_image textures[9], uint32_t *primaryIds,
                   uint64_t stats[3], int tileModulo, int tileRemainder);
+/* The reference's compile-time ENABLE_AO (ShaderTypes.h:155-157, Raytracing.metal:405-409,442-446,475-479; default 0):
+ * when on, a material with MATERIAL_TEXTURE_AO samples its ambient-occlusion map (x channel), which scales the
+ * throughput of the next bounce (Raytracing.metal:672,748), and debug view 5 shows it. */
+void oracle_set_enable_ao(oracle_ctx *c, int enable);
 /* Environment extension (include/rt_b200.h rt_environment; texels in HOST memory here). NULL switches it off. */
 int oracle_set_environment(oracle_ctx *c, const rt_environment *env);
 void oracle_sample_environment(const rt_environment *env, const float dir[3], float out_rgb[3]); /* KAT probe */

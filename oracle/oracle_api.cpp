@@ -33,6 +33,7 @@ struct oracle_ctx {
   Tlas tlas;
   int maxSubmeshes = 1;
   rt_environment env{};
+  bool enableAO = false;
 };
 
 static void packDescriptor(const float m[16], uint64_t asId, rt_instance_descriptor &d) {
@@ -165,6 +166,7 @@ int oracle_render(oracle_ctx *c, const rt_uniforms *uniforms, const rt_image tex
   a.maxSubmeshes = c->maxSubmeshes;
   a.primaryIds = primaryIds;
   a.env = c->env;
+  a.enableAO = c->enableAO;
   if (!textures[RT_TEXTURE_RANDOM].data || !textures[RT_TEXTURE_PREVIOUS_ACCUMULATION].data) return -1;
   if (tileModulo < 1) tileModulo = 1;
   int tilesX = (uniforms->width + 15) / 16, tilesY = (uniforms->height + 15) / 16;
@@ -286,6 +288,10 @@ int oracle_environment_cdf(const float *texels, int width, int height, float *ou
   }
   marginal[height] = 1.0f;
   return 0;
+}
+
+void oracle_set_enable_ao(oracle_ctx *c, int enable) {
+  if (c) c->enableAO = enable != 0;
 }
 
 int oracle_set_environment(oracle_ctx *c, const rt_environment *env) {

@@ -22,6 +22,7 @@ struct KernelArgs {
   int maxSubmeshes;                       // function constant 1
   uint32_t *primaryIds;                   // optional probe: 4 x u32 per pixel (instance, geometry, primitive, t bits)
   rt_environment env{};                   // extension (rt_b200.h): texelsDev == nullptr means off (reference behaviour)
+  bool enableAO = false;                  // the reference's compile-time ENABLE_AO (ShaderTypes.h:155-157), default 0
 };
 
 struct PixelStats {

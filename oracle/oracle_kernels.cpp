@@ -458,7 +458,8 @@ void raytracingKernelPixel(int tidx, int tidy, const KernelArgs &a, PixelStats &
       bool hasNormalMap = (textureFlags & RT_MATERIAL_TEXTURE_NORMAL) != 0;
       bool hasRoughnessMap = (textureFlags & RT_MATERIAL_TEXTURE_ROUGHNESS) != 0;
       bool hasMetallicMap = (textureFlags & RT_MATERIAL_TEXTURE_METALLIC) != 0;
-      bool hasAOMap = false; // ENABLE_AO == 0 (ShaderTypes.h:155-157)
+      // #if ENABLE_AO (Raytracing.metal:405-409): a build-time switch in the reference, a per-context one here
+      bool hasAOMap = a.enableAO && (textureFlags & RT_MATERIAL_TEXTURE_AO) != 0;
       bool hasOpacityMap = (textureFlags & RT_MATERIAL_TEXTURE_OPACITY) != 0;
       bool hasEmissionMap = (textureFlags & RT_MATERIAL_TEXTURE_EMISSION) != 0;
 
@@ -478,6 +479,7 @@ void raytracingKernelPixel(int tidx, int tidy, const KernelArgs &a, PixelStats &
       float metallic = 0.0f;
       if (hasMetallicMap) metallic = sampleTexture(resource.metallicMap, texCoord).x;
       float ao = 1.0f;
+      if (hasAOMap) ao = sampleTexture(resource.aoMap, texCoord).x; // #if ENABLE_AO (Raytracing.metal:442-446)
       float opacity = clampf(material.opacity, 0.0f, 1.0f);
       if (hasOpacityMap) opacity *= sampleTexture(resource.opacityMap, texCoord).x;
       float3 emission = f3(material.emission);
@@ -502,7 +504,7 @@ void raytracingKernelPixel(int tidx, int tidy, const KernelArgs &a, PixelStats &
         } else if (uniforms.debugTextureMode == RT_DEBUG_METALLIC) {
           debugColor = make3(metallic);
         } else if (uniforms.debugTextureMode == RT_DEBUG_AO) {
-          debugColor = make3(1.0f, 0.0f, 1.0f);
+          debugColor = a.enableAO ? make3(ao) : make3(1.0f, 0.0f, 1.0f); // #if ENABLE_AO (Raytracing.metal:475-479)
         } else if (uniforms.debugTextureMode == RT_DEBUG_EMISSION) {
           debugColor = emission;
         } else if (uniforms.debugTextureMode == RT_DEBUG_MOTION) {

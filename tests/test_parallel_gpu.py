@@ -14,16 +14,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 W, H, FRAMES = 200, 136, 3
 
 
-def _scene():
+def _scene(name):
     from metal4_raytracing_b200 import scene
-    sc, u, seed = scene.Scene.named("K5small", W, H, assets=None)
+    sc, u, seed = scene.Scene.named(name, W, H, assets=None)
     u.samplesPerPixel, u.maxBounces = 2, 3
     return sc, u, scene.seed_image(W, H, seed)
 
 
-def _render(ctx, world, rank, mode, dist=None):
+def _render(ctx, world, rank, mode, dist=None, name="K5small"):
     from metal4_raytracing_b200 import _abi as A, device, parallel
-    sc, u, seeds = _scene()
+    sc, u, seeds = _scene(name)
     rnd = device.Renderer(ctx, sc, W, H, seeds=seeds)
     xchg = parallel.FrameExchange(rnd, world, rank, mode=mode)
     frames = []
@@ -39,11 +39,12 @@ def _render(ctx, world, rank, mode, dist=None):
             torch.cuda.synchronize()
             dist.barrier()
         frames.append(rnd.read_image(A.TEXTURE_ACCUMULATION).copy())
+    xchg.close()
     rnd.close()
     return np.stack(frames)
 
 
-def _worker(rank, world, port, mode, out_dir):
+def _worker(rank, world, port, mode, out_dir, name, own_stream):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     import torch
@@ -52,18 +53,29 @@ def _worker(rank, world, port, mode, out_dir):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
     ctx = device.Context(rank)
-    stream = torch.cuda.Stream(device=rank)
-    torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
-    np.save(os.path.join(out_dir, f"{mode}_rank{rank}.npy"), _render(ctx, world, rank, mode, dist))
+    if not own_stream:
+        # the caller moves the library onto torch's stream (what bench.py does); with own_stream the library keeps
+        # the stream rt_create gave it and FrameExchange has to order NCCL against that one (parallel.py)
+        stream = torch.cuda.Stream(device=rank)
+        torch.cuda.set_stream(stream)
+        ctx.set_stream(stream.cuda_stream)
+    np.save(os.path.join(out_dir, f"{mode}_rank{rank}.npy"), _render(ctx, world, rank, mode, dist, name))
     ctx.close()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["peer", "gather"])
-def test_two_gpu_frame_equals_single_gpu(tmp_path, mode):
+def _world():
+    """Ranks to test with: every visible GPU up to RT_TEST_WORLD (default 2; the 8-rank run sets it to 8)."""
     import torch
-    if torch.cuda.device_count() < 2:
+    return min(torch.cuda.device_count(), int(os.environ.get("RT_TEST_WORLD", "2")))
+
+
+@pytest.mark.parametrize("own_stream", [False, True], ids=["torch-stream", "library-stream"])
+@pytest.mark.parametrize("name", ["K5small", "K3small"])
+@pytest.mark.parametrize("mode", ["peer", "gather"])
+def test_multi_gpu_frame_equals_single_gpu(tmp_path, mode, name, own_stream):
+    world = _world()
+    if world < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
     from metal4_raytracing_b200 import device
@@ -71,10 +83,10 @@ def test_two_gpu_frame_equals_single_gpu(tmp_path, mode):
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_worker, args=(2, port, mode, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, port, mode, str(tmp_path), name, own_stream), nprocs=world, join=True)
     ctx = device.Context(0)
-    ref = _render(ctx, 1, 0, mode)
+    ref = _render(ctx, 1, 0, mode, name=name)
     ctx.close()
-    for r in range(2):
+    for r in range(world):
         got = np.load(os.path.join(tmp_path, f"{mode}_rank{r}.npy"))
-        assert np.array_equal(got.view(np.uint16), ref.view(np.uint16)), f"{mode}: rank {r} frame differs"
+        assert np.array_equal(got.view(np.uint16), ref.view(np.uint16)), f"{mode}/{name}: rank {r} of {world} differs"
