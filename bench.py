@@ -214,26 +214,28 @@ class Rig:
             self.dist.destroy_process_group()
 
 
-def measure(rig, workload, steps, warmup, e2e=True, sampler=None, verify=False):
-    """Device-timed frames (+ optionally the e2e loop and the N-rank == 1-rank frame check) of one workload."""
+def measure(rig, workload, steps, warmup, e2e=True, sampler=None, verify=False, slice_of=1):
+    """Device-timed frames (+ optionally the e2e loop and the N-rank == 1-rank frame check) of one workload.
+    slice_of > 1 (tuning aid, single process): render only the tiles rank 0 of `slice_of` ranks would own."""
     torch = rig.torch
     from metal4_raytracing_b200 import _abi as A
     from metal4_raytracing_b200 import device, parallel, scene
     world, rank, ctx = rig.world, rig.rank, rig.ctx
+    tile_world = slice_of if (world == 1 and slice_of > 1) else world
     sc, u, seeds, w, h = build_scene(workload)
     rnd = device.Renderer(ctx, sc, w, h, seeds=seeds)
     if workload == "K3env":
         rnd.set_environment(scene.procedural_sky(4096, 2048), 0.75, importance=True)
     xchg = parallel.FrameExchange(rnd, world, rank, mode=rig.exchange)
     animated = workload == "K5"
-    pixels_owned = int(parallel.owner_mask(w, h, world, rank).sum())
+    pixels_owned = int(parallel.owner_mask(w, h, tile_world, rank).sum())
 
     def frame(i, count=False):
         u.frameIndex = i
         if animated:
             sc.animate(i / 60.0)
             rnd.update()
-        rnd.draw(u, count_rays=count, tile_modulo=world, tile_remainder=rank, peers=xchg.peers_for_next_draw())
+        rnd.draw(u, count_rays=count, tile_modulo=tile_world, tile_remainder=rank, peers=xchg.peers_for_next_draw())
         xchg.finish_frame()
 
     # ---- warm-up ------------------------------------------------------------------------------------------
@@ -251,7 +253,8 @@ def measure(rig, workload, steps, warmup, e2e=True, sampler=None, verify=False):
     ctx.kernel_timing(True)  # one event after each library launch, on the stream it was launched on
     rig.barrier()
     for k, i in enumerate(range(warmup + 1, warmup + 1 + steps)):
-        rig.flush.fill_(k & 0xFF)  # L2 flush, outside the per-frame events
+        if not os.environ.get("BENCH_NO_FLUSH"):  # diagnosis only: what the cold L2 costs a frame
+            rig.flush.fill_(k & 0xFF)  # L2 flush, outside the per-frame events
         ev[k][0].record()
         frame(i, count="accumulate")  # ray counters: three warp-aggregated atomics per warp, always on
         ev[k][1].record()
@@ -290,7 +293,7 @@ def measure(rig, workload, steps, warmup, e2e=True, sampler=None, verify=False):
             if animated:
                 sc.animate(i / 60.0)
             rnd.update()  # pinned H2D: instance descriptors, lights, (palettes); TLAS update
-            rnd.draw(u, tile_modulo=world, tile_remainder=rank, peers=xchg.peers_for_next_draw())
+            rnd.draw(u, tile_modulo=tile_world, tile_remainder=rank, peers=xchg.peers_for_next_draw())
             if in_flight is not None:
                 ctx.download_wait(in_flight)  # frame i - 1 is on the host before anyone may overwrite its image
             xchg.finish_frame()
@@ -410,6 +413,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the short passes of the other configurations (N = 1)")
     ap.add_argument("--no-verify", action="store_true", help="skip the N-rank == 1-rank frame check (N > 1)")
+    ap.add_argument("--slice", type=int, default=1, help="tuning aid (1 GPU): render only rank 0's tiles of this many "
+                                                          "ranks; the line is marked and is not a bench result")
     args = ap.parse_args()
     steps, warmup = max(1, args.steps), max(3, args.warmup) if args.impl == "ours" else max(0, args.warmup)
     rank = int(os.environ.get("RANK", "0"))
@@ -438,7 +443,10 @@ def main():
 
     rig = Rig(world, rank, local_rank, args.exchange)
     sampler = ClockSampler(local_rank)
-    res = measure(rig, args.workload, steps, warmup, e2e=not args.no_e2e, sampler=sampler, verify=not args.no_verify)
+    res = measure(rig, args.workload, steps, warmup, e2e=not args.no_e2e, sampler=sampler, verify=not args.no_verify,
+                  slice_of=args.slice)
+    if args.slice > 1:
+        config["slice"] = f"TUNING RUN: only the tiles of rank 0 of {args.slice} (no exchange); not a bench result"
     clocks = sampler.summary()
     roofline = roofline_of(res)
 

@@ -252,8 +252,9 @@ uint64_t rt_host_sync_count(rt_context *ctx);
 int rt_set_trace_mode(rt_context *ctx, int mode);
 /* Tuning knobs that never change results: "trace_mode" (0/1), "traversal_variant" (0..2, traverse.cuh),
  * "blocks_per_sm" (persistent grid size of the wavefront kernels), "sample_batch" (1..64, samples of a pixel the
- * wavefront layout keeps in flight at once; default 16), "pipeline_lanes" (1..4, default 2: independent tile subsets
- * of a dispatch whose kernel sequences run on separate streams so that launch tails overlap), "ploc_radius" (builder: PLOC neighbour search radius for
+ * wavefront layout keeps in flight at once; default 16), "pipeline_lanes" (1..4 independent tile subsets of a
+ * dispatch whose kernel sequences run on separate streams so that launch tails overlap; default 0 = two lanes for
+ * dispatches of at least 16 M paths, otherwise one), "ploc_radius" (builder: PLOC neighbour search radius for
  * acceleration structures built after the call, default 16; 0 = plain LBVH), "leaf_size" / "tlas_leaf_size" (1..3
  * triangles / instances per leaf slot of a wide node, defaults 3 / 1). */
 int rt_set_option(rt_context *ctx, const char *key, int value);

@@ -188,7 +188,7 @@ struct rt_context {
   size_t wfBytes[rtb::kMaxLanes] = {};
   // pipeline lanes: a dispatch is split into `pipelineLanes` interleaved tile subsets whose kernel sequences run on
   // their own streams, so that the tail of one lane's persistent launch is filled by the other lane's next launch
-  int pipelineLanes = 2;
+  int pipelineLanes = 0; // 0 = auto (two lanes for dispatches of >= 16 M paths, else one)
   cudaStream_t laneStream[rtb::kMaxLanes] = {};
   cudaEvent_t evFork = nullptr, evLaneDone[rtb::kMaxLanes] = {};
   // per-light constants derived once per rt_trace (trace.cu k_prepare_lights)

@@ -673,7 +673,7 @@ int rt_set_option(rt_context *ctx, const char *key, int value) {
     return 0;
   }
   if (k == "pipeline_lanes") {
-    RT_CHECK(value >= 1 && value <= rtb::kMaxLanes, "rt_set_option: pipeline_lanes is 1..4");
+    RT_CHECK(value >= 0 && value <= rtb::kMaxLanes, "rt_set_option: pipeline_lanes is 0 (auto) or 1..4");
     ctx->pipelineLanes = value;
     return 0;
   }

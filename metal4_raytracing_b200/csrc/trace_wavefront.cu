@@ -684,7 +684,6 @@ int sortQueue(rt_context *ctx, const TraceParams &P, WfState &W, uint32_t **queu
 // to be empty ends after one load.
 int launchTraceWavefront(rt_context *ctx, const TraceParams &P0) {
   const rt_uniforms &U = P0.uniforms;
-  const int tileCount = P0.tilesX * P0.tilesY;
   const int baseSamples = std::max(U.samplesPerPixel, 1);
   const int maxExtraSamples = (U.enableMotionAdaptiveSampling != 0) ? std::max(U.motionSamplingMaxExtraSamples, 0) : 0;
   const int sampleLoopBound = baseSamples + maxExtraSamples;
@@ -692,9 +691,17 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P0) {
   // a refraction does not consume a bounce until transparencyPasses > maxBounces (Raytracing.metal:563-575)
   // without glass (RT_TRACE_HINT_NO_GLASS) every segment consumes a bounce: exactly maxBounces segments
   const int maxSegments = (P0.hints & RT_TRACE_HINT_NO_GLASS) ? maxBounces : maxBounces * (maxBounces + 1);
+  const int tileCount = P0.tilesX * P0.tilesY;
   const int ownedAll = (tileCount - P0.tileRemainder + P0.tileModulo - 1) / P0.tileModulo;
   // ray sorting reads queue lengths back (an experiment, off by default): one lane, on the context's stream
-  int lanes = ctx->sortRays > 0 ? 1 : std::max(1, std::min(std::min(ctx->pipelineLanes, kMaxLanes), ownedAll));
+  // pipeline_lanes 0 = auto: two lanes once the dispatch is large enough for the overlap to outweigh the doubled launch
+  // count (measured, profiles/r2_lanes.md: +2.4 % on the 33 M-path benchmark frame, -1 ... -3 % on frames of 2 - 4 M paths)
+  int wanted = ctx->pipelineLanes;
+  if (wanted <= 0) {
+    const size_t paths = size_t(ownedAll) * 256u * size_t(std::max(1, std::min(ctx->sampleBatch, sampleLoopBound)));
+    wanted = paths >= (size_t(16) << 20) ? 2 : 1;
+  }
+  int lanes = ctx->sortRays > 0 ? 1 : std::max(1, std::min(std::min(wanted, kMaxLanes), ownedAll));
   struct Lane {
     TraceParams P;
     WfState W;
