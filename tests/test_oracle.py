@@ -406,3 +406,33 @@ def test_more_golden_frames(name):
     for key in ("ids", "image", "depth", "motion", "stats") + (("normal",) if "normal" in g else ()):
         a, b = got[key], g[key]
         assert a.shape == b.shape and a.tobytes() == b.tobytes(), key
+
+
+def test_enable_ao_switch_in_the_oracle():
+    """ENABLE_AO (ShaderTypes.h:155-157; Raytracing.metal:405-409,442-446,475-479,672,748): off — the reference's shipping
+    build — a bound ambient-occlusion map changes nothing; on, it scales the bounce throughput (darker or equal
+    everywhere) and debug view 5 shows the sampled value instead of magenta."""
+    from metal4_raytracing_b200 import _abi as A
+    w, h = 96, 64
+
+    def render(bind, enable, debug=0):
+        sc, u, seed = scene.Scene.named("K2tex", w, h, assets=None)
+        if bind:
+            sc.bind_texture(0, 0, A.SLOT_AO, sc.add_texture_procedural("valuenoise", 64, 64, seed=5, srgb=False))
+        u.samplesPerPixel, u.maxBounces, u.debugTextureMode = 2, 3, debug
+        orc = oracle.Oracle(sc)
+        orc.set_enable_ao(enable)
+        imgs = oracle.FrameImages(w, h, scene.seed_image(w, h, seed))
+        orc.render(u, imgs)
+        return imgs.output.astype(np.float32)[..., :3]
+
+    plain = render(False, False)
+    assert np.array_equal(render(True, False), plain)
+    assert np.array_equal(render(False, True), plain)  # the switch alone, without a map, changes nothing
+    on = render(True, True)
+    assert not np.array_equal(on, plain) and on.sum() < plain.sum()
+    dbg_off, dbg_on = render(True, False, A.DEBUG_AO), render(True, True, A.DEBUG_AO)
+    hit = dbg_off.sum(-1) > 0
+    assert hit.any() and np.all(dbg_off[hit][:, 1] == 0.0) and np.all(dbg_off[hit][:, 0] == dbg_off[hit][:, 2])  # magenta
+    textured = (dbg_on[..., 0] == dbg_on[..., 1]) & (dbg_on[..., 1] == dbg_on[..., 2]) & hit
+    assert textured.any()

@@ -256,6 +256,53 @@ def test_png_decoder(assets):
     assert (t.width, t.height) == (ref.shape[1], ref.shape[0]) and np.array_equal(got, ref) and t.srgb == 1
 
 
+def _png_chunk(kind, data):
+    import struct
+    import zlib
+    return struct.pack(">I", len(data)) + kind + data + struct.pack(">I", zlib.crc32(kind + data) & 0xFFFFFFFF)
+
+
+def _load_png_through_mtl(tmp_path, blob, name):
+    """The scene library decodes PNGs when an MTL names one: returns the bound texture record or None when the file was
+    rejected (the material then keeps its 1x1 fallback)."""
+    (tmp_path / f"{name}.png").write_bytes(blob)
+    (tmp_path / f"{name}.mtl").write_text(f"newmtl a\nKd 1 1 1\nmap_Kd {name}.png\n")
+    (tmp_path / f"{name}.obj").write_text(f"mtllib {name}.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\nusemtl a\nf 1/1 2/2 3/3\n")
+    sc = scene.Scene()
+    m = sc.add_obj(str(tmp_path / f"{name}.obj"))
+    d = sc.desc()
+    t = d.textures[d.meshes[m].submeshes[0].textureIndex[A.SLOT_BASECOLOR]]
+    return (t.width, t.height, bytes(t.texels[0:4])) if (d.meshes[m].submeshes[0].material.textureFlags & 1) else None
+
+
+def test_png_decoder_rejects_hostile_files(tmp_path):
+    """The decoder does not trust the file: short or repeated IHDR, dimensions whose byte counts would wrap
+    size_t, truncated chunks and bad filter bytes are refused — the load fails cleanly, nothing is read or written out
+    of bounds and nothing is thrown through the C boundary."""
+    import struct
+    import zlib
+    sig = b"\x89PNG\r\n\x1a\n"
+
+    def ihdr(w, h, depth=8, ctype=6):
+        return _png_chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0))
+
+    good_rows = b"".join(b"\x00" + bytes([10 * y, 20, 30, 255] * 2) for y in range(2))
+    good = sig + ihdr(2, 2) + _png_chunk(b"IDAT", zlib.compress(good_rows)) + _png_chunk(b"IEND", b"")
+    assert _load_png_through_mtl(tmp_path, good, "good") == (2, 2, bytes([0, 20, 30, 255]))
+    hostile = {
+        "short_ihdr": sig + _png_chunk(b"IHDR", b"\x00\x00\x00\x02") + _png_chunk(b"IEND", b""),
+        "wrapping_dims": sig + ihdr(1 << 31, 1 << 30, 16, 6) + _png_chunk(b"IDAT", zlib.compress(b"\x00" * 64)) + _png_chunk(b"IEND", b""),
+        "huge_dims": sig + ihdr(70000, 70000) + _png_chunk(b"IDAT", zlib.compress(b"\x00" * 64)) + _png_chunk(b"IEND", b""),
+        "zero_dims": sig + ihdr(0, 4) + _png_chunk(b"IEND", b""),
+        "two_headers": sig + ihdr(2, 2) + ihdr(4096, 4096) + _png_chunk(b"IDAT", zlib.compress(good_rows)) + _png_chunk(b"IEND", b""),
+        "truncated_chunk": sig + ihdr(2, 2) + struct.pack(">I", 1 << 30) + b"IDAT" + b"\x00" * 8,
+        "bad_filter": sig + ihdr(2, 2) + _png_chunk(b"IDAT", zlib.compress(b"\x09" + bytes(8) + b"\x00" + bytes(8))) + _png_chunk(b"IEND", b""),
+        "short_data": sig + ihdr(2, 2) + _png_chunk(b"IDAT", zlib.compress(b"\x00" * 5)) + _png_chunk(b"IEND", b""),
+    }
+    for name, blob in hostile.items():
+        assert _load_png_through_mtl(tmp_path, blob, name) is None, name
+
+
 def _rgbe_rows(rng, w, h):
     px = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
     px[..., 3] = rng.integers(120, 140, (h, w), dtype=np.uint8)
