@@ -62,8 +62,8 @@ int main(int argc, char **argv) {
   CHECK(rtr_set_seeds(renderer, seeds.data()), rtr_last_error);
 
   uint64_t *countersDev = nullptr;
-  CHECK(rt_malloc(ctx, 72, reinterpret_cast<void **>(&countersDev)), rt_last_error);
-  CHECK(rt_memset(ctx, countersDev, 0, 72), rt_last_error);
+  CHECK(rt_malloc(ctx, 192, reinterpret_cast<void **>(&countersDev)), rt_last_error);
+  CHECK(rt_memset(ctx, countersDev, 0, 192), rt_last_error);
   rt_trace_options options{};
   options.rayCountersDev = countersDev;
 

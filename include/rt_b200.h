@@ -154,9 +154,10 @@ typedef struct rt_trace_options {
   int32_t tileRemainder; /*   tileRemainder (0/1 and 0 = every tile) */
   uint32_t *primaryIdsDev;   /* probe: 4 x u32 per pixel (instance, geometry, primitive, t bits) of sample 0's
                                 first intersect call; 0xFFFFFFFF x4 on a miss. NULL = off */
-  uint64_t *rayCountersDev;  /* probe: 9 x u64, accumulated: {closest-hit rays, any-hit rays, closest hits} and, filled
+  uint64_t *rayCountersDev;  /* probe: 24 x u64, accumulated: {closest-hit rays, any-hit rays, closest hits} and, filled
                                 only by the counter build of the library (-DRT_COUNT_WORK), {node steps, triangle
-                                tests, instance entries} of the closest-hit rays and the same three of the any-hit rays */
+                                tests, instance entries} of the closest-hit rays, the same three of the any-hit rays,
+                                a histogram of iterations per ray and the warps' iterations after their queue ran dry */
   void *const *peerAccumulation; /* multi-GPU: tileModulo device pointers to every rank's destination
                                     accumulation image (same format/size); owned tiles are also stored there
                                     through NVLink peer mappings. NULL = local only */

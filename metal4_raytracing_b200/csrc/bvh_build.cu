@@ -138,7 +138,7 @@ __global__ void k_triangle_bounds(const GeomEntry *geoms, uint32_t geomCount, ui
 // One thread per instance: world box of the BLAS bounds, world->object matrix (double cofactor inverse, the
 // exact op order of oracle/oracle_bvh.cpp invertAffine4x3), traversal record.
 __global__ void k_instance_bounds(const rt_instance_descriptor *desc, uint32_t n, InstanceRecord *records,
-                                  float4 *primLo, float4 *primHi, BoundsAtomics *bounds) {
+                                  float4 *primLo, float4 *primHi, float4 *instanceBox, BoundsAtomics *bounds) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = i < n;
   float3 lo = make_float3(0, 0, 0), hi = lo;
@@ -199,6 +199,9 @@ __global__ void k_instance_bounds(const rt_instance_descriptor *desc, uint32_t n
     }
     primLo[i] = make_float4(lo.x, lo.y, lo.z, 0.0f);
     primHi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    // kept with the TLAS for the flat traversal of small scenes (an empty instance is a point; entering it is a no-op)
+    instanceBox[2 * i] = primLo[i];
+    instanceBox[2 * i + 1] = primHi[i];
   }
   reduceBounds(bounds, lo, hi, valid);
 }
@@ -770,11 +773,13 @@ __global__ void k_write_blas_header(BlasHeader *h, const WideNode *nodes, const 
 }
 
 __global__ void k_write_tlas_header(TlasHeader *h, const WideNode *nodes, const InstanceRecord *instances,
-                                    const uint32_t *leafInstance, uint32_t instanceCount, uint32_t nodeCount) {
+                                    const uint32_t *leafInstance, const float4 *instanceBox, uint32_t instanceCount,
+                                    uint32_t nodeCount) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   h->nodes = nodes;
   h->instances = instances;
   h->leafInstance = leafInstance;
+  h->instanceBox = instanceBox;
   h->instanceCount = instanceCount;
   h->nodeCount = nodeCount;
 }
@@ -1345,14 +1350,16 @@ int buildTlas(rt_context *ctx, AccelObject *as, const rt_instance_descriptor *de
   if (count > as->primCapacity) {
     if (as->primCapacity) RT_CUDA(RT_SYNC_STREAM(ctx, st)); // the old arrays may still be in use
     if (as->instances) cudaFree(as->instances);
+    if (as->instanceBox) cudaFree(as->instanceBox);
     if (as->leafPrim) cudaFree(as->leafPrim);
     if (as->nodes) cudaFree(as->nodes);
     if (as->nodeBox) cudaFree(as->nodeBox);
     if (as->nodeParent) cudaFree(as->nodeParent);
     if (as->nodePending) cudaFree(as->nodePending);
     as->instances = nullptr, as->leafPrim = nullptr, as->nodes = nullptr, as->nodeBox = nullptr;
-    as->nodeParent = nullptr, as->nodePending = nullptr;
+    as->nodeParent = nullptr, as->nodePending = nullptr, as->instanceBox = nullptr;
     RT_CUDA(cudaMalloc(&as->instances, size_t(count) * sizeof(InstanceRecord)));
+    RT_CUDA(cudaMalloc(&as->instanceBox, size_t(count) * 2 * sizeof(float4)));
     RT_CUDA(cudaMalloc(&as->leafPrim, size_t(count) * sizeof(uint32_t)));
     RT_CUDA(cudaMalloc(&as->nodes, size_t(count) * sizeof(WideNode)));
     RT_CUDA(cudaMalloc(&as->nodeBox, size_t(count) * 2 * sizeof(float4)));
@@ -1367,7 +1374,7 @@ int buildTlas(rt_context *ctx, AccelObject *as, const rt_instance_descriptor *de
   if (count == 0) {
     as->nodeCount = 0;
     as->deviceBuilt = false;
-    k_write_tlas_header<<<1, 32, 0, st>>>(static_cast<TlasHeader *>(as->headerDev), nullptr, nullptr, nullptr, 0, 0);
+    k_write_tlas_header<<<1, 32, 0, st>>>(static_cast<TlasHeader *>(as->headerDev), nullptr, nullptr, nullptr, nullptr, 0, 0);
     ++ctx->launches;
     return 0;
   }
@@ -1380,7 +1387,7 @@ int buildTlas(rt_context *ctx, AccelObject *as, const rt_instance_descriptor *de
   float4 *primLo = bump.take<float4>(count), *primHi = bump.take<float4>(count);
   BoundsAtomics *bounds = bump.take<BoundsAtomics>(1);
   k_init_bounds<<<1, 32, 0, st>>>(bounds);
-  k_instance_bounds<<<gridFor(count, 128), 128, 0, st>>>(descDev, count, as->instances, primLo, primHi, bounds);
+  k_instance_bounds<<<gridFor(count, 128), 128, 0, st>>>(descDev, count, as->instances, primLo, primHi, as->instanceBox, bounds);
   ctx->launches += 2;
   if (count <= 8) { // one wide node written by one thread: build and refit are the same thing
     k_tlas_small<<<1, 32, 0, st>>>(primLo, primHi, count, as->nodes, as->nodeBox, as->leafPrim);
@@ -1451,10 +1458,10 @@ int buildTlas(rt_context *ctx, AccelObject *as, const rt_instance_descriptor *de
   }
   as->treeValid = true;
   k_write_tlas_header<<<1, 32, 0, st>>>(static_cast<TlasHeader *>(as->headerDev), as->nodes, as->instances,
-                                        as->leafPrim, count, as->nodeCount);
+                                        as->leafPrim, as->instanceBox, count, as->nodeCount);
   ++ctx->launches;
   RT_CUDA(cudaGetLastError());
-  as->bytes = sizeof(TlasHeader) + size_t(as->primCapacity) * (sizeof(InstanceRecord) + 4 + sizeof(WideNode) + 32 + 8);
+  as->bytes = sizeof(TlasHeader) + size_t(as->primCapacity) * (sizeof(InstanceRecord) + 32 + 4 + sizeof(WideNode) + 32 + 8);
   return 0;
 }
 
@@ -1465,6 +1472,7 @@ void destroyAccel(AccelObject *as) {
   cudaFree(as->nodeBox);
   cudaFree(as->tris);
   cudaFree(as->instances);
+  cudaFree(as->instanceBox);
   cudaFree(as->leafPrim);
   cudaFree(as->triSource);
   cudaFree(as->geomTableDev);

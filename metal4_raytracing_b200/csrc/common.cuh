@@ -85,9 +85,14 @@ struct TlasHeader {
   const WideNode *nodes;
   const InstanceRecord *instances; // indexed by instance id (descriptor order)
   const uint32_t *leafInstance;    // leaf slot (primBase + offset) -> instance id
+  const float4 *instanceBox;       // world box of instance i: [2 i] = lo, [2 i + 1] = hi (exact floats, k_instance_bounds)
   uint32_t instanceCount;
   uint32_t nodeCount;
 };
+// A TLAS of at most this many instances (the reference's scenes have 2 - 8, AppScene.swift:14-28) is one wide node whose
+// leaf slot k holds instance k; the traversal then tests a new ray against the instances' world boxes directly instead of
+// stepping through that node (traverse.cuh LaneTraversal::begin).
+constexpr uint32_t kFlatTlasMax = 8;
 
 // Result of a device-side TLAS build (bvh_build.cu k_tlas_build_cta): lives in device memory, is copied to pinned host
 // memory after every build without waiting, and is looked at one library call later (status != 0 = tree too deep for
@@ -114,6 +119,7 @@ struct AccelObject {
   float4 *nodeBox = nullptr;   // exact float box of each wide node: 2 x float4 per node
   TriRecord *tris = nullptr;   // BLAS
   InstanceRecord *instances = nullptr; // TLAS (in descriptor order)
+  float4 *instanceBox = nullptr;       // TLAS: world boxes in descriptor order (lo, hi)
   uint32_t *leafPrim = nullptr; // TLAS: leaf slot -> instance index (the node's primBase + offset indexes this)
   uint2 *triSource = nullptr;   // BLAS: per triangle slot (geometry, primitive) — refit source mapping
   uint32_t *nodeParent = nullptr, *nodePending = nullptr; // refittable BLAS / TLAS: parent links, per-refit child counters

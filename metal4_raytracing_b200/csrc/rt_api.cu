@@ -638,7 +638,7 @@ int rt_set_option(rt_context *ctx, const char *key, int value) {
   const std::string k(key);
   if (k == "trace_mode") return rt_set_trace_mode(ctx, value);
   if (k == "traversal_variant") {
-    RT_CHECK(value >= 0 && value <= 5, "rt_set_option: traversal_variant is 0..5 (refill at 0/8/16/24/4/2 idle lanes)");
+    RT_CHECK(value >= 0 && value <= 2, "rt_set_option: traversal_variant is 0..2 (idle lanes refilled never / at 8 / at 16)");
     ctx->traversalVariant = value;
     return 0;
   }

@@ -117,6 +117,7 @@ int fillTraceParams(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT],
   P.tlas.nodes = tl->nodes;
   P.tlas.instances = tl->instances;
   P.tlas.leafInstance = tl->leafPrim;
+  P.tlas.instanceBox = tl->instanceBox;
   P.tlas.instanceCount = tl->primCount;
   P.tlas.nodeCount = tl->primCount ? tl->nodeCount : 0u;
   P.tlasRootBox = tl->nodeBox;

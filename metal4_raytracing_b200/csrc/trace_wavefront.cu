@@ -251,7 +251,9 @@ constexpr int kStepsPerCheck = RT_STEPS_PER_CHECK;
 #endif
 // RT_CONVERGED: LaneTraversal::stepConverged; bit 0 = an entry stage before the node stage, bit 2 = one after it,
 // bit 1 = early finish, bit 3 = entry and triangle share one stage as in stepFused, bits 4-5 = extra triangle stages
-// Default 22: entry after the node stage, early finish, two triangle stages (measured best of the combinations, tune34-38)
+// Default 22 + per-instantiation entry order: early finish, two triangle stages, and the entry stage after the node stage
+// for a real TLAS (the best fixed order, tune34-38) but before it in the kernels instantiated for a flat TLAS
+// (<= 8 instances, traverse.cuh begin()): profiles/r2_experiments.md section 5.
 #ifndef RT_CONVERGED
 #define RT_CONVERGED 22
 #endif
@@ -269,10 +271,16 @@ __device__ __forceinline__ void countWork(const TraceParams &P, const LaneTraver
   atomicAdd(c + 0, (unsigned long long)t.nNodes);
   atomicAdd(c + 1, (unsigned long long)t.nTris);
   atomicAdd(c + 2, (unsigned long long)t.nEntries);
+  // iterations this ray lived for: histogram over <= 4, 8, 16, 32, 64, 128, 256, more (rayCounters[9..16]) and the maximum
+  const uint32_t it = t.nIters;
+  const int bin = it <= 4 ? 0 : it <= 8 ? 1 : it <= 16 ? 2 : it <= 32 ? 3 : it <= 64 ? 4 : it <= 128 ? 5 : it <= 256 ? 6 : 7;
+  atomicAdd(P.rayCounters + 9 + bin, 1ull);
+  atomicMax(P.rayCounters + 17, (unsigned long long)it);
+  atomicAdd(P.rayCounters + 18, (unsigned long long)it);
 }
 #endif
 
-template <bool kAny, int kRefill, typename Finish>
+template <bool kAny, int kRefill, bool kFlat, typename Finish>
 __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t *__restrict__ queue, uint32_t count,
                                            uint32_t *cursor, const float4 *__restrict__ rayO,
                                            const float4 *__restrict__ rayD, bool cameraRays, uint2 *sharedStack,
@@ -289,6 +297,9 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
 #endif
   bool active = false, exhausted = false;
   uint32_t slot = 0;
+#ifdef RT_COUNT_WORK
+  uint32_t tailIters = 0; // warp iterations after the queue ran dry
+#endif
   while (true) {
     const unsigned idle = __ballot_sync(full, !active);
     if (idle == full && exhausted) break;
@@ -308,16 +319,20 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
             o = make_float4(P.uniforms.camera.position.x, P.uniforms.camera.position.y, P.uniforms.camera.position.z, 0.0f);
           else
             o = RT_LDS(rayO + slot);
-          t.begin(P.tlas, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, kAny ? d.w : INFINITY);
+          t.template begin<kFlat>(P.tlas, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, kAny ? d.w : INFINITY);
           active = true;
         }
       }
       if (base >= count && idle == full) break;
     }
+#ifdef RT_COUNT_WORK
+    if (exhausted) tailIters += uint32_t(kStepsPerCheck);
+#endif
 #pragma unroll 1
     for (int k = 0; k < kStepsPerCheck; ++k) {
 #if RT_CONVERGED > 0
-      if (t.template stepConverged<(RT_CONVERGED & 1) != 0, (RT_CONVERGED & 4) != 0, (RT_CONVERGED & 2) != 0, (RT_CONVERGED & 8) != 0, 1 + ((RT_CONVERGED >> 4) & 3)>(P.tlas, stack, active)) {
+      // flat TLAS: entry stage before the node stage only; otherwise as RT_CONVERGED says
+      if (t.template stepConverged<kFlat || (RT_CONVERGED & 1) != 0, !kFlat && (RT_CONVERGED & 4) != 0, (RT_CONVERGED & 2) != 0, (RT_CONVERGED & 8) != 0, 1 + ((RT_CONVERGED >> 4) & 3)>(P.tlas, stack, active)) {
 #elif RT_FUSED_PRIMS > 0
       if (active && !t.template stepFused<RT_FUSED_PRIMS>(P.tlas, stack)) {
 #else
@@ -331,6 +346,13 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
       }
     }
   }
+#ifdef RT_COUNT_WORK
+  if (P.rayCounters != nullptr && lane == 0) { // [19] sum, [20] max of warp iterations spent after the queue ran dry, [21] warps
+    atomicAdd(P.rayCounters + 19, (unsigned long long)tailIters);
+    atomicMax(P.rayCounters + 20, (unsigned long long)tailIters);
+    atomicAdd(P.rayCounters + 21, 1ull);
+  }
+#endif
 }
 
 // One launch of the persistent traversal kernel does up to two jobs: the closest-hit rays of segment k (queue qin)
@@ -338,7 +360,7 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
 // that shade kernel, so putting them in one launch lets warps that run out of closest-hit rays go straight on to
 // shadow rays instead of idling through the tail of a separate launch (a persistent launch has a ~50 us tail, which
 // matters once a GPU holds only a slice of the frame). The closest-hit rays go first: they are the longer ones.
-template <int kRefill>
+template <int kRefill, bool kFlat>
 __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse(const __grid_constant__ TraceParams P, const WfState W,
                                                                                  int qin, int firstSegment, int cameraRays,
                                                                                  int doClosest, int doShadow, int shadowParity) {
@@ -355,7 +377,7 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse
       W.counts[10 + nextParity] = 0u;
     }
     const uint32_t count = W.counts[pathCount(qin)];
-    traceQueue<false, kRefill>(P, W.queue[qin], count, W.counts + 3, W.rayO, W.rayD, cameraRays != 0, s_stack,
+    traceQueue<false, kRefill, kFlat>(P, W.queue[qin], count, W.counts + 3, W.rayO, W.rayD, cameraRays != 0, s_stack,
                                [&](uint32_t slot, const LaneTraversal<false> &t) {
                                  RT_STS(W.hitA + slot, make_float4(t.found ? t.hit.t : INFINITY, t.hit.u, t.hit.v,
                                                                    __uint_as_float(t.hit.primitive)));
@@ -374,7 +396,7 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse
   }
   if (doShadow) {
     const uint32_t count = W.counts[shadowCount(shadowParity)];
-    traceQueue<true, kRefill>(P, W.shadowQueue, count, W.counts + 10 + shadowParity, W.rayO, W.shD, false, s_stack,
+    traceQueue<true, kRefill, kFlat>(P, W.shadowQueue, count, W.counts + 10 + shadowParity, W.rayO, W.shD, false, s_stack,
                               [&](uint32_t slot, const LaneTraversal<true> &t) {
                                 if (!t.found) { // unoccluded: the light sample contributes
                                   const float4 c = RT_LDS(W.shC + slot);
@@ -753,14 +775,19 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P0) {
     const WfState &W = ln.W;
     cudaStream_t st = ln.st;
     const int qin = ln.qin;
-    switch (ctx->traversalVariant) {
-      case 1: k_wf_traverse<8><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
-      case 2: k_wf_traverse<16><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
-      case 3: k_wf_traverse<24><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
-      case 4: k_wf_traverse<4><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
-      case 5: k_wf_traverse<2><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
-      default: k_wf_traverse<0><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); break;
+    // instantiations: lane refill threshold (traversal_variant 0 / 1 / 2 = never / 8 / 16 idle lanes) x TLAS kind
+    const bool flat = P.tlas.instanceCount <= kFlatTlasMax && P.tlas.instanceBox != nullptr;
+#define RT_LAUNCH_TRAVERSE(R, F) \
+  k_wf_traverse<R, F><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity)
+    switch (ctx->traversalVariant * 2 + (flat ? 1 : 0)) {
+      case 0: RT_LAUNCH_TRAVERSE(0, false); break;
+      case 1: RT_LAUNCH_TRAVERSE(0, true); break;
+      case 4: RT_LAUNCH_TRAVERSE(16, false); break;
+      case 5: RT_LAUNCH_TRAVERSE(16, true); break;
+      case 3: RT_LAUNCH_TRAVERSE(8, true); break;
+      default: RT_LAUNCH_TRAVERSE(8, false); break;
     }
+#undef RT_LAUNCH_TRAVERSE
   };
   int prevS0 = 0, prevN = 0;
   for (int s0 = 0; s0 < sampleLoopBound;) {

@@ -295,7 +295,7 @@ struct LaneTraversal {
 #ifdef RT_COUNT_WORK
   // counter build (tools/count_work.py): work done for this ray — node steps, triangle tests, instance entries.
   // bench.py turns them into counted bytes per ray (80 B per node, 48 B per triangle, 64 B per instance record)
-  uint32_t nNodes, nTris, nEntries;
+  uint32_t nNodes, nTris, nEntries, nIters;
 #define RT_COUNT(x) (++(x))
 #else
 #define RT_COUNT(x) ((void)0)
@@ -303,6 +303,7 @@ struct LaneTraversal {
   // the traversal stack lives outside (a plain local array passed to every step) so that the compiler keeps the
   // scalar members above in registers instead of placing the whole object in local memory
 
+  template <bool kFlatAllowed = true>
   __device__ __forceinline__ void begin(const TlasHeader &tlas, float ox_, float oy_, float oz_, float dx_,
                                         float dy_, float dz_, float tmin_, float tmax_) {
     ox = ox_, oy = oy_, oz = oz_, dx = dx_, dy = dy_, dz = dz_, tmin = tmin_, tmax = tmax_;
@@ -311,7 +312,7 @@ struct LaneTraversal {
     hit.instance = hit.geometry = hit.primitive = 0u;
     found = false;
 #ifdef RT_COUNT_WORK
-    nNodes = nTris = nEntries = 0u;
+    nNodes = nTris = nEntries = nIters = 0u;
 #endif
     sp = 0;
     instanceSp = -1;
@@ -325,6 +326,33 @@ struct LaneTraversal {
     tri = TriSetup{};
     ngroup = make_uint2(0u, nodeCount != 0 ? 0x80000000u : 0u);
     tgroup = make_uint2(0u, 0u);
+#ifndef RT_NO_FLAT_TLAS
+    // Small scenes (<= kFlatTlasMax instances, a uniform property of the launch): the TLAS is one wide node whose leaf
+    // slot k is instance k, and testing the ray against the k exact world boxes right here — a dozen instructions per
+    // instance, executed by every lane that just received a ray — replaces that node's step (268 instructions at ~21
+    // of 32 lanes, and a third to a half of all node steps of such scenes). The test is conservative (widened by a
+    // few ulp of the magnitudes involved, as in intersectChildren), so exactly the instances the node test would have
+    // reported, or fewer, are queued: results are unchanged.
+    if (kFlatAllowed && tlas.instanceCount <= kFlatTlasMax && tlas.instanceBox != nullptr) {
+      const float cx = ox * box.idx, cy = oy * box.idy, cz = oz * box.idz;
+      uint32_t mask = 0u;
+      for (uint32_t k = 0; k < tlas.instanceCount; ++k) {
+        const float4 lo = __ldg(tlas.instanceBox + 2 * k), hi = __ldg(tlas.instanceBox + 2 * k + 1);
+        const float ax = lo.x * box.idx, bx = hi.x * box.idx, ay = lo.y * box.idy, by = hi.y * box.idy,
+                    az = lo.z * box.idz, bz = hi.z * box.idz;
+        const float eps = 6.0e-7f;
+        const float wx = eps * (fmaxf(fabsf(ax), fabsf(bx)) + fabsf(cx)), wy = eps * (fmaxf(fabsf(ay), fabsf(by)) + fabsf(cy)),
+                    wz = eps * (fmaxf(fabsf(az), fabsf(bz)) + fabsf(cz));
+        const float tn = fmaxf(fmaxf(fminf(ax - cx, bx - cx) - wx, fminf(ay - cy, by - cy) - wy),
+                               fmaxf(fminf(az - cz, bz - cz) - wz, tmin_));
+        const float tf = fminf(fminf(fmaxf(ax - cx, bx - cx) + wx, fmaxf(ay - cy, by - cy) + wy),
+                               fminf(fmaxf(az - cz, bz - cz) + wz, tmax_));
+        if (tn <= tf) mask |= 1u << k;
+      }
+      ngroup = make_uint2(0u, 0u);
+      tgroup = make_uint2(0u, mask);
+    }
+#endif
   }
 
   // take the nearest pending child of ngroup, test its eight children
@@ -490,6 +518,12 @@ struct LaneTraversal {
   template <bool kEntryBefore, bool kEntryAfter, bool kEarlyFinish, bool kCombined, int kTriangles, typename Stack>
   __device__ __forceinline__ bool stepConverged(const TlasHeader &tlas, Stack &stack, bool active) {
     bool alive = active;
+#ifdef RT_COUNT_WORK
+    if (active) ++nIters;
+#endif
+    // Which entry stage exists is chosen per kernel instantiation (trace_wavefront.cu): a flat TLAS (begin()) hands every
+    // new ray its instances directly, so the entry comes first and the BLAS root is tested in the same iteration; with a
+    // real TLAS the node step produces the instances, so the entry follows it.
     if (alive && tgroup.y == 0u && ngroup.y <= 0x00FFFFFFu) alive = popStep(tlas, stack);
     __syncwarp();
     if (kEntryBefore && !kCombined) {

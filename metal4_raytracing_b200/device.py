@@ -456,10 +456,10 @@ class Renderer:
             opt.primaryIdsDev = self._ids_dev
         if count_rays:  # True: reset then count this frame; "accumulate": keep adding to the counters
             if self._counters_dev is None:
-                self._counters_dev = self.ctx.malloc(72)
-                self.ctx.memset(self._counters_dev, 0, 72)
+                self._counters_dev = self.ctx.malloc(192)
+                self.ctx.memset(self._counters_dev, 0, 192)
             if count_rays is True:
-                self.ctx.memset(self._counters_dev, 0, 72)
+                self.ctx.memset(self._counters_dev, 0, 192)
             opt.rayCountersDev = self._counters_dev
         if peers is not None:
             arr = (C.c_void_p * len(peers))(*peers)
@@ -473,15 +473,18 @@ class Renderer:
 
     def reset_ray_counters(self):
         if self._counters_dev is None:
-            self._counters_dev = self.ctx.malloc(72)
-        self.ctx.memset(self._counters_dev, 0, 72)
+            self._counters_dev = self.ctx.malloc(192)
+        self.ctx.memset(self._counters_dev, 0, 192)
 
     def read_ray_counters(self):
-        c = self.ctx.download(self._counters_dev, (9,), np.uint64)
+        c = self.ctx.download(self._counters_dev, (24,), np.uint64)
         out = {"closest": int(c[0]), "any": int(c[1]), "hits": int(c[2]), "rays": int(c[0] + c[1])}
         if c[3:].any():  # counter build of the library (RT_COUNT_WORK, tools/count_work.py)
             out["work"] = {"closest": {"nodes": int(c[3]), "triangles": int(c[4]), "entries": int(c[5])},
-                           "any": {"nodes": int(c[6]), "triangles": int(c[7]), "entries": int(c[8])}}
+                           "any": {"nodes": int(c[6]), "triangles": int(c[7]), "entries": int(c[8])},
+                           "iterations_histogram": {"bins": [4, 8, 16, 32, 64, 128, 256, "more"],
+                                                    "rays": [int(x) for x in c[9:17]], "max": int(c[17]), "sum": int(c[18])},
+                           "tail": {"warp_iterations_sum": int(c[19]), "warp_iterations_max": int(c[20]), "warps": int(c[21])}}
         return out
 
     def image_info(self, index):

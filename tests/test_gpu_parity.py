@@ -833,7 +833,7 @@ def test_environment_extension(mode):
 @pytest.mark.parametrize("options", [
     {"ploc_radius": 0}, {"ploc_radius": 4}, {"ploc_radius": 64},           # LBVH vs PLOC hierarchies
     {"sample_batch": 1}, {"sample_batch": 3},                              # samples in flight per pixel
-    {"traversal_variant": 0}, {"traversal_variant": 3}, {"blocks_per_sm": 2}, {"trace_mode": 0},
+    {"traversal_variant": 0}, {"traversal_variant": 2}, {"blocks_per_sm": 2}, {"trace_mode": 0},
     {"pipeline_lanes": 1}, {"pipeline_lanes": 2}, {"pipeline_lanes": 3},  # tile subsets of a dispatch on separate streams
 ])
 def test_tuning_options_never_change_results(options):
