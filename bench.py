@@ -461,7 +461,8 @@ def main():
                 others[name] = {"workload": workload_text(name), "mrays": round(r["mrays"], 1),
                                 "ms": round(r["total_ms_max"] / r["steps"], 3), "e2e": r["e2e"]["value"],
                                 "e2e_ms": r["e2e"]["ms_per_step"], "rays_per_frame": int(r["rays_all"] / r["steps"]),
-                                "roofline_frac": rl["frac"],
+                                "roofline_frac": rl["frac"], "counted_frac": (rl.get("counted") or {}).get("frac"),
+                                "issue_frac": (rl.get("issue") or {}).get("thread_instruction_frac"),
                                 "kernels_ms": {k: v["ms_per_step"] for k, v in rl["kernels"].items()}}
             except Exception as exc:  # a missing asset directory must not cost the headline line
                 others[name] = {"error": f"{type(exc).__name__}: {exc}"}

@@ -74,8 +74,18 @@ __device__ __forceinline__ float pow5(float x) {
   float x4 = x2 * x2;
   return x4 * x;
 }
+#ifdef RT_FAST_SHADE
+// fast-shade build (csrc/Makefile `fast`): float library functions (<= 2 ulp) instead of double evaluation rounded once
+__device__ __forceinline__ float sinDet(float x) { return sinf(x); }
+__device__ __forceinline__ float cosDet(float x) { return cosf(x); }
+__device__ __forceinline__ float atan2Det(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ float acosDet(float x) { return acosf(x); }
+#else
 __device__ __forceinline__ float sinDet(float x) { return float(sin(double(x))); }
 __device__ __forceinline__ float cosDet(float x) { return float(cos(double(x))); }
+__device__ __forceinline__ float atan2Det(float y, float x) { return float(atan2(double(y), double(x))); }
+__device__ __forceinline__ float acosDet(float x) { return float(acos(double(x))); }
+#endif
 
 constexpr float kPi = 3.14159265358979323846f;
 
@@ -167,8 +177,8 @@ __device__ __forceinline__ float halton(int i, int d) {
 // floats; the bilinear blend uses the same a + (b - a) t form as the material textures.
 constexpr float kInvTwoPi = 0.15915494309189535f, kInvPi = 0.3183098861837907f;
 __device__ __forceinline__ f3 sampleEnvironment(const rt_environment &env, f3 d) {
-  const float phi = float(atan2(double(d.z), double(d.x)));
-  const float theta = float(acos(double(clampf(d.y, -1.0f, 1.0f))));
+  const float phi = atan2Det(d.z, d.x);
+  const float theta = acosDet(clampf(d.y, -1.0f, 1.0f));
   const float u = phi * kInvTwoPi + 0.5f, v = theta * kInvPi;
   const float x = u * float(env.width) - 0.5f, y = v * float(env.height) - 0.5f;
   const float fx = floorf(x), fy = floorf(y);
@@ -208,8 +218,8 @@ __device__ __forceinline__ float environmentTexelPdf(const rt_environment &env, 
   return (pr * pc) / (kTwoPiSquared * fmaxf(sinTheta, 1e-6f));
 }
 __device__ __forceinline__ float environmentPdf(const rt_environment &env, f3 d) {
-  const float phi = float(atan2(double(d.z), double(d.x)));
-  const float theta = float(acos(double(clampf(d.y, -1.0f, 1.0f))));
+  const float phi = atan2Det(d.z, d.x);
+  const float theta = acosDet(clampf(d.y, -1.0f, 1.0f));
   const float u = phi * kInvTwoPi + 0.5f, v = theta * kInvPi;
   const int x = min(max(int(floorf(u * float(env.width))), 0), env.width - 1);
   const int y = min(max(int(floorf(v * float(env.height))), 0), env.height - 1);

@@ -27,9 +27,26 @@
 
 #include "path_step.cuh"
 
+// This file is compiled twice (csrc/Makefile): with -DRT_TU_TRAVERSE into the traversal kernel + the host launcher, and
+// with -DRT_TU_SHADE into the generate / shade / resolve kernels. The split lets the two halves take different compiler
+// flags: the traversal always keeps -fmad=false (ids are part of the bit-exact contract), the shading half can be built
+// with FMA contraction and float sincosf / atan2f / acosf (-DRT_FAST_SHADE, `make fast`, librt_b200_fast.so) to measure
+// what the numeric contract costs. Without either macro everything lands in one object (tools/build_variants.sh).
+#if !defined(RT_TU_TRAVERSE) && !defined(RT_TU_SHADE)
+#define RT_TU_TRAVERSE 1
+#define RT_TU_SHADE 1
+#endif
+
 namespace rtb {
 
-namespace {
+struct WfState;
+// launch wrappers of the shading half (defined under RT_TU_SHADE)
+void wfLaunchGenerate(int grid, cudaStream_t st, const TraceParams &P, const WfState &W, int s0, int n, int prevS0, int prevN,
+                      int baseSamples, int maxExtraSamples);
+void wfLaunchShade(bool textures, bool plain, int grid, cudaStream_t st, const TraceParams &P, const WfState &W, int qin,
+                   int s0, int cameraRays, int parity);
+void wfLaunchResolve(int grid, cudaStream_t st, const TraceParams &P, const WfState &W, int lastS0, int lastN);
+int wfShadeIsFast(); // 1 when the shading half was built with RT_FAST_SHADE
 
 constexpr int kBlock = 256;
 // traversal kernels: small CTAs free their registers as soon as their rays finish; min-blocks caps registers
@@ -51,7 +68,7 @@ constexpr int kTraceBlock = RT_TRACE_BLOCK;
 
 // Path slot = b * capacity + pixelSlot for sample b of the batch in flight: sample-major, so a warp (32 pixels of
 // one tile, same sample) touches consecutive state records.
-struct WfState {
+struct WfState { // same definition in both translation units
   uint32_t capacity; // pixel slots = owned tiles * 256
   uint32_t batch;    // samples of a pixel in flight at once; path slots = capacity * batch
   // per path slot
@@ -75,6 +92,8 @@ struct WfState {
   void *sortTemp;
   size_t sortTempBytes;
 };
+
+namespace {
 
 __device__ __forceinline__ void slotPixel(const TraceParams &P, uint32_t slot, int &px, int &py, bool &valid) {
   valid = ownedPixel(P, int(slot >> 8), int(slot & 255u), px, py);
@@ -128,6 +147,7 @@ __device__ __forceinline__ void foldBatch(const WfState &W, uint32_t pixelSlot, 
   }
 }
 
+#ifdef RT_TU_SHADE
 // Starts the samples [s0, s0 + n) of every owned pixel after folding the previous batch [prevS0, prevS0 + prevN).
 // The first batch never extends past baseSamples, so whether one of its samples exists does not depend on the
 // motion-adaptive count, which is evaluated right after sample 0 has been folded (Raytracing.metal:779-789).
@@ -208,6 +228,9 @@ __global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ 
   }
 }
 
+#endif // RT_TU_SHADE
+
+#ifdef RT_TU_TRAVERSE
 // Ray reordering (option sort_rays, off by default): key = direction octant (3 bits) | Morton code of the origin in
 // a 128^3 grid over the TLAS bounds (21 bits). Rays of one warp then start in the same region and walk the tree in
 // the same child order. Results do not depend on queue order, so this only moves time between kernels.
@@ -409,6 +432,9 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse
   }
 }
 
+#endif // RT_TU_TRAVERSE
+
+#ifdef RT_TU_SHADE
 // RT_SHADE_COMPACT: hits compacted per warp before shading (see k_wf_shade)
 #ifndef RT_SHADE_COMPACT
 #define RT_SHADE_COMPACT 1
@@ -621,6 +647,9 @@ __global__ void __launch_bounds__(kBlock) k_wf_resolve(const __grid_constant__ T
   }
 }
 
+#endif // RT_TU_SHADE
+
+#ifdef RT_TU_TRAVERSE
 int ensureState(rt_context *ctx, int lane, uint32_t capacity, uint32_t batch, WfState &out) {
   const size_t paths = size_t(capacity) * batch;
   size_t sortTempBytes = 0;
@@ -694,7 +723,36 @@ int sortQueue(rt_context *ctx, const TraceParams &P, WfState &W, uint32_t **queu
   return 0;
 }
 
+#endif // RT_TU_TRAVERSE
+
 } // namespace
+
+#ifdef RT_TU_SHADE
+void wfLaunchGenerate(int grid, cudaStream_t st, const TraceParams &P, const WfState &W, int s0, int n, int prevS0, int prevN,
+                      int baseSamples, int maxExtraSamples) {
+  k_wf_generate<<<grid, kBlock, 0, st>>>(P, W, s0, n, prevS0, prevN, baseSamples, maxExtraSamples);
+}
+// the shade kernel is specialised on what the host knows: texture hint, plain PBR without debug views
+void wfLaunchShade(bool textures, bool plain, int grid, cudaStream_t st, const TraceParams &P, const WfState &W, int qin,
+                   int s0, int cameraRays, int parity) {
+  if (textures && plain) k_wf_shade<true, true><<<grid, kBlock, 0, st>>>(P, W, qin, s0, cameraRays, parity);
+  else if (textures) k_wf_shade<true, false><<<grid, kBlock, 0, st>>>(P, W, qin, s0, cameraRays, parity);
+  else if (plain) k_wf_shade<false, true><<<grid, kBlock, 0, st>>>(P, W, qin, s0, cameraRays, parity);
+  else k_wf_shade<false, false><<<grid, kBlock, 0, st>>>(P, W, qin, s0, cameraRays, parity);
+}
+void wfLaunchResolve(int grid, cudaStream_t st, const TraceParams &P, const WfState &W, int lastS0, int lastN) {
+  k_wf_resolve<<<grid, kBlock, 0, st>>>(P, W, lastS0, lastN);
+}
+int wfShadeIsFast() {
+#ifdef RT_FAST_SHADE
+  return 1;
+#else
+  return 0;
+#endif
+}
+#endif // RT_TU_SHADE
+
+#ifdef RT_TU_TRAVERSE
 
 // One dispatch = `lanes` independent pipelines over interleaved tile subsets (lane l of L on rank r of N renders the
 // tiles with tile % (N L) == r + l N — the multi-GPU tile partition applied once more), each with its own path state,
@@ -797,7 +855,7 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P0) {
       if (ln.W.capacity == 0) continue;
       RT_CUDA(cudaMemsetAsync(ln.W.counts, 0, 128, ln.st));
       if (ln.id < 0) ctx->mark(-1);
-      k_wf_generate<<<ln.persistent, kBlock, 0, ln.st>>>(ln.P, ln.W, s0, n, prevS0, prevN, baseSamples, maxExtraSamples);
+      wfLaunchGenerate(ln.persistent, ln.st, ln.P, ln.W, s0, n, prevS0, prevN, baseSamples, maxExtraSamples);
       timed(ln, RT_KERNEL_GENERATE);
       ln.qin = 0;
       ln.shadowPending = false;
@@ -825,14 +883,10 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P0) {
           traverse(ln, first, segment == 0, 1, 0, parity);
           timed(ln, RT_KERNEL_TRACE);
         }
-        { // the shade kernel is specialised on what the host knows: texture hint, plain PBR without debug views
+        {
           const bool textures = (P.hints & RT_TRACE_HINT_UNTEXTURED) == 0u;
           const bool plain = U.debugTextureMode == RT_DEBUG_NONE && U.shadingMode != RT_SHADING_LEGACY && !environmentIsLight(P);
-          const int qin = ln.qin, cam = segment == 0;
-          if (textures && plain) k_wf_shade<true, true><<<ln.persistent, kBlock, 0, ln.st>>>(P, W, qin, s0, cam, parity);
-          else if (textures) k_wf_shade<true, false><<<ln.persistent, kBlock, 0, ln.st>>>(P, W, qin, s0, cam, parity);
-          else if (plain) k_wf_shade<false, true><<<ln.persistent, kBlock, 0, ln.st>>>(P, W, qin, s0, cam, parity);
-          else k_wf_shade<false, false><<<ln.persistent, kBlock, 0, ln.st>>>(P, W, qin, s0, cam, parity);
+          wfLaunchShade(textures, plain, ln.persistent, ln.st, P, W, ln.qin, s0, segment == 0, parity);
         }
         timed(ln, RT_KERNEL_SHADE);
         ln.shadowPending = true;
@@ -853,7 +907,7 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P0) {
   }
   for (Lane &ln : L) {
     if (ln.W.capacity == 0) continue;
-    k_wf_resolve<<<ln.persistent, kBlock, 0, ln.st>>>(ln.P, ln.W, prevS0, prevN);
+    wfLaunchResolve(ln.persistent, ln.st, ln.P, ln.W, prevS0, prevN);
     timed(ln, RT_KERNEL_RESOLVE);
   }
   if (lanes > 1) { // join: the context's stream continues after every lane
@@ -866,5 +920,7 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P0) {
   RT_CUDA(cudaGetLastError());
   return 0;
 }
+
+#endif // RT_TU_TRAVERSE
 
 } // namespace rtb

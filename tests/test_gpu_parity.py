@@ -1056,3 +1056,38 @@ def test_async_readback_matches_blocking_readback(gpu_ctx):
     with pytest.raises(device.RtError):
         gpu_ctx.download_wait(tickets[-1] + 100)
     rnd.close()
+
+
+def test_fast_shade_build_within_tolerance(tmp_path):
+    """librt_b200_fast.so (csrc/Makefile `fast`): shading with FMA contraction and float sin / cos / atan2 / acos. Opt-in,
+    measured in profiles/r2_fast_shade.md; its frames must stay within the north-star bars — primary ids identical
+    (traversal is the strict build) up to camera-ray rounding, radiance relative RMSE < 1e-3 — while the default library
+    stays bit-exact (every other test in this file)."""
+    import subprocess
+    import sys
+    fast = os.path.join(os.path.dirname(device.LIB_PATH), "librt_b200_fast.so")
+    if not os.path.isfile(fast):
+        pytest.skip("librt_b200_fast.so not built (make -C metal4_raytracing_b200/csrc fast)")
+    w, h = 224, 144
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+        "from metal4_raytracing_b200 import device, scene, _abi as A\n"
+        f"sc, u, seed = scene.Scene.named('K2tex', {w}, {h}, assets=None)\n"
+        "u.samplesPerPixel, u.maxBounces = 4, 3\n"
+        "ctx = device.Context(0)\n"
+        f"rnd = device.Renderer(ctx, sc, {w}, {h}, seeds=scene.seed_image({w}, {h}, seed))\n"
+        "rnd.draw(u, want_ids=True)\n"
+        f"np.savez({str(tmp_path / 'fast.npz')!r}, img=rnd.read_image(A.TEXTURE_ACCUMULATION), ids=rnd.read_ids())\n"
+    )
+    env = dict(os.environ, RT_B200_LIBNAME="librt_b200_fast.so")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
+    got = np.load(tmp_path / "fast.npz")
+    sc, u, seed = scene.Scene.named("K2tex", w, h, assets=None)
+    u.samplesPerPixel, u.maxBounces = 4, 3
+    seeds = scene.seed_image(w, h, seed)
+    orc = oracle.Oracle(sc)
+    imgs = oracle.FrameImages(w, h, seeds)
+    _, ref_ids = orc.render(u, imgs, want_ids=True)
+    assert float((got["ids"][..., :3] != ref_ids[..., :3]).any(-1).mean()) <= ID_TOL
+    assert rel_rmse(got["img"], imgs.output) < RMSE_TOL

@@ -8,7 +8,7 @@ make -j6 >/dev/null 2>&1
 build() { # tag, defines...
   tag=$1; shift
   mkdir -p /tmp/variants/$tag
-  for f in trace trace_wavefront selftest; do
+  for f in trace trace_wavefront selftest; do # one object for both halves of trace_wavefront.cu
     $NVCC $FLAGS "$@" -c $f.cu -o /tmp/variants/$tag/$f.o 2> /tmp/variants/$tag/$f.log &
   done
   wait
