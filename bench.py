@@ -223,19 +223,27 @@ def measure(rig, workload, steps, warmup, e2e=True, sampler=None, verify=False, 
     world, rank, ctx = rig.world, rig.rank, rig.ctx
     tile_world = slice_of if (world == 1 and slice_of > 1) else world
     sc, u, seeds, w, h = build_scene(workload)
-    rnd = device.Renderer(ctx, sc, w, h, seeds=seeds)
+    by_samples = world > 1 and rig.exchange == "samples"
+    if by_samples:  # shares of the frame are summed in fp32; the motion-adaptive features need sample 0 on every rank
+        u.enableMotionAdaptiveSampling = u.enableMotionAdaptiveAccumulation = 0
+    rnd = device.Renderer(ctx, sc, w, h, seeds=seeds, fp32=by_samples)
     if workload == "K3env":
         rnd.set_environment(scene.procedural_sky(4096, 2048), 0.75, importance=True)
     xchg = parallel.FrameExchange(rnd, world, rank, mode=rig.exchange)
     animated = workload == "K5"
-    pixels_owned = int(parallel.owner_mask(w, h, tile_world, rank).sum())
+    pixels_owned = w * h if by_samples else int(parallel.owner_mask(w, h, tile_world, rank).sum())
+
+    def partition():
+        if by_samples:
+            return xchg.draw_partition()
+        return {"tile_modulo": tile_world, "tile_remainder": rank, "peers": xchg.peers_for_next_draw()}
 
     def frame(i, count=False):
         u.frameIndex = i
         if animated:
             sc.animate(i / 60.0)
             rnd.update()
-        rnd.draw(u, count_rays=count, tile_modulo=tile_world, tile_remainder=rank, peers=xchg.peers_for_next_draw())
+        rnd.draw(u, count_rays=count, **partition())
         xchg.finish_frame()
 
     # ---- warm-up ------------------------------------------------------------------------------------------
@@ -293,7 +301,7 @@ def measure(rig, workload, steps, warmup, e2e=True, sampler=None, verify=False, 
             if animated:
                 sc.animate(i / 60.0)
             rnd.update()  # pinned H2D: instance descriptors, lights, (palettes); TLAS update
-            rnd.draw(u, tile_modulo=tile_world, tile_remainder=rank, peers=xchg.peers_for_next_draw())
+            rnd.draw(u, **partition())
             if in_flight is not None:
                 ctx.download_wait(in_flight)  # frame i - 1 is on the host before anyone may overwrite its image
             xchg.finish_frame()
@@ -324,10 +332,11 @@ def measure(rig, workload, steps, warmup, e2e=True, sampler=None, verify=False, 
                 if animated and f:
                     sc.animate(f / 60.0)
                     rnd.update()
-                rnd.draw(u, tile_modulo=modulo, tile_remainder=remainder,
-                         peers=xchg.peers_for_next_draw() if exchange else None)
                 if exchange:
+                    rnd.draw(u, **partition())
                     xchg.finish_frame()
+                else:
+                    rnd.draw(u, tile_modulo=modulo, tile_remainder=remainder)
         two_frames(world, rank, True)
         rig.barrier()
         assembled = rnd.read_image(A.TEXTURE_ACCUMULATION).copy() if rank == 0 else None
@@ -336,7 +345,12 @@ def measure(rig, workload, steps, warmup, e2e=True, sampler=None, verify=False, 
             two_frames(1, 0, False)
             ctx.sync()
             alone = rnd.read_image(A.TEXTURE_ACCUMULATION)
-            res["frame_equal"] = bool(np.array_equal(assembled.view(np.uint16), alone.view(np.uint16)))
+            if by_samples:  # float sums reassociated by the all-reduce: equal to rounding
+                diff = float(np.abs(assembled.astype(np.float64) - alone).max() / max(1.0, float(np.abs(alone).max())))
+                res["frame_equal"] = bool(diff <= 4e-6)
+                res["frame_max_rel_diff"] = diff
+            else:
+                res["frame_equal"] = bool(np.array_equal(assembled.view(np.uint16), alone.view(np.uint16)))
             res["frame_sha256"] = {"assembled": hashlib.sha256(assembled.tobytes()).hexdigest()[:16],
                                    "one_rank": hashlib.sha256(alone.tobytes()).hexdigest()[:16]}
         rig.barrier()
@@ -408,7 +422,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="K3", choices=sorted(WORKLOADS))
-    ap.add_argument("--exchange", default="peer", choices=["peer", "gather"])
+    ap.add_argument("--exchange", default="peer", choices=["peer", "gather", "samples"],
+                    help="N > 1: frame assembly — tile partition with NVLink peer stores (default) or an NCCL all-gather, "
+                         "or the sample partition with an NCCL all-reduce of rgba32f shares (parallel.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the short passes of the other configurations (N = 1)")
@@ -422,8 +438,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": workload_text(args.workload),
               "l2": "new sample index every frame + 256 MiB L2 flush between timed frames",
-              "sharding": "interleaved 16x16 tiles, BVH replicated" if world > 1 else "single GPU",
-              "images": "rgba16f accumulation (reference format)"}
+              "sharding": ("single GPU" if world == 1 else "samples s % N == rank of every pixel, BVH replicated, NCCL all-reduce "
+                           "of the rgba32f frame" if args.exchange == "samples" else "interleaved 16x16 tiles, BVH replicated"),
+              "images": "rgba32f accumulation (shares are summed)" if (world > 1 and args.exchange == "samples")
+                        else "rgba16f accumulation (reference format)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -483,6 +501,8 @@ def main():
                 "exchange": args.exchange if world > 1 else None, "frame_equal": res["frame_equal"]}
         if res.get("frame_sha256"):
             line["frame_sha256"] = res["frame_sha256"]
+        if "frame_max_rel_diff" in res:
+            line["frame_max_rel_diff"] = res["frame_max_rel_diff"]
         if others is not None:
             line["others"] = others
         print(json.dumps(line), flush=True)

@@ -164,6 +164,16 @@ typedef struct rt_trace_options {
   const rt_environment *environment; /* HOST pointer; NULL = the reference's behaviour (a miss is black) */
   uint32_t hints;                    /* RT_TRACE_HINT_* promises of the caller; 0 = none */
   uint32_t _pad;
+  int32_t sampleModulo;  /* multi-GPU sample partition (the alternative to tiles for multi-spp frames): */
+  int32_t sampleRemainder; /* this call traces the samples s of every pixel with s % sampleModulo == sampleRemainder
+                            (0/1 and 0 = every sample) and writes its share of the frame,
+                              (sum of its samples) / samplesPerPixel * (1 - w)  [+ w * history on the call with remainder 0],
+                            w = the EMA history weight (0 on frame 0), so that the SUM of the destination images of all
+                            sampleModulo calls is the frame (an NCCL all-reduce when the calls run on different GPUs;
+                            metal4_raytracing_b200/parallel.py mode "samples"). Needs an rgba32f destination, tileModulo
+                            <= 1 and both motion-adaptive features off. Depth, motion, G-buffer and primary ids come
+                            from the call that owns sample 0. Float sums are reassociated, so the frame equals the
+                            single-call frame to rounding (relative 1e-6), not bit for bit as the tile partition does. */
 } rt_trace_options;
 /* The caller promises that no Material bound in this dispatch has a textureFlags bit set. The shading kernel is then
  * a build without the texture paths (about a tenth faster); a material that breaks the promise is shaded as if its

@@ -29,6 +29,7 @@ struct TraceParams {
   const float *srgbLut;
   int maxSubmeshes;
   int tileModulo, tileRemainder;
+  int sampleModulo, sampleRemainder; // sample partition (rt_trace_options): this dispatch owns samples s % modulo == remainder
   int tilesX, tilesY;
   uint32_t *primaryIds;
   unsigned long long *rayCounters;
@@ -480,7 +481,17 @@ __device__ __forceinline__ void resolvePixel(const TraceParams &P, int px, int p
   const rt_uniforms &U = P.uniforms;
   const size_t pixelIndex = size_t(py) * size_t(U.width) + size_t(px);
   totalColor = totalColor / float(max(totalSamples, 1));
-  if (U.frameIndex > 0) {
+  if (P.sampleModulo > 1) {
+    // sample partition: this dispatch's share of the frame; the shares of all dispatches add up to mix(mean, history, w)
+    if (U.frameIndex > 0) {
+      const float historyWeight = clampf(U.accumulationWeight, 0.0f, 0.95f);
+      totalColor = totalColor * (1.0f - historyWeight);
+      if (P.sampleRemainder == 0) {
+        const f4 pc = readImage(P.images[RT_TEXTURE_ACCUMULATION], px, py);
+        totalColor = totalColor + mk3(pc.x, pc.y, pc.z) * historyWeight;
+      }
+    }
+  } else if (U.frameIndex > 0) {
     const f4 pc = readImage(P.images[RT_TEXTURE_ACCUMULATION], px, py);
     float historyWeight = clampf(U.accumulationWeight, 0.0f, 0.95f);
     if (U.enableMotionAdaptiveAccumulation != 0) {
@@ -494,7 +505,8 @@ __device__ __forceinline__ void resolvePixel(const TraceParams &P, int px, int p
     }
     totalColor = mix(totalColor, mk3(pc.x, pc.y, pc.z), historyWeight);
   }
-  const f4 outColor = {totalColor.x, totalColor.y, totalColor.z, 1.0f};
+  // alpha is 1 (Raytracing.metal:819); under the sample partition only the share that owns sample 0 carries it, so the sum does
+  const f4 outColor = {totalColor.x, totalColor.y, totalColor.z, (P.sampleModulo > 1 && P.sampleRemainder != 0) ? 0.0f : 1.0f};
   writeImage(P.images[RT_TEXTURE_PREVIOUS_ACCUMULATION], px, py, outColor);
   for (int p = 0; p < P.peerCount; ++p) // multi-GPU: publish owned pixels into every rank's frame over NVLink
     if (P.peerAccumulation[p] != nullptr && P.peerAccumulation[p] != P.images[RT_TEXTURE_PREVIOUS_ACCUMULATION].data)

@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(256) k_trace_megakernel(const __grid_constant_
   int totalSamples = baseSamples;
 
   for (int sampleIndex = 0; sampleIndex < totalSamples; ++sampleIndex) {
+    if (sampleIndex % P.sampleModulo != P.sampleRemainder) continue; // sample partition: another dispatch owns it
     const int hIndex = haltonIndex(U, offset, sampleStride, sampleIndex);
     PathState s;
     startPath(U, px, py, hIndex, s);
@@ -148,6 +149,15 @@ int fillTraceParams(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT],
   P.tileModulo = (opt && opt->tileModulo > 1) ? opt->tileModulo : 1;
   P.tileRemainder = (opt && opt->tileModulo > 1) ? opt->tileRemainder : 0;
   RT_CHECK(P.tileRemainder >= 0 && P.tileRemainder < P.tileModulo, "rt_trace: tileRemainder out of range");
+  P.sampleModulo = (opt && opt->sampleModulo > 1) ? opt->sampleModulo : 1;
+  P.sampleRemainder = (opt && opt->sampleModulo > 1) ? opt->sampleRemainder : 0;
+  RT_CHECK(P.sampleRemainder >= 0 && P.sampleRemainder < P.sampleModulo, "rt_trace: sampleRemainder out of range");
+  if (P.sampleModulo > 1) {
+    RT_CHECK(P.tileModulo == 1, "rt_trace: the sample partition and the tile partition cannot be combined");
+    RT_CHECK(dst.format == RT_FORMAT_RGBA32_FLOAT, "rt_trace: the sample partition needs an rgba32f destination (shares are summed)");
+    RT_CHECK(P.uniforms.enableMotionAdaptiveSampling == 0 && P.uniforms.enableMotionAdaptiveAccumulation == 0,
+             "rt_trace: the sample partition needs both motion-adaptive features off (they depend on sample 0's motion)");
+  }
   P.tilesX = (P.uniforms.width + 15) / 16;
   P.tilesY = (P.uniforms.height + 15) / 16;
   P.primaryIds = opt ? opt->primaryIdsDev : nullptr;

@@ -197,7 +197,9 @@ __global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ 
     for (int b = 0; b < n; ++b) {
       const int sampleIndex = s0 + b;
       const uint32_t slot = uint32_t(b) * W.capacity + pixelSlot;
-      if (valid && sampleIndex < totalSamples) {
+      if (valid && sampleIndex < totalSamples && sampleIndex % P.sampleModulo != P.sampleRemainder) {
+        RT_STS(W.rad + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f)); // sample partition: another dispatch owns it; folds as 0
+      } else if (valid && sampleIndex < totalSamples) {
         const int hIndex = haltonIndex(U, offset, sampleStride, sampleIndex);
         PathState s;
         startPath(U, px, py, hIndex, s);

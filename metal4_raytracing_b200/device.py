@@ -54,7 +54,8 @@ class DenoiseFrame(C.Structure):
 class TraceOptions(C.Structure):
     _fields_ = [("tileModulo", C.c_int32), ("tileRemainder", C.c_int32), ("primaryIdsDev", C.c_void_p),
                 ("rayCountersDev", C.c_void_p), ("peerAccumulation", C.POINTER(C.c_void_p)),
-                ("environment", C.POINTER(Environment)), ("hints", C.c_uint32), ("_pad", C.c_uint32)]
+                ("environment", C.POINTER(Environment)), ("hints", C.c_uint32), ("_pad", C.c_uint32),
+                ("sampleModulo", C.c_int32), ("sampleRemainder", C.c_int32)]
 
 
 class AsInfo(C.Structure):
@@ -445,8 +446,10 @@ class Renderer:
                 flags = ENV_IMPORTANCE
             self._env = Environment(self._env_dev, t.shape[1], t.shape[0], float(intensity), flags, self._env_cdf_dev)
 
-    def draw(self, uniforms, want_ids=False, count_rays=False, tile_modulo=1, tile_remainder=0, peers=None, hints=0):
+    def draw(self, uniforms, want_ids=False, count_rays=False, tile_modulo=1, tile_remainder=0, peers=None, hints=0,
+             sample_modulo=1, sample_remainder=0):
         opt = TraceOptions()
+        opt.sampleModulo, opt.sampleRemainder = sample_modulo, sample_remainder
         opt.hints = hints  # RT_TRACE_HINT_*; rtr_draw adds RT_TRACE_HINT_UNTEXTURED itself when the scene has no maps
         opt.tileModulo, opt.tileRemainder = tile_modulo, tile_remainder
         if want_ids:

@@ -9,6 +9,14 @@ is the assembly of the displayed frame:
                compute and exchange in one kernel; ranks then meet at a stream-ordered NCCL barrier;
   * "gather" — rt_pack_tiles -> torch.distributed all_gather_into_tensor (NCCL) -> rt_unpack_tiles.
 
+A third mode partitions samples instead of pixels (SURVEY.md §8e's alternative for multi-spp frames):
+
+  * "samples" — rank g traces the samples s of every pixel with s % N == g (rt_trace_options.sampleModulo) and writes
+               its share of the frame; one NCCL all-reduce (sum) of the rgba32f frame makes every rank hold the frame, which
+               is also the history of the next one. Per-rank work is 1/N of the rays over the whole screen (perfectly
+               balanced, no ownership pattern), the exchange is the full frame every frame (33 MB at 1080p), and float
+               sums are reassociated: equal to the single-GPU frame to rounding, not bit for bit.
+
 The tile arithmetic and the slab layout are plain host logic and are shared with the CPU (gloo) tests.
 """
 import ctypes as C
@@ -108,6 +116,12 @@ class FrameExchange:
         L.rt_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
         if world_size > 1 and mode == "peer":
             self._open_peers()
+        if world_size > 1 and mode == "samples":
+            info = renderer.image_info(A.TEXTURE_ACCUMULATION)
+            if info.format != A.FORMAT_RGBA32_FLOAT:
+                raise ValueError('exchange mode "samples" sums shares of the frame: create the Renderer with fp32=True')
+            self._sum = torch.empty(renderer.width * renderer.height * 4, dtype=torch.float32,
+                                    device=f"cuda:{self.ctx.device}")
         if world_size > 1 and mode == "gather":
             info = renderer.image_info(A.TEXTURE_ACCUMULATION)
             bpp = {A.FORMAT_RGBA16_FLOAT: 8, A.FORMAT_RGBA32_FLOAT: 16}[info.format]
@@ -156,6 +170,14 @@ class FrameExchange:
             self._imported = []
         self._peers = None
 
+    def draw_partition(self):
+        """Keyword arguments for Renderer.draw that give this rank its share of the frame under the chosen mode."""
+        if self.world == 1:
+            return {}
+        if self.mode == "samples":
+            return {"sample_modulo": self.world, "sample_remainder": self.rank}
+        return {"tile_modulo": self.world, "tile_remainder": self.rank, "peers": self.peers_for_next_draw()}
+
     def peers_for_next_draw(self):
         """Peer pointers matching the image the next draw writes (TextureIndexPreviousAccumulation)."""
         if self.world == 1 or self.mode != "peer":
@@ -169,7 +191,13 @@ class FrameExchange:
             return
         A, L = self.A, self.D.lib()
         with self.torch.cuda.stream(self._library_stream()):  # NCCL orders itself against the *current* stream
-            if self.mode == "gather":
+            if self.mode == "samples":
+                img = self.r.image_info(A.TEXTURE_ACCUMULATION)
+                nbytes = self._sum.numel() * 4
+                self.ctx.copy(self._sum.data_ptr(), img.data, nbytes)
+                self.dist.all_reduce(self._sum)  # sum of the ranks' shares = the frame (and the next frame's history)
+                self.ctx.copy(img.data, self._sum.data_ptr(), nbytes)
+            elif self.mode == "gather":
                 img = self.r.image_info(A.TEXTURE_ACCUMULATION)
                 self.D._check(L.rt_pack_tiles(self.ctx._h, C.byref(img), self._slab.data_ptr(), self.world, self.rank))
                 self.dist.all_gather_into_tensor(self._all, self._slab)

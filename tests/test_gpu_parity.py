@@ -1091,3 +1091,42 @@ def test_fast_shade_build_within_tolerance(tmp_path):
     _, ref_ids = orc.render(u, imgs, want_ids=True)
     assert float((got["ids"][..., :3] != ref_ids[..., :3]).any(-1).mean()) <= ID_TOL
     assert rel_rmse(got["img"], imgs.output) < RMSE_TOL
+
+
+@pytest.mark.parametrize("mode", [1, 0], ids=["wavefront", "megakernel"])
+def test_sample_partition_shares_sum_to_the_frame(mode):
+    """rt_trace_options.sampleModulo (rank r takes samples r, r + N, ...): the shares N dispatches write
+    add up to the frame one dispatch renders — over EMA frames too, the sum being the next frame's history — to float
+    rounding (the per-sample radiances are the same bits; only the order of the additions differs)."""
+    w, h, n = 192, 128, 4
+    sc, u, seed = scene.Scene.named("K3small", w, h, assets=None)
+    u.samplesPerPixel, u.maxBounces = 8, 3
+    u.enableMotionAdaptiveSampling = u.enableMotionAdaptiveAccumulation = 0
+    seeds = scene.seed_image(w, h, seed)
+    ctx = device.Context(0)
+    ctx.set_trace_mode(mode)
+    try:
+        full = device.Renderer(ctx, sc, w, h, seeds=seeds, fp32=True)
+        parts = [device.Renderer(ctx, sc, w, h, seeds=seeds, fp32=True) for _ in range(n)]
+        for f in range(3):
+            u.frameIndex = f
+            full.draw(u, count_rays=True)
+            ref = full.read_image(A.TEXTURE_ACCUMULATION).astype(np.float64)
+            total, rays = np.zeros_like(ref), 0
+            for r, part in enumerate(parts):
+                part.draw(u, count_rays=True, sample_modulo=n, sample_remainder=r)
+                total += part.read_image(A.TEXTURE_ACCUMULATION).astype(np.float64)
+                rays += part.read_ray_counters()["rays"]
+            assert rays == full.read_ray_counters()["rays"]  # every sample traced exactly once
+            assert np.abs(total - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max()), f"frame {f}"
+            summed = total.astype(np.float32)
+            for part in parts:  # what the all-reduce leaves on every rank: the frame, next frame's history
+                ctx.upload(summed, part.image_info(A.TEXTURE_ACCUMULATION).data)
+            assert np.array_equal(parts[0].read_image(A.TEXTURE_DEPTH), full.read_image(A.TEXTURE_DEPTH))  # sample 0's owner
+        with pytest.raises(device.RtError):  # shares are summed: an fp16 destination is refused
+            half = device.Renderer(ctx, sc, w, h, seeds=seeds)
+            half.draw(u, sample_modulo=2, sample_remainder=0)
+        for r in [full] + parts:
+            r.close()
+    finally:
+        ctx.close()
