@@ -199,8 +199,11 @@ __global__ void k_instance_bounds(const rt_instance_descriptor *desc, uint32_t n
     }
     primLo[i] = make_float4(lo.x, lo.y, lo.z, 0.0f);
     primHi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
-    // kept with the TLAS for the flat traversal of small scenes (an empty instance is a point; entering it is a no-op)
-    instanceBox[2 * i] = primLo[i];
+    // kept with the TLAS for the flat traversal of small scenes (an empty instance is a point; entering it is a no-op);
+    // lo.w = 1 marks an instance without nodes to traverse (empty, or a single-leaf BLAS tested directly): a ray whose box
+    // test reaches only such instances is a cheap ray (trace_wavefront.cu queues those separately)
+    const bool nodeless = empty || (blas->nodeCount == 1 && blas->triCount <= 24);
+    instanceBox[2 * i] = make_float4(lo.x, lo.y, lo.z, nodeless ? 1.0f : 0.0f);
     instanceBox[2 * i + 1] = primHi[i];
   }
   reduceBounds(bounds, lo, hi, valid);

@@ -194,6 +194,7 @@ struct rt_context {
   size_t wfBytes[rtb::kMaxLanes] = {};
   // pipeline lanes: a dispatch is split into `pipelineLanes` interleaved tile subsets whose kernel sequences run on
   // their own streams, so that the tail of one lane's persistent launch is filled by the other lane's next launch
+  int classifyRays = 1;  // flat TLAS: queue rays by class (reaches a BLAS with nodes / cheap), long rays first
   int pipelineLanes = 0; // 0 = auto (two lanes for dispatches of >= 16 M paths, else one)
   cudaStream_t laneStream[rtb::kMaxLanes] = {};
   cudaEvent_t evFork = nullptr, evLaneDone[rtb::kMaxLanes] = {};

@@ -677,6 +677,11 @@ int rt_set_option(rt_context *ctx, const char *key, int value) {
     ctx->pipelineLanes = value;
     return 0;
   }
+  if (k == "classify_rays") {
+    RT_CHECK(value == 0 || value == 1, "rt_set_option: classify_rays is 0 or 1");
+    ctx->classifyRays = value;
+    return 0;
+  }
   if (k == "blocks_per_sm") {
     RT_CHECK(value >= 1 && value <= 32, "rt_set_option: blocks_per_sm is 1..32");
     ctx->blocksPerSm = value;

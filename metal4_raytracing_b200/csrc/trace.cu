@@ -97,6 +97,25 @@ __global__ void k_prepare_lights(const rt_light *lights, int count, float4 *deri
   derived[i] = make_float4(d.x, d.y, d.z, cosDet(lights[i].coneAngle));
 }
 
+// Flat TLAS: the union of the world boxes of the instances that have nodes to traverse (instanceBox lo.w == 0), once per
+// dispatch; an inverted box (nothing can reach it) when there is none. Feeds rayReachesNodes (traverse.cuh).
+__global__ void k_prepare_classes(const float4 *instanceBox, uint32_t count, float4 *unionBox) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  for (uint32_t k = 0; k < count; ++k) {
+    const float4 l = instanceBox[2 * k], h = instanceBox[2 * k + 1];
+    if (l.w != 0.0f) continue;
+    lo[0] = fminf(lo[0], l.x), lo[1] = fminf(lo[1], l.y), lo[2] = fminf(lo[2], l.z);
+    hi[0] = fmaxf(hi[0], h.x), hi[1] = fmaxf(hi[1], h.y), hi[2] = fmaxf(hi[2], h.z);
+  }
+  if (lo[0] > hi[0]) { // no instance with nodes: a box far outside any scene, so every ray is cheap
+    lo[0] = lo[1] = lo[2] = 1.0e30f;
+    hi[0] = hi[1] = hi[2] = 1.0000001e30f;
+  }
+  unionBox[0] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+  unionBox[1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+}
+
 int fillTraceParams(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], const rt_image textures[RT_TEXTURE_COUNT],
                     int maxSubmeshes, const rt_trace_options *opt, TraceParams &P) {
   RT_CHECK(buffers != nullptr && textures != nullptr, "rt_trace: null argument table");
@@ -141,10 +160,11 @@ int fillTraceParams(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT],
     ctx->lightDerivedDev = nullptr;
     ctx->lightDerivedCap = 0;
     const int cap = std::max(16, P.uniforms.lightCount);
-    RT_CUDA(cudaMalloc(&ctx->lightDerivedDev, size_t(cap) * sizeof(float4)));
+    RT_CUDA(cudaMalloc(&ctx->lightDerivedDev, size_t(cap + 2) * sizeof(float4))); // + the union box of k_prepare_classes
     ctx->lightDerivedCap = cap;
   }
   P.lightDerived = ctx->lightDerivedDev;
+  P.nodeUnionBox = ctx->lightDerivedDev + ctx->lightDerivedCap;
   P.maxSubmeshes = maxSubmeshes;
   P.tileModulo = (opt && opt->tileModulo > 1) ? opt->tileModulo : 1;
   P.tileRemainder = (opt && opt->tileModulo > 1) ? opt->tileRemainder : 0;
@@ -188,6 +208,10 @@ int launchTrace(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], con
   k_prepare_lights<<<(P.uniforms.lightCount + 63) / 64, 64, 0, ctx->stream>>>(P.lights, P.uniforms.lightCount,
                                                                                ctx->lightDerivedDev);
   ++ctx->launches;
+  if (P.tlas.instanceCount <= kFlatTlasMax && P.tlas.instanceBox != nullptr) {
+    k_prepare_classes<<<1, 32, 0, ctx->stream>>>(P.tlas.instanceBox, P.tlas.instanceCount, ctx->lightDerivedDev + ctx->lightDerivedCap);
+    ++ctx->launches;
+  }
   // the wavefront layout packs (bounce, step, transparency passes) into 10 bits each; deeper paths than that
   // (maxBounces > 31, far beyond anything the reference's UI offers) run in the megakernel
   if (ctx->traceMode == 1 && P.uniforms.maxBounces <= 31) return launchTraceWavefront(ctx, P);

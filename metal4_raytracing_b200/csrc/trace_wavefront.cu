@@ -71,6 +71,9 @@ constexpr int kTraceBlock = RT_TRACE_BLOCK;
 struct WfState { // same definition in both translation units
   uint32_t capacity; // pixel slots = owned tiles * 256
   uint32_t batch;    // samples of a pixel in flight at once; path slots = capacity * batch
+  uint32_t queueCapacity; // entries of each queue array (= path slots): class B entries fill it from the back
+  uint32_t classify;      // 1: rays are queued by class (flat TLAS): A = reaches a BLAS with nodes, from the front of the
+                          // queue; B = cheap (misses, single-leaf instances only), from the back. 0: everything is class A
   // per path slot
   float4 *rayO, *rayD; // rayD.w: sample (halton) index bits on camera rays, packed (bounce, step, transparency
                        // passes) afterwards; rayO doubles as the origin of the segment's shadow ray
@@ -84,6 +87,9 @@ struct WfState { // same definition in both translation units
   float4 *mot;  // motion.xy, prevMotion.xy
   float4 *misc; // depth, flags bits (1 = hadPrimaryHit, 2 = wroteGBuffer), seed offset bits, unused
   uint32_t *queue[2], *shadowQueue;
+  uint32_t *shadeQueue[2]; // classify: the paths of queue[q] once more in plain append order — what the shade kernel walks
+                           // (consecutive entries = neighbouring path slots, so its state accesses stay coalesced; walking
+                           // the class-ordered queue cost it 33 %, profiles/r2_experiments.md section 6)
   uint32_t *counts; // [pathCount(q)] path queues, [3] trace cursor, [shadowCount(p)] shadow queue length and [10 + p] shadow cursor of
                     // segment parity p (double-buffered: the shadow rays of segment k are traced in the same launch
                     // as the closest-hit rays of segment k + 1)
@@ -103,6 +109,14 @@ __device__ __forceinline__ void slotPixel(const TraceParams &P, uint32_t slot, i
 // the shadow queue of parity qin, so those two lengths share an aligned 64-bit word and one atomic serves both.
 __host__ __device__ __forceinline__ int pathCount(int q) { return q == 1 ? 16 : 18; }
 __host__ __device__ __forceinline__ int shadowCount(int p) { return p == 0 ? 17 : 19; }
+// the same for the class B ends of the queues (entries stored from the back of the array), eight words further on
+__host__ __device__ __forceinline__ int pathCountB(int q) { return pathCount(q) + 8; }
+__host__ __device__ __forceinline__ int plainCount(int q) { return q == 1 ? 20 : 21; } // length of shadeQueue[q]
+__host__ __device__ __forceinline__ int shadowCountB(int p) { return shadowCount(p) + 8; }
+// entry j of a two-ended queue holding countA class A entries at the front and the class B entries at the back
+__device__ __forceinline__ uint32_t queueEntry(const uint32_t *__restrict__ queue, uint32_t capacity, uint32_t countA, uint32_t j) {
+  return j < countA ? queue[j] : queue[capacity - 1u - (j - countA)];
+}
 
 // Appends `slot` to the path queue (lanes with pushPath) and to the shadow queue (lanes with pushShadow) with one
 // 64-bit atomic per warp: low word = path queue length, high word = shadow queue length (`pair` points at both).
@@ -121,6 +135,42 @@ __device__ __forceinline__ void queuePushBoth(uint32_t *pathQueue, uint32_t *sha
   const unsigned below = (1u << lane) - 1u;
   if (pushPath) pathQueue[uint32_t(base) + __popc(vp & below)] = slot;
   if (pushShadow) shadowQueue[uint32_t(base >> 32) + __popc(vs & below)] = slot;
+}
+
+// The same with classes: class A entries go to the front of the queues (lengths in pairA), class B entries to the back
+// (lengths in pairB); one 64-bit atomic per class that has entries.
+__device__ __forceinline__ void queuePushClassified(uint32_t *pathQueue, uint32_t *shadowQueue, uint32_t *pairA, uint32_t *pairB,
+                                                    uint32_t capacity, bool pushPath, bool pathIsB, bool pushShadow,
+                                                    bool shadowIsB, uint32_t slot, uint32_t *plainQueue, uint32_t *plainLength) {
+  // called by whole warps. The three reservations (class A pair, class B pair, plain path order) are issued by three
+  // different lanes so that they are in flight together: the shade kernel is latency-bound and three atomics in a row
+  // cost it a fifth of its time.
+  const unsigned full = 0xFFFFFFFFu;
+  const unsigned vp = __ballot_sync(full, pushPath), vs = __ballot_sync(full, pushShadow);
+  if ((vp | vs) == 0u) return;
+  const unsigned vpB = __ballot_sync(full, pushPath && pathIsB), vsB = __ballot_sync(full, pushShadow && shadowIsB);
+  const unsigned vpA = vp & ~vpB, vsA = vs & ~vsB;
+  const int lane = threadIdx.x & 31;
+  unsigned long long got = 0ull;
+  if (lane == 0 && (vpA | vsA) != 0u)
+    got = atomicAdd(reinterpret_cast<unsigned long long *>(pairA),
+                    (unsigned long long)__popc(vpA) | ((unsigned long long)__popc(vsA) << 32));
+  if (lane == 1 && (vpB | vsB) != 0u)
+    got = atomicAdd(reinterpret_cast<unsigned long long *>(pairB),
+                    (unsigned long long)__popc(vpB) | ((unsigned long long)__popc(vsB) << 32));
+  if (lane == 2 && vp != 0u) got = (unsigned long long)atomicAdd(plainLength, uint32_t(__popc(vp)));
+  const unsigned long long baseA = __shfl_sync(full, got, 0), baseB = __shfl_sync(full, got, 1);
+  const uint32_t basePlain = uint32_t(__shfl_sync(full, got, 2));
+  const unsigned below = (1u << lane) - 1u;
+  if (pushPath) {
+    plainQueue[basePlain + __popc(vp & below)] = slot; // the next shade pass walks this one
+    if (!pathIsB) pathQueue[uint32_t(baseA) + __popc(vpA & below)] = slot;
+    else pathQueue[capacity - 1u - (uint32_t(baseB) + __popc(vpB & below))] = slot;
+  }
+  if (pushShadow) {
+    if (!shadowIsB) shadowQueue[uint32_t(baseA >> 32) + __popc(vsA & below)] = slot;
+    else shadowQueue[capacity - 1u - (uint32_t(baseB >> 32) + __popc(vsB & below))] = slot;
+  }
 }
 
 // Appends `slot` for every lane with `push` set; one atomic per warp.
@@ -151,6 +201,7 @@ __device__ __forceinline__ void foldBatch(const WfState &W, uint32_t pixelSlot, 
 // Starts the samples [s0, s0 + n) of every owned pixel after folding the previous batch [prevS0, prevS0 + prevN).
 // The first batch never extends past baseSamples, so whether one of its samples exists does not depend on the
 // motion-adaptive count, which is evaluated right after sample 0 has been folded (Raytracing.metal:779-789).
+template <bool kClassify>
 __global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ TraceParams P, const WfState W, int s0,
                                                         int n, int prevS0, int prevN, int baseSamples,
                                                         int maxExtraSamples) {
@@ -194,6 +245,7 @@ __global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ 
       RT_STS(W.tot + pixelSlot, make_float4(total.x, total.y, total.z, __uint_as_float(uint32_t(totalSamples))));
     }
     unsigned long long pushed = 0ull; // bit b: sample b of this pixel has a camera ray to trace (batch <= 64)
+    unsigned long long cheap = 0ull;  // bit b: that ray is class B (W.classify: it reaches no BLAS with nodes)
     for (int b = 0; b < n; ++b) {
       const int sampleIndex = s0 + b;
       const uint32_t slot = uint32_t(b) * W.capacity + pixelSlot;
@@ -206,30 +258,44 @@ __global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ 
         // a camera ray's other state is implied (origin = camera, throughput 1, radiance 0, counters 0): the first
         // segment's trace and shade kernels supply it themselves, so only 16 of the 80 bytes are written here
         RT_STS(W.rayD + slot, make_float4(s.dir.x, s.dir.y, s.dir.z, __int_as_float(hIndex)));
-        if (U.maxBounces > 0) pushed |= 1ull << b;
-        else RT_STS(W.rad + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f)); // never traced: folds as black
+        if (U.maxBounces > 0) {
+          pushed |= 1ull << b;
+          if (kClassify && !rayReachesNodes(P.nodeUnionBox, s.origin.x, s.origin.y, s.origin.z, s.dir.x, s.dir.y, s.dir.z, 0.0f, INFINITY))
+            cheap |= 1ull << b;
+        } else {
+          RT_STS(W.rad + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f)); // never traced: folds as black
+        }
       }
     }
-    // one reservation per warp for all of its samples (one atomic instead of n); entries stay sample-major, so 32
-    // consecutive queue entries are still 32 consecutive path slots
+    // one reservation per warp and class for all of its samples (instead of n atomics); entries stay sample-major, so 32
+    // consecutive queue entries of a class are still up to 32 consecutive path slots
     const unsigned full = 0xFFFFFFFFu;
-    uint32_t total = 0;
-    for (int b = 0; b < n; ++b) total += uint32_t(__popc(__ballot_sync(full, (pushed >> b) & 1ull)));
-    if (total != 0u) {
-      const int lane = threadIdx.x & 31;
-      uint32_t run = 0;
-      if (lane == 0) run = atomicAdd(W.counts + pathCount(0), total);
-      run = __shfl_sync(full, run, 0);
-      for (int b = 0; b < n; ++b) {
-        const bool push = (pushed >> b) & 1ull;
-        const unsigned votes = __ballot_sync(full, push);
-        if (push) W.queue[0][run + uint32_t(__popc(votes & ((1u << lane) - 1u)))] = uint32_t(b) * W.capacity + pixelSlot;
-        run += uint32_t(__popc(votes));
+    const int lane = threadIdx.x & 31;
+    // per warp: how many rays of each kind, one reservation each — issued by different lanes so they overlap
+    uint32_t totalA = 0, totalB = 0;
+    for (int b = 0; b < n; ++b) {
+      totalA += uint32_t(__popc(__ballot_sync(full, ((pushed & ~cheap) >> b) & 1ull)));
+      totalB += uint32_t(__popc(__ballot_sync(full, ((pushed & cheap) >> b) & 1ull)));
+    }
+    uint32_t got = 0;
+    if (lane == 0 && totalA != 0u) got = atomicAdd(W.counts + pathCount(0), totalA);
+    if (kClassify && lane == 1 && totalB != 0u) got = atomicAdd(W.counts + pathCountB(0), totalB);
+    if (kClassify && lane == 2 && totalA + totalB != 0u) got = atomicAdd(W.counts + plainCount(0), totalA + totalB);
+    uint32_t runA = __shfl_sync(full, got, 0), runB = __shfl_sync(full, got, 1), runPlain = __shfl_sync(full, got, 2);
+    if (totalA + totalB != 0u) {
+      for (int b = 0; b < n; ++b) { // entries stay sample-major: consecutive entries of a kind are up to 32 consecutive slots
+        const bool push = (pushed >> b) & 1ull, isB = (cheap >> b) & 1ull;
+        const unsigned votes = __ballot_sync(full, push), votesB = __ballot_sync(full, push && isB);
+        const unsigned votesA = votes & ~votesB, below = (1u << lane) - 1u;
+        const uint32_t slot = uint32_t(b) * W.capacity + pixelSlot;
+        if (push && !isB) W.queue[0][runA + uint32_t(__popc(votesA & below))] = slot;
+        if (push && isB) W.queue[0][W.queueCapacity - 1u - (runB + uint32_t(__popc(votesB & below)))] = slot;
+        if (kClassify && push) W.shadeQueue[0][runPlain + uint32_t(__popc(votes & below))] = slot;
+        runA += uint32_t(__popc(votesA)), runB += uint32_t(__popc(votesB)), runPlain += uint32_t(__popc(votes));
       }
     }
   }
 }
-
 #endif // RT_TU_SHADE
 
 #ifdef RT_TU_TRAVERSE
@@ -306,8 +372,9 @@ __device__ __forceinline__ void countWork(const TraceParams &P, const LaneTraver
 #endif
 
 template <bool kAny, int kRefill, bool kFlat, typename Finish>
-__device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t *__restrict__ queue, uint32_t count,
-                                           uint32_t *cursor, const float4 *__restrict__ rayO,
+__device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t *__restrict__ queue, uint32_t countA,
+                                           uint32_t countB, uint32_t queueCapacity, uint32_t *cursor,
+                                           const float4 *__restrict__ rayO,
                                            const float4 *__restrict__ rayD, bool cameraRays, uint2 *sharedStack,
                                            Finish finish) {
   const unsigned full = 0xFFFFFFFFu;
@@ -322,6 +389,7 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
 #endif
   bool active = false, exhausted = false;
   uint32_t slot = 0;
+  const uint32_t count = countA + countB; // the cursor walks the class A entries (front) first, then class B (back)
 #ifdef RT_COUNT_WORK
   uint32_t tailIters = 0; // warp iterations after the queue ran dry
 #endif
@@ -337,7 +405,7 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
       if (!active) {
         const uint32_t j = base + uint32_t(__popc(idle & ((1u << lane) - 1u)));
         if (j < count) {
-          slot = queue[j];
+          slot = queueEntry(queue, queueCapacity, countA, j);
           const float4 d = RT_LDS(rayD + slot);
           float4 o;
           if (!kAny && cameraRays) // first segment: every ray starts at the camera (k_wf_generate)
@@ -398,11 +466,15 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse
     const int nextParity = doShadow ? (shadowParity ^ 1) : shadowParity; // parity of the segment traced here
     if (blockIdx.x == 0 && threadIdx.x == 0) { // the queues this segment's shade kernel appends to start empty
       W.counts[pathCount(qin ^ 1)] = 0u;
+      W.counts[pathCountB(qin ^ 1)] = 0u;
+      W.counts[plainCount(qin ^ 1)] = 0u;
       W.counts[shadowCount(nextParity)] = 0u;
+      W.counts[shadowCountB(nextParity)] = 0u;
       W.counts[10 + nextParity] = 0u;
     }
-    const uint32_t count = W.counts[pathCount(qin)];
-    traceQueue<false, kRefill, kFlat>(P, W.queue[qin], count, W.counts + 3, W.rayO, W.rayD, cameraRays != 0, s_stack,
+    const uint32_t countA = W.counts[pathCount(qin)], countB = W.counts[pathCountB(qin)];
+    traceQueue<false, kRefill, kFlat>(P, W.queue[qin], countA, countB, W.queueCapacity, W.counts + 3, W.rayO, W.rayD,
+                                      cameraRays != 0, s_stack,
                                [&](uint32_t slot, const LaneTraversal<false> &t) {
                                  RT_STS(W.hitA + slot, make_float4(t.found ? t.hit.t : INFINITY, t.hit.u, t.hit.v,
                                                                    __uint_as_float(t.hit.primitive)));
@@ -417,11 +489,13 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse
                                    reinterpret_cast<uint4 *>(P.primaryIds)[size_t(py) * size_t(P.uniforms.width) + size_t(px)] = id;
                                  }
                                });
-    if (P.rayCounters != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.rayCounters + 0, (unsigned long long)count);
+    if (P.rayCounters != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+      atomicAdd(P.rayCounters + 0, (unsigned long long)countA + (unsigned long long)countB);
   }
   if (doShadow) {
-    const uint32_t count = W.counts[shadowCount(shadowParity)];
-    traceQueue<true, kRefill, kFlat>(P, W.shadowQueue, count, W.counts + 10 + shadowParity, W.rayO, W.shD, false, s_stack,
+    const uint32_t countA = W.counts[shadowCount(shadowParity)], countB = W.counts[shadowCountB(shadowParity)];
+    traceQueue<true, kRefill, kFlat>(P, W.shadowQueue, countA, countB, W.queueCapacity, W.counts + 10 + shadowParity, W.rayO,
+                                     W.shD, false, s_stack,
                               [&](uint32_t slot, const LaneTraversal<true> &t) {
                                 if (!t.found) { // unoccluded: the light sample contributes
                                   const float4 c = RT_LDS(W.shC + slot);
@@ -430,10 +504,10 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse
                                   RT_STS(W.rad + slot, r);
                                 }
                               });
-    if (P.rayCounters != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.rayCounters + 1, (unsigned long long)count);
+    if (P.rayCounters != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+      atomicAdd(P.rayCounters + 1, (unsigned long long)countA + (unsigned long long)countB);
   }
 }
-
 #endif // RT_TU_TRAVERSE
 
 #ifdef RT_TU_SHADE
@@ -444,16 +518,20 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse
 #ifndef RT_SHADE_MINBLOCKS
 #define RT_SHADE_MINBLOCKS 4 // 64 registers: measured faster than 128 (the kernel is bound by gather latency; more warps hide it)
 #endif
-template <bool kTextures, bool kPlain>
+template <bool kTextures, bool kPlain, bool kClassify>
 __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const __grid_constant__ TraceParams P,
                                                                          const WfState W, int qin, int s0,
                                                                          int cameraRays, int shadowParity) {
   if (blockIdx.x == 0 && threadIdx.x == 0) W.counts[3] = 0u; // cursor of the next trace kernel
-  const uint32_t count = W.counts[pathCount(qin)];
-  const uint32_t *queue = W.queue[qin];
+  // the paths of this segment: with classes the plain-order copy, otherwise the queue the traversal walked
+  constexpr bool classify = kClassify;
+  const uint32_t count = classify ? W.counts[plainCount(qin)] : W.counts[pathCount(qin)];
+  const uint32_t *queue = classify ? W.shadeQueue[qin] : W.queue[qin];
+  uint32_t *plainOut = classify ? W.shadeQueue[qin ^ 1] : nullptr;
   uint32_t hitCount = 0; // this thread's closest hits, added to the probe counter once per warp at the end
-  // one hit: the path state in, shadeSegment, the state of the next segment and of the shadow ray out
-  auto shadeHit = [&](uint32_t slot, const float4 &ha, bool &pushPath, bool &pushShadow) {
+  // one hit: the path state in, shadeSegment, the state of the next segment and of the shadow ray out; pathIsB / shadowIsB:
+  // the class of the ray it emits (WfState::classify)
+  auto shadeHit = [&](uint32_t slot, const float4 &ha, bool &pushPath, bool &pushShadow, bool &pathIsB, bool &shadowIsB) {
     const uint32_t b = slot / W.capacity; // sample of the batch, pixel slot
     const uint32_t pixelSlot = slot - b * W.capacity;
     const int sampleIndex = s0 + int(b);
@@ -505,6 +583,8 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
       const uint32_t packed = uint32_t(s.bounce) | (uint32_t(s.step) << 10) | (uint32_t(s.transparencyPasses) << 20);
       RT_STS(W.rayD + slot, make_float4(s.dir.x, s.dir.y, s.dir.z, __uint_as_float(packed)));
       RT_STS(W.thr + slot, make_float4(s.throughput.x, s.throughput.y, s.throughput.z, th.w));
+      if (classify)
+        pathIsB = !rayReachesNodes(P.nodeUnionBox, s.origin.x, s.origin.y, s.origin.z, s.dir.x, s.dir.y, s.dir.z, 0.0f, INFINITY);
     }
     // the shadow ray starts where the next segment starts (shadeSegment: both are hit + N * 1e-3), so one origin
     // record serves both; a path that ends but still has a shadow ray to trace stores it for that alone
@@ -530,6 +610,13 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
       pushShadow = true;
       RT_STS(W.shD + slot, make_float4(shadow.dir.x, shadow.dir.y, shadow.dir.z, shadow.tmax));
       RT_STS(W.shC + slot, make_float4(shadow.contribution.x, shadow.contribution.y, shadow.contribution.z, 0.0f));
+      // its origin is the record written above (the next segment's origin, or its own when the path ends here)
+      const f3 so = pushPath ? s.origin : shadow.origin;
+#ifndef RT_CLASSIFY_SHADOW
+#define RT_CLASSIFY_SHADOW 1 // 0: only path rays are queued by class; shadow rays all go to the front of their queue
+#endif
+      if (classify && RT_CLASSIFY_SHADOW)
+        shadowIsB = !rayReachesNodes(P.nodeUnionBox, so.x, so.y, so.z, shadow.dir.x, shadow.dir.y, shadow.dir.z, 0.0f, shadow.tmax);
     }
   };
   // a miss: a camera ray still has to leave radiance 0 behind for the fold (k_wf_generate did not write it); with the
@@ -589,15 +676,20 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
     while (listed >= 32u || (round == rounds && listed != 0u)) {
       const uint32_t take = min(listed, 32u);
       listed -= take;
-      bool pushPath = false, pushShadow = false;
+      bool pushPath = false, pushShadow = false, pathIsB = false, shadowIsB = false;
       uint32_t slot = 0;
       if (lane < take) {
         slot = mySlots[listed + lane];
-        shadeHit(slot, RT_LDS(W.hitA + slot), pushPath, pushShadow);
+        shadeHit(slot, RT_LDS(W.hitA + slot), pushPath, pushShadow, pathIsB, shadowIsB);
         ++hitCount;
       }
-      // shadowParity == qin (both are the segment's parity), so the two lengths are the halves of one 64-bit word
-      queuePushBoth(W.queue[qin ^ 1], W.shadowQueue, W.counts + pathCount(qin ^ 1), pushPath, pushShadow, slot);
+      // shadowParity == qin (both are the segment's parity), so the two lengths of a class are the halves of one 64-bit word
+      if (classify)
+        queuePushClassified(W.queue[qin ^ 1], W.shadowQueue, W.counts + pathCount(qin ^ 1), W.counts + pathCountB(qin ^ 1),
+                            W.queueCapacity, pushPath, pathIsB, pushShadow, shadowIsB, slot, plainOut,
+                            W.counts + plainCount(qin ^ 1));
+      else
+        queuePushBoth(W.queue[qin ^ 1], W.shadowQueue, W.counts + pathCount(qin ^ 1), pushPath, pushShadow, slot);
     }
     __syncwarp();
   }
@@ -605,7 +697,7 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
   const uint32_t rounds = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   for (uint32_t round = 0; round < rounds; ++round, j += gridDim.x * blockDim.x) { // whole warps stay in the loop
-    bool pushPath = false, pushShadow = false;
+    bool pushPath = false, pushShadow = false, pathIsB = false, shadowIsB = false;
     uint32_t slot = 0;
     float4 ha = make_float4(INFINITY, 0.0f, 0.0f, 0.0f);
     if (j < count) {
@@ -613,13 +705,17 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
       ha = RT_LDS(W.hitA + slot);
     }
     if (ha.x < INFINITY) {
-      shadeHit(slot, ha, pushPath, pushShadow);
+      shadeHit(slot, ha, pushPath, pushShadow, pathIsB, shadowIsB);
       ++hitCount;
     } else if (j < count && missesMatter) {
       shadeMissed(slot);
     }
-    // shadowParity == qin (both are the segment's parity), so the two lengths are the halves of one 64-bit word
-    queuePushBoth(W.queue[qin ^ 1], W.shadowQueue, W.counts + pathCount(qin ^ 1), pushPath, pushShadow, slot);
+    if (classify)
+      queuePushClassified(W.queue[qin ^ 1], W.shadowQueue, W.counts + pathCount(qin ^ 1), W.counts + pathCountB(qin ^ 1),
+                          W.queueCapacity, pushPath, pathIsB, pushShadow, shadowIsB, slot, plainOut,
+                          W.counts + plainCount(qin ^ 1));
+    else
+      queuePushBoth(W.queue[qin ^ 1], W.shadowQueue, W.counts + pathCount(qin ^ 1), pushPath, pushShadow, slot);
   }
 #endif
   if (P.rayCounters != nullptr) {
@@ -658,7 +754,7 @@ int ensureState(rt_context *ctx, int lane, uint32_t capacity, uint32_t batch, Wf
   if (ctx->sortRays > 0)
     cub::DeviceRadixSort::SortPairs(nullptr, sortTempBytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
                                     (uint32_t *)nullptr, int(paths), 0, 24, ctx->stream);
-  const size_t need = 256 + 8 * (paths * 16 + 256) + 3 * (size_t(capacity) * 16 + 256) + 3 * (paths * 4 + 256) +
+  const size_t need = 256 + 8 * (paths * 16 + 256) + 3 * (size_t(capacity) * 16 + 256) + 5 * (paths * 4 + 256) +
                       (ctx->sortRays > 0 ? 3 * (paths * 4 + 256) + sortTempBytes + 256 : 0);
   if (ctx->wfState[lane] == nullptr || ctx->wfBytes[lane] < need) {
     RT_CUDA(RT_SYNC_STREAM(ctx, ctx->stream)); // every lane joined the context's stream at the end of its last dispatch
@@ -677,6 +773,8 @@ int ensureState(rt_context *ctx, int lane, uint32_t capacity, uint32_t batch, Wf
   WfState s{};
   s.capacity = capacity;
   s.batch = batch;
+  s.queueCapacity = uint32_t(paths);
+  s.classify = 0u;
   const size_t v = paths * 16, pv = size_t(capacity) * 16;
   s.counts = static_cast<uint32_t *>(take(256));
   s.rayO = static_cast<float4 *>(take(v));
@@ -693,6 +791,8 @@ int ensureState(rt_context *ctx, int lane, uint32_t capacity, uint32_t batch, Wf
   s.queue[0] = static_cast<uint32_t *>(take(paths * 4));
   s.queue[1] = static_cast<uint32_t *>(take(paths * 4));
   s.shadowQueue = static_cast<uint32_t *>(take(paths * 4));
+  s.shadeQueue[0] = static_cast<uint32_t *>(take(paths * 4));
+  s.shadeQueue[1] = static_cast<uint32_t *>(take(paths * 4));
   if (ctx->sortRays > 0) {
     s.sortKeys[0] = static_cast<uint32_t *>(take(paths * 4));
     s.sortKeys[1] = static_cast<uint32_t *>(take(paths * 4));
@@ -732,15 +832,22 @@ int sortQueue(rt_context *ctx, const TraceParams &P, WfState &W, uint32_t **queu
 #ifdef RT_TU_SHADE
 void wfLaunchGenerate(int grid, cudaStream_t st, const TraceParams &P, const WfState &W, int s0, int n, int prevS0, int prevN,
                       int baseSamples, int maxExtraSamples) {
-  k_wf_generate<<<grid, kBlock, 0, st>>>(P, W, s0, n, prevS0, prevN, baseSamples, maxExtraSamples);
+  if (W.classify != 0u) k_wf_generate<true><<<grid, kBlock, 0, st>>>(P, W, s0, n, prevS0, prevN, baseSamples, maxExtraSamples);
+  else k_wf_generate<false><<<grid, kBlock, 0, st>>>(P, W, s0, n, prevS0, prevN, baseSamples, maxExtraSamples);
 }
 // the shade kernel is specialised on what the host knows: texture hint, plain PBR without debug views
 void wfLaunchShade(bool textures, bool plain, int grid, cudaStream_t st, const TraceParams &P, const WfState &W, int qin,
                    int s0, int cameraRays, int parity) {
-  if (textures && plain) k_wf_shade<true, true><<<grid, kBlock, 0, st>>>(P, W, qin, s0, cameraRays, parity);
-  else if (textures) k_wf_shade<true, false><<<grid, kBlock, 0, st>>>(P, W, qin, s0, cameraRays, parity);
-  else if (plain) k_wf_shade<false, true><<<grid, kBlock, 0, st>>>(P, W, qin, s0, cameraRays, parity);
-  else k_wf_shade<false, false><<<grid, kBlock, 0, st>>>(P, W, qin, s0, cameraRays, parity);
+#define RT_SHADE(T, PL)                                                                                       \
+  do {                                                                                                         \
+    if (W.classify != 0u) k_wf_shade<T, PL, true><<<grid, kBlock, 0, st>>>(P, W, qin, s0, cameraRays, parity); \
+    else k_wf_shade<T, PL, false><<<grid, kBlock, 0, st>>>(P, W, qin, s0, cameraRays, parity);                 \
+  } while (0)
+  if (textures && plain) RT_SHADE(true, true);
+  else if (textures) RT_SHADE(true, false);
+  else if (plain) RT_SHADE(false, true);
+  else RT_SHADE(false, false);
+#undef RT_SHADE
 }
 void wfLaunchResolve(int grid, cudaStream_t st, const TraceParams &P, const WfState &W, int lastS0, int lastN) {
   k_wf_resolve<<<grid, kBlock, 0, st>>>(P, W, lastS0, lastN);
@@ -811,6 +918,10 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P0) {
     if (U.debugTextureMode == RT_DEBUG_MOTION) batch = 1;
     RT_TRY(ensureState(ctx, l, std::max(capacity, 256u), uint32_t(batch), ln.W));
     ln.W.capacity = capacity;
+    // rays queued by class (A: reaches a BLAS with nodes, B: cheap) when the TLAS is flat; the ray-sorting experiment
+    // works on plain queues
+    ln.W.classify = (ctx->classifyRays != 0 && ctx->sortRays == 0 && P0.tlas.instanceCount <= kFlatTlasMax &&
+                     P0.tlas.instanceBox != nullptr) ? 1u : 0u;
     ln.id = lanes > 1 ? l : -1;
     ln.st = lanes > 1 ? ctx->laneStream[l] : ctx->stream;
     const int slotBlocks = (int(capacity) + kBlock - 1) / kBlock;

@@ -835,6 +835,7 @@ def test_environment_extension(mode):
     {"sample_batch": 1}, {"sample_batch": 3},                              # samples in flight per pixel
     {"traversal_variant": 0}, {"traversal_variant": 2}, {"blocks_per_sm": 2}, {"trace_mode": 0},
     {"pipeline_lanes": 1}, {"pipeline_lanes": 2}, {"pipeline_lanes": 3},  # tile subsets of a dispatch on separate streams
+    {"classify_rays": 0},                                                  # rays queued by class (flat TLAS) or not
 ])
 def test_tuning_options_never_change_results(options):
     """Builder choice (LBVH / PLOC radius), sample batching, lane-refill threshold, grid size and kernel layout are
