@@ -25,7 +25,7 @@ struct TraceParams {
   const rt_instance_descriptor *prevInstances;
   const rt_light *lights;
   const float4 *lightDerived; // per light: normalize(direction).xyz, cos(coneAngle) — hoisted out of the per-hit code
-  const float4 *nodeUnionBox; // flat TLAS: union box (lo, hi) of the instances whose BLAS has nodes (k_prepare_classes)
+  const float4 *nodeUnionBox; // flat TLAS: bounding sphere (centre, radius) of the instances whose BLAS has nodes (k_prepare_classes)
   rt_image images[RT_TEXTURE_COUNT];
   const float *srgbLut;
   int maxSubmeshes;

@@ -97,9 +97,9 @@ __global__ void k_prepare_lights(const rt_light *lights, int count, float4 *deri
   derived[i] = make_float4(d.x, d.y, d.z, cosDet(lights[i].coneAngle));
 }
 
-// Flat TLAS: the union of the world boxes of the instances that have nodes to traverse (instanceBox lo.w == 0), once per
-// dispatch; an inverted box (nothing can reach it) when there is none. Feeds rayReachesNodes (traverse.cuh).
-__global__ void k_prepare_classes(const float4 *instanceBox, uint32_t count, float4 *unionBox) {
+// Flat TLAS: bounding sphere (centre, radius) of the union of the world boxes of the instances that have nodes to traverse
+// (instanceBox lo.w == 0), once per dispatch; a far-away point when there is none. Feeds rayReachesNodes (traverse.cuh).
+__global__ void k_prepare_classes(const float4 *instanceBox, uint32_t count, float4 *sphere) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
   for (uint32_t k = 0; k < count; ++k) {
@@ -108,12 +108,12 @@ __global__ void k_prepare_classes(const float4 *instanceBox, uint32_t count, flo
     lo[0] = fminf(lo[0], l.x), lo[1] = fminf(lo[1], l.y), lo[2] = fminf(lo[2], l.z);
     hi[0] = fmaxf(hi[0], h.x), hi[1] = fmaxf(hi[1], h.y), hi[2] = fmaxf(hi[2], h.z);
   }
-  if (lo[0] > hi[0]) { // no instance with nodes: a box far outside any scene, so every ray is cheap
-    lo[0] = lo[1] = lo[2] = 1.0e30f;
-    hi[0] = hi[1] = hi[2] = 1.0000001e30f;
+  if (lo[0] > hi[0]) { // no instance with nodes: every ray is cheap
+    sphere[0] = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.0f);
+    return;
   }
-  unionBox[0] = make_float4(lo[0], lo[1], lo[2], 0.0f);
-  unionBox[1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+  const float ex = 0.5f * (hi[0] - lo[0]), ey = 0.5f * (hi[1] - lo[1]), ez = 0.5f * (hi[2] - lo[2]);
+  sphere[0] = make_float4(0.5f * (lo[0] + hi[0]), 0.5f * (lo[1] + hi[1]), 0.5f * (lo[2] + hi[2]), sqrtf(ex * ex + ey * ey + ez * ez));
 }
 
 int fillTraceParams(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], const rt_image textures[RT_TEXTURE_COUNT],

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(kBlock) k_wf_generate(const __grid_constant__ 
         RT_STS(W.rayD + slot, make_float4(s.dir.x, s.dir.y, s.dir.z, __int_as_float(hIndex)));
         if (U.maxBounces > 0) {
           pushed |= 1ull << b;
-          if (kClassify && !rayReachesNodes(P.nodeUnionBox, s.origin.x, s.origin.y, s.origin.z, s.dir.x, s.dir.y, s.dir.z, 0.0f, INFINITY))
+          if (kClassify && !rayReachesNodes(P.nodeUnionBox, s.origin.x, s.origin.y, s.origin.z, s.dir.x, s.dir.y, s.dir.z, INFINITY))
             cheap |= 1ull << b;
         } else {
           RT_STS(W.rad + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f)); // never traced: folds as black
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
       RT_STS(W.rayD + slot, make_float4(s.dir.x, s.dir.y, s.dir.z, __uint_as_float(packed)));
       RT_STS(W.thr + slot, make_float4(s.throughput.x, s.throughput.y, s.throughput.z, th.w));
       if (classify)
-        pathIsB = !rayReachesNodes(P.nodeUnionBox, s.origin.x, s.origin.y, s.origin.z, s.dir.x, s.dir.y, s.dir.z, 0.0f, INFINITY);
+        pathIsB = !rayReachesNodes(P.nodeUnionBox, s.origin.x, s.origin.y, s.origin.z, s.dir.x, s.dir.y, s.dir.z, INFINITY);
     }
     // the shadow ray starts where the next segment starts (shadeSegment: both are hit + N * 1e-3), so one origin
     // record serves both; a path that ends but still has a shadow ray to trace stores it for that alone
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
 #define RT_CLASSIFY_SHADOW 1 // 0: only path rays are queued by class; shadow rays all go to the front of their queue
 #endif
       if (classify && RT_CLASSIFY_SHADOW)
-        shadowIsB = !rayReachesNodes(P.nodeUnionBox, so.x, so.y, so.z, shadow.dir.x, shadow.dir.y, shadow.dir.z, 0.0f, shadow.tmax);
+        shadowIsB = !rayReachesNodes(P.nodeUnionBox, so.x, so.y, so.z, shadow.dir.x, shadow.dir.y, shadow.dir.z, shadow.tmax);
     }
   };
   // a miss: a camera ray still has to leave radiance 0 behind for the fold (k_wf_generate did not write it); with the

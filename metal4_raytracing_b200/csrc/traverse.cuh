@@ -272,27 +272,21 @@ __device__ __forceinline__ uint32_t intersectChildren(const uint4 &n0, const uin
   return hitmask;
 }
 
-// Flat TLAS only (<= kFlatTlasMax instances): can the ray reach an instance whose BLAS has nodes to traverse? Rays that
-// cannot — they miss everything, or reach only single-leaf instances such as the reference's planes — live for two or
-// three iterations; the others walk a BVH. The wavefront kernels queue the two classes at opposite ends of a queue so
-// that warps hold rays of one kind and the long rays start first. The test is one conservative slab test against the
-// union box of the instances with nodes (`unionBox`: lo, hi; written once per dispatch by k_prepare_classes), widened
-// like the tests of LaneTraversal::begin, so a ray classified cheap never queues a BLAS with nodes there. Only the
-// order of the work depends on it, never a result.
-__device__ __forceinline__ bool rayReachesNodes(const float4 *__restrict__ unionBox, float ox, float oy, float oz, float dx,
-                                                float dy, float dz, float tmin, float tmax) {
-  const float4 lo = __ldg(unionBox), hi = __ldg(unionBox + 1);
-  const float idx = safeInverse(dx), idy = safeInverse(dy), idz = safeInverse(dz);
-  const float cx = ox * idx, cy = oy * idy, cz = oz * idz;
-  const float ax = lo.x * idx, bx = hi.x * idx, ay = lo.y * idy, by = hi.y * idy, az = lo.z * idz, bz = hi.z * idz;
-  const float eps = 6.0e-7f;
-  const float wx = eps * (fmaxf(fabsf(ax), fabsf(bx)) + fabsf(cx)), wy = eps * (fmaxf(fabsf(ay), fabsf(by)) + fabsf(cy)),
-              wz = eps * (fmaxf(fabsf(az), fabsf(bz)) + fabsf(cz));
-  const float tn = fmaxf(fmaxf(fminf(ax - cx, bx - cx) - wx, fminf(ay - cy, by - cy) - wy),
-                         fmaxf(fminf(az - cz, bz - cz) - wz, tmin));
-  const float tf = fminf(fminf(fmaxf(ax - cx, bx - cx) + wx, fmaxf(ay - cy, by - cy) + wy),
-                         fminf(fmaxf(az - cz, bz - cz) + wz, tmax));
-  return tn <= tf;
+// Flat TLAS only (<= kFlatTlasMax instances): is the ray likely to reach an instance whose BLAS has nodes to traverse?
+// Rays that do not — they miss everything, or reach only single-leaf instances such as the reference's planes — live
+// for two or three iterations; the others walk a BVH. The wavefront kernels queue the two classes at opposite ends of a
+// queue so that warps hold rays of one kind and the long rays start first. Only the ORDER of the work depends on the
+// answer, never a result, so the test is the cheapest one that separates the classes well rather than a conservative
+// one: the ray (unit direction) against the bounding sphere of the union box of the instances with nodes (`sphere` =
+// centre xyz, radius; written once per dispatch by k_prepare_classes). About 25 instructions, no reciprocals — the
+// slab test it replaced cost the shade kernel twice that for the same split.
+__device__ __forceinline__ bool rayReachesNodes(const float4 *__restrict__ sphere, float ox, float oy, float oz, float dx,
+                                                float dy, float dz, float tmax) {
+  const float4 s = __ldg(sphere);
+  const float px = s.x - ox, py = s.y - oy, pz = s.z - oz;
+  const float along = px * dx + py * dy + pz * dz;       // distance along the ray to the point closest to the centre
+  const float c = px * px + py * py + pz * pz - s.w * s.w; // <= 0: the origin is inside the sphere
+  return c <= 0.0f || (along > 0.0f && along * along >= c && along - s.w <= tmax);
 }
 
 // Two-level traversal of one ray as an explicit state machine, so a kernel can either run it to completion
