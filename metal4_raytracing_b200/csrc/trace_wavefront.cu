@@ -578,7 +578,11 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
     const bool hadGBuffer = prim.wroteGBuffer;
     ShadowRequest shadow;
     pushPath = shadeSegment<kTextures, kPlain>(P, s, hit, hIndex, sampleIndex, mk2(m4.z, m4.w), prim, shadow);
-    RT_STS(W.rad + slot, make_float4(s.radiance.x, s.radiance.y, s.radiance.z, 0.0f));
+    // the radiance record changes only where the surface emits (or a debug view / the environment writes it): most hits
+    // leave it as it is, and 16 of the ~180 bytes a hit moves need not be written back. A camera ray's record does not
+    // exist yet (k_wf_generate wrote only the direction).
+    if (cameraRays || s.radiance.x != ra.x || s.radiance.y != ra.y || s.radiance.z != ra.z)
+      RT_STS(W.rad + slot, make_float4(s.radiance.x, s.radiance.y, s.radiance.z, 0.0f));
     if (pushPath) { // a path that ends here (every path of the last segment) leaves only its radiance behind
       const uint32_t packed = uint32_t(s.bounce) | (uint32_t(s.step) << 10) | (uint32_t(s.transparencyPasses) << 20);
       RT_STS(W.rayD + slot, make_float4(s.dir.x, s.dir.y, s.dir.z, __uint_as_float(packed)));
