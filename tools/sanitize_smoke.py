@@ -23,6 +23,37 @@ for name, kw in (("K3small", {}), ("K5small", {"gpu_skeleton": True}), ("K4small
     img = ctx.tonemap(rnd.image_info(A.TEXTURE_ACCUMULATION))
     print(name, rnd.read_ray_counters(), int(img.sum()))
     ctx.set_trace_mode(0); rnd.draw(u); ctx.set_trace_mode(1)
+    for key, value in (("pipeline_lanes", 2), ("classify_rays", 0), ("pipeline_lanes", 0), ("classify_rays", 1)):
+        ctx.set_option(key, value); rnd.draw(u)
+    rnd.close()
+    # round 2 paths: TLAS rebuild by one CTA vs refit, sample partition (fp32 shares), glass (all segment passes launched)
+    reb = device.Renderer(ctx, sc, w, h, seeds=scene.seed_image(w, h, seed), fp32=True, tlas_rebuild=True, **kw)
+    u.enableMotionAdaptiveSampling = u.enableMotionAdaptiveAccumulation = 0
+    for r in range(2):
+        reb.update(); reb.draw(u, sample_modulo=2, sample_remainder=r)
+    reb.close()
+# a TLAS over many instances (one-CTA PLOC + collapse, then refits) and a glass material
+rng = np.random.default_rng(3)
+sc = scene.Scene()
+ball = sc.add_procedural("uvsphere", 10, 8)
+m = sc.get_material(ball); m.refractionIndex, m.opacity = 1.5, 0.1; sc.set_material(ball, 0, m)
+for i in range(300):
+    sc.add_instance(ball, tuple(rng.uniform(-3, 3, 3)), (0, float(rng.uniform(0, 6)), 0), 0.15)
+sc.add_instance(sc.add_procedural("plane"), (0, -3.2, 0), (0, 0, 0), 8.0)
+sc.default_lights()
+u = scene.default_uniforms(w, h)
+u.camera = scene.orbit_camera(w, h, (0, 0, 0), 0.4, 0.3, 9.0, 45.0); u.previousCamera = u.camera
+u.samplesPerPixel, u.maxBounces, u.lightCount = 2, 3, sc.desc().lightCount
+for rebuild in (False, True):
+    rnd = device.Renderer(ctx, sc, w, h, seeds=scene.seed_image(w, h, 5), tlas_rebuild=rebuild)
+    for f in range(3):
+        u.frameIndex = f
+        if f:
+            for i in range(300):
+                sc.set_instance_transform(i, tuple(rng.uniform(-3, 3, 3)), (0, 0.1 * f, 0), 0.15)
+            rnd.update()
+        rnd.draw(u, count_rays=True)
+    print("swarm rebuild" if rebuild else "swarm refit", rnd.read_ray_counters(), ctx.as_info(rnd.tlas_id()).wideNodeCount)
     rnd.close()
 ctx.close()
 print("done")
