@@ -641,8 +641,11 @@ __global__ void k_emit_triangles(const GeomEntry *geoms, uint32_t geomCount, con
 }
 
 // Refit step 1: re-read the vertices of every triangle slot.
-__global__ void k_refresh_triangles(const GeomEntry *geoms, uint32_t n, const uint2 *triSource, TriRecord *tris) {
+__global__ void k_refresh_triangles(const GeomEntry *geoms, uint32_t n, const uint2 *triSource, TriRecord *tris,
+                                    const WideNode *nodes, uint32_t nodeCount, uint32_t *pending) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  // the per-refit child counters of the bottom-up pass ride along (there are fewer nodes than triangles)
+  if (i < nodeCount) pending[i] = uint32_t(__popc(nodes[i].w[0].w >> 24));
   if (i >= n) return;
   uint2 src = triSource[i];
   const GeomEntry ge = geoms[src.x];
@@ -740,26 +743,123 @@ __global__ void k_node_parents(const WideNode *nodes, uint32_t nodeCount, uint32
   const uint32_t internal = uint32_t(__popc(nodes[i].w[0].w >> 24)), childBase = nodes[i].w[1].x;
   for (uint32_t k = 0; k < internal; ++k) parent[childBase + k] = i;
 }
-__global__ void k_refit_pending(const WideNode *nodes, uint32_t nodeCount, uint32_t *pending) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nodeCount) pending[i] = uint32_t(__popc(nodes[i].w[0].w >> 24));
-}
-
-// Refit step 2 in one launch: threads start at the nodes that have no internal children and walk up; the thread that
+// Refit step 2 in one launch: the walk starts at the nodes that have no internal children and goes up; whoever
 // delivers a node's last child refits that node (the other deliverers stop). Replaces one launch per tree level —
 // on a 100 k-vertex mesh the level launches were latency-bound and cost 0.15 ms per frame.
-__global__ void k_refit_bottom_up(WideNode *nodes, float4 *nodeBox, const TriRecord *tris, uint32_t nodeCount,
-                                  const uint32_t *parent, uint32_t *pending) {
-  uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
-  if (node >= nodeCount || (nodes[node].w[0].w >> 24) != 0u) return;
-  const TriangleLeaves leaves{tris};
+// One WARP per node: lane s < 8 owns child slot s — its box from the
+// child node or from its <= 3 triangles, then its six quantised bytes — and the node box is a warp reduction. The
+// arithmetic per child is that of refitNode / quantiseNode, so the nodes come out bit-identical; what changes is the
+// length of the dependent chain: a node costs one child's work instead of eight children's, and the walk from the leaves
+// to the root is ~7 such steps (one thread per node made the refit of a 100 k-vertex mesh a 0.14 ms latency chain).
+__device__ __forceinline__ void quantiseAxis(float lo, float hi, uint32_t &ebyte, float &scale) {
+  float ext = hi - lo;
+  int e;
+  if (!(ext > 0.0f)) {
+    e = -126;
+  } else {
+    float m = frexpf(ext / 255.0f, &e); // ext/255 = m * 2^e, m in [0.5, 1)
+    if (m == 0.5f) e -= 1;
+    e = max(e, -126);
+    while (double(ext) / ldexp(1.0, e) > 255.0) ++e;
+  }
+  e = min(e, 100);
+  ebyte = uint32_t(e + 127);
+  scale = __uint_as_float(ebyte << 23);
+}
+
+__device__ void refitNodeWarp(WideNode *nodes, float4 *nodeBox, const TriRecord *tris, uint32_t idx) {
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const uint4 w0 = nodes[idx].w[0], w1 = nodes[idx].w[1]; // same address for the whole warp: one transaction each
+  const uint32_t imask = w0.w >> 24, childBase = w1.x, primBase = w1.y;
+  const int s = lane & 7; // lanes 8..31 mirror lanes 0..7 (keeps the shuffles below full-warp)
+  const uint32_t m = ((s < 4 ? w1.z : w1.w) >> (8 * (s & 3))) & 0xFFu;
+  const bool present = m != 0u;
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  if (present) {
+    if (imask & (1u << s)) {
+      const uint32_t c = childBase + uint32_t(__popc(imask & ((1u << s) - 1u)));
+      const float4 l = __ldcg(nodeBox + 2 * c), h = __ldcg(nodeBox + 2 * c + 1);
+      lo[0] = l.x, lo[1] = l.y, lo[2] = l.z, hi[0] = h.x, hi[1] = h.y, hi[2] = h.z;
+    } else {
+      const uint32_t cnt = (m >> 5) == 1 ? 1 : ((m >> 5) == 3 ? 2 : 3);
+      const TriangleLeaves leaves{tris};
+      for (uint32_t k = 0; k < cnt; ++k) leaves.grow(primBase + (m & 31u) + k, lo, hi);
+    }
+    if (lo[0] > hi[0]) // only non-finite triangles in this slot: an empty box at the origin
+      for (int a = 0; a < 3; ++a) lo[a] = hi[a] = 0.0f;
+  }
+  float nlo[3], nhi[3];
+  for (int a = 0; a < 3; ++a) {
+    nlo[a] = present ? lo[a] : FLT_MAX;
+    nhi[a] = present ? hi[a] : -FLT_MAX;
+    for (int o = 4; o > 0; o >>= 1) { // over the eight slots (the three mirror groups reduce the same values)
+      nlo[a] = fminf(nlo[a], __shfl_xor_sync(full, nlo[a], o));
+      nhi[a] = fmaxf(nhi[a], __shfl_xor_sync(full, nhi[a], o));
+    }
+  }
+  uint32_t ebyte[3];
+  float scale[3];
+  for (int a = 0; a < 3; ++a) quantiseAxis(nlo[a], nhi[a], ebyte[a], scale[a]);
+  uint32_t q[6] = {0, 0, 0, 0, 0, 0}; // this slot's bytes: lo xyz, hi xyz
+  if (present) {
+    for (int a = 0; a < 3; ++a) {
+      const double sc = double(scale[a]), org = double(nlo[a]);
+      int ql = int(floor((double(lo[a]) - org) / sc));
+      int qh = int(ceil((double(hi[a]) - org) / sc));
+      ql = max(0, min(255, ql));
+      qh = max(0, min(255, qh));
+      while (ql > 0 && org + double(ql) * sc > double(lo[a])) --ql;
+      while (qh < 255 && org + double(qh) * sc < double(hi[a])) ++qh;
+      if (qh < ql) qh = ql;
+      q[a] = uint32_t(ql), q[3 + a] = uint32_t(qh);
+    }
+  }
+  // words of the node: array a = two words, byte (s & 3) of word (s >> 2) belongs to slot s
+  uint32_t word[6][2];
+  for (int a = 0; a < 6; ++a) {
+    const uint32_t b0 = __shfl_sync(full, q[a], 0), b1 = __shfl_sync(full, q[a], 1), b2 = __shfl_sync(full, q[a], 2),
+                   b3 = __shfl_sync(full, q[a], 3), b4 = __shfl_sync(full, q[a], 4), b5 = __shfl_sync(full, q[a], 5),
+                   b6 = __shfl_sync(full, q[a], 6), b7 = __shfl_sync(full, q[a], 7);
+    word[a][0] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    word[a][1] = b4 | (b5 << 8) | (b6 << 16) | (b7 << 24);
+  }
+  if (lane == 0) {
+    nodes[idx].w[0] = make_uint4(__float_as_uint(nlo[0]), __float_as_uint(nlo[1]), __float_as_uint(nlo[2]),
+                                 ebyte[0] | (ebyte[1] << 8) | (ebyte[2] << 16) | (imask << 24));
+    nodes[idx].w[2] = make_uint4(word[0][0], word[0][1], word[1][0], word[1][1]);
+    nodes[idx].w[3] = make_uint4(word[2][0], word[2][1], word[3][0], word[3][1]);
+    nodes[idx].w[4] = make_uint4(word[4][0], word[4][1], word[5][0], word[5][1]);
+    nodeBox[2 * idx] = make_float4(nlo[0], nlo[1], nlo[2], 0.0f);
+    nodeBox[2 * idx + 1] = make_float4(nhi[0], nhi[1], nhi[2], 0.0f);
+  }
+}
+
+__global__ void k_refit_bottom_up_warp(WideNode *nodes, float4 *nodeBox, const TriRecord *tris, uint32_t nodeCount,
+                                       const uint32_t *parent, uint32_t *pending, BlasHeader *header, uint32_t triCount) {
+  const unsigned full = 0xFFFFFFFFu;
+  uint32_t node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (node >= nodeCount || (nodes[node].w[0].w >> 24) != 0u) return; // whole warps leave together
   while (true) {
-    refitNode(nodes, nodeBox, leaves, node);
-    __threadfence();
-    const uint32_t p = parent[node];
-    if (p == 0xFFFFFFFFu) return;
-    if (atomicSub(pending + p, 1u) != 1u) return; // a sibling subtree is still being refitted
-    node = p;
+    refitNodeWarp(nodes, nodeBox, tris, node);
+    uint32_t next = 0xFFFFFFFFu;
+    if ((threadIdx.x & 31) == 0) {
+      __threadfence();
+      const uint32_t p = parent[node];
+      if (p != 0xFFFFFFFFu && atomicSub(pending + p, 1u) == 1u) next = p; // delivered the last child: refit the parent
+      if (p == 0xFFFFFFFFu) { // the root is done: the header's bounds are its box (what k_write_blas_header writes)
+        const float4 lo = nodeBox[0], hi = nodeBox[1];
+        header->nodes = nodes;
+        header->tris = tris;
+        header->triCount = triCount;
+        header->nodeCount = nodeCount;
+        header->boundsLo[0] = lo.x, header->boundsLo[1] = lo.y, header->boundsLo[2] = lo.z;
+        header->boundsHi[0] = hi.x, header->boundsHi[1] = hi.y, header->boundsHi[2] = hi.z;
+      }
+    }
+    next = __shfl_sync(full, next, 0);
+    if (next == 0xFFFFFFFFu) return;
+    node = next;
   }
 }
 
@@ -1303,16 +1403,14 @@ int refitBlas(rt_context *ctx, AccelObject *as, const rt_triangle_geometry *geom
   RT_CHECK(n == as->primCount, "rt_blas_refit: triangle count differs from the build");
   if (n == 0) return 0;
   cudaStream_t st = ctx->stream;
-  k_refresh_triangles<<<gridFor(n, 256), 256, 0, st>>>(static_cast<const GeomEntry *>(as->geomTableDev), n,
-                                                        as->triSource, as->tris);
-  ++ctx->launches;
-  k_refit_pending<<<gridFor(as->nodeCount, 256), 256, 0, st>>>(as->nodes, as->nodeCount, as->nodePending);
-  k_refit_bottom_up<<<gridFor(as->nodeCount, 128), 128, 0, st>>>(as->nodes, as->nodeBox, as->tris, as->nodeCount,
-                                                                  as->nodeParent, as->nodePending);
+  // two launches: triangle records + child counters, then the bottom-up pass (whose last warp also writes the header)
+  k_refresh_triangles<<<gridFor(std::max(n, as->nodeCount), 256), 256, 0, st>>>(static_cast<const GeomEntry *>(as->geomTableDev), n,
+                                                                               as->triSource, as->tris, as->nodes, as->nodeCount,
+                                                                               as->nodePending);
+  k_refit_bottom_up_warp<<<gridFor(as->nodeCount * 32u, 128), 128, 0, st>>>(as->nodes, as->nodeBox, as->tris, as->nodeCount,
+                                                                            as->nodeParent, as->nodePending,
+                                                                            static_cast<BlasHeader *>(as->headerDev), n);
   ctx->launches += 2;
-  k_write_blas_header<<<1, 32, 0, st>>>(static_cast<BlasHeader *>(as->headerDev), as->nodes, as->tris, as->nodeBox, n,
-                                        as->nodeCount);
-  ++ctx->launches;
   RT_CUDA(cudaGetLastError());
   return 0;
 }
