@@ -89,7 +89,7 @@ int main(int argc, char **argv) {
     environment.texelsDev = envTexelsDev;
     environment.width = ew, environment.height = eh;
     environment.intensity = envIntensity;
-    environment.flags = RT_ENV_IMPORTANCE;
+    environment.flags = RT_ENV_IMPORTANCE | RT_ENV_GUIDED; // the table below comes from rt_environment_cdf
     environment.cdfDev = envCdfDev;
     options.environment = &environment;
   }

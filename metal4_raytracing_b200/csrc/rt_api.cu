@@ -591,7 +591,19 @@ int rt_selftest_child_boxes(rt_context *ctx, uint64_t id, uint32_t raysPerNode, 
 
 size_t rt_environment_cdf_floats(int32_t width, int32_t height) {
   if (width <= 0 || height <= 0) return 0;
-  return size_t(height + 1) + size_t(height) * size_t(width + 1);
+  // marginal + conditional rows, then the guide tables (RT_ENV_GUIDED): 65 entries for the marginal and for every row
+  return size_t(height + 1) + size_t(height) * size_t(width + 1) + size_t(RT_ENV_GUIDE_CELLS + 1) * size_t(height + 1);
+}
+
+// guide[k] = largest i in [0, n] with c[i] <= k / RT_ENV_GUIDE_CELLS (float comparison, as the device search does)
+static void buildGuide(const float *c, int n, float *guideOut) {
+  int i = 0;
+  for (int k = 0; k <= RT_ENV_GUIDE_CELLS; ++k) {
+    const float bound = float(k) / float(RT_ENV_GUIDE_CELLS);
+    while (i + 1 <= n && c[i + 1] <= bound) ++i;
+    const uint32_t v = uint32_t(i);
+    std::memcpy(guideOut + k, &v, 4);
+  }
 }
 
 // rt_b200.h RT_ENV_IMPORTANCE: marginal over rows + one conditional per row, running sums in double
@@ -629,6 +641,11 @@ int rt_environment_cdf(const float *texelsHost, int32_t width, int32_t height, f
     marginal[y + 1] = total > 0.0 ? float(run / total) : float(double(y + 1) / double(height));
   }
   marginal[height] = 1.0f;
+  // guide tables: where a search for xi may start (the device narrows [lo, hi) to the cells of xi's 1/64 bucket first)
+  float *guides = cdfOutHost + (height + 1) + size_t(height) * size_t(width + 1);
+  buildGuide(marginal, height, guides);
+  for (int y = 0; y < height; ++y)
+    buildGuide(rows + size_t(y) * size_t(width + 1), width, guides + size_t(y + 1) * size_t(RT_ENV_GUIDE_CELLS + 1));
   return 0;
 }
 

@@ -209,6 +209,18 @@ __device__ __forceinline__ int cdfFind(const float *__restrict__ c, int n, float
   }
   return lo;
 }
+// The same cell, found from a narrower start (RT_ENV_GUIDED): guide[k] = largest i with c[i] <= k / 64, so for xi in
+// bucket k, c[guide[k]] <= xi and c[guide[k + 1] + 1] > xi — the invariant of the search above, entered later.
+__device__ __forceinline__ int cdfFindGuided(const float *__restrict__ c, int n, float xi, const float *__restrict__ guide) {
+  const int k = min(int(xi * float(RT_ENV_GUIDE_CELLS)), RT_ENV_GUIDE_CELLS - 1);
+  int lo = int(__float_as_uint(__ldg(guide + k))), hi = min(int(__float_as_uint(__ldg(guide + k + 1))) + 1, n);
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(c + mid) <= xi) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
 // solid-angle density of the texel (x, y) at polar sine sinTheta
 __device__ __forceinline__ float environmentTexelPdf(const rt_environment &env, int x, int y, float sinTheta) {
   const float *marginal = env.cdfDev;
@@ -228,11 +240,14 @@ __device__ __forceinline__ float environmentPdf(const rt_environment &env, f3 d)
 // direction drawn from the table with (xi.x -> row, xi.y -> column); returns its density
 __device__ __forceinline__ float sampleEnvironmentDirection(const rt_environment &env, f2 xi, f3 &dir) {
   const float *marginal = env.cdfDev;
-  const int y = cdfFind(marginal, env.height, xi.x);
+  const bool guided = (env.flags & RT_ENV_GUIDED) != 0u;
+  const float *guides = env.cdfDev + (env.height + 1) + size_t(env.height) * size_t(env.width + 1);
+  const int y = guided ? cdfFindGuided(marginal, env.height, xi.x, guides) : cdfFind(marginal, env.height, xi.x);
   const float m0 = __ldg(marginal + y), m1 = __ldg(marginal + y + 1);
   const float dy = (xi.x - m0) / (m1 - m0);
   const float *row = env.cdfDev + (env.height + 1) + size_t(y) * size_t(env.width + 1);
-  const int x = cdfFind(row, env.width, xi.y);
+  const int x = guided ? cdfFindGuided(row, env.width, xi.y, guides + size_t(y + 1) * size_t(RT_ENV_GUIDE_CELLS + 1))
+                       : cdfFind(row, env.width, xi.y);
   const float c0 = __ldg(row + x), c1 = __ldg(row + x + 1);
   const float dx = (xi.y - c0) / (c1 - c0);
   const float u = (float(x) + dx) / float(env.width), v = (float(y) + dy) / float(env.height);

@@ -30,6 +30,7 @@ class Environment(C.Structure):
 
 
 ENV_IMPORTANCE = 1  # RT_ENV_IMPORTANCE
+ENV_GUIDED = 2      # RT_ENV_GUIDED: the table carries rt_environment_cdf's guide tables
 
 
 def environment_cdf(texels):
@@ -443,7 +444,7 @@ class Renderer:
             flags = 0
             if importance:
                 self._env_cdf_dev = self.ctx.upload(environment_cdf(t))
-                flags = ENV_IMPORTANCE
+                flags = ENV_IMPORTANCE | ENV_GUIDED
             self._env = Environment(self._env_dev, t.shape[1], t.shape[0], float(intensity), flags, self._env_cdf_dev)
 
     def draw(self, uniforms, want_ids=False, count_rays=False, tile_modulo=1, tile_remainder=0, peers=None, hints=0,

@@ -335,7 +335,20 @@ def test_environment_importance_tables():
     from metal4_raytracing_b200 import device, scene
     sky = scene.procedural_sky(64, 32)
     a, b = device.environment_cdf(sky), oracle.environment_cdf(sky)
-    assert a.shape == b.shape == ((32 + 1) + 32 * (64 + 1),) and np.array_equal(a, b)
+    n = (32 + 1) + 32 * (64 + 1)
+    assert b.shape == (n,) and a.shape == (n + 65 * 33,) and np.array_equal(a[:n], b)
+    # RT_ENV_GUIDED: behind the running sums, 65 guide entries for the marginal and for every row — guide[k] = the largest
+    # cell index whose running sum is <= k / 64, i.e. where the plain search for any xi of that bucket would still be right
+    guides = a[n:].view(np.uint32).reshape(33, 65)
+    sums = [a[:33]] + [a[33 + y * 65: 33 + (y + 1) * 65] for y in range(32)]
+    for g, c in zip(guides, sums):
+        cells = len(c) - 1
+        for k in (0, 1, 17, 40, 63, 64):
+            assert g[k] == max(i for i in range(cells + 1) if c[i] <= np.float32(k) / np.float32(64)), (k, g[k])
+        for xi in np.float32([0.0, 0.013, 0.31, 0.5, 0.77, 0.999]):
+            k = min(int(xi * 64), 63)
+            want = max(i for i in range(cells) if c[i] <= xi)  # what the search from [0, n) returns
+            assert g[k] <= want < min(g[k + 1] + 1, cells) or want == g[k]
     h, w = 16, 8
     t = oracle.environment_cdf(np.full((h, w, 4), 0.25, np.float32))
     marginal, rows = t[:h + 1], t[h + 1:].reshape(h, w + 1)
