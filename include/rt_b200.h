@@ -273,7 +273,8 @@ int rt_set_trace_mode(rt_context *ctx, int mode);
  * "blocks_per_sm" (persistent grid size of the wavefront kernels), "sample_batch" (1..64, samples of a pixel the
  * wavefront layout keeps in flight at once; default 16), "pipeline_lanes" (1..4 independent tile subsets of a
  * dispatch whose kernel sequences run on separate streams so that launch tails overlap; default 0 = two lanes for
- * dispatches of at least 16 M paths, otherwise one), "ploc_radius" (builder: PLOC neighbour search radius for
+ * dispatches of at least 16 M paths, otherwise one), "classify_rays" (0 / 1, default 1: with a TLAS of at most 8 instances
+ * new rays are queued by class — likely to walk a BVH / cheap — so that warps hold rays of one kind and the long rays start first), "ploc_radius" (builder: PLOC neighbour search radius for
  * acceleration structures built after the call, default 16; 0 = plain LBVH), "leaf_size" / "tlas_leaf_size" (1..3
  * triangles / instances per leaf slot of a wide node, defaults 3 / 1). */
 int rt_set_option(rt_context *ctx, const char *key, int value);
