@@ -275,7 +275,8 @@ int rt_set_trace_mode(rt_context *ctx, int mode);
  * dispatch whose kernel sequences run on separate streams so that launch tails overlap; default 0 = two lanes for
  * dispatches of at least 16 M paths, otherwise one), "classify_rays" (0 / 1, default 1: with a TLAS of at most 8 instances
  * new rays are queued by class — likely to walk a BVH / cheap — so that warps hold rays of one kind and the long rays start first), "ploc_radius" (builder: PLOC neighbour search radius for
- * acceleration structures built after the call, default 16; 0 = plain LBVH), "leaf_size" / "tlas_leaf_size" (1..3
+ * acceleration structures built after the call, default 16; 0 = plain LBVH), "tlas_ploc_radius" (the same for instance
+ * acceleration structures; default 0 = automatic, up to 256 for small instance counts), "leaf_size" / "tlas_leaf_size" (1..3
  * triangles / instances per leaf slot of a wide node, defaults 3 / 1). */
 int rt_set_option(rt_context *ctx, const char *key, int value);
 /* Per-kernel-class device timing (bench.py's roofline of the dominant kernel). While enabled, the library records

@@ -1537,7 +1537,11 @@ int buildTlas(rt_context *ctx, AccelObject *as, const rt_instance_descriptor *de
     uint32_t *queueA = bump.take<uint32_t>(count), *queueB = bump.take<uint32_t>(count);
     CollapseCounters *counters = bump.take<CollapseCounters>(1);
     RT_CHECK(bump.offset <= bump.capacity, "internal: build scratch overflow (TLAS)");
-    const int radius = std::max(1, ctx->plocRadius > 0 ? ctx->plocRadius : 8);
+    // The TLAS is small next to the rays that walk it, so its search window is wide: on the 4,096-instance scene a window of
+    // 256 instead of 16 takes 8 % off the frame (profiles/r2_experiments.md 8) and saturates there. The one-CTA build costs
+    // count * 2 * radius distance evaluations per round, hence the cap by count; the per-frame path is the refit anyway.
+    const int automatic = std::min(256, std::max(std::max(ctx->plocRadius, 16), int((1u << 20) / count)));
+    const int radius = ctx->tlasPlocRadius > 0 ? ctx->tlasPlocRadius : automatic;
     k_tlas_build_cta<<<1, kTlasCtaThreads, 0, st>>>(count, primLo, primHi, valsB, t, ca, cb, nearest, radius, queueA, queueB,
                                                     counters, as->nodes, as->nodeBox, as->leafPrim,
                                                     uint32_t(std::min(std::max(ctx->tlasLeafSize, 1), kMaxLeafPrims)),
@@ -1551,7 +1555,8 @@ int buildTlas(rt_context *ctx, AccelObject *as, const rt_instance_descriptor *de
     as->nodeCount = 1; // a lower bound until the info arrives; the traversal only needs "not empty"
   } else {
     // beyond the one-CTA builder: the general builder, which reads counters back between rounds and levels
-    RT_TRY(buildWideTree(ctx, as, count, primLo, primHi, bounds, bump, as->leafPrim, ctx->plocRadius));
+    RT_TRY(buildWideTree(ctx, as, count, primLo, primHi, bounds, bump, as->leafPrim,
+                         ctx->tlasPlocRadius > 0 ? ctx->tlasPlocRadius : ctx->plocRadius));
     RT_CHECK(as->levelStart.size() - 1 <= kMaxTlasLevels, "TLAS too deep for the traversal stack");
     k_node_parents<<<gridFor(as->nodeCount, 256), 256, 0, st>>>(as->nodes, as->nodeCount, as->nodeParent);
     ++ctx->launches;

@@ -181,6 +181,7 @@ struct rt_context {
   int tlasLeafSize = 1;     // the same for TLAS builds: instances per leaf slot. 1: entering an instance costs far more than a
                             // triangle test, so no instance is entered because it shares a leaf box (4096-instance scene: -10 % frame)
   int plocRadius = 16;      // BVH builder: PLOC search radius; 0 = plain LBVH (Karras) hierarchy
+  int tlasPlocRadius = 0;   // the same for TLAS builds; 0 = automatic (wide for small TLASes, bvh_build.cu buildTlas)
   int sampleBatch = 16;     // samples of a pixel in flight at once in the wavefront layout (1 = one sample per pass)
   int blocksPerSm = 6;      // persistent grid of the traversal kernels = smCount * blocksPerSm (resident CTAs at 80 regs)
   std::unordered_map<uint64_t, rtb::AccelObject *> accels;

@@ -684,6 +684,11 @@ int rt_set_option(rt_context *ctx, const char *key, int value) {
     ctx->plocRadius = value;
     return 0;
   }
+  if (k == "tlas_ploc_radius") {
+    RT_CHECK(value >= 0 && value <= 65536, "rt_set_option: tlas_ploc_radius is 0 (automatic) .. 65536");
+    ctx->tlasPlocRadius = value;
+    return 0;
+  }
   if (k == "sample_batch") {
     RT_CHECK(value >= 1 && value <= 64, "rt_set_option: sample_batch is 1..64");
     ctx->sampleBatch = value;

@@ -197,13 +197,14 @@ def _swarm(w, h, count, seed=9):
     return sc, u, poses
 
 
-@pytest.mark.parametrize("count", [40, 700])
-def test_tlas_refit_rebuild_and_no_host_sync(gpu_ctx, count):
+@pytest.mark.parametrize("count,radius", [(40, 0), (700, 0), (700, 5)])
+def test_tlas_refit_rebuild_and_no_host_sync(gpu_ctx, count, radius):
     """rt_tlas_refit (the reference's per-frame path when refitting is supported, Renderer.swift:1084-1202) against a
     full rebuild and against the oracle while every instance moves: identical frames; and in steady state neither
     rtr_update (refit or one-CTA rebuild) nor rtr_draw blocks the host on the device."""
     w, h = 224, 144
     frames = {}
+    gpu_ctx.set_option("tlas_ploc_radius", radius)  # 0 = automatic (wide: 256 at these counts), 5 = a narrow window
     for rebuild in (False, True):
         sc, u, poses = _swarm(w, h, count)
         seeds = scene.seed_image(w, h, 21)
@@ -237,6 +238,7 @@ def test_tlas_refit_rebuild_and_no_host_sync(gpu_ctx, count):
         assert info.primitiveCount == count + 1 and info.wideNodeCount >= (count + 1) // 8 and info.levelCount >= 2
         frames[rebuild] = out
         rnd.close()
+    gpu_ctx.set_option("tlas_ploc_radius", 0)
     for a, b in zip(frames[False], frames[True]):
         assert np.array_equal(a.view(np.uint16), b.view(np.uint16))
 
