@@ -351,7 +351,7 @@ def test_radiance_hdr_reader(tmp_path):
     assert len(body) < px.nbytes + 4 * h and np.array_equal(scene.load_hdr(rle), want)
     from metal4_raytracing_b200 import device
     table = device.environment_cdf(scene.load_hdr(rle))
-    assert table.shape == ((h + 1) + h * (w + 1),) and table[h] == 1.0
+    assert table.shape == ((h + 1) + h * (w + 1) + 65 * (h + 1),) and table[h] == 1.0  # CDF rows + 64-cell guide tables
     for name, data in (("magic.hdr", b"P6\n" + px.tobytes()), ("short.hdr", header + px.tobytes()[:100]),
                        ("format.hdr", header.replace(b"rgbe", b"xyze") + px.tobytes()),
                        ("run.hdr", header + bytes([2, 2, 0, w, 128 + 100, 7]))):
