@@ -270,7 +270,8 @@ uint64_t rt_host_sync_count(rt_context *ctx);
 /* Select the trace kernel layout: 0 = megakernel, 1 = wavefront (default). */
 int rt_set_trace_mode(rt_context *ctx, int mode);
 /* Tuning knobs that never change results: "trace_mode" (0/1), "traversal_variant" (0..2, traverse.cuh),
- * "blocks_per_sm" (persistent grid size of the wavefront kernels), "sample_batch" (1..64, samples of a pixel the
+ * "blocks_per_sm" (persistent grid size of the traversal kernels; default 0 = as many CTAs as are resident: 8 per SM
+ * for dispatches of at least 6 M paths per pipeline lane, otherwise 7), "sample_batch" (1..64, samples of a pixel the
  * wavefront layout keeps in flight at once; default 16), "pipeline_lanes" (1..4 independent tile subsets of a
  * dispatch whose kernel sequences run on separate streams so that launch tails overlap; default 0 = two lanes for
  * dispatches of at least 16 M paths, otherwise one), "classify_rays" (0 / 1, default 1: with a TLAS of at most 8 instances

@@ -183,7 +183,8 @@ struct rt_context {
   int plocRadius = 16;      // BVH builder: PLOC search radius; 0 = plain LBVH (Karras) hierarchy
   int tlasPlocRadius = 0;   // the same for TLAS builds; 0 = automatic (wide for small TLASes, bvh_build.cu buildTlas)
   int sampleBatch = 16;     // samples of a pixel in flight at once in the wavefront layout (1 = one sample per pass)
-  int blocksPerSm = 6;      // persistent grid of the traversal kernels = smCount * blocksPerSm (resident CTAs at 80 regs)
+  int blocksPerSm = 0;      // persistent grid of the traversal kernels = smCount * blocksPerSm; 0 = the resident CTA count
+                            // of the build the dispatch uses (7 or 8, trace_wavefront.cu)
   std::unordered_map<uint64_t, rtb::AccelObject *> accels;
   // reusable build scratch
   void *scratch = nullptr;

@@ -705,7 +705,7 @@ int rt_set_option(rt_context *ctx, const char *key, int value) {
     return 0;
   }
   if (k == "blocks_per_sm") {
-    RT_CHECK(value >= 1 && value <= 32, "rt_set_option: blocks_per_sm is 1..32");
+    RT_CHECK(value >= 0 && value <= 32, "rt_set_option: blocks_per_sm is 0 (automatic) or 1..32");
     ctx->blocksPerSm = value;
     return 0;
   }

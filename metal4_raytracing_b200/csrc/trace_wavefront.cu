@@ -53,9 +53,30 @@ constexpr int kBlock = 256;
 #ifndef RT_TRACE_BLOCK
 #define RT_TRACE_BLOCK 128
 #endif
-#ifndef RT_TRACE_MINBLOCKS
-#define RT_TRACE_MINBLOCKS 6
+// Two builds of every traversal kernel: 7 resident CTAs per SM (72 registers, no spills) and 8 (64 registers, 36 bytes of
+// spills). Eight are 1 - 2 % faster on launches of tens of millions of rays, seven on small ones (more resident warps
+// lengthen the tail of a persistent launch): launchTraceWavefront picks by the size of the dispatch. RT_TRACE_MINBLOCKS
+// forces one value (tools/build_variants.sh). With the ray and the hit ids behind the stack (traverse.cuh, RT_SLIM_LANE)
+// the kernel needs 72 registers where it needed 80 + spills for 6 CTAs (profiles/r2_experiments.md section 9).
+#ifdef RT_TRACE_MINBLOCKS
+constexpr int kMinBlocksSmall = RT_TRACE_MINBLOCKS, kMinBlocksLarge = RT_TRACE_MINBLOCKS;
+#else
+constexpr int kMinBlocksSmall = 7, kMinBlocksLarge = 8;
 #endif
+// RT_PREFETCH > 0 (an experiment, measured slower: profiles/r2_experiments.md section 10): entries of a per-warp ring in
+// shared memory into which the next rays are copied by cp.async ahead of time (traceQueuePrefetch); RT_PREFETCH_LARGE /
+// RT_PREFETCH_SMALL say which of the two builds get it
+#ifndef RT_PREFETCH
+#define RT_PREFETCH 0
+#endif
+#ifndef RT_PREFETCH_SMALL
+#define RT_PREFETCH_SMALL 0
+#endif
+#ifndef RT_PREFETCH_LARGE
+#define RT_PREFETCH_LARGE 1
+#endif
+constexpr bool kPrefetchLarge = RT_PREFETCH > 0 && RT_PREFETCH_LARGE != 0, kPrefetchSmall = RT_PREFETCH > 0 && RT_PREFETCH_SMALL != 0;
+constexpr size_t kLargeDispatchPaths = size_t(6) << 20; // path slots per pipeline lane from which the 8-CTA build is used
 constexpr int kTraceBlock = RT_TRACE_BLOCK;
 // streaming (evict-first) access for the per-path state so it does not push the BVH out of L2
 #ifdef RT_NO_STREAMING_HINTS
@@ -81,7 +102,8 @@ struct WfState { // same definition in both translation units
   float4 *rad;  // radiance.xyz
   float4 *hitA; // t (+inf = miss), u, v, primitive bits
   uint2 *hitB;  // instance, geometry (written for hits only)
-  float4 *shD, *shC;   // shadow ray direction + tmax, contribution (its origin is rayO)
+  float4 *shD, *shC;   // shadow ray direction + tmax; the path's radiance + the light sample's contribution = what rad
+                       // becomes when the shadow ray is unoccluded (its origin is rayO)
   // per pixel slot
   float4 *tot;  // totalColor.xyz, w = totalSamples bits
   float4 *mot;  // motion.xy, prevMotion.xy
@@ -348,6 +370,11 @@ constexpr int kStepsPerCheck = RT_STEPS_PER_CHECK;
 #ifndef RT_CONVERGED
 #define RT_CONVERGED 22
 #endif
+// RT_COOP_TRIS: the triangle stages of stepConverged are done by the warp together, 32 pending (lane, triangle) pairs per
+// pass (LaneTraversal::triangleStageCoop); 0: every lane tests its own next triangle
+#ifndef RT_COOP_TRIS
+#define RT_COOP_TRIS 0
+#endif
 // entries of each lane's traversal stack kept in shared memory (0 = all in local memory), traverse.cuh SplitStack
 #ifndef RT_SHARED_STACK
 #define RT_SHARED_STACK 0
@@ -376,7 +403,7 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
                                            uint32_t countB, uint32_t queueCapacity, uint32_t *cursor,
                                            const float4 *__restrict__ rayO,
                                            const float4 *__restrict__ rayD, bool cameraRays, uint2 *sharedStack,
-                                           Finish finish) {
+                                           uint32_t *warpPairs, Finish finish) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   LaneTraversal<kAny> t;
@@ -388,7 +415,9 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
   (void)sharedStack;
 #endif
   bool active = false, exhausted = false;
+#if !RT_SLIM_LANE
   uint32_t slot = 0;
+#endif
   const uint32_t count = countA + countB; // the cursor walks the class A entries (front) first, then class B (back)
 #ifdef RT_COUNT_WORK
   uint32_t tailIters = 0; // warp iterations after the queue ran dry
@@ -405,14 +434,19 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
       if (!active) {
         const uint32_t j = base + uint32_t(__popc(idle & ((1u << lane) - 1u)));
         if (j < count) {
-          slot = queueEntry(queue, queueCapacity, countA, j);
-          const float4 d = RT_LDS(rayD + slot);
+          const uint32_t newSlot = queueEntry(queue, queueCapacity, countA, j);
+#if RT_SLIM_LANE
+          stack.set(kSlotPath, make_uint2(newSlot, 0u)); // read again when the ray has finished
+#else
+          slot = newSlot;
+#endif
+          const float4 d = RT_LDS(rayD + newSlot);
           float4 o;
           if (!kAny && cameraRays) // first segment: every ray starts at the camera (k_wf_generate)
             o = make_float4(P.uniforms.camera.position.x, P.uniforms.camera.position.y, P.uniforms.camera.position.z, 0.0f);
           else
-            o = RT_LDS(rayO + slot);
-          t.template begin<kFlat>(P.tlas, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, kAny ? d.w : INFINITY);
+            o = RT_LDS(rayO + newSlot);
+          t.template begin<kFlat>(P.tlas, stack, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, kAny ? d.w : INFINITY);
           active = true;
         }
       }
@@ -425,13 +459,17 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
     for (int k = 0; k < kStepsPerCheck; ++k) {
 #if RT_CONVERGED > 0
       // flat TLAS: entry stage before the node stage only; otherwise as RT_CONVERGED says
-      if (t.template stepConverged<kFlat || (RT_CONVERGED & 1) != 0, !kFlat && (RT_CONVERGED & 4) != 0, (RT_CONVERGED & 2) != 0, (RT_CONVERGED & 8) != 0, 1 + ((RT_CONVERGED >> 4) & 3)>(P.tlas, stack, active)) {
+      if (t.template stepConverged<kFlat || (RT_CONVERGED & 1) != 0, !kFlat && (RT_CONVERGED & 4) != 0, (RT_CONVERGED & 2) != 0, (RT_CONVERGED & 8) != 0, 1 + ((RT_CONVERGED >> 4) & 3), RT_COOP_TRIS != 0>(P.tlas, stack, active, warpPairs)) {
 #elif RT_FUSED_PRIMS > 0
       if (active && !t.template stepFused<RT_FUSED_PRIMS>(P.tlas, stack)) {
 #else
       if (active && !t.step(P.tlas, stack)) {
 #endif
-        finish(slot, t);
+#if RT_SLIM_LANE
+        const uint32_t slot = stack.get(kSlotPath).x;
+#endif
+        if constexpr (kAny) finish(slot, t.found, RayHit{}, nullptr);
+        else finish(slot, t.found, t.result(stack), nullptr);
 #ifdef RT_COUNT_WORK
         countWork<kAny>(P, t);
 #endif
@@ -448,19 +486,192 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
 #endif
 }
 
+// RT_PREFETCH > 0 — the experiment of profiles/r2_experiments.md section 10, measured 15 - 44 % slower and off by default.
+// The classic loop above fetches rays when lanes go idle: an atomic on the cursor, the queue entry, then the ray's records
+// — three dependent trips to L2 / DRAM during which the whole (converged) warp waits; ncu's source view charges a sixth
+// of the traversal kernel's stall samples to them. Here the trips are taken ahead of time, one per iteration of the
+// warp, and without registers: the cursor is advanced by a chunk whose result is picked up an iteration later, the
+// chunk's queue entries are copied into the ring half a ring at a time, and the rays they name — origin, direction and,
+// for shadow rays, the radiance record to write when unoccluded — follow, global -> shared by cp.async (LDGSTS, L2
+// evict-first), while the warp traverses. A lane that goes idle takes its next ray from shared memory. What it costs:
+// 6.6 KB of shared memory per CTA taken from the L1 that caches the BVH, a supply of half a ring per two iterations
+// (rays that live for two or three iterations drain it faster), and bookkeeping in every iteration.
+#if RT_PREFETCH > 0
+struct __align__(16) PrefetchRing {
+  float4 o[RT_PREFETCH], d[RT_PREFETCH], c[RT_PREFETCH];
+  uint32_t slot[RT_PREFETCH];
+};
+__device__ __forceinline__ void cpAsync16(void *sharedDst, const void *globalSrc) {
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(uint32_t(__cvta_generic_to_shared(sharedDst))),
+               "l"(globalSrc), "l"(policy)
+               : "memory");
+}
+
+template <bool kAny, int kRefill, bool kFlat, typename Finish>
+__device__ __forceinline__ void traceQueuePrefetch(const TraceParams &P, const uint32_t *__restrict__ queue, uint32_t countA,
+                                                   uint32_t countB, uint32_t queueCapacity, uint32_t *cursor,
+                                                   const float4 *__restrict__ rayO, const float4 *__restrict__ rayD,
+                                                   const float4 *__restrict__ rayC, bool cameraRays, uint2 *sharedStack,
+                                                   uint32_t *warpPairs, PrefetchRing *ring, Finish finish) {
+  constexpr uint32_t kRing = RT_PREFETCH, kHalf = kRing / 2, kChunk = kRing;
+  static_assert((kRing & (kRing - 1)) == 0 && kRing >= 16 && kRing <= 64, "RT_PREFETCH: 16, 32 or 64");
+  const unsigned full = 0xFFFFFFFFu;
+  const uint32_t lane = threadIdx.x & 31u;
+  LaneTraversal<kAny> t;
+#if RT_SHARED_STACK > 0
+  SplitStack<RT_SHARED_STACK, kTraceBlock> stack;
+  stack.shared = sharedStack + threadIdx.x;
+#else
+  LocalStack stack;
+  (void)sharedStack;
+#endif
+  bool active = false;
+  const uint32_t count = countA + countB; // the cursor walks the class A entries (front) first, then class B (back)
+  // The state of the prefetcher is warp-uniform and packed into two registers (as nine variables it cost the kernel 250
+  // bytes of spills at 64 registers). rangeNext: the next queue entry to fetch; the cursor advances by kChunk from 0, so
+  // the chunk it belongs to ends at the next multiple of kChunk. Lane 0's rangeNext also receives the cursor's old
+  // value while an advance is in flight. pf: bits 0-5 head (first ready ring position), 6-12 ready rays, 13-18 rays of
+  // the fetch in flight, 19-20 its stage (1: queue entries on their way into ring->slot, 2: rays on their way),
+  // 21 the ring half the next fetch fills, 22 cursor advance in flight, 23 cursor past the end, 24 chunk used up.
+  uint32_t rangeNext = 0;
+  constexpr uint32_t kHeadMask = 63u, kAvailShift = 6, kAvailMask = 127u << 6, kCountShift = 13, kCountMask = 63u << 13,
+                     kStageShift = 19, kStageMask = 3u << 19, kTailHalf = 1u << 21, kAtomicPending = 1u << 22, kNoMore = 1u << 23,
+                     kRangeEmpty = 1u << 24;
+  uint32_t pf = kRangeEmpty | (count == 0u ? kNoMore : 0u);
+#ifdef RT_COUNT_WORK
+  uint32_t tailIters = 0;
+#endif
+  while (true) {
+    // the fetch pipeline advances one stage per iteration
+    const uint32_t stage = (pf & kStageMask) >> kStageShift;
+    if (stage != 0u) {
+      const uint32_t fetchCount = (pf & kCountMask) >> kCountShift;
+      const uint32_t e = ((pf & kTailHalf) ? 0u : kHalf) + lane; // the half filled now is the one before the tail half
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (stage == 1u) { // the queue entries have arrived in ring->slot: fetch the rays they name
+        if (lane < fetchCount) {
+          const uint32_t slot = ring->slot[e];
+          if (kAny || !cameraRays) cpAsync16(&ring->o[e], rayO + slot);
+          cpAsync16(&ring->d[e], rayD + slot);
+          if (kAny) cpAsync16(&ring->c[e], rayC + slot);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        pf += 1u << kStageShift;
+      } else { // the rays have arrived
+        __syncwarp();
+        if ((pf & kAvailMask) == 0u) pf = (pf & ~kHeadMask) | ((pf & kTailHalf) ? 0u : kHalf);
+        pf = (pf + (fetchCount << kAvailShift)) & ~(kStageMask | kCountMask);
+      }
+    }
+    if (pf & kAtomicPending) { // the cursor's value from the last iteration
+      rangeNext = __shfl_sync(full, rangeNext, 0);
+      pf &= ~(kAtomicPending | kRangeEmpty);
+      if (rangeNext >= count) pf |= kNoMore | kRangeEmpty;
+    }
+    if ((pf & (kStageMask | kRangeEmpty)) == 0u &&
+        ((pf & kAvailMask) == 0u || (((pf & kHeadMask) / kHalf) != ((pf & kTailHalf) ? 1u : 0u)))) {
+      // start a fetch into the tail half: its queue entries -> ring->slot
+      const uint32_t chunkEnd = min((rangeNext | (kChunk - 1u)) + 1u, count);
+      const uint32_t fetchCount = min(kHalf, chunkEnd - rangeNext);
+      if (lane < fetchCount) {
+        const uint32_t j = rangeNext + lane;
+        const uint32_t *src = j < countA ? queue + j : queue + (queueCapacity - 1u - (j - countA));
+        const uint32_t dst = uint32_t(__cvta_generic_to_shared(&ring->slot[((pf & kTailHalf) ? kHalf : 0u) + lane]));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      rangeNext += fetchCount;
+      if (rangeNext == chunkEnd) pf |= kRangeEmpty;
+      pf = (pf ^ kTailHalf) | (fetchCount << kCountShift) | (1u << kStageShift);
+    }
+    if ((pf & (kRangeEmpty | kNoMore | kAtomicPending)) == kRangeEmpty) { // reserve the next chunk; picked up an iteration later
+      if (lane == 0u) rangeNext = atomicAdd(cursor, kChunk);
+      pf |= kAtomicPending;
+    }
+    const unsigned idle = __ballot_sync(full, !active);
+    const bool drained = (pf & (kNoMore | kAtomicPending | kStageMask | kAvailMask)) == kNoMore;
+    if (idle == full && drained) break;
+    if ((pf & kAvailMask) != 0u && (idle == full || (kRefill > 0 && __popc(idle) >= kRefill))) {
+      const uint32_t avail = (pf & kAvailMask) >> kAvailShift, headPos = pf & kHeadMask;
+      const uint32_t take = min(uint32_t(__popc(idle)), avail);
+      const uint32_t rank = uint32_t(__popc(idle & ((1u << lane) - 1u)));
+      if (!active && rank < take) {
+        const uint32_t e = (headPos + rank) & (kRing - 1u);
+        const uint32_t newSlot = ring->slot[e];
+        stack.set(kSlotPath, make_uint2(newSlot, 0u));
+        const float4 d = ring->d[e];
+        float4 o;
+        if (!kAny && cameraRays)
+          o = make_float4(P.uniforms.camera.position.x, P.uniforms.camera.position.y, P.uniforms.camera.position.z, 0.0f);
+        else
+          o = ring->o[e];
+        if (kAny) {
+          const float4 c = ring->c[e];
+          stack.set(kSlotCarry0, make_uint2(__float_as_uint(c.x), __float_as_uint(c.y)));
+          stack.set(kSlotCarry1, make_uint2(__float_as_uint(c.z), __float_as_uint(c.w)));
+        }
+        t.template begin<kFlat>(P.tlas, stack, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, kAny ? d.w : INFINITY);
+        active = true;
+      }
+      pf = (pf & ~(kHeadMask | kAvailMask)) | ((headPos + take) & (kRing - 1u)) | ((avail - take) << kAvailShift);
+      __syncwarp(); // the ring entries just read may be refilled from the next iteration on
+    }
+#ifdef RT_COUNT_WORK
+    if (drained) tailIters += uint32_t(kStepsPerCheck);
+#endif
+#pragma unroll 1
+    for (int k = 0; k < kStepsPerCheck; ++k) {
+      if (t.template stepConverged<kFlat || (RT_CONVERGED & 1) != 0, !kFlat && (RT_CONVERGED & 4) != 0, (RT_CONVERGED & 2) != 0, (RT_CONVERGED & 8) != 0, 1 + ((RT_CONVERGED >> 4) & 3), RT_COOP_TRIS != 0>(P.tlas, stack, active, warpPairs)) {
+        const uint32_t slot = stack.get(kSlotPath).x;
+        if constexpr (kAny) {
+          const uint2 c0 = stack.get(kSlotCarry0), c1 = stack.get(kSlotCarry1);
+          const float4 carried = make_float4(__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c1.x), __uint_as_float(c1.y));
+          finish(slot, t.found, RayHit{}, &carried);
+        } else {
+          finish(slot, t.found, t.result(stack), nullptr);
+        }
+#ifdef RT_COUNT_WORK
+        countWork<kAny>(P, t);
+#endif
+        active = false;
+      }
+    }
+  }
+#ifdef RT_COUNT_WORK
+  if (P.rayCounters != nullptr && lane == 0u) {
+    atomicAdd(P.rayCounters + 19, (unsigned long long)tailIters);
+    atomicMax(P.rayCounters + 20, (unsigned long long)tailIters);
+    atomicAdd(P.rayCounters + 21, 1ull);
+  }
+#endif
+}
+#endif // RT_PREFETCH > 0
+
 // One launch of the persistent traversal kernel does up to two jobs: the closest-hit rays of segment k (queue qin)
 // and then the any-hit shadow rays the shade kernel of segment k - 1 emitted (parity shadowParity). Both only depend on
 // that shade kernel, so putting them in one launch lets warps that run out of closest-hit rays go straight on to
 // shadow rays instead of idling through the tail of a separate launch (a persistent launch has a ~50 us tail, which
 // matters once a GPU holds only a slice of the frame). The closest-hit rays go first: they are the longer ones.
-template <int kRefill, bool kFlat>
-__global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse(const __grid_constant__ TraceParams P, const WfState W,
+template <int kRefill, bool kFlat, int kMinBlocks, bool kPrefetch>
+__global__ void __launch_bounds__(kTraceBlock, kMinBlocks) k_wf_traverse(const __grid_constant__ TraceParams P, const WfState W,
                                                                                  int qin, int firstSegment, int cameraRays,
                                                                                  int doClosest, int doShadow, int shadowParity) {
 #if RT_SHARED_STACK > 0
   __shared__ uint2 s_stack[RT_SHARED_STACK * kTraceBlock]; // [entry][thread], used by both phases in turn
 #else
   uint2 *s_stack = nullptr;
+#endif
+#if RT_COOP_TRIS
+  __shared__ uint32_t s_pairs[kTraceBlock]; // 32 words per warp: the pair list of the cooperative triangle stage
+  uint32_t *warpPairs = s_pairs + (threadIdx.x & ~31u);
+#else
+  uint32_t *warpPairs = nullptr; // no static shared memory: the whole L1 stays a cache for the BVH
+#endif
+#if RT_PREFETCH > 0
+  __shared__ PrefetchRing s_ring[kPrefetch ? kTraceBlock / 32 : 1];
+  PrefetchRing *ring = s_ring + (kPrefetch ? (threadIdx.x >> 5) : 0);
 #endif
   if (doClosest) {
     const int nextParity = doShadow ? (shadowParity ^ 1) : shadowParity; // parity of the segment traced here
@@ -473,37 +684,45 @@ __global__ void __launch_bounds__(kTraceBlock, RT_TRACE_MINBLOCKS) k_wf_traverse
       W.counts[10 + nextParity] = 0u;
     }
     const uint32_t countA = W.counts[pathCount(qin)], countB = W.counts[pathCountB(qin)];
-    traceQueue<false, kRefill, kFlat>(P, W.queue[qin], countA, countB, W.queueCapacity, W.counts + 3, W.rayO, W.rayD,
-                                      cameraRays != 0, s_stack,
-                               [&](uint32_t slot, const LaneTraversal<false> &t) {
-                                 RT_STS(W.hitA + slot, make_float4(t.found ? t.hit.t : INFINITY, t.hit.u, t.hit.v,
-                                                                   __uint_as_float(t.hit.primitive)));
-                                 if (t.found)
-                                   RT_STS(W.hitB + slot, make_uint2(t.hit.instance, t.hit.geometry));
+    auto finishClosest = [&](uint32_t slot, bool found, const RayHit &hit, const float4 *) {
+                                 RT_STS(W.hitA + slot, make_float4(found ? hit.t : INFINITY, hit.u, hit.v,
+                                                                   __uint_as_float(hit.primitive)));
+                                 if (found)
+                                   RT_STS(W.hitB + slot, make_uint2(hit.instance, hit.geometry));
                                  if (firstSegment && P.primaryIds != nullptr && slot < W.capacity) { // sample 0
                                    int px, py;
                                    bool valid;
                                    slotPixel(P, slot, px, py, valid);
-                                   const uint4 id = t.found ? make_uint4(t.hit.instance, t.hit.geometry, t.hit.primitive, __float_as_uint(t.hit.t))
+                                   const uint4 id = found ? make_uint4(hit.instance, hit.geometry, hit.primitive, __float_as_uint(hit.t))
                                                             : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
                                    reinterpret_cast<uint4 *>(P.primaryIds)[size_t(py) * size_t(P.uniforms.width) + size_t(px)] = id;
                                  }
-                               });
+                               };
+#if RT_PREFETCH > 0
+    if constexpr (kPrefetch)
+      traceQueuePrefetch<false, kRefill, kFlat>(P, W.queue[qin], countA, countB, W.queueCapacity, W.counts + 3, W.rayO, W.rayD,
+                                                nullptr, cameraRays != 0, s_stack, warpPairs, ring, finishClosest);
+    else
+#endif
+      traceQueue<false, kRefill, kFlat>(P, W.queue[qin], countA, countB, W.queueCapacity, W.counts + 3, W.rayO, W.rayD,
+                                        cameraRays != 0, s_stack, warpPairs, finishClosest);
     if (P.rayCounters != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
       atomicAdd(P.rayCounters + 0, (unsigned long long)countA + (unsigned long long)countB);
   }
   if (doShadow) {
     const uint32_t countA = W.counts[shadowCount(shadowParity)], countB = W.counts[shadowCountB(shadowParity)];
-    traceQueue<true, kRefill, kFlat>(P, W.shadowQueue, countA, countB, W.queueCapacity, W.counts + 10 + shadowParity, W.rayO,
-                                     W.shD, false, s_stack,
-                              [&](uint32_t slot, const LaneTraversal<true> &t) {
-                                if (!t.found) { // unoccluded: the light sample contributes
-                                  const float4 c = RT_LDS(W.shC + slot);
-                                  float4 r = RT_LDS(W.rad + slot);
-                                  r.x = r.x + c.x, r.y = r.y + c.y, r.z = r.z + c.z;
-                                  RT_STS(W.rad + slot, r);
-                                }
-                              });
+    auto finishShadow = [&](uint32_t slot, bool found, const RayHit &, const float4 *carried) {
+                                if (!found) // unoccluded: the light sample contributes (shC = radiance + contribution)
+                                  RT_STS(W.rad + slot, carried != nullptr ? *carried : RT_LDS(W.shC + slot));
+                              };
+#if RT_PREFETCH > 0
+    if constexpr (kPrefetch)
+      traceQueuePrefetch<true, kRefill, kFlat>(P, W.shadowQueue, countA, countB, W.queueCapacity, W.counts + 10 + shadowParity,
+                                               W.rayO, W.shD, W.shC, false, s_stack, warpPairs, ring, finishShadow);
+    else
+#endif
+      traceQueue<true, kRefill, kFlat>(P, W.shadowQueue, countA, countB, W.queueCapacity, W.counts + 10 + shadowParity, W.rayO,
+                                       W.shD, false, s_stack, warpPairs, finishShadow);
     if (P.rayCounters != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
       atomicAdd(P.rayCounters + 1, (unsigned long long)countA + (unsigned long long)countB);
   }
@@ -613,7 +832,9 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
     if (shadow.valid) {
       pushShadow = true;
       RT_STS(W.shD + slot, make_float4(shadow.dir.x, shadow.dir.y, shadow.dir.z, shadow.tmax));
-      RT_STS(W.shC + slot, make_float4(shadow.contribution.x, shadow.contribution.y, shadow.contribution.z, 0.0f));
+      // what the path's radiance becomes if the shadow ray gets through: the traversal kernel only has to copy it
+      RT_STS(W.shC + slot, make_float4(s.radiance.x + shadow.contribution.x, s.radiance.y + shadow.contribution.y,
+                                       s.radiance.z + shadow.contribution.z, 0.0f));
       // its origin is the record written above (the next segment's origin, or its own when the path ends here)
       const f3 so = pushPath ? s.origin : shadow.origin;
 #ifndef RT_CLASSIFY_SHADOW
@@ -933,8 +1154,10 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P0) {
   }
   const int batch = int(L[0].W.batch); // lane 0 owns the most tiles, so its batch is the smallest; all lanes use it
   for (Lane &ln : L) ln.W.batch = uint32_t(batch);
-  // traversal kernels: exactly the resident CTA count (they pull work from a cursor), blocks_per_sm overrides
-  const int traceGrid = ctx->smCount * std::max(1, ctx->blocksPerSm);
+  // traversal kernels: exactly the resident CTA count (they pull work from a cursor): 8 per SM for large dispatches, 7 for
+  // small ones (see kMinBlocksSmall); blocks_per_sm > 0 overrides the grid size
+  const bool largeDispatch = size_t(L[0].W.capacity) * size_t(batch) >= kLargeDispatchPaths;
+  const int traceGrid = ctx->smCount * (ctx->blocksPerSm > 0 ? ctx->blocksPerSm : (largeDispatch ? kMinBlocksLarge : kMinBlocksSmall));
   if (lanes > 1) { // fork: the lanes start after everything enqueued on the context's stream so far
     ctx->mark(-1);
     RT_CUDA(cudaEventRecord(ctx->evFork, ctx->stream));
@@ -952,8 +1175,13 @@ int launchTraceWavefront(rt_context *ctx, const TraceParams &P0) {
     const int qin = ln.qin;
     // instantiations: lane refill threshold (traversal_variant 0 / 1 / 2 = never / 8 / 16 idle lanes) x TLAS kind
     const bool flat = P.tlas.instanceCount <= kFlatTlasMax && P.tlas.instanceBox != nullptr;
-#define RT_LAUNCH_TRAVERSE(R, F) \
-  k_wf_traverse<R, F><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity)
+#define RT_LAUNCH_TRAVERSE(R, F)                                                                                              \
+  do {                                                                                                                       \
+    if (largeDispatch)                                                                                                       \
+      k_wf_traverse<R, F, kMinBlocksLarge, kPrefetchLarge><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); \
+    else                                                                                                                     \
+      k_wf_traverse<R, F, kMinBlocksSmall, kPrefetchSmall><<<traceGrid, kTraceBlock, 0, st>>>(P, W, qin, first, cameraRays, doClosest, doShadow, shadowParity); \
+  } while (0)
     switch (ctx->traversalVariant * 2 + (flat ? 1 : 0)) {
       case 0: RT_LAUNCH_TRAVERSE(0, false); break;
       case 1: RT_LAUNCH_TRAVERSE(0, true); break;

@@ -24,20 +24,32 @@ struct RayHit {
 };
 
 constexpr int kStackSize = 48;
+// RT_SLIM_LANE: the state of a ray that is touched once or twice in its life — the world-space ray (needed again only
+// when an instance is entered or left), the (u, v) and ids of the best hit (written on an accepted hit, read at the
+// end) and the path slot — lives in kStackExtra entries behind the traversal stack (local memory, L1) instead of 12
+// registers per lane. The traversal kernel then fits 72 registers with hardly a spill: 7 CTAs per SM instead of 6
+// (profiles/r2_experiments.md section 9).
+#ifndef RT_SLIM_LANE
+#define RT_SLIM_LANE 1
+#endif
+constexpr int kStackExtra = 9;
+constexpr int kSlotHitUV = kStackSize, kSlotHitIds = kStackSize + 1, kSlotHitPrim = kStackSize + 2, kSlotRay0 = kStackSize + 3,
+              kSlotRay1 = kStackSize + 4, kSlotRay2 = kStackSize + 5, kSlotPath = kStackSize + 6,
+              kSlotCarry0 = kStackSize + 7, kSlotCarry1 = kStackSize + 8; // what the kernel carries along for the ray's end
 
 // Traversal stack of one lane. LocalStack: a plain array (local memory, served by L1). SplitStack: the first
 // kShared entries — all a ray normally needs — live in shared memory, laid out [entry][thread] so a warp's accesses
 // are conflict-free; deeper entries spill to a local array. Pops then cost a shared-memory load instead of a local
 // load that competes with the BVH nodes for L1 lines.
 struct LocalStack {
-  uint2 e[kStackSize];
+  uint2 e[kStackSize + kStackExtra];
   __device__ __forceinline__ void set(int i, uint2 v) { e[i] = v; }
   __device__ __forceinline__ uint2 get(int i) const { return e[i]; }
 };
 template <int kShared, int kThreads>
 struct SplitStack {
   uint2 *shared; // &smem[threadIdx.x]; entry i at shared[i * kThreads]
-  uint2 spill[kStackSize - kShared];
+  uint2 spill[kStackSize - kShared + kStackExtra];
   __device__ __forceinline__ void set(int i, uint2 v) {
     if (i < kShared) shared[i * kThreads] = v;
     else spill[i - kShared] = v;
@@ -59,10 +71,17 @@ __device__ __forceinline__ float pickMasked(float x, float y, float z, const Axi
 }
 
 struct TriSetup { // Woop et al. per-ray constants in the current space
-  AxisMask kx, ky, kz;
+  uint32_t axes;    // kx | ky << 2 | kz << 4: the permutation as three axis numbers (one register instead of six masks;
+                    // a lane keeps this for as long as it is inside an instance, whoever tests a triangle expands it)
   float Sx, Sy, Sz;
   float ox, oy, oz; // origin permuted to (kx, ky, kz)
 };
+struct TriAxes { // the permutation of a TriSetup as select masks (pickMasked)
+  AxisMask kx, ky, kz;
+};
+__device__ __forceinline__ TriAxes expandAxes(uint32_t axes) {
+  return {axisMask(int(axes & 3u)), axisMask(int((axes >> 2) & 3u)), axisMask(int((axes >> 4) & 3u))};
+}
 
 __device__ __forceinline__ TriSetup makeTriSetup(float ox, float oy, float oz, float dx, float dy, float dz) {
   TriSetup s;
@@ -70,17 +89,18 @@ __device__ __forceinline__ TriSetup makeTriSetup(float ox, float oy, float oz, f
   const int kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
   const int k1 = kz == 2 ? 0 : kz + 1;
   const int k2 = k1 == 2 ? 0 : k1 + 1;
-  s.kz = axisMask(kz);
-  const float dkz = pickMasked(dx, dy, dz, s.kz);
+  const AxisMask mz = axisMask(kz);
+  const float dkz = pickMasked(dx, dy, dz, mz);
   const bool swap = dkz < 0.0f; // keeps the winding
-  s.kx = axisMask(swap ? k2 : k1);
-  s.ky = axisMask(swap ? k1 : k2);
-  s.Sx = pickMasked(dx, dy, dz, s.kx) / dkz;
-  s.Sy = pickMasked(dx, dy, dz, s.ky) / dkz;
+  const int kx = swap ? k2 : k1, ky = swap ? k1 : k2;
+  const AxisMask mx = axisMask(kx), my = axisMask(ky);
+  s.axes = uint32_t(kx) | (uint32_t(ky) << 2) | (uint32_t(kz) << 4);
+  s.Sx = pickMasked(dx, dy, dz, mx) / dkz;
+  s.Sy = pickMasked(dx, dy, dz, my) / dkz;
   s.Sz = 1.0f / dkz;
-  s.ox = pickMasked(ox, oy, oz, s.kx);
-  s.oy = pickMasked(ox, oy, oz, s.ky);
-  s.oz = pickMasked(ox, oy, oz, s.kz);
+  s.ox = pickMasked(ox, oy, oz, mx);
+  s.oy = pickMasked(ox, oy, oz, my);
+  s.oz = pickMasked(ox, oy, oz, mz);
   return s;
 }
 
@@ -88,12 +108,13 @@ __device__ __forceinline__ TriSetup makeTriSetup(float ox, float oy, float oz, f
 __device__ __forceinline__ bool intersectTriangle(const TriSetup &s, const float4 &v0, const float4 &v1,
                                                   const float4 &v2, float tmin, float tmax, float &tOut, float &uOut,
                                                   float &vOut) {
-  const float Akx = pickMasked(v0.x, v0.y, v0.z, s.kx) - s.ox, Aky = pickMasked(v0.x, v0.y, v0.z, s.ky) - s.oy,
-              Akz = pickMasked(v0.x, v0.y, v0.z, s.kz) - s.oz;
-  const float Bkx = pickMasked(v1.x, v1.y, v1.z, s.kx) - s.ox, Bky = pickMasked(v1.x, v1.y, v1.z, s.ky) - s.oy,
-              Bkz = pickMasked(v1.x, v1.y, v1.z, s.kz) - s.oz;
-  const float Ckx = pickMasked(v2.x, v2.y, v2.z, s.kx) - s.ox, Cky = pickMasked(v2.x, v2.y, v2.z, s.ky) - s.oy,
-              Ckz = pickMasked(v2.x, v2.y, v2.z, s.kz) - s.oz;
+  const TriAxes a = expandAxes(s.axes);
+  const float Akx = pickMasked(v0.x, v0.y, v0.z, a.kx) - s.ox, Aky = pickMasked(v0.x, v0.y, v0.z, a.ky) - s.oy,
+              Akz = pickMasked(v0.x, v0.y, v0.z, a.kz) - s.oz;
+  const float Bkx = pickMasked(v1.x, v1.y, v1.z, a.kx) - s.ox, Bky = pickMasked(v1.x, v1.y, v1.z, a.ky) - s.oy,
+              Bkz = pickMasked(v1.x, v1.y, v1.z, a.kz) - s.oz;
+  const float Ckx = pickMasked(v2.x, v2.y, v2.z, a.kx) - s.ox, Cky = pickMasked(v2.x, v2.y, v2.z, a.ky) - s.oy,
+              Ckz = pickMasked(v2.x, v2.y, v2.z, a.kz) - s.oz;
   const float Ax = Akx - s.Sx * Akz, Ay = Aky - s.Sy * Akz;
   const float Bx = Bkx - s.Sx * Bkz, By = Bky - s.Sy * Bkz;
   const float Cx = Ckx - s.Sx * Ckz, Cy = Cky - s.Sy * Ckz;
@@ -126,8 +147,10 @@ struct BoxSetup { // per-ray constants for the quantised child-box tests in the 
   float idx, idy, idz; // 1 / direction (zero components replaced by a tiny value of the same sign)
   float ox, oy, oz;
   uint32_t octinv;     // 7 ^ (sign bits of the direction): permutes slots into front-to-back priority
-  uint32_t one;        // bits of 1.0f held in a register the compiler cannot fold (see byteAsUnitFloat)
 };
+// The bits of 1.0f as a value the compiler cannot fold into an immediate (see byteAsUnitFloat): derived from a kernel
+// parameter (a node count is always < 2^31), so it is uniform, costs no per-lane state and can be rematerialised.
+__device__ __forceinline__ uint32_t unfoldableOne(uint32_t anyCountBelow2G) { return 0x3F800000u | (anyCountBelow2G >> 31); }
 
 // 1 / d for the box tests only: they just have to be conservative, so the single-instruction reciprocal
 // (MUFU.RCP, <= 1 ulp) is enough — its error is covered by the widening `eps` in intersectChildren.
@@ -139,10 +162,8 @@ __device__ __forceinline__ float safeInverse(float d) {
   return r;
 }
 
-__device__ __forceinline__ BoxSetup makeBoxSetup(float ox, float oy, float oz, float dx, float dy, float dz,
-                                                 uint32_t one = 0x3F800000u) {
+__device__ __forceinline__ BoxSetup makeBoxSetup(float ox, float oy, float oz, float dx, float dy, float dz) {
   BoxSetup b;
-  b.one = one;
   b.idx = safeInverse(dx);
   b.idy = safeInverse(dy);
   b.idz = safeInverse(dz);
@@ -218,7 +239,7 @@ __device__ __forceinline__ float byteAsUnitFloat(uint32_t word, uint32_t one) {
 // priority, bits 0..23 leaf primitives relative to primBase.
 __device__ __forceinline__ uint32_t intersectChildren(const uint4 &n0, const uint4 &n1, const uint4 &n2,
                                                       const uint4 &n3, const uint4 &n4, const BoxSetup &b, float tmin,
-                                                      float tmax) {
+                                                      float tmax, uint32_t one = 0x3F800000u) {
   // per-axis scale 2^(e-127) times 2^15 (the builder keeps e small enough for the sum not to overflow)
   const float sx = __uint_as_float(((n0.w & 0xFFu) + 15u) << 23), sy = __uint_as_float((((n0.w >> 8) & 0xFFu) + 15u) << 23),
               sz = __uint_as_float((((n0.w >> 16) & 0xFFu) + 15u) << 23);
@@ -255,9 +276,9 @@ __device__ __forceinline__ uint32_t intersectChildren(const uint4 &n0, const uin
     const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u; // empty slots contribute no bits
 #define RT_CHILD(k)                                                                                                  \
   {                                                                                                                  \
-    const float tnx = fmaf(byteAsUnitFloat<k>(nearx, b.one), aix, nox), tfx = fmaf(byteAsUnitFloat<k>(farx, b.one), aix, fox); \
-    const float tny = fmaf(byteAsUnitFloat<k>(neary, b.one), aiy, noy), tfy = fmaf(byteAsUnitFloat<k>(fary, b.one), aiy, foy); \
-    const float tnz = fmaf(byteAsUnitFloat<k>(nearz, b.one), aiz, noz), tfz = fmaf(byteAsUnitFloat<k>(farz, b.one), aiz, foz); \
+    const float tnx = fmaf(byteAsUnitFloat<k>(nearx, one), aix, nox), tfx = fmaf(byteAsUnitFloat<k>(farx, one), aix, fox); \
+    const float tny = fmaf(byteAsUnitFloat<k>(neary, one), aiy, noy), tfy = fmaf(byteAsUnitFloat<k>(fary, one), aiy, foy); \
+    const float tnz = fmaf(byteAsUnitFloat<k>(nearz, one), aiz, noz), tfz = fmaf(byteAsUnitFloat<k>(farz, one), aiz, foz); \
     const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                                       \
     const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                                       \
     if (tn <= tf) {                                                                                                  \
@@ -297,7 +318,10 @@ __device__ __forceinline__ bool rayReachesNodes(const float4 *__restrict__ spher
 // kAny: the traversal ends at the first accepted triangle (found == occluded).
 template <bool kAny>
 struct LaneTraversal {
-  float ox, oy, oz, dx, dy, dz, tmin, tmax; // world-space ray
+#if !RT_SLIM_LANE
+  float ox, oy, oz, dx, dy, dz; // world-space ray
+#endif
+  float tmin, tmax;
   // the TLAS arrays are not kept here: every step takes the TlasHeader that sits in the kernel's parameter space, so
   // those uniform pointers cost constant-bank operands instead of six registers per lane
   const uint4 *nodes;
@@ -307,7 +331,7 @@ struct LaneTraversal {
   uint2 ngroup, tgroup;
   int sp, instanceSp; // instanceSp: stack depth at which the current instance was entered; -1 = world space
   uint32_t instance;
-  RayHit hit;
+  RayHit hit; // RT_SLIM_LANE: only hit.t is kept here, the rest of the best hit is in the stack's extra entries
   bool found;
 #ifdef RT_COUNT_WORK
   // counter build (tools/count_work.py): work done for this ray — node steps, triangle tests, instance entries.
@@ -320,10 +344,83 @@ struct LaneTraversal {
   // the traversal stack lives outside (a plain local array passed to every step) so that the compiler keeps the
   // scalar members above in registers instead of placing the whole object in local memory
 
-  template <bool kFlatAllowed = true>
-  __device__ __forceinline__ void begin(const TlasHeader &tlas, float ox_, float oy_, float oz_, float dx_,
+  template <typename Stack>
+  __device__ __forceinline__ void worldRay(const Stack &stack, float &ox_, float &oy_, float &oz_, float &dx_, float &dy_,
+                                           float &dz_) const {
+#if RT_SLIM_LANE
+    const uint2 a = stack.get(kSlotRay0), b = stack.get(kSlotRay1), c = stack.get(kSlotRay2);
+    ox_ = __uint_as_float(a.x), oy_ = __uint_as_float(a.y), oz_ = __uint_as_float(b.x);
+    dx_ = __uint_as_float(b.y), dy_ = __uint_as_float(c.x), dz_ = __uint_as_float(c.y);
+#else
+    (void)stack;
+    ox_ = ox, oy_ = oy, oz_ = oz, dx_ = dx, dy_ = dy, dz_ = dz;
+#endif
+  }
+
+  // the result of a finished closest-hit traversal (hit.t == tmax and !found when nothing was hit)
+  template <typename Stack>
+  __device__ __forceinline__ RayHit result(const Stack &stack) const {
+#if RT_SLIM_LANE
+    RayHit h;
+    h.t = hit.t;
+    h.u = h.v = 0.0f;
+    h.instance = h.geometry = h.primitive = 0u;
+    if (found) {
+      const uint2 uv = stack.get(kSlotHitUV), ids = stack.get(kSlotHitIds);
+      h.u = __uint_as_float(uv.x), h.v = __uint_as_float(uv.y);
+      h.instance = ids.x, h.geometry = ids.y;
+      h.primitive = stack.get(kSlotHitPrim).x;
+    }
+    return h;
+#else
+    (void)stack;
+    return hit;
+#endif
+  }
+
+  // a triangle of the current instance was hit at t in (tmin, tmax): keep it if it is the best so far
+  template <typename Stack>
+  __device__ __forceinline__ void acceptHit(Stack &stack, float t, float u, float v, uint32_t geom, uint32_t prim) {
+    bool better = t < hit.t;
+    if (!better && found && t == hit.t) {
+#if RT_SLIM_LANE
+      const uint2 ids = stack.get(kSlotHitIds);
+      const uint32_t bestPrim = stack.get(kSlotHitPrim).x;
+      better = instance < ids.x || (instance == ids.x && (geom < ids.y || (geom == ids.y && prim < bestPrim)));
+#else
+      better = instance < hit.instance ||
+               (instance == hit.instance && (geom < hit.geometry || (geom == hit.geometry && prim < hit.primitive)));
+#endif
+    }
+    if (better) {
+      found = true;
+      hit.t = t;
+#if RT_SLIM_LANE
+      stack.set(kSlotHitUV, make_uint2(__float_as_uint(u), __float_as_uint(v)));
+      stack.set(kSlotHitIds, make_uint2(instance, geom));
+      stack.set(kSlotHitPrim, make_uint2(prim, 0u));
+#else
+      hit.u = u;
+      hit.v = v;
+      hit.instance = instance;
+      hit.geometry = geom;
+      hit.primitive = prim;
+#endif
+    }
+  }
+
+  template <bool kFlatAllowed = true, typename Stack>
+  __device__ __forceinline__ void begin(const TlasHeader &tlas, Stack &stack, float ox_, float oy_, float oz_, float dx_,
                                         float dy_, float dz_, float tmin_, float tmax_) {
-    ox = ox_, oy = oy_, oz = oz_, dx = dx_, dy = dy_, dz = dz_, tmin = tmin_, tmax = tmax_;
+    const float ox = ox_, oy = oy_, oz = oz_, dx = dx_, dy = dy_, dz = dz_;
+#if RT_SLIM_LANE
+    stack.set(kSlotRay0, make_uint2(__float_as_uint(ox), __float_as_uint(oy)));
+    stack.set(kSlotRay1, make_uint2(__float_as_uint(oz), __float_as_uint(dx)));
+    stack.set(kSlotRay2, make_uint2(__float_as_uint(dy), __float_as_uint(dz)));
+#else
+    this->ox = ox_, this->oy = oy_, this->oz = oz_, this->dx = dx_, this->dy = dy_, this->dz = dz_;
+#endif
+    tmin = tmin_, tmax = tmax_;
     hit.t = tmax_;
     hit.u = hit.v = 0.0f;
     hit.instance = hit.geometry = hit.primitive = 0u;
@@ -338,8 +435,7 @@ struct LaneTraversal {
     tris = nullptr;
     // an empty TLAS has nothing pending: the first step() pops an empty stack and finishes
     const uint32_t nodeCount = tlas.nodeCount;
-    // 1.0f, but derived from a kernel parameter so that it is not folded into an immediate (nodeCount < 2^31 always)
-    box = makeBoxSetup(ox, oy, oz, dx, dy, dz, 0x3F800000u | (nodeCount >> 31));
+    box = makeBoxSetup(ox, oy, oz, dx, dy, dz);
     tri = TriSetup{};
     ngroup = make_uint2(0u, nodeCount != 0 ? 0x80000000u : 0u);
     tgroup = make_uint2(0u, 0u);
@@ -374,7 +470,7 @@ struct LaneTraversal {
 
   // take the nearest pending child of ngroup, test its eight children
   template <typename Stack>
-  __device__ __forceinline__ void nodeStep(Stack &stack) {
+  __device__ __forceinline__ void nodeStep(const TlasHeader &tlas, Stack &stack) {
     RT_COUNT(nNodes);
     const uint32_t hits = ngroup.y;
     const uint32_t bit = 31u - uint32_t(__clz(int(hits)));
@@ -387,7 +483,7 @@ struct LaneTraversal {
 #ifdef RT_LEGACY_CHILD_TEST
     const uint32_t hitmask = intersectChildrenLegacy(n0, n1, n2, n3, n4, box, tmin, hit.t);
 #else
-    const uint32_t hitmask = intersectChildren(n0, n1, n2, n3, n4, box, tmin, hit.t);
+    const uint32_t hitmask = intersectChildren(n0, n1, n2, n3, n4, box, tmin, hit.t, unfoldableOne(tlas.nodeCount));
 #endif
     ngroup = make_uint2(n1.x, (hitmask & 0xFF000000u) | (n0.w >> 24));
     tgroup = make_uint2(n1.y, hitmask & 0x00FFFFFFu);
@@ -400,7 +496,7 @@ struct LaneTraversal {
       enterInstance(tlas, stack);
       return false;
     }
-    return triangleStep();
+    return triangleStep(stack);
   }
 
   // tgroup holds TLAS leaf entries (instanceSp < 0): enter the next instance
@@ -420,6 +516,8 @@ struct LaneTraversal {
       tgroup.y = 0u;
       ngroup = make_uint2(0u, 0u);
       if (bn != nullptr) {
+        float ox, oy, oz, dx, dy, dz;
+        worldRay(stack, ox, oy, oz, dx, dy, dz);
         const float lox = ((r0.x * ox + r0.y * oy) + r0.z * oz) + r0.w;
         const float loy = ((r1.x * ox + r1.y * oy) + r1.z * oz) + r1.w;
         const float loz = ((r2.x * ox + r2.y * oy) + r2.z * oz) + r2.w;
@@ -440,7 +538,7 @@ struct LaneTraversal {
           // popStep sees from `nodes` that there is nothing to restore when the instance is left
           tgroup = make_uint2(0u, 0xFFFFFFFFu >> (32u - direct));
         } else {
-          box = makeBoxSetup(lox, loy, loz, ldx, ldy, ldz, box.one);
+          box = makeBoxSetup(lox, loy, loz, ldx, ldy, ldz);
           nodes = reinterpret_cast<const uint4 *>(bn);
           ngroup = make_uint2(0u, 0x80000000u);
         }
@@ -450,30 +548,96 @@ struct LaneTraversal {
 
   // tgroup holds triangles of the current BLAS (instanceSp >= 0): test the next one.
   // Returns true when an any-hit query is satisfied.
-  __device__ __forceinline__ bool triangleStep() {
+  template <typename Stack>
+  __device__ __forceinline__ bool triangleStep(Stack &stack) {
     RT_COUNT(nTris);
     const uint32_t bit = uint32_t(__ffs(int(tgroup.y))) - 1u;
     tgroup.y &= ~(1u << bit);
     const float4 *tp = tris + size_t(tgroup.x + bit) * 3;
     const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
     float t, u, v;
-    if (intersectTriangle(tri, v0, v1, v2, tmin, tmax, t, u, v)) {
+    if (intersectTriangle(tri, v0, v1, v2, tmin, kAny ? hit.t : tmax, t, u, v)) { // any-hit: hit.t stays tmax
       if (kAny) return true;
-      const uint32_t prim = __float_as_uint(v0.w), geom = __float_as_uint(v1.w);
-      bool better = t < hit.t;
-      if (!better && found && t == hit.t) {
-        better = instance < hit.instance ||
-                 (instance == hit.instance && (geom < hit.geometry || (geom == hit.geometry && prim < hit.primitive)));
-      }
-      if (better) {
-        found = true;
-        hit.t = t;
-        hit.u = u;
-        hit.v = v;
-        hit.instance = instance;
-        hit.geometry = geom;
-        hit.primitive = prim;
-      }
+      acceptHit(stack, t, u, v, __float_as_uint(v1.w), __float_as_uint(v0.w));
+    }
+    return false;
+  }
+
+  // The triangle stage of stepConverged, done by the warp together (kCoop). Every lane calls it; `want` = this lane is
+  // inside an instance with triangles pending. In a warp of incoherent rays about a quarter of the lanes have triangles
+  // to test in any one iteration, and testing them where they sit ran the ~110 instructions of the watertight test at 7 - 9
+  // of 32 threads, twice per iteration (profiles/r2_experiments.md section 9). Here the pending (lane, triangle) pairs of
+  // the whole warp are numbered by a prefix sum over the lanes' triangle counts, the first 32 of them are listed in
+  // shared memory, lane p tests pair p — it fetches the owner's Woop constants, triangle base and t range by shuffle —
+  // and a ballot hands the outcome back: an any-hit owner only needs to know whether one of its pairs hit, a closest-hit
+  // owner fetches the (t, u, v, ids) of each of its hits from the lane that found it. One pass retires up to 32 triangles
+  // however they are spread over the lanes. The arithmetic of a test does not depend on the lane that runs it, and the
+  // best hit under (t, instance, geometry, primitive) does not depend on the order the candidates arrive in, so results
+  // are unchanged. Returns true when this lane's any-hit query has just been satisfied.
+  template <typename Stack>
+  __device__ __forceinline__ bool triangleStageCoop(Stack &stack, bool want, uint32_t *pairs) {
+    const unsigned full = 0xFFFFFFFFu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = want ? uint32_t(__popc(tgroup.y)) : 0u;
+    uint32_t incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(full, incl, d);
+      if (lane >= uint32_t(d)) incl += up;
+    }
+    const uint32_t excl = incl - n;
+    const uint32_t total = min(__shfl_sync(full, incl, 31), 32u);
+    const uint32_t base = tgroup.x;
+    uint32_t consumed = 0u;
+    if (want && excl < 32u) { // list my triangles: pair number -> (owner lane, bit of the owner's leaf mask)
+      uint32_t m = tgroup.y, p = excl;
+      do {
+        const uint32_t b = uint32_t(__ffs(int(m))) - 1u;
+        m &= m - 1u;
+        pairs[p++] = lane | (b << 8);
+      } while (m != 0u && p < 32u);
+      consumed = p - excl;
+      tgroup.y = m; // what did not fit waits for the next pass
+#ifdef RT_COUNT_WORK
+      nTris += consumed;
+#endif
+    }
+    __syncwarp();
+    const bool testing = lane < total;
+    uint32_t owner = lane, bit = 0u;
+    if (testing) {
+      const uint32_t pr = pairs[lane];
+      owner = pr & 31u;
+      bit = pr >> 8;
+    }
+    TriSetup s;
+    s.axes = __shfl_sync(full, tri.axes, owner);
+    s.Sx = __shfl_sync(full, tri.Sx, owner), s.Sy = __shfl_sync(full, tri.Sy, owner), s.Sz = __shfl_sync(full, tri.Sz, owner);
+    s.ox = __shfl_sync(full, tri.ox, owner), s.oy = __shfl_sync(full, tri.oy, owner), s.oz = __shfl_sync(full, tri.oz, owner);
+    const uintptr_t trisBits = reinterpret_cast<uintptr_t>(tris);
+    const uint32_t tlo = __shfl_sync(full, uint32_t(trisBits), owner), thi = __shfl_sync(full, uint32_t(trisBits >> 32), owner);
+    const uint32_t obase = __shfl_sync(full, base, owner);
+    const float otmin = __shfl_sync(full, tmin, owner), otmax = __shfl_sync(full, tmax, owner);
+    bool hitHere = false;
+    float t = 0.0f, u = 0.0f, v = 0.0f;
+    uint32_t prim = 0u, geom = 0u;
+    if (testing) {
+      const float4 *tp = reinterpret_cast<const float4 *>(uintptr_t(tlo) | (uintptr_t(thi) << 32)) + size_t(obase + bit) * 3;
+      const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+      hitHere = intersectTriangle(s, v0, v1, v2, otmin, otmax, t, u, v);
+      prim = __float_as_uint(v0.w), geom = __float_as_uint(v1.w);
+    }
+    const unsigned hits = __ballot_sync(full, hitHere);
+    if (hits == 0u) return false;
+    unsigned mine = consumed != 0u ? ((hits >> excl) & (0xFFFFFFFFu >> (32u - consumed))) : 0u;
+    if (kAny) return mine != 0u;
+    while (__ballot_sync(full, mine != 0u) != 0u) { // warp-uniform: one round per hit of the owner with the most hits
+      const bool have = mine != 0u;
+      const uint32_t src = have ? excl + uint32_t(__ffs(int(mine))) - 1u : lane;
+      mine &= mine - 1u;
+      const float ht = __shfl_sync(full, t, src), hu = __shfl_sync(full, u, src), hv = __shfl_sync(full, v, src);
+      const uint32_t hp = __shfl_sync(full, prim, src), hg = __shfl_sync(full, geom, src);
+      if (have) acceptHit(stack, ht, hu, hv, hg, hp);
     }
     return false;
   }
@@ -485,7 +649,9 @@ struct LaneTraversal {
     if (sp == instanceSp) {
       instanceSp = -1;
       if (nodes != reinterpret_cast<const uint4 *>(tlas.nodes)) { // a directly-tested BLAS never replaced them
-        box = makeBoxSetup(ox, oy, oz, dx, dy, dz, box.one);
+        float ox, oy, oz, dx, dy, dz;
+        worldRay(stack, ox, oy, oz, dx, dy, dz);
+        box = makeBoxSetup(ox, oy, oz, dx, dy, dz);
         nodes = reinterpret_cast<const uint4 *>(tlas.nodes);
       }
     }
@@ -510,7 +676,7 @@ struct LaneTraversal {
     if (tgroup.y == 0u && ngroup.y <= 0x00FFFFFFu) {
       if (!popStep(tlas, stack)) return false;
     }
-    if (tgroup.y == 0u && ngroup.y > 0x00FFFFFFu) nodeStep(stack);
+    if (tgroup.y == 0u && ngroup.y > 0x00FFFFFFu) nodeStep(tlas, stack);
 #pragma unroll
     for (int k = 0; k < kPrims; ++k) {
       if (tgroup.y != 0u) {
@@ -532,8 +698,8 @@ struct LaneTraversal {
   // earlier stage running apart from those that did not — ncu showed the same thread instructions in 1.3-1.5x the
   // warp instructions (profiles/r1_traversal.md, step 12). Per lane the order of node, entry and triangle tests is
   // the one stepFused has, so results are unchanged. Returns true when this lane's ray has just finished.
-  template <bool kEntryBefore, bool kEntryAfter, bool kEarlyFinish, bool kCombined, int kTriangles, typename Stack>
-  __device__ __forceinline__ bool stepConverged(const TlasHeader &tlas, Stack &stack, bool active) {
+  template <bool kEntryBefore, bool kEntryAfter, bool kEarlyFinish, bool kCombined, int kTriangles, bool kCoop, typename Stack>
+  __device__ __forceinline__ bool stepConverged(const TlasHeader &tlas, Stack &stack, bool active, uint32_t *pairs) {
     bool alive = active;
 #ifdef RT_COUNT_WORK
     if (active) ++nIters;
@@ -547,7 +713,7 @@ struct LaneTraversal {
       if (alive && tgroup.y != 0u && instanceSp < 0) enterInstance(tlas, stack);
       __syncwarp();
     }
-    if (alive && tgroup.y == 0u && ngroup.y > 0x00FFFFFFu) nodeStep(stack);
+    if (alive && tgroup.y == 0u && ngroup.y > 0x00FFFFFFu) nodeStep(tlas, stack);
     __syncwarp();
     if (kEntryAfter && !kCombined) {
       if (alive && tgroup.y != 0u && instanceSp < 0) enterInstance(tlas, stack);
@@ -557,10 +723,21 @@ struct LaneTraversal {
     if (kCombined) {
       if (alive && tgroup.y != 0u) satisfied = primitiveStep(tlas, stack);
       __syncwarp();
+    } else if (kCoop) {
+      // the warp tests its pending triangles together, 32 per pass (triangleStageCoop); a second pass only when more than
+      // 32 were pending
+#pragma unroll
+      for (int k = 0; k < kTriangles; ++k) {
+        const bool want = alive && !satisfied && tgroup.y != 0u && instanceSp >= 0;
+        if (__ballot_sync(0xFFFFFFFFu, want) != 0u) {
+          if (triangleStageCoop(stack, want, pairs)) satisfied = true;
+        }
+        __syncwarp();
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < kTriangles; ++k) {
-        if (alive && !satisfied && tgroup.y != 0u && instanceSp >= 0) satisfied = triangleStep();
+        if (alive && !satisfied && tgroup.y != 0u && instanceSp >= 0) satisfied = triangleStep(stack);
         __syncwarp();
       }
     }
@@ -583,7 +760,7 @@ struct LaneTraversal {
       return true;
     }
     if (ngroup.y > 0x00FFFFFFu) {
-      nodeStep(stack);
+      nodeStep(tlas, stack);
       return true;
     }
     return popStep(tlas, stack);
@@ -597,10 +774,10 @@ __device__ __forceinline__ bool traverseScene(const TlasHeader &tlas, float ox, 
                                               float dx, float dy, float dz, float tmin, float tmax, RayHit &hit) {
   LaneTraversal<kAny> t;
   LocalStack stack;
-  t.begin(tlas, ox, oy, oz, dx, dy, dz, tmin, tmax);
+  t.begin(tlas, stack, ox, oy, oz, dx, dy, dz, tmin, tmax);
   while (t.step(tlas, stack)) {
   }
-  hit = t.hit;
+  hit = t.result(stack);
   return t.found;
 }
 

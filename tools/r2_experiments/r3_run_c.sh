@@ -1,0 +1,16 @@
+#!/bin/bash
+# slim lane state (ray + hit ids behind the stack): parity tests, then 6 / 7 / 8 CTAs per SM
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r3c_pytest.log 2>&1; tail -3 gpurun_out/r3c_pytest.log
+run() { # lib options workload extra
+  RT_B200_LIBNAME=$1 RT_B200_OPTIONS=$2 timeout 300 python bench.py --steps 5 --warmup 3 --workload $3 $4 --no-others --no-cpu-baseline --no-e2e 2>/dev/null | tail -1 | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print('$1 $2 $3 $4', d['value'], d['ms_per_step'], {k:round(v['ms_per_step'],3) for k,v in d['roofline']['kernels'].items()})"
+}
+for spec in "librt_b200.so blocks_per_sm=6" "librt_b200_mb7.so blocks_per_sm=7" "librt_b200_mb8.so blocks_per_sm=8" "librt_b200_fat7.so blocks_per_sm=7"; do
+  set -- $spec
+  run $1 $2 K3 ""
+  run $1 $2 K3headline ""
+  run $1 $2 K3 "--slice 8"
+  run $1 $2 K4 ""
+  run $1 $2 K2 ""
+done
