@@ -96,6 +96,25 @@ typedef struct rt_as_info {
 } rt_as_info;
 int rt_as_get_info(rt_context *ctx, uint64_t id, rt_as_info *out);
 
+/* rt_intersect: the reference's intersector call on its own — intersector<triangle_data, instancing>::intersect()
+ * for a closest hit (Raytracing.metal:301-318) or, with RT_INTERSECT_ANY, accept_any_intersection(true) as for its shadow
+ * rays (:664-665, :730-737) — over `count` caller-supplied rays in DEVICE memory against the TLAS `tlasId`. hitsDev[i]
+ * answers raysDev[i]: closest hit = smallest t with tmin < t < tmax, ties -> smallest (instance, geometry, primitive);
+ * (u, v) are the weights of the triangle's second and third vertex (Metal's triangle_barycentric_coord); a miss has
+ * t = +inf and ids 0xFFFFFFFF. RT_INTERSECT_ANY: t = 0 when anything lies in (tmin, tmax), +inf otherwise; the other
+ * fields are not meaningful. The direction need not be normalised (t is in units of its length). Stream-ordered, no
+ * host synchronisation; it runs the same traversal iteration as rt_trace. */
+typedef struct rt_ray {
+  float origin[3], tmin;
+  float direction[3], tmax;
+} rt_ray; /* 32 bytes, 16-byte aligned in device memory */
+typedef struct rt_ray_hit {
+  float t, u, v;
+  uint32_t instance, geometry, primitive;
+} rt_ray_hit; /* 24 bytes */
+#define RT_INTERSECT_ANY 1u
+int rt_intersect(rt_context *ctx, uint64_t tlasId, const rt_ray *raysDev, uint32_t count, uint32_t flags, rt_ray_hit *hitsDev);
+
 /* ---- kernels ------------------------------------------------------------------------------------------------
  * rt_skin: skinningKernel dispatch (Skinning.metal:7-49; SkinningPass.swift:160-211). buffers[] is the argument
  * table indexed by BufferIndex: 10 rest positions, 11 rest normals, 12 joint indices (ushort4), 13 joint weights

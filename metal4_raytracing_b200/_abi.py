@@ -48,6 +48,7 @@ FORMAT_RGBA32_FLOAT = 7
 
 AS_FLAG_COMPACT = 1
 AS_FLAG_REFITTABLE = 2
+INTERSECT_ANY = 1  # rt_intersect flags
 
 SLOT_BASECOLOR, SLOT_NORMAL, SLOT_ROUGHNESS, SLOT_METALLIC, SLOT_AO, SLOT_OPACITY, SLOT_EMISSION = range(7)
 

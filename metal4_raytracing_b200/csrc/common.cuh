@@ -228,6 +228,7 @@ int launchTonemap(rt_context *ctx, const rt_image *src, uint8_t *dst, uint32_t f
 int packTiles(rt_context *ctx, const rt_image *image, void *slab, int modulo, int remainder);
 int unpackTiles(rt_context *ctx, const void *slabs, const rt_image *image, int modulo);
 int selftestChildBoxes(rt_context *ctx, AccelObject *as, uint32_t raysPerNode, uint32_t seed, unsigned long long outHost[11]);
+int launchIntersect(rt_context *ctx, const AccelObject *tl, const rt_ray *rays, uint32_t count, uint32_t flags, rt_ray_hit *hits);
 int launchTrace(rt_context *ctx, const void *const buffers[RT_BUFFER_COUNT], const rt_image textures[RT_TEXTURE_COUNT],
                 int maxSubmeshes, const rt_trace_options *opt);
 } // namespace rtb

@@ -580,6 +580,17 @@ int rt_kernel_timing_read(rt_context *ctx, float msByClass[RT_KERNEL_CLASS_COUNT
   return 0;
 }
 
+int rt_intersect(rt_context *ctx, uint64_t tlasId, const rt_ray *raysDev, uint32_t count, uint32_t flags, rt_ray_hit *hitsDev) {
+  RT_CTX(ctx);
+  RT_CHECK(count == 0 || (raysDev != nullptr && hitsDev != nullptr), "rt_intersect: null ray or hit array");
+  RT_CHECK((reinterpret_cast<uintptr_t>(raysDev) & 15u) == 0, "rt_intersect: raysDev must be 16-byte aligned");
+  RT_CHECK((flags & ~RT_INTERSECT_ANY) == 0u, "rt_intersect: unknown flag");
+  auto it = ctx->accels.find(tlasId);
+  RT_CHECK(it != ctx->accels.end() && it->second->isTlas, "rt_intersect: not a TLAS id from rt_tlas_build");
+  RT_TRY(checkTlasInfo(ctx, it->second, false));
+  return launchIntersect(ctx, it->second, raysDev, count, flags, hitsDev);
+}
+
 int rt_selftest_child_boxes(rt_context *ctx, uint64_t id, uint32_t raysPerNode, uint32_t seed, uint64_t out[11]) {
   RT_CTX(ctx);
   RT_CHECK(out != nullptr && raysPerNode > 0, "rt_selftest_child_boxes: bad arguments");

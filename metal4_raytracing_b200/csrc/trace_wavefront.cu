@@ -734,11 +734,17 @@ __global__ void __launch_bounds__(kTraceBlock, kMinBlocks) k_wf_traverse(const _
 #ifndef RT_SHADE_COMPACT
 #define RT_SHADE_COMPACT 1
 #endif
+// threads per CTA and resident CTAs per SM of the shade kernel: together they set its register budget
+// (65536 / (block x minblocks)); 256 x 4 = 64 registers
+#ifndef RT_SHADE_BLOCK
+#define RT_SHADE_BLOCK 256
+#endif
 #ifndef RT_SHADE_MINBLOCKS
 #define RT_SHADE_MINBLOCKS 4 // 64 registers: measured faster than 128 (the kernel is bound by gather latency; more warps hide it)
 #endif
+constexpr int kShadeBlock = RT_SHADE_BLOCK;
 template <bool kTextures, bool kPlain, bool kClassify>
-__global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const __grid_constant__ TraceParams P,
+__global__ void __launch_bounds__(kShadeBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const __grid_constant__ TraceParams P,
                                                                          const WfState W, int qin, int s0,
                                                                          int cameraRays, int shadowParity) {
   if (blockIdx.x == 0 && threadIdx.x == 0) W.counts[3] = 0u; // cursor of the next trace kernel
@@ -869,7 +875,7 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MINBLOCKS) k_wf_shade(const _
   // left after the last round is the only partial pass. On bounce segments 40 % of the entries are hits: shading
   // them where they sit keeps ~13 lanes of a warp busy, this keeps 32 — and the number of resident warps, which is
   // what hides the gather latency, stays what it was (compacting per CTA took warps away and was slower).
-  __shared__ uint32_t s_slots[kBlock / 32][96];
+  __shared__ uint32_t s_slots[kShadeBlock / 32][96];
   uint32_t *mySlots = s_slots[threadIdx.x >> 5];
   const uint32_t lane = threadIdx.x & 31u;
   const unsigned below = (1u << lane) - 1u;
@@ -1065,8 +1071,8 @@ void wfLaunchShade(bool textures, bool plain, int grid, cudaStream_t st, const T
                    int s0, int cameraRays, int parity) {
 #define RT_SHADE(T, PL)                                                                                       \
   do {                                                                                                         \
-    if (W.classify != 0u) k_wf_shade<T, PL, true><<<grid, kBlock, 0, st>>>(P, W, qin, s0, cameraRays, parity); \
-    else k_wf_shade<T, PL, false><<<grid, kBlock, 0, st>>>(P, W, qin, s0, cameraRays, parity);                 \
+    if (W.classify != 0u) k_wf_shade<T, PL, true><<<grid * (kBlock / kShadeBlock), kShadeBlock, 0, st>>>(P, W, qin, s0, cameraRays, parity); \
+    else k_wf_shade<T, PL, false><<<grid * (kBlock / kShadeBlock), kShadeBlock, 0, st>>>(P, W, qin, s0, cameraRays, parity);                 \
   } while (0)
   if (textures && plain) RT_SHADE(true, true);
   else if (textures) RT_SHADE(true, false);

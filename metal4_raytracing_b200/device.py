@@ -76,8 +76,12 @@ EXPORTS = [
     "rt_tonemap", "rt_temporal_filter", "rt_download_async", "rt_download_wait", "rt_fence", "rt_fence_wait",
     "rtr_last_error", "rtr_create", "rtr_destroy", "rtr_set_seeds", "rtr_update", "rtr_draw", "rtr_read_image",
     "rtr_image_info", "rtr_reset_accumulation", "rtr_read_mesh_streams", "rtr_get_blas_id", "rtr_get_tlas_id",
-    "rtr_mesh_count", "rt_environment_cdf_floats", "rt_environment_cdf", "rt_spatial_filter",
+    "rtr_mesh_count", "rt_environment_cdf_floats", "rt_environment_cdf", "rt_spatial_filter", "rt_intersect",
 ]
+
+
+RAY_HIT_DTYPE = np.dtype([("t", np.float32), ("u", np.float32), ("v", np.float32), ("instance", np.uint32),
+                          ("geometry", np.uint32), ("primitive", np.uint32)])  # rt_ray_hit, 24 bytes
 
 
 def lib():
@@ -120,6 +124,7 @@ def lib():
     L.rt_host_sync_count.argtypes = [vp]
     L.rt_tlas_destroy.argtypes = [vp, u64]
     L.rt_as_get_info.argtypes = [vp, u64, C.POINTER(AsInfo)]
+    L.rt_intersect.argtypes = [vp, u64, vp, u32, u32, vp]
     L.rt_skin.argtypes = [vp, C.POINTER(vp), u32]
     L.rt_trace.argtypes = [vp, C.POINTER(vp), C.POINTER(A.Image), i32, i32, C.POINTER(TraceOptions)]
     L.rt_texture_create.argtypes = [vp, vp, i32, i32, i32, C.POINTER(vp)]
@@ -360,6 +365,23 @@ class Context:
         info = AsInfo()
         _check(lib().rt_as_get_info(self._h, as_id, C.byref(info)))
         return info
+
+    def intersect(self, tlas, rays, any_hit=False):
+        """rt_intersect: rays = float32 array (n, 8) of origin, tmin, direction, tmax. Returns a structured array with
+        the fields of rt_ray_hit (t, u, v, instance, geometry, primitive)."""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        n = rays.shape[0]
+        out = np.zeros(n, RAY_HIT_DTYPE)
+        if n == 0:
+            return out
+        rdev, hdev = self.upload(rays), self.malloc(n * RAY_HIT_DTYPE.itemsize)
+        try:
+            _check(lib().rt_intersect(self._h, tlas, rdev, n, A.INTERSECT_ANY if any_hit else 0, hdev))
+            out = self.download(hdev, (n,), RAY_HIT_DTYPE)
+        finally:
+            self.free(rdev)
+            self.free(hdev)
+        return out
 
     # -- kernels -----------------------------------------------------------------------------------------------
     def skin(self, table, vertex_count):

@@ -12,7 +12,7 @@ build() { # tag, defines...
     $NVCC $FLAGS "$@" -c $f.cu -o /tmp/variants/$tag/$f.o 2> /tmp/variants/$tag/$f.log &
   done
   wait
-  $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/librt_b200_$tag.so rt_api.o bvh_build.o skin.o tiles.o post.o host/renderer.o /tmp/variants/$tag/trace.o /tmp/variants/$tag/trace_wavefront.o /tmp/variants/$tag/selftest.o -cudart static
+  $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/librt_b200_$tag.so rt_api.o bvh_build.o skin.o tiles.o post.o intersect.o host/renderer.o /tmp/variants/$tag/trace.o /tmp/variants/$tag/trace_wavefront.o /tmp/variants/$tag/selftest.o -cudart static
   echo "$tag: $(grep -A2 'k_wf_traverseILi8' /tmp/variants/$tag/trace_wavefront.log | grep -o 'Used [0-9]* registers' | head -1) $(grep -A1 'k_wf_traverseILi8' /tmp/variants/$tag/trace_wavefront.log | grep -o '[0-9]* bytes spill stores' | head -1)"
 }
 for spec in "$@"; do
