@@ -226,6 +226,28 @@ __device__ __forceinline__ uint32_t intersectChildrenLegacy(const uint4 &n0, con
 }
 
 
+// Packed single precision (sm_100a): two floats in a 64-bit register pair, one instruction for both. Each half is the
+// IEEE round-to-nearest result of the scalar operation, so results are bit-identical to the unpacked code.
+// RT_PACKED_FMA=1 uses it for the child-box test (24 FFMA2 instead of 48 FFMA per node). Measured and left off: K3 19.70
+// against 19.03 ms, K4 70.0 against 66.9 — the register pairs cost 100 bytes of spills at 64 registers and the issue
+// slots saved do not make up for it (profiles/r2_experiments.md section 11).
+#ifndef RT_PACKED_FMA
+#define RT_PACKED_FMA 0
+#endif
+__device__ __forceinline__ unsigned long long packF2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpackF2(unsigned long long v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, float b, unsigned long long c) { // a * (b, b) + c
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(packF2(b, b)), "l"(c));
+  return r;
+}
+
 // Quantised byte -> float without an integer conversion: PRMT drops the byte into mantissa bits 8..15 of 1.0f,
 // giving 1 + q * 2^-15 exactly; the 2^15 is folded into the per-axis scale and the 1 into the offset.
 // `one` must live in a register: PRMT takes a single immediate, and with a literal 1.0f the compiler spends it on
@@ -274,6 +296,25 @@ __device__ __forceinline__ uint32_t intersectChildren(const uint4 &n0, const uin
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(innerMask4) : "r"(isInner4 << 3), "r"(0u), "r"(0xBA98u));
     const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1F1F1F1Fu;
     const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u; // empty slots contribute no bits
+#if RT_PACKED_FMA
+  // sm_100a's packed single-precision FMA (FFMA2: two independent round-to-nearest FMAs on a register pair, the scale
+  // broadcast from one register): the near and the far plane of an axis in one instruction, 24 instead of 48 per node
+  const unsigned long long offx = packF2(nox, fox), offy = packF2(noy, foy), offz = packF2(noz, foz);
+#define RT_CHILD(k)                                                                                                  \
+  {                                                                                                                  \
+    float tnx, tfx, tny, tfy, tnz, tfz;                                                                              \
+    unpackF2(fma2(packF2(byteAsUnitFloat<k>(nearx, one), byteAsUnitFloat<k>(farx, one)), aix, offx), tnx, tfx);      \
+    unpackF2(fma2(packF2(byteAsUnitFloat<k>(neary, one), byteAsUnitFloat<k>(fary, one)), aiy, offy), tny, tfy);      \
+    unpackF2(fma2(packF2(byteAsUnitFloat<k>(nearz, one), byteAsUnitFloat<k>(farz, one)), aiz, offz), tnz, tfz);      \
+    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                                       \
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                                       \
+    if (tn <= tf) {                                                                                                  \
+      const uint32_t bits = __byte_perm(childBits4, 0u, 0x4440u | uint32_t(k));                                      \
+      const uint32_t index = __byte_perm(bitIndex4, 0u, 0x4440u | uint32_t(k));                                      \
+      hitmask |= bits << index;                                                                                      \
+    }                                                                                                                \
+  }
+#else
 #define RT_CHILD(k)                                                                                                  \
   {                                                                                                                  \
     const float tnx = fmaf(byteAsUnitFloat<k>(nearx, one), aix, nox), tfx = fmaf(byteAsUnitFloat<k>(farx, one), aix, fox); \
@@ -287,6 +328,7 @@ __device__ __forceinline__ uint32_t intersectChildren(const uint4 &n0, const uin
       hitmask |= bits << index;                                                                                      \
     }                                                                                                                \
   }
+#endif
     RT_CHILD(0) RT_CHILD(1) RT_CHILD(2) RT_CHILD(3)
 #undef RT_CHILD
   }
