@@ -54,6 +54,13 @@ for rebuild in (False, True):
             rnd.update()
         rnd.draw(u, count_rays=True)
     print("swarm rebuild" if rebuild else "swarm refit", rnd.read_ray_counters(), ctx.as_info(rnd.tlas_id()).wideNodeCount)
+    # rt_intersect on the same TLAS: closest and any hit, un-normalised directions, tmin / tmax windows
+    rays = np.zeros((1000, 8), np.float32)
+    rays[:, 0:3] = rng.uniform(-6, 6, (1000, 3)); rays[:, 4:7] = rng.uniform(-1, 1, (1000, 3)) - 0.2 * rays[:, 0:3]
+    rays[:, 3] = 0.01; rays[:, 7] = np.where(rng.random(1000) < 0.5, 2.0, np.inf)
+    hc, ha = ctx.intersect(rnd.tlas_id(), rays), ctx.intersect(rnd.tlas_id(), rays, any_hit=True)
+    assert np.array_equal(np.isfinite(hc["t"]), np.isfinite(ha["t"]))
+    print("intersect", int(np.isfinite(hc["t"]).sum()), "of 1000 rays hit")
     rnd.close()
 ctx.close()
 print("done")
