@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(kIntersectBlock, 7) k_intersect(const TlasHead
       t.template begin<kFlat>(tlas, stack, a.x, a.y, a.z, b.x, b.y, b.z, a.w, b.w); // origin, tmin | direction, tmax
     }
     while (__ballot_sync(full, active) != 0u) {
-      if (t.template stepConverged<kFlat, !kFlat, true, false, 2, false>(tlas, stack, active, nullptr)) {
+      if (t.template stepConverged<kFlat, !kFlat, true, false, 2, 0>(tlas, stack, active, nullptr)) {
         const RayHit h = t.result(stack);
         rt_ray_hit out;
         out.t = t.found ? (kAny ? 0.0f : h.t) : INFINITY;

@@ -370,10 +370,17 @@ constexpr int kStepsPerCheck = RT_STEPS_PER_CHECK;
 #ifndef RT_CONVERGED
 #define RT_CONVERGED 22
 #endif
-// RT_COOP_TRIS: the triangle stages of stepConverged are done by the warp together, 32 pending (lane, triangle) pairs per
-// pass (LaneTraversal::triangleStageCoop); 0: every lane tests its own next triangle
+// RT_COOP_TRIS: 1 = the triangle stages of stepConverged are done by the warp together, 32 pending (lane, triangle) pairs
+// per pass (LaneTraversal::triangleStageCoop); 2 = only when some lane has more than one triangle pending; 0: every lane
+// tests its own next triangle
 #ifndef RT_COOP_TRIS
 #define RT_COOP_TRIS 0
+#endif
+// The same switch for the any-hit (shadow) rays, where the cooperative pass only has to hand back one bit per owner and
+// testing every pending triangle at once finds an occluder sooner. Default 2: K3 -0.6 %, K4 -1.3 %, the 1-spp frame and a
+// rank's slice of an 8-GPU frame -2 ... -2.7 %; for closest hits the same stage costs K3 2 % (experiment log 9a, 9c).
+#ifndef RT_COOP_ANY
+#define RT_COOP_ANY 2
 #endif
 // entries of each lane's traversal stack kept in shared memory (0 = all in local memory), traverse.cuh SplitStack
 #ifndef RT_SHARED_STACK
@@ -459,7 +466,7 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
     for (int k = 0; k < kStepsPerCheck; ++k) {
 #if RT_CONVERGED > 0
       // flat TLAS: entry stage before the node stage only; otherwise as RT_CONVERGED says
-      if (t.template stepConverged<kFlat || (RT_CONVERGED & 1) != 0, !kFlat && (RT_CONVERGED & 4) != 0, (RT_CONVERGED & 2) != 0, (RT_CONVERGED & 8) != 0, 1 + ((RT_CONVERGED >> 4) & 3), RT_COOP_TRIS != 0>(P.tlas, stack, active, warpPairs)) {
+      if (t.template stepConverged<kFlat || (RT_CONVERGED & 1) != 0, !kFlat && (RT_CONVERGED & 4) != 0, (RT_CONVERGED & 2) != 0, (RT_CONVERGED & 8) != 0, 1 + ((RT_CONVERGED >> 4) & 3), (kAny ? RT_COOP_ANY : RT_COOP_TRIS)>(P.tlas, stack, active, warpPairs)) {
 #elif RT_FUSED_PRIMS > 0
       if (active && !t.template stepFused<RT_FUSED_PRIMS>(P.tlas, stack)) {
 #else
@@ -623,7 +630,7 @@ __device__ __forceinline__ void traceQueuePrefetch(const TraceParams &P, const u
 #endif
 #pragma unroll 1
     for (int k = 0; k < kStepsPerCheck; ++k) {
-      if (t.template stepConverged<kFlat || (RT_CONVERGED & 1) != 0, !kFlat && (RT_CONVERGED & 4) != 0, (RT_CONVERGED & 2) != 0, (RT_CONVERGED & 8) != 0, 1 + ((RT_CONVERGED >> 4) & 3), RT_COOP_TRIS != 0>(P.tlas, stack, active, warpPairs)) {
+      if (t.template stepConverged<kFlat || (RT_CONVERGED & 1) != 0, !kFlat && (RT_CONVERGED & 4) != 0, (RT_CONVERGED & 2) != 0, (RT_CONVERGED & 8) != 0, 1 + ((RT_CONVERGED >> 4) & 3), (kAny ? RT_COOP_ANY : RT_COOP_TRIS)>(P.tlas, stack, active, warpPairs)) {
         const uint32_t slot = stack.get(kSlotPath).x;
         if constexpr (kAny) {
           const uint2 c0 = stack.get(kSlotCarry0), c1 = stack.get(kSlotCarry1);
@@ -663,7 +670,7 @@ __global__ void __launch_bounds__(kTraceBlock, kMinBlocks) k_wf_traverse(const _
 #else
   uint2 *s_stack = nullptr;
 #endif
-#if RT_COOP_TRIS
+#if RT_COOP_TRIS || RT_COOP_ANY
   __shared__ uint32_t s_pairs[kTraceBlock]; // 32 words per warp: the pair list of the cooperative triangle stage
   uint32_t *warpPairs = s_pairs + (threadIdx.x & ~31u);
 #else

@@ -740,7 +740,7 @@ struct LaneTraversal {
   // earlier stage running apart from those that did not — ncu showed the same thread instructions in 1.3-1.5x the
   // warp instructions (profiles/r1_traversal.md, step 12). Per lane the order of node, entry and triangle tests is
   // the one stepFused has, so results are unchanged. Returns true when this lane's ray has just finished.
-  template <bool kEntryBefore, bool kEntryAfter, bool kEarlyFinish, bool kCombined, int kTriangles, bool kCoop, typename Stack>
+  template <bool kEntryBefore, bool kEntryAfter, bool kEarlyFinish, bool kCombined, int kTriangles, int kCoop, typename Stack>
   __device__ __forceinline__ bool stepConverged(const TlasHeader &tlas, Stack &stack, bool active, uint32_t *pairs) {
     bool alive = active;
 #ifdef RT_COUNT_WORK
@@ -772,7 +772,13 @@ struct LaneTraversal {
       for (int k = 0; k < kTriangles; ++k) {
         const bool want = alive && !satisfied && tgroup.y != 0u && instanceSp >= 0;
         if (__ballot_sync(0xFFFFFFFFu, want) != 0u) {
-          if (triangleStageCoop(stack, want, pairs)) satisfied = true;
+          // kCoop == 2: when no lane has more than one triangle pending there is nothing to redistribute and every lane
+          // tests its own in place (the cheaper stage); the cooperative pass runs when it replaces two or more of those
+          if (kCoop == 2 && __ballot_sync(0xFFFFFFFFu, want && (tgroup.y & (tgroup.y - 1u)) != 0u) == 0u) {
+            if (want) satisfied = triangleStep(stack);
+          } else if (triangleStageCoop(stack, want, pairs)) {
+            satisfied = true;
+          }
         }
         __syncwarp();
       }
