@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 import oracle
+from brute_force import brute_force_hits, uv_sphere
 from metal4_raytracing_b200 import _abi as A
 from metal4_raytracing_b200 import device, parallel, scene
 
@@ -1134,70 +1135,6 @@ def test_sample_partition_shares_sum_to_the_frame(mode):
     finally:
         ctx.close()
 
-def _uv_sphere(rings, sectors, radius):
-    """Vertices (n, 4) float32 and triangles (m, 3) int32 of a latitude / longitude sphere, poles included."""
-    v = [(0.0, radius, 0.0)]
-    for r in range(1, rings):
-        th = np.pi * r / rings
-        for s in range(sectors):
-            ph = 2.0 * np.pi * s / sectors
-            v.append((radius * np.sin(th) * np.cos(ph), radius * np.cos(th), radius * np.sin(th) * np.sin(ph)))
-    v.append((0.0, -radius, 0.0))
-    tri = []
-    for s in range(sectors):
-        tri.append((0, 1 + (s + 1) % sectors, 1 + s))
-    for r in range(rings - 2):
-        a, b = 1 + r * sectors, 1 + (r + 1) * sectors
-        for s in range(sectors):
-            s1 = (s + 1) % sectors
-            tri += [(a + s, a + s1, b + s), (a + s1, b + s1, b + s)]
-    last, a = len(v) - 1, 1 + (rings - 2) * sectors
-    for s in range(sectors):
-        tri.append((last, a + s, a + (s + 1) % sectors))
-    verts = np.zeros((len(v), 4), np.float32)
-    verts[:, :3] = np.array(v, np.float32)
-    return verts, np.array(tri, np.int32)
-
-
-def _brute_force_hits(tris_world, owner, rays):
-    """float64 Moeller-Trumbore of every ray against every world-space triangle: per ray the two smallest t in
-    (tmin, tmax) and the index of the smallest; independent of the library's BVH, transforms and triangle test."""
-    o, d = rays[:, 0:3].astype(np.float64), rays[:, 4:7].astype(np.float64)
-    tmin, tmax = rays[:, 3].astype(np.float64), rays[:, 7].astype(np.float64)
-    v0, e1, e2 = tris_world[:, 0], tris_world[:, 1] - tris_world[:, 0], tris_world[:, 2] - tris_world[:, 0]
-    best = np.full(len(rays), np.inf)
-    second = np.full(len(rays), np.inf)
-    arg = np.full(len(rays), -1, np.int64)
-    margin = np.full(len(rays), np.inf)  # how far inside the winning triangle's edges the hit lies (barycentric units)
-    for lo in range(0, len(rays), 256):
-        O, D = o[lo:lo + 256, None, :], d[lo:lo + 256, None, :]
-        p = np.cross(D, e2[None])
-        det = np.einsum("rtk,tk->rt", p, e1)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            inv = 1.0 / det
-            s = O - v0[None]
-            u = np.einsum("rtk,rtk->rt", s, p) * inv
-            q = np.cross(s, e1[None])
-            v = np.einsum("rtk,rtk->rt", np.broadcast_to(D, q.shape), q) * inv
-            t = np.einsum("rtk,tk->rt", q, e2) * inv
-        t_all = t
-        ok = (np.abs(det) > 0) & (u >= 0) & (v >= 0) & (u + v <= 1) & (t > tmin[lo:lo + 256, None]) & (t < tmax[lo:lo + 256, None])
-        t = np.where(ok, t, np.inf)
-        order = np.argsort(t, axis=1)[:, :2]
-        rows = np.arange(t.shape[0])
-        best[lo:lo + 256] = t[rows, order[:, 0]]
-        second[lo:lo + 256] = t[rows, order[:, 1]]
-        arg[lo:lo + 256] = np.where(np.isfinite(t[rows, order[:, 0]]), order[:, 0], -1)
-        uu, vv = u[rows, order[:, 0]], v[rows, order[:, 0]]
-        inside = np.where(arg[lo:lo + 256] >= 0, np.minimum(np.minimum(uu, vv), 1.0 - uu - vv), 1.0)
-        # a ray that passes within a hair of an edge of ANY triangle in range may legitimately come out differently in
-        # float32 and float64: margin 0 takes it out of the comparison
-        in_range = (np.abs(det) > 0) & (t_all > tmin[lo:lo + 256, None] - 1e-4) & (t_all < tmax[lo:lo + 256, None] + 1e-4)
-        edge_any = (in_range & (np.abs(np.minimum(np.minimum(u, v), 1 - u - v)) < 1e-4)).any(axis=1)
-        margin[lo:lo + 256] = np.where(edge_any, 0.0, inside)
-    return best, second, arg, margin
-
-
 @pytest.mark.parametrize("instances", [3, 40])
 def test_intersect_against_brute_force(gpu_ctx, instances):
     """rt_intersect — the shipped traversal iteration on caller-supplied rays — against a float64 brute force over
@@ -1205,7 +1142,7 @@ def test_intersect_against_brute_force(gpu_ctx, instances):
     shared with the GPU path would show here. 3 instances take the flat-TLAS kernels, 40 the real
     TLAS; geometry 1 of the two-geometry BLAS is a grid of quads, instance transforms rotate, scale unevenly and move."""
     rng = np.random.default_rng(17 + instances)
-    sph_v, sph_t = _uv_sphere(24, 32, 1.0)                      # 1472 triangles
+    sph_v, sph_t = uv_sphere(24, 32, 1.0)                      # 1472 triangles
     g = np.linspace(-1.5, 1.5, 13, dtype=np.float32)
     gx, gz = np.meshgrid(g, g, indexing="ij")
     grid_v = np.zeros((169, 4), np.float32)
@@ -1252,7 +1189,7 @@ def test_intersect_against_brute_force(gpu_ctx, instances):
     rays[: n // 8, 4:7] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, n // 8)] * rng.choice([-1.0, 1.0], (n // 8, 1))
     rays[:, 3] = np.where(rng.random(n) < 0.3, rng.uniform(0.0, 0.4, n), 0.0)
     rays[:, 7] = np.where(rng.random(n) < 0.4, rng.uniform(0.3, 2.0, n), np.inf)
-    best, second, arg, margin = _brute_force_hits(tris_world, owner, rays)
+    best, second, arg, margin = brute_force_hits(tris_world, owner, rays)
     hits = gpu_ctx.intersect(tlas, rays)
     occl = gpu_ctx.intersect(tlas, rays, any_hit=True)
     clear = np.isfinite(best) & (margin > 1e-3)                   # the float64 winner is hit well inside its edges
