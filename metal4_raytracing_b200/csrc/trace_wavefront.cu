@@ -376,6 +376,10 @@ constexpr int kStepsPerCheck = RT_STEPS_PER_CHECK;
 #ifndef RT_COOP_TRIS
 #define RT_COOP_TRIS 0
 #endif
+// the closest-hit switch of the kernels built for a real TLAS (more than 8 instances); follows RT_COOP_TRIS unless set
+#ifndef RT_COOP_TRIS_REAL
+#define RT_COOP_TRIS_REAL RT_COOP_TRIS
+#endif
 // The same switch for the any-hit (shadow) rays, where the cooperative pass only has to hand back one bit per owner and
 // testing every pending triangle at once finds an occluder sooner. Default 2: K3 -0.6 %, K4 -1.3 %, the 1-spp frame and a
 // rank's slice of an 8-GPU frame -2 ... -2.7 %; for closest hits the same stage costs K3 2 % (experiment log 9a, 9c).
@@ -466,7 +470,7 @@ __device__ __forceinline__ void traceQueue(const TraceParams &P, const uint32_t 
     for (int k = 0; k < kStepsPerCheck; ++k) {
 #if RT_CONVERGED > 0
       // flat TLAS: entry stage before the node stage only; otherwise as RT_CONVERGED says
-      if (t.template stepConverged<kFlat || (RT_CONVERGED & 1) != 0, !kFlat && (RT_CONVERGED & 4) != 0, (RT_CONVERGED & 2) != 0, (RT_CONVERGED & 8) != 0, 1 + ((RT_CONVERGED >> 4) & 3), (kAny ? RT_COOP_ANY : RT_COOP_TRIS)>(P.tlas, stack, active, warpPairs)) {
+      if (t.template stepConverged<kFlat || (RT_CONVERGED & 1) != 0, !kFlat && (RT_CONVERGED & 4) != 0, (RT_CONVERGED & 2) != 0, (RT_CONVERGED & 8) != 0, 1 + ((RT_CONVERGED >> 4) & 3), (kAny ? RT_COOP_ANY : (kFlat ? RT_COOP_TRIS : RT_COOP_TRIS_REAL))>(P.tlas, stack, active, warpPairs)) {
 #elif RT_FUSED_PRIMS > 0
       if (active && !t.template stepFused<RT_FUSED_PRIMS>(P.tlas, stack)) {
 #else
@@ -630,7 +634,7 @@ __device__ __forceinline__ void traceQueuePrefetch(const TraceParams &P, const u
 #endif
 #pragma unroll 1
     for (int k = 0; k < kStepsPerCheck; ++k) {
-      if (t.template stepConverged<kFlat || (RT_CONVERGED & 1) != 0, !kFlat && (RT_CONVERGED & 4) != 0, (RT_CONVERGED & 2) != 0, (RT_CONVERGED & 8) != 0, 1 + ((RT_CONVERGED >> 4) & 3), (kAny ? RT_COOP_ANY : RT_COOP_TRIS)>(P.tlas, stack, active, warpPairs)) {
+      if (t.template stepConverged<kFlat || (RT_CONVERGED & 1) != 0, !kFlat && (RT_CONVERGED & 4) != 0, (RT_CONVERGED & 2) != 0, (RT_CONVERGED & 8) != 0, 1 + ((RT_CONVERGED >> 4) & 3), (kAny ? RT_COOP_ANY : (kFlat ? RT_COOP_TRIS : RT_COOP_TRIS_REAL))>(P.tlas, stack, active, warpPairs)) {
         const uint32_t slot = stack.get(kSlotPath).x;
         if constexpr (kAny) {
           const uint2 c0 = stack.get(kSlotCarry0), c1 = stack.get(kSlotCarry1);
@@ -670,7 +674,7 @@ __global__ void __launch_bounds__(kTraceBlock, kMinBlocks) k_wf_traverse(const _
 #else
   uint2 *s_stack = nullptr;
 #endif
-#if RT_COOP_TRIS || RT_COOP_ANY
+#if RT_COOP_TRIS || RT_COOP_ANY || RT_COOP_TRIS_REAL
   __shared__ uint32_t s_pairs[kTraceBlock]; // 32 words per warp: the pair list of the cooperative triangle stage
   uint32_t *warpPairs = s_pairs + (threadIdx.x & ~31u);
 #else
